@@ -1,0 +1,121 @@
+/*
+ * pcc_b200.h -- C ABI of libpcc_b200.so, the B200 (sm_100a) implementation of the geometric hot path of
+ * rhmes/point-cloud-compression.
+ *
+ * The reference has no FFI for this path: it calls plain Python functions (its own pn_kit helpers and the
+ * PyTorch3D ops it imports).  Each entry point below replaces one of those calls; the Python host code in
+ * point-cloud-compression_b200/pcc_b200/ binds them with ctypes and keeps the reference's signatures
+ * (INTEGRATION.md shows the binding).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to a dense, contiguous, caller-owned buffer (float32 / int64);
+ *     the library allocates nothing persistent and never synchronises the host (except pcc_fps_f32 for
+ *     clouds that need a cooperative launch, which only queries occupancy once per process);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); kernels are only enqueued;
+ *   - return 0 on success, a negative PCC_ERR_* for an argument error, a positive cudaError_t if a launch
+ *     failed; pcc_last_error_string() describes the last failure on the calling thread;
+ *   - no C++ exception crosses this boundary, and there is NO CPU fallback: unsupported shapes are errors.
+ *   - squared distances follow the reference CPU arithmetic bit for bit:
+ *         d2 = fl(fl(fl(dx*dx) + fl(dy*dy)) + fl(dz*dz))      (no FMA contraction)
+ *     and every tie goes to the lowest index.
+ */
+#ifndef PCC_B200_H
+#define PCC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCC_ERR_INVALID_ARGUMENT (-1)
+#define PCC_ERR_UNSUPPORTED (-2)
+
+#define PCC_MAX_KNN_K 1024
+
+/* Library version (major*10000 + minor*100 + patch) and the last error text of the calling thread. */
+int pcc_version(void);
+const char *pcc_last_error_string(void);
+
+/*
+ * Farthest point sampling of `npoint` indices from each of B clouds of N points.
+ * Replaces pn_kit.farthest_point_sample_batch (/root/reference/pn_kit.py:309-330): pass the reference's
+ * torch.randint draw in start_idx[B] (device int64) and init_dist = 1e10;
+ * and pytorch3d.ops.sample_farthest_points (/root/reference/pointnet_sa_module.py:10-13): start_idx = NULL
+ * (start at index 0), init_dist = FLT_MAX.
+ * out_idx[B, npoint] int64; entries k >= N are -1 (PyTorch3D padding when npoint > N).
+ * Clouds with N > 8192 are spread over several co-resident CTAs and need a device `workspace` of
+ * pcc_fps_workspace_bytes(B, N, npoint) bytes (0 for N <= 8192 -> NULL allowed).
+ */
+int64_t pcc_fps_workspace_bytes(int B, int N, int npoint);
+int pcc_fps_f32(const float *xyz, int B, int N, int npoint, const int64_t *start_idx, float init_dist,
+                int64_t *out_idx, void *workspace, void *stream);
+
+/*
+ * K nearest neighbours of every q[b, i] among p[b, :], ascending in (d2, idx).
+ * Replaces pytorch3d.ops.knn_points (call sites /root/reference/train.py:185, compress.py:71, pn_kit.py:190,
+ * pppe_pcd_ae.py:599, eval.py:132).  1 <= K <= PCC_MAX_KNN_K.
+ *   out_d2 [B,P1,K] float32, out_idx [B,P1,K] int64; slots k >= P2 hold d2 = 0, idx = 0.
+ *   out_nn (nullable) [B,P1,K,3]: the gathered neighbours (return_nn=True); with centre_sub != 0 the query is
+ *   subtracted (the `grouped_xyz -= centre` that follows every reference call: train.py:188, compress.py:72,
+ *   pn_kit.py:191) and the result is multiplied by nn_scale (train.py:192, compress.py:108; pass 1.0f to
+ *   leave it out -- the multiply is a separately rounded fp32 op, as in the reference).
+ */
+int pcc_knn_f32(const float *q, const float *p, int B, int P1, int P2, int K, float *out_d2, int64_t *out_idx,
+                float *out_nn, int centre_sub, float nn_scale, void *stream);
+
+/*
+ * Ball query: the first K indices j (in index order) with d2(q[b,i], p[b,j]) < radius*radius.
+ * Replaces pytorch3d.ops.ball_query (/root/reference/pointnet_sa_module.py:16-19).
+ *   out_idx [B,P1,K] int64 padded with -1; out_d2 (nullable) [B,P1,K] padded with 0.
+ */
+int pcc_ball_query_f32(const float *q, const float *p, int B, int P1, int P2, int K, float radius,
+                       int64_t *out_idx, float *out_d2, void *stream);
+
+/*
+ * Row gather out[b, m, :] = feat[b, idx[b, m], :] for feat [B,N,C], idx [B,M] (any [B,S] / [B,S,K] index
+ * tensor flattened).  Replaces pn_kit.index_points (/root/reference/pn_kit.py:332-360), pytorch3d knn_gather
+ * (/root/reference/pointnet_sa_module.py:28) and the torch.gather at pointnet_sa_module.py:68.
+ * Indices must lie in [0, N); negative indices are an error the caller clamps away first, as the reference does
+ * (pointnet_sa_module.py:27).  pcc_gather_bwd_f32 scatter-adds grad_out into grad_feat (zero-filled by caller).
+ */
+int pcc_gather_f32(const float *feat, const int64_t *idx, int B, int N, int C, int64_t M, float *out,
+                   void *stream);
+int pcc_gather_bwd_f32(const float *grad_out, const int64_t *idx, int B, int N, int C, int64_t M,
+                       float *grad_feat, void *stream);
+
+/*
+ * Nearest neighbour (K = 1) of every q[b, i] in p[b, :]: out_d2 [B,P1], out_idx (nullable) [B,P1] int64.
+ * The inner step of the D1 PSNR loop (/root/reference/eval.py:68-81) and of chamfer_distance.
+ * `workspace` must hold pcc_nn1_workspace_bytes(B, P1, P2) bytes (may be 0 -> NULL allowed).
+ */
+int64_t pcc_nn1_workspace_bytes(int B, int P1, int P2);
+int pcc_nn1_f32(const float *q, const float *p, int B, int P1, int P2, float *out_d2, int64_t *out_idx,
+                void *workspace, void *stream);
+
+/*
+ * Chamfer distance, both directions, point_reduction = batch_reduction = "mean".
+ * Replaces pytorch3d.loss.chamfer_distance (/root/reference/AE.py:67, PPPF_AE.py:168, pppe_pcd_ae.py:820,
+ * eval.py:204).
+ *   out_dx [B,P1], out_ix [B,P1] (nullable), out_dy [B,P2], out_iy [B,P2] (nullable): per-point minima
+ *   (bit-exact) and their argmins (needed by the backward);
+ *   out_per_cloud [B] float32: mean_i dx + mean_j dy of each cloud;  out_loss [1] float32: their mean.
+ * `workspace` must hold pcc_chamfer_workspace_bytes(B, P1, P2) bytes.
+ */
+int64_t pcc_chamfer_workspace_bytes(int B, int P1, int P2);
+int pcc_chamfer_fwd_f32(const float *x, const float *y, int B, int P1, int P2, float *out_dx, int64_t *out_ix,
+                        float *out_dy, int64_t *out_iy, float *out_per_cloud, float *out_loss, void *workspace,
+                        void *stream);
+
+/*
+ * Chamfer backward (PyTorch3D knn_points_backward through both K=1 searches):
+ *   gx[b,i] += 2*wx*(x_i - y_ix[i]),  gy[b,ix[i]] -= same   with wx = grad_loss / (B*P1), and symmetrically
+ *   with wy = grad_loss / (B*P2).   grad_loss is a DEVICE scalar.  gx, gy are overwritten (zeroed inside).
+ */
+int pcc_chamfer_bwd_f32(const float *x, const float *y, const int64_t *ix, const int64_t *iy, int B, int P1,
+                        int P2, const float *grad_loss, float *gx, float *gy, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCC_B200_H */

@@ -1,0 +1,167 @@
+"""ctypes front end of the CPU oracle (oracle/pcc_oracle.c).  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this module.
+Every function takes and returns CPU numpy arrays (float32 / int64) and mirrors the signature of the reference
+function it restates; see pcc_oracle.c for the reference file:line of each.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libpcc_oracle.so")
+_lib = None
+
+_f32p = ctypes.POINTER(ctypes.c_float)
+_i64p = ctypes.POINTER(ctypes.c_int64)
+_f64p = ctypes.POINTER(ctypes.c_double)
+_i64 = ctypes.c_int64
+
+
+def build(force=False):
+    """Compile libpcc_oracle.so with the recipe in oracle/Makefile."""
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(
+            os.path.join(_HERE, "pcc_oracle.c")):
+        subprocess.check_call(["make", "-C", _HERE, "-s"], env={k: v for k, v in os.environ.items() if k != "CC"})
+    return _LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = ctypes.CDLL(_LIB_PATH)
+        L.orc_num_threads.restype = ctypes.c_int
+        L.orc_fps.argtypes = [_f32p, _i64, _i64, _i64, _i64p, ctypes.c_float, ctypes.c_int, _i64p, ctypes.c_int]
+        L.orc_gather.argtypes = [_f32p, _i64p, _i64, _i64, _i64, _i64, _f32p]
+        L.orc_knn.argtypes = [_f32p, _f32p, _i64, _i64, _i64, _i64, _f32p, _i64p, ctypes.c_int]
+        L.orc_ball_query.argtypes = [_f32p, _f32p, _i64, _i64, _i64, _i64, ctypes.c_float, _i64p, _f32p,
+                                     ctypes.c_int]
+        L.orc_nn1.argtypes = [_f32p, _f32p, _i64, _i64, _i64, _f32p, _i64p, ctypes.c_int]
+        L.orc_chamfer.argtypes = [_f32p, _f32p, _i64, _i64, _i64, _f32p, _i64p, _f32p, _i64p, _f64p, ctypes.c_int]
+        L.orc_chamfer.restype = ctypes.c_double
+        L.orc_chamfer_bwd.argtypes = [_f32p, _f32p, _i64p, _i64p, _i64, _i64, _i64, ctypes.c_float, _f32p, _f32p]
+        L.orc_d1_psnr.argtypes = [_f32p, _i64, _f32p, _i64, _f64p]
+        L.orc_d1_psnr.restype = ctypes.c_double
+        _lib = L
+    return _lib
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _pf(a):
+    return a.ctypes.data_as(_f32p)
+
+
+def _pi(a):
+    return a.ctypes.data_as(_i64p)
+
+
+def num_threads():
+    return int(lib().orc_num_threads())
+
+
+def fps(xyz, npoint, start_idx=None, init_dist=1e10, pad_beyond_n=False, threads=1):
+    """pn_kit.farthest_point_sample_batch (start_idx = the reference's randint draw, init 1e10) or PyTorch3D
+    sample_farthest_points (start_idx=None, init FLT_MAX, pad_beyond_n=True)."""
+    xyz = _f32(xyz)
+    B, N, _ = xyz.shape
+    out = np.empty((B, npoint), dtype=np.int64)
+    si = None
+    if start_idx is not None:
+        si = np.ascontiguousarray(start_idx, dtype=np.int64)
+    lib().orc_fps(_pf(xyz), B, N, npoint, _pi(si) if si is not None else None, np.float32(init_dist),
+                  int(bool(pad_beyond_n)), _pi(out), threads)
+    return out
+
+
+FLT_MAX = float(np.finfo(np.float32).max)
+
+
+def sample_farthest_points(points, K):
+    """PyTorch3D semantics (pointnet_sa_module.py:10-13): returns (gathered points, idx); idx padded with -1."""
+    idx = fps(points, K, None, FLT_MAX, True)
+    pts = gather(points, np.maximum(idx, 0))
+    pts[idx < 0] = 0.0  # masked_gather zeroes the padded rows
+    return pts, idx
+
+
+def gather(feat, idx):
+    """index_points / knn_gather: feat [B,N,C], idx [B,...] -> [B,...,C]."""
+    feat = _f32(feat)
+    idx = np.ascontiguousarray(idx, dtype=np.int64)
+    B, N, C = feat.shape
+    M = int(np.prod(idx.shape[1:])) if idx.ndim > 1 else 1
+    out = np.empty((B, M, C), dtype=np.float32)
+    lib().orc_gather(_pf(feat), _pi(idx), B, N, C, M, _pf(out))
+    return out.reshape(tuple(idx.shape) + (C,))
+
+
+def knn_points(p1, p2, K, return_nn=False, threads=1):
+    p1, p2 = _f32(p1), _f32(p2)
+    B, P1, _ = p1.shape
+    P2 = p2.shape[1]
+    d = np.empty((B, P1, K), dtype=np.float32)
+    i = np.empty((B, P1, K), dtype=np.int64)
+    lib().orc_knn(_pf(p1), _pf(p2), B, P1, P2, K, _pf(d), _pi(i), threads)
+    nn = gather(p2, i) if return_nn else None
+    return d, i, nn
+
+
+def ball_query(p1, p2, K, radius, threads=1):
+    p1, p2 = _f32(p1), _f32(p2)
+    B, P1, _ = p1.shape
+    P2 = p2.shape[1]
+    i = np.empty((B, P1, K), dtype=np.int64)
+    d = np.empty((B, P1, K), dtype=np.float32)
+    lib().orc_ball_query(_pf(p1), _pf(p2), B, P1, P2, K, np.float32(radius), _pi(i), _pf(d), threads)
+    return d, i
+
+
+def nn1(p1, p2, threads=1):
+    p1, p2 = _f32(p1), _f32(p2)
+    B, P1, _ = p1.shape
+    P2 = p2.shape[1]
+    d = np.empty((B, P1), dtype=np.float32)
+    i = np.empty((B, P1), dtype=np.int64)
+    lib().orc_nn1(_pf(p1), _pf(p2), B, P1, P2, _pf(d), _pi(i), threads)
+    return d, i
+
+
+def chamfer(x, y, threads=1):
+    """Returns (loss, per_cloud[B], dx[B,P1], ix, dy[B,P2], iy)."""
+    x, y = _f32(x), _f32(y)
+    B, P1, _ = x.shape
+    P2 = y.shape[1]
+    dx = np.empty((B, P1), dtype=np.float32)
+    ix = np.empty((B, P1), dtype=np.int64)
+    dy = np.empty((B, P2), dtype=np.float32)
+    iy = np.empty((B, P2), dtype=np.int64)
+    pc = np.empty((B,), dtype=np.float64)
+    loss = lib().orc_chamfer(_pf(x), _pf(y), B, P1, P2, _pf(dx), _pi(ix), _pf(dy), _pi(iy),
+                             pc.ctypes.data_as(_f64p), threads)
+    return float(loss), pc, dx, ix, dy, iy
+
+
+def chamfer_bwd(x, y, ix, iy, grad=1.0):
+    x, y = _f32(x), _f32(y)
+    B, P1, _ = x.shape
+    P2 = y.shape[1]
+    gx = np.zeros_like(x)
+    gy = np.zeros_like(y)
+    ix = np.ascontiguousarray(ix, dtype=np.int64)
+    iy = np.ascontiguousarray(iy, dtype=np.int64)
+    lib().orc_chamfer_bwd(_pf(x), _pf(y), _pi(ix), _pi(iy), B, P1, P2, np.float32(grad), _pf(gx), _pf(gy))
+    return gx, gy
+
+
+def d1_psnr(orig, recon):
+    """eval.py:43-98 point-to-point PSNR (float64), returns (psnr_db, mse)."""
+    orig, recon = _f32(orig), _f32(recon)
+    mse = ctypes.c_double(0.0)
+    psnr = lib().orc_d1_psnr(_pf(orig), orig.shape[0], _pf(recon), recon.shape[0], ctypes.byref(mse))
+    return float(psnr), float(mse.value)

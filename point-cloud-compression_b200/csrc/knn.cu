@@ -1,0 +1,293 @@
+// Brute-force K nearest neighbours for sm_100a, bit-exact to PyTorch3D's CPU knn_points
+// (call sites /root/reference/train.py:185, compress.py:71, pn_kit.py:190, pppe_pcd_ae.py:599, eval.py:132).
+//
+// Result definition: the K smallest (d2, idx) pairs in lexicographic order, ascending -- exactly what the
+// upstream max-heap of (dist, idx) tuples produces.  Because the result is fully determined by the set of
+// un-fused d2 values, any selection algorithm gives identical output; two are used:
+//
+// knn_warp_kernel  (any 1 <= K <= 1024): one WARP per query, candidates staged in shared-memory tiles shared
+//   by the CTA's warps.  Each lane evaluates one candidate per step and packs (d2 bits, idx) into a u64 key
+//   whose unsigned order is the lexicographic order.  Keys below the current K-th best are appended (ballot +
+//   popc compaction) to a per-warp shared buffer of 2*Kp keys; when it fills, a warp-level bitonic sort keeps
+//   the best K and tightens the threshold.  After warm-up almost every 32-candidate step is rejected by one
+//   ballot, so the cost is ~12 instructions per pair.
+//
+// knn_thread_kernel (K <= 32, small candidate sets, many queries -- the in-patch 256x256 K=16 search of
+//   pn_kit.SetAbstraction): one THREAD per query, sorted top-K in registers, candidates read as float4
+//   shared-memory broadcasts, results staged through shared memory so global writes are coalesced.
+//
+// Both kernels are CUDA-core / shared-memory bound: inputs are 12 B per point, read once per CTA.
+#include "pcc_common.cuh"
+
+namespace pcc {
+
+constexpr int KNN_TILE = 1024;
+
+// ---- warp-per-query kernel -------------------------------------------------------------------------------
+__device__ __forceinline__ void warp_bitonic_sort(unsigned long long *keys, int cap) {
+    const unsigned lane = lane_id();
+    for (int k = 2; k <= cap; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = lane; t < (cap >> 1); t += 32) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int l = i | j;
+                const bool up = (i & k) == 0;
+                const unsigned long long a = keys[i], b = keys[l];
+                if ((a > b) == up) {
+                    keys[i] = b;
+                    keys[l] = a;
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// Keep the K smallest of keys[0..count): pad to cap, sort, return min(count, K).
+__device__ __forceinline__ int warp_select(unsigned long long *keys, int count, int cap, int K) {
+    for (int t = count + lane_id(); t < cap; t += 32) keys[t] = KEY_MAX;
+    __syncwarp();
+    warp_bitonic_sort(keys, cap);
+    return count < K ? count : K;
+}
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+knn_warp_kernel(const float *__restrict__ q, const float *__restrict__ p, int P1, int P2, int K, int cap,
+                float *__restrict__ out_d2, int64_t *__restrict__ out_idx, float *__restrict__ out_nn,
+                int centre_sub, float nn_scale) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *tx = reinterpret_cast<float *>(smem_raw);
+    float *ty = tx + KNN_TILE;
+    float *tz = ty + KNN_TILE;
+    unsigned long long *all_keys = reinterpret_cast<unsigned long long *>(tz + KNN_TILE);
+
+    const int b = blockIdx.y;
+    const unsigned lane = lane_id();
+    const int warp = threadIdx.x >> 5;
+    const int qi = blockIdx.x * WARPS + warp;
+    const bool active = qi < P1;
+    const float *pc = p + static_cast<size_t>(b) * P2 * 3;
+    unsigned long long *keys = all_keys + static_cast<size_t>(warp) * cap;
+
+    float qx = 0.f, qy = 0.f, qz = 0.f;
+    if (active) {
+        const float *qp = q + (static_cast<size_t>(b) * P1 + qi) * 3;
+        qx = qp[0];
+        qy = qp[1];
+        qz = qp[2];
+    }
+    int count = 0;
+    unsigned long long thresh = KEY_MAX;
+
+    for (int t0 = 0; t0 < P2; t0 += KNN_TILE) {
+        const int tn = min(KNN_TILE, P2 - t0);
+        __syncthreads();  // previous tile fully consumed
+        for (int e = threadIdx.x; e < tn * 3; e += WARPS * 32) {
+            const float v = pc[static_cast<size_t>(t0) * 3 + e];
+            const int pt = e / 3, c = e - pt * 3;
+            (c == 0 ? tx : (c == 1 ? ty : tz))[pt] = v;
+        }
+        __syncthreads();
+        if (!active) continue;
+        for (int c0 = 0; c0 < tn; c0 += 32) {
+            const int j = c0 + lane;
+            unsigned long long key = KEY_MAX;
+            if (j < tn) key = pack_key(dist2_rn(qx, qy, qz, tx[j], ty[j], tz[j]), static_cast<unsigned>(t0 + j));
+            const bool pass = key < thresh;
+            const unsigned m = __ballot_sync(FULL_MASK, pass);
+            if (m == 0u) continue;
+            if (pass) keys[count + __popc(m & ((1u << lane) - 1u))] = key;
+            count += __popc(m);
+            if (count + 32 > cap) {
+                __syncwarp();
+                count = warp_select(keys, count, cap, K);
+                thresh = count >= K ? keys[K - 1] : KEY_MAX;
+            }
+        }
+    }
+    if (!active) return;
+    __syncwarp();
+    count = warp_select(keys, count, cap, K);
+
+    const size_t obase = (static_cast<size_t>(b) * P1 + qi) * K;
+    for (int k = lane; k < K; k += 32) {
+        float d = 0.0f;
+        unsigned idx = 0u;
+        if (k < count) {
+            const unsigned long long key = keys[k];
+            d = key_d2(key);
+            idx = key_idx(key);
+        }
+        out_d2[obase + k] = d;
+        out_idx[obase + k] = static_cast<int64_t>(idx);
+        if (out_nn) {
+            float nx = pc[static_cast<size_t>(idx) * 3 + 0], ny = pc[static_cast<size_t>(idx) * 3 + 1],
+                  nz = pc[static_cast<size_t>(idx) * 3 + 2];
+            if (centre_sub) {
+                nx = __fsub_rn(nx, qx);
+                ny = __fsub_rn(ny, qy);
+                nz = __fsub_rn(nz, qz);
+            }
+            if (nn_scale != 1.0f) {
+                nx = __fmul_rn(nx, nn_scale);
+                ny = __fmul_rn(ny, nn_scale);
+                nz = __fmul_rn(nz, nn_scale);
+            }
+            float *o = out_nn + (obase + k) * 3;
+            o[0] = nx;
+            o[1] = ny;
+            o[2] = nz;
+        }
+    }
+}
+
+// ---- thread-per-query kernel ---------------------------------------------------------------------------------
+constexpr int KT_THREADS = 256;
+
+template <int KT>
+__global__ void __launch_bounds__(KT_THREADS)
+knn_thread_kernel(const float *__restrict__ q, const float *__restrict__ p, int P1, int P2, int K,
+                  float *__restrict__ out_d2, int64_t *__restrict__ out_idx, float *__restrict__ out_nn,
+                  int centre_sub, float nn_scale) {
+    constexpr int STAGE_LD = KT + 1;
+    constexpr int TILE_BYTES = KNN_TILE * 16;
+    constexpr int STAGE_BYTES = KT_THREADS * STAGE_LD * 4;
+    __shared__ __align__(16) unsigned char smem_raw[TILE_BYTES > STAGE_BYTES ? TILE_BYTES : STAGE_BYTES];
+    __shared__ float sq[KT_THREADS * 3];
+    float4 *tile = reinterpret_cast<float4 *>(smem_raw);
+    unsigned *stage = reinterpret_cast<unsigned *>(smem_raw);
+
+    const int b = blockIdx.y;
+    const int q0 = blockIdx.x * KT_THREADS;
+    const int qi = q0 + threadIdx.x;
+    const bool active = qi < P1;
+    const float *pc = p + static_cast<size_t>(b) * P2 * 3;
+
+    float qx = 0.f, qy = 0.f, qz = 0.f;
+    if (active) {
+        const float *qp = q + (static_cast<size_t>(b) * P1 + qi) * 3;
+        qx = qp[0];
+        qy = qp[1];
+        qz = qp[2];
+    }
+    sq[threadIdx.x * 3 + 0] = qx;
+    sq[threadIdx.x * 3 + 1] = qy;
+    sq[threadIdx.x * 3 + 2] = qz;
+
+    float dl[KT];
+    unsigned il[KT];
+#pragma unroll
+    for (int s = 0; s < KT; ++s) {
+        dl[s] = __int_as_float(0x7f800000);  // +inf: unfilled
+        il[s] = 0u;
+    }
+
+    for (int t0 = 0; t0 < P2; t0 += KNN_TILE) {
+        const int tn = min(KNN_TILE, P2 - t0);
+        __syncthreads();
+        for (int pt = threadIdx.x; pt < tn; pt += KT_THREADS) {
+            const float *s = pc + static_cast<size_t>(t0 + pt) * 3;
+            tile[pt] = make_float4(s[0], s[1], s[2], 0.f);
+        }
+        __syncthreads();
+        for (int j = 0; j < tn; ++j) {
+            const float4 c = tile[j];
+            const float d = dist2_rn(qx, qy, qz, c.x, c.y, c.z);
+            if (d < dl[KT - 1]) {  // strict: an equal distance with a larger index never displaces
+                dl[KT - 1] = d;
+                il[KT - 1] = static_cast<unsigned>(t0 + j);
+#pragma unroll
+                for (int s = KT - 1; s > 0; --s) {
+                    const bool sw = dl[s] < dl[s - 1];  // strict keeps earlier (lower) indices first on ties
+                    const float dlo = sw ? dl[s] : dl[s - 1], dhi = sw ? dl[s - 1] : dl[s];
+                    const unsigned ilo = sw ? il[s] : il[s - 1], ihi = sw ? il[s - 1] : il[s];
+                    dl[s - 1] = dlo;
+                    dl[s] = dhi;
+                    il[s - 1] = ilo;
+                    il[s] = ihi;
+                }
+            }
+        }
+    }
+    __syncthreads();  // tile no longer needed: reuse as output staging
+
+    const int nq = min(KT_THREADS, P1 - q0);
+    const int valid = P2 < K ? P2 : K;
+    const size_t obase = (static_cast<size_t>(b) * P1 + q0) * K;
+    // distances
+#pragma unroll
+    for (int s = 0; s < KT; ++s) stage[threadIdx.x * STAGE_LD + s] = s < valid ? __float_as_uint(dl[s]) : 0u;
+    __syncthreads();
+    for (int e = threadIdx.x; e < nq * K; e += KT_THREADS) {
+        const int ql = e / K, k = e - ql * K;
+        out_d2[obase + e] = __uint_as_float(stage[ql * STAGE_LD + k]);
+    }
+    __syncthreads();
+    // indices (+ gathered neighbours)
+#pragma unroll
+    for (int s = 0; s < KT; ++s) stage[threadIdx.x * STAGE_LD + s] = s < valid ? il[s] : 0u;
+    __syncthreads();
+    for (int e = threadIdx.x; e < nq * K; e += KT_THREADS) {
+        const int ql = e / K, k = e - ql * K;
+        out_idx[obase + e] = static_cast<int64_t>(stage[ql * STAGE_LD + k]);
+    }
+    if (out_nn) {
+        for (int e = threadIdx.x; e < nq * K * 3; e += KT_THREADS) {
+            const int pk = e / 3, c = e - pk * 3;
+            const int ql = pk / K, k = pk - ql * K;
+            float v = pc[static_cast<size_t>(stage[ql * STAGE_LD + k]) * 3 + c];
+            if (centre_sub) v = __fsub_rn(v, sq[ql * 3 + c]);
+            if (nn_scale != 1.0f) v = __fmul_rn(v, nn_scale);
+            out_nn[obase * 3 + e] = v;
+        }
+    }
+}
+
+template <int KT>
+static int launch_thread(const float *q, const float *p, int B, int P1, int P2, int K, float *out_d2,
+                         int64_t *out_idx, float *out_nn, int centre_sub, float nn_scale, cudaStream_t st) {
+    dim3 grid((P1 + KT_THREADS - 1) / KT_THREADS, B);
+    knn_thread_kernel<KT><<<grid, KT_THREADS, 0, st>>>(q, p, P1, P2, K, out_d2, out_idx, out_nn, centre_sub, nn_scale);
+    return check_launch("knn_thread_kernel");
+}
+
+}  // namespace pcc
+
+PCC_API int pcc_knn_f32(const float *q, const float *p, int B, int P1, int P2, int K, float *out_d2, int64_t *out_idx,
+                        float *out_nn, int centre_sub, float nn_scale, void *stream) {
+    using namespace pcc;
+    PCC_REQUIRE(q && p && out_d2 && out_idx, "pcc_knn_f32: null pointer");
+    PCC_REQUIRE(B >= 0 && P1 >= 0 && P2 >= 1, "pcc_knn_f32: bad shape B=%d P1=%d P2=%d", B, P1, P2);
+    PCC_REQUIRE(K >= 1 && K <= PCC_MAX_KNN_K, "pcc_knn_f32: K=%d outside [1,%d]", K, PCC_MAX_KNN_K);
+    PCC_REQUIRE(B <= 65535, "pcc_knn_f32: B=%d exceeds 65535", B);
+    if (B == 0 || P1 == 0) return 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+    const long long nq = static_cast<long long>(B) * P1;
+    if (K <= 32 && P2 <= KNN_TILE && nq >= 32768) {
+        if (K <= 8) return launch_thread<8>(q, p, B, P1, P2, K, out_d2, out_idx, out_nn, centre_sub, nn_scale, st);
+        if (K <= 16) return launch_thread<16>(q, p, B, P1, P2, K, out_d2, out_idx, out_nn, centre_sub, nn_scale, st);
+        return launch_thread<32>(q, p, B, P1, P2, K, out_d2, out_idx, out_nn, centre_sub, nn_scale, st);
+    }
+
+    int kp = 32;
+    while (kp < K) kp <<= 1;
+    const int cap = 2 * kp;
+    // 8 warps per CTA; fewer when the key buffers would not fit (K = 1024 -> 16 KB per warp).
+    constexpr int W = 8;
+    const size_t smem = 3 * KNN_TILE * sizeof(float) + static_cast<size_t>(W) * cap * sizeof(unsigned long long);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(knn_warp_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             3 * KNN_TILE * 4 + W * 2 * PCC_MAX_KNN_K * 8);
+        if (e != cudaSuccess) {
+            set_error("pcc_knn_f32: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+            return static_cast<int>(e);
+        }
+        attr_set = true;
+    }
+    dim3 grid((P1 + W - 1) / W, B);
+    knn_warp_kernel<W><<<grid, W * 32, smem, st>>>(q, p, P1, P2, K, cap, out_d2, out_idx, out_nn, centre_sub, nn_scale);
+    return check_launch("knn_warp_kernel");
+}

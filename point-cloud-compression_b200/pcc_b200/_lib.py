@@ -1,0 +1,59 @@
+"""ctypes binding of libpcc_b200.so (the C ABI declared in include/pcc_b200.h).
+
+There is no CPU fallback: if the shared library is missing the import fails loudly, and every op raises when
+handed a non-CUDA tensor.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpcc_b200.so")
+
+_vp = ctypes.c_void_p
+_i = ctypes.c_int
+_i64 = ctypes.c_int64
+_f = ctypes.c_float
+
+# name -> (restype, argtypes); mirrors include/pcc_b200.h one to one
+SIGNATURES = {
+    "pcc_version": (_i, []),
+    "pcc_last_error_string": (ctypes.c_char_p, []),
+    "pcc_fps_workspace_bytes": (_i64, [_i, _i, _i]),
+    "pcc_fps_f32": (_i, [_vp, _i, _i, _i, _vp, _f, _vp, _vp, _vp]),
+    "pcc_knn_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _f, _vp]),
+    "pcc_ball_query_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
+    "pcc_gather_f32": (_i, [_vp, _vp, _i, _i, _i, _i64, _vp, _vp]),
+    "pcc_gather_bwd_f32": (_i, [_vp, _vp, _i, _i, _i, _i64, _vp, _vp]),
+    "pcc_nn1_workspace_bytes": (_i64, [_i, _i, _i]),
+    "pcc_nn1_f32": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "pcc_chamfer_workspace_bytes": (_i64, [_i, _i, _i]),
+    "pcc_chamfer_fwd_f32": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pcc_chamfer_bwd_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+}
+
+_lib = None
+
+
+def load():
+    """Load libpcc_b200.so and declare every entry point.  Raises if the library has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `make -C point-cloud-compression_b200` "
+                "(or __graft_entry__.build()); pcc_b200 has no CPU fallback")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().pcc_last_error_string().decode("utf-8", "replace")
+        if rc < 0:
+            raise ValueError(f"{what}: {msg} (code {rc})")
+        raise RuntimeError(f"{what}: CUDA error {rc}: {msg}")

@@ -1,0 +1,186 @@
+"""Tensor-level host functions over the C ABI: the B200 implementation of the reference's geometric ops.
+
+Every function takes CUDA float32 tensors, enqueues hand-written sm_100a kernels on the current torch stream and
+returns torch tensors; nothing here computes on the CPU.  Signatures follow the reference call sites cited in
+include/pcc_b200.h.
+"""
+import collections
+
+import torch
+
+from . import _lib
+
+_KNN = collections.namedtuple("KNN", "dists idx knn")  # same fields as pytorch3d.ops.knn._KNN
+FLT_MAX = 3.4028234663852886e38
+
+
+def _cuda_f32(t, name):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"pcc_b200: {name} must be a CUDA tensor (there is no CPU path)")
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return t.data_ptr() if t is not None else None
+
+
+def _check_pair(p1, p2):
+    if p1.dim() != 3 or p2.dim() != 3:
+        raise ValueError("pcc_b200: point tensors must have shape [B, P, 3]")
+    if p1.shape[0] != p2.shape[0]:
+        raise ValueError("pts1 and pts2 must have the same batch dimension.")
+    if p1.shape[2] != 3 or p2.shape[2] != 3:
+        raise ValueError("pcc_b200: only 3-D points are supported (pts1 and pts2 must have the same point dimension 3).")
+
+
+def fps(xyz, npoint, start_idx=None, init_dist=1e10):
+    """Farthest point sampling.  start_idx [B] int64 (device) or None (= start at 0).  Returns int64 [B,npoint]."""
+    lib = _lib.load()
+    xyz = _cuda_f32(xyz, "xyz")
+    B, N, C = xyz.shape
+    if C != 3:
+        raise ValueError("pcc_b200.fps: xyz must be [B, N, 3]")
+    out = torch.empty((B, npoint), dtype=torch.int64, device=xyz.device)
+    if start_idx is not None:
+        start_idx = start_idx.to(device=xyz.device, dtype=torch.int64).contiguous()
+    with torch.cuda.device(xyz.device):
+        ws_bytes = lib.pcc_fps_workspace_bytes(B, N, npoint)
+        ws = torch.empty((max(ws_bytes, 1),), dtype=torch.uint8, device=xyz.device) if ws_bytes else None
+        _lib.check(lib.pcc_fps_f32(_ptr(xyz), B, N, npoint, _ptr(start_idx), init_dist, _ptr(out), _ptr(ws), _stream()),
+                   "pcc_fps_f32")
+    return out
+
+
+def knn(p1, p2, K, return_nn=False, centre_sub=False, nn_scale=1.0):
+    """K nearest neighbours: (dists [B,P1,K] squared, idx int64 [B,P1,K], nn [B,P1,K,3] or None)."""
+    lib = _lib.load()
+    p1, p2 = _cuda_f32(p1, "p1"), _cuda_f32(p2, "p2")
+    _check_pair(p1, p2)
+    B, P1, _ = p1.shape
+    P2 = p2.shape[1]
+    d = torch.empty((B, P1, K), dtype=torch.float32, device=p1.device)
+    i = torch.empty((B, P1, K), dtype=torch.int64, device=p1.device)
+    nn = torch.empty((B, P1, K, 3), dtype=torch.float32, device=p1.device) if return_nn else None
+    with torch.cuda.device(p1.device):
+        _lib.check(lib.pcc_knn_f32(_ptr(p1), _ptr(p2), B, P1, P2, K, _ptr(d), _ptr(i), _ptr(nn), int(centre_sub),
+                                   float(nn_scale), _stream()), "pcc_knn_f32")
+    return d, i, nn
+
+
+def ball_query(p1, p2, K, radius, return_dists=True):
+    lib = _lib.load()
+    p1, p2 = _cuda_f32(p1, "p1"), _cuda_f32(p2, "p2")
+    _check_pair(p1, p2)
+    B, P1, _ = p1.shape
+    P2 = p2.shape[1]
+    i = torch.empty((B, P1, K), dtype=torch.int64, device=p1.device)
+    d = torch.empty((B, P1, K), dtype=torch.float32, device=p1.device) if return_dists else None
+    with torch.cuda.device(p1.device):
+        _lib.check(lib.pcc_ball_query_f32(_ptr(p1), _ptr(p2), B, P1, P2, K, float(radius), _ptr(i), _ptr(d), _stream()),
+                   "pcc_ball_query_f32")
+    return d, i
+
+
+class _Gather(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feat, idx):
+        lib = _lib.load()
+        B, N, C = feat.shape
+        M = idx.numel() // max(B, 1)
+        out = torch.empty(tuple(idx.shape) + (C,), dtype=torch.float32, device=feat.device)
+        with torch.cuda.device(feat.device):
+            _lib.check(lib.pcc_gather_f32(_ptr(feat), _ptr(idx), B, N, C, M, _ptr(out), _stream()), "pcc_gather_f32")
+        ctx.save_for_backward(idx)
+        ctx.shape = (B, N, C, M)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = _lib.load()
+        (idx,) = ctx.saved_tensors
+        B, N, C, M = ctx.shape
+        grad_out = grad_out.contiguous().float()
+        grad_feat = torch.zeros((B, N, C), dtype=torch.float32, device=grad_out.device)
+        with torch.cuda.device(grad_out.device):
+            _lib.check(lib.pcc_gather_bwd_f32(_ptr(grad_out), _ptr(idx), B, N, C, M, _ptr(grad_feat), _stream()),
+                       "pcc_gather_bwd_f32")
+        return grad_feat, None
+
+
+def gather(feat, idx):
+    """out[b, ..., :] = feat[b, idx[b, ...], :]; differentiable w.r.t. feat.  idx must lie in [0, N)."""
+    feat = _cuda_f32(feat, "feat")
+    if feat.dim() != 3 or idx.shape[0] != feat.shape[0]:
+        raise ValueError("pcc_b200.gather: feat must be [B,N,C] and idx [B,...]")
+    idx = idx.to(device=feat.device, dtype=torch.int64).contiguous()
+    return _Gather.apply(feat, idx)
+
+
+def nn1(p1, p2, return_idx=True):
+    """Nearest neighbour of each p1 point in p2: (d2 [B,P1], idx int64 [B,P1] or None)."""
+    lib = _lib.load()
+    p1, p2 = _cuda_f32(p1, "p1"), _cuda_f32(p2, "p2")
+    _check_pair(p1, p2)
+    B, P1, _ = p1.shape
+    P2 = p2.shape[1]
+    d = torch.empty((B, P1), dtype=torch.float32, device=p1.device)
+    i = torch.empty((B, P1), dtype=torch.int64, device=p1.device) if return_idx else None
+    with torch.cuda.device(p1.device):
+        ws = torch.empty((max(lib.pcc_nn1_workspace_bytes(B, P1, P2), 8),), dtype=torch.uint8, device=p1.device)
+        _lib.check(lib.pcc_nn1_f32(_ptr(p1), _ptr(p2), B, P1, P2, _ptr(d), _ptr(i), _ptr(ws), _stream()), "pcc_nn1_f32")
+    return d, i
+
+
+def chamfer_forward(x, y, want_idx=True):
+    """Returns dict(loss [scalar tensor], per_cloud [B], dx, ix, dy, iy)."""
+    lib = _lib.load()
+    x, y = _cuda_f32(x, "x"), _cuda_f32(y, "y")
+    _check_pair(x, y)
+    B, P1, _ = x.shape
+    P2 = y.shape[1]
+    dev = x.device
+    dx = torch.empty((B, P1), dtype=torch.float32, device=dev)
+    dy = torch.empty((B, P2), dtype=torch.float32, device=dev)
+    ix = torch.empty((B, P1), dtype=torch.int64, device=dev) if want_idx else None
+    iy = torch.empty((B, P2), dtype=torch.int64, device=dev) if want_idx else None
+    per_cloud = torch.empty((B,), dtype=torch.float32, device=dev)
+    loss = torch.empty((1,), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        ws = torch.empty((max(lib.pcc_chamfer_workspace_bytes(B, P1, P2), 8),), dtype=torch.uint8, device=dev)
+        _lib.check(lib.pcc_chamfer_fwd_f32(_ptr(x), _ptr(y), B, P1, P2, _ptr(dx), _ptr(ix), _ptr(dy), _ptr(iy),
+                                           _ptr(per_cloud), _ptr(loss), _ptr(ws), _stream()), "pcc_chamfer_fwd_f32")
+    return dict(loss=loss.reshape(()), per_cloud=per_cloud, dx=dx, ix=ix, dy=dy, iy=iy)
+
+
+class _Chamfer(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, y):
+        r = chamfer_forward(x, y, want_idx=True)
+        ctx.save_for_backward(x, y, r["ix"], r["iy"])
+        return r["loss"]
+
+    @staticmethod
+    def backward(ctx, grad):
+        lib = _lib.load()
+        x, y, ix, iy = ctx.saved_tensors
+        x, y = x.contiguous().float(), y.contiguous().float()
+        B, P1, _ = x.shape
+        P2 = y.shape[1]
+        gx = torch.empty_like(x)
+        gy = torch.empty_like(y)
+        g = grad.detach().to(device=x.device, dtype=torch.float32).reshape(1).contiguous()
+        with torch.cuda.device(x.device):
+            _lib.check(lib.pcc_chamfer_bwd_f32(_ptr(x), _ptr(y), _ptr(ix), _ptr(iy), B, P1, P2, _ptr(g), _ptr(gx),
+                                               _ptr(gy), _stream()), "pcc_chamfer_bwd_f32")
+        return gx, gy
+
+
+def chamfer(x, y):
+    """Differentiable Chamfer distance (mean/mean), scalar tensor."""
+    return _Chamfer.apply(_cuda_f32(x, "x"), _cuda_f32(y, "y"))

@@ -1,0 +1,121 @@
+"""Mint the golden vectors under tests/golden/ (run HERE, where /root/reference exists):
+
+    python tests/golden/make_golden.py
+
+* ref_fps_gather.npz  -- outputs of the REFERENCE's own pn_kit.farthest_point_sample_batch / index_points
+                         (imported from /root/reference), including the CPU-RNG start indices it drew.
+* p3d_ops.npz         -- outputs of the oracle restatement of the PyTorch3D ops (knn_points, ball_query,
+                         sample_farthest_points, chamfer_distance) on seeded inputs, cross-checked here against
+                         an independent torch brute-force statement before being written.  PyTorch3D itself
+                         cannot be installed in this image, so these are "parity unpinned" w.r.t. the package.
+Inputs are regenerated from seeds by the tests (tools/synth.py); the files keep inputs too, so a drift in
+the generator is caught.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import oracle as orc  # noqa: E402
+from oracle import ref_loader  # noqa: E402
+from tools import synth  # noqa: E402
+
+
+def ref_fps_gather():
+    pn = ref_loader.load("pn_kit")
+    out = {}
+    cases = {
+        "modelnet": (synth.modelnet_like(2, 8192, seed=11), 64),
+        "grid": (synth.grid_quantised(3, 1000, depth=3, seed=12), 37),
+        "perm": (synth.uniform_cube(2, 257, seed=13), 257),
+        "tiny": (synth.uniform_cube(4, 16, seed=14), 5),
+    }
+    for name, (xyz, npoint) in cases.items():
+        torch.manual_seed(11)  # the reference scripts seed 11 (train.py:18-20)
+        state = torch.get_rng_state()
+        t = torch.from_numpy(xyz)
+        idx = pn.farthest_point_sample_batch(t, npoint)
+        torch.set_rng_state(state)
+        start = torch.randint(0, xyz.shape[1], (xyz.shape[0],), dtype=torch.long)
+        assert torch.equal(idx[:, 0], start)
+        g = pn.index_points(t, idx)
+        out[f"{name}_xyz"] = xyz
+        out[f"{name}_npoint"] = np.int64(npoint)
+        out[f"{name}_start"] = start.numpy()
+        out[f"{name}_idx"] = idx.numpy()
+        out[f"{name}_gather"] = g.numpy()
+        # [B,S,K] form of index_points
+        idx3 = torch.from_numpy(np.random.default_rng(5).integers(0, xyz.shape[1], (xyz.shape[0], 7, 3)))
+        out[f"{name}_idx3"] = idx3.numpy()
+        out[f"{name}_gather3"] = pn.index_points(t, idx3).numpy()
+        assert np.array_equal(orc.fps(xyz, npoint, start.numpy(), 1e10), idx.numpy()), name
+        assert np.array_equal(orc.gather(xyz, idx.numpy()), g.numpy()), name
+    np.savez_compressed(os.path.join(HERE, "ref_fps_gather.npz"), **out)
+    print("ref_fps_gather.npz:", {k: v.shape for k, v in out.items() if k.endswith("_idx")})
+
+
+def _torch_knn(q, p, K):
+    D = ((torch.from_numpy(q)[:, :, None, :] - torch.from_numpy(p)[:, None, :, :]) ** 2).sum(-1)
+    ds, js = torch.sort(D, dim=2, stable=True)
+    return ds[:, :, :K].numpy(), js[:, :, :K].numpy()
+
+
+def p3d_ops():
+    out = {}
+    # kNN: smooth + tie-heavy + duplicated queries (the reference's <= 8 distinct centres, appendix B-2)
+    p = synth.modelnet_like(2, 2048, seed=21)
+    q = orc.gather(p, orc.fps(p, 16, np.zeros(2, np.int64), 1e10))
+    qg = ((np.floor(q * 2) + 0.5) / 2).astype(np.float32)  # depth-1 octant centres, many duplicates
+    pg = synth.grid_quantised(2, 700, depth=3, seed=22)
+    for name, (a, b, K) in {"knn_patch": (q, p, 256), "knn_dupq": (qg, p, 64), "knn_ties": (pg[:, :50], pg, 33),
+                            "knn_self": (p[:, :256], p[:, :256], 16), "knn_kgtn": (q, p[:, :10], 16)}.items():
+        d, i, nn = orc.knn_points(a, b, K, True)
+        if b.shape[1] >= K:
+            td, ti = _torch_knn(a, b, K)
+            assert np.array_equal(td, d) and np.array_equal(ti, i), name
+        out[f"{name}_q"], out[f"{name}_p"], out[f"{name}_K"] = a, b, np.int64(K)
+        out[f"{name}_d"], out[f"{name}_i"], out[f"{name}_nn"] = d, i, nn
+    # ball query incl. the exact boundary d2 == r2 (grid points at distance exactly 0.25)
+    for name, (a, b, K, r) in {"ball_sa1": (q, p, 32, 0.2), "ball_edge": (pg[:, :40], pg, 16, 0.25),
+                               "ball_few": (q, p, 64, 0.05)}.items():
+        d, i = orc.ball_query(a, b, K, r)
+        D = ((torch.from_numpy(a)[:, :, None, :] - torch.from_numpy(b)[:, None, :, :]) ** 2).sum(-1).numpy()
+        r2 = np.float32(r) * np.float32(r)
+        for bb in range(a.shape[0]):
+            for qq in range(a.shape[1]):
+                hits = np.nonzero(D[bb, qq] < r2)[0][:K]
+                assert np.array_equal(i[bb, qq, :len(hits)], hits) and np.all(i[bb, qq, len(hits):] == -1), name
+        out[f"{name}_q"], out[f"{name}_p"], out[f"{name}_K"], out[f"{name}_r"] = a, b, np.int64(K), np.float32(r)
+        out[f"{name}_d"], out[f"{name}_i"] = d, i
+    # sample_farthest_points (start 0, FLT_MAX init, -1 padding when K > N)
+    for name, (a, K) in {"sfp": (p, 128), "sfp_pad": (p[:, :20], 32), "sfp_ties": (pg, 64)}.items():
+        pts, idx = orc.sample_farthest_points(a, K)
+        out[f"{name}_x"], out[f"{name}_K"], out[f"{name}_idx"], out[f"{name}_pts"] = a, np.int64(K), idx, pts
+    # chamfer
+    x = synth.modelnet_like(2, 1024, seed=23)
+    y = synth.decompressed_like(x, seed=24)[:, :900]
+    loss, pc, dx, ix, dy, iy = orc.chamfer(x, y)
+    D = ((torch.from_numpy(x)[:, :, None, :] - torch.from_numpy(y)[:, None, :, :]) ** 2).sum(-1)
+    tdx, tix = D.min(2)
+    tdy, tiy = D.min(1)
+    assert np.array_equal(tdx.numpy(), dx) and np.array_equal(tdy.numpy(), dy)
+    assert np.array_equal(tix.numpy(), ix) and np.array_equal(tiy.numpy(), iy)
+    tl = (tdx.sum(1) / 1024 + tdy.sum(1) / 900).sum() / 2
+    assert abs(tl.item() - loss) <= 1e-5 * abs(loss)
+    gx, gy = orc.chamfer_bwd(x, y, ix, iy, 1.0)
+    out.update(cham_x=x, cham_y=y, cham_loss=np.float64(loss), cham_pc=pc, cham_dx=dx, cham_ix=ix, cham_dy=dy,
+               cham_iy=iy, cham_gx=gx, cham_gy=gy)
+    psnr, mse = orc.d1_psnr(x[0], y[0])
+    out.update(d1_psnr=np.float64(psnr), d1_mse=np.float64(mse))
+    np.savez_compressed(os.path.join(HERE, "p3d_ops.npz"), **out)
+    print("p3d_ops.npz written:", len(out), "arrays")
+
+
+if __name__ == "__main__":
+    ref_fps_gather()
+    p3d_ops()

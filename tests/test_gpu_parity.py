@@ -1,0 +1,226 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the committed golden vectors.
+Bit-exact for indices and per-point squared distances; Chamfer scalar within 1e-5 relative (fp32 sum order)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tools import synth
+
+pytestmark = pytest.mark.gpu
+
+CHAMFER_RTOL = 1e-5  # north_star: "Chamfer within 1e-5 relative"
+
+
+@pytest.fixture(scope="module")
+def pcc():
+    import __graft_entry__  # noqa: F401  (sets sys.path)
+    import pcc_b200
+    assert torch.cuda.is_available()
+    pcc_b200._lib.load()
+    return pcc_b200
+
+
+@pytest.fixture(scope="module")
+def orc():
+    from oracle import oracle
+    oracle.lib()
+    return oracle
+
+
+@pytest.fixture(scope="module")
+def g_ref(golden_dir):
+    return np.load(os.path.join(golden_dir, "ref_fps_gather.npz"))
+
+
+@pytest.fixture(scope="module")
+def g_p3d(golden_dir):
+    return np.load(os.path.join(golden_dir, "p3d_ops.npz"))
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+# ---- FPS ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["modelnet", "grid", "perm", "tiny"])
+def test_fps_gather_reference_golden(pcc, g_ref, name):
+    xyz = cu(g_ref[f"{name}_xyz"])
+    idx = pcc.ops.fps(xyz, int(g_ref[f"{name}_npoint"]), cu(g_ref[f"{name}_start"]), 1e10)
+    assert np.array_equal(idx.cpu().numpy(), g_ref[f"{name}_idx"])
+    assert np.array_equal(pcc.index_points(xyz, idx).cpu().numpy(), g_ref[f"{name}_gather"])
+    assert np.array_equal(pcc.index_points(xyz, cu(g_ref[f"{name}_idx3"])).cpu().numpy(), g_ref[f"{name}_gather3"])
+
+
+def test_fps_reference_rng_protocol(pcc, g_ref):
+    """pn_kit.farthest_point_sample_batch draws its start index from the CPU global RNG (pn_kit.py:321)."""
+    torch.manual_seed(11)
+    idx = pcc.farthest_point_sample_batch(cu(g_ref["modelnet_xyz"]), 64)
+    assert np.array_equal(idx.cpu().numpy(), g_ref["modelnet_idx"])
+
+
+@pytest.mark.parametrize("B,N,S", [(3, 100, 100), (2, 128, 40), (2, 129, 64), (2, 300, 300), (2, 777, 99),
+                                   (2, 2048, 512), (1, 4097, 65), (2, 8192, 64), (32, 8192, 64)])
+def test_fps_sizes_vs_oracle(pcc, orc, B, N, S):
+    xyz = synth.uniform_cube(B, N, seed=N + S) if N % 2 else synth.grid_quantised(B, N, depth=3, seed=N)
+    start = np.random.default_rng(N).integers(0, N, B)
+    got = pcc.ops.fps(cu(xyz), S, cu(start), 1e10).cpu().numpy()
+    assert np.array_equal(got, orc.fps(xyz, S, start, 1e10, threads=8))
+
+
+def test_fps_multi_cta_cloud(pcc, orc):
+    """N > 8192: the cooperative multi-CTA kernel (the 1M-point scene path at a size the oracle finishes fast)."""
+    for B, N, S in [(1, 20000, 200), (2, 9000, 64), (1, 100_000, 64)]:
+        xyz = synth.scene_like(N, seed=N)[0][None].repeat(B, 0) if N > 50000 else synth.uniform_cube(B, N, seed=N)
+        start = np.arange(B) * 17
+        got = pcc.ops.fps(cu(xyz), S, cu(start), 1e10).cpu().numpy()
+        assert np.array_equal(got, orc.fps(xyz, S, start, 1e10, threads=8))
+
+
+@pytest.mark.parametrize("name", ["sfp", "sfp_pad", "sfp_ties"])
+def test_sample_farthest_points_golden(pcc, g_p3d, name):
+    pts, idx = pcc.sample_farthest_points(cu(g_p3d[f"{name}_x"]), K=int(g_p3d[f"{name}_K"]))
+    assert np.array_equal(idx.cpu().numpy(), g_p3d[f"{name}_idx"])
+    assert np.array_equal(pts.cpu().numpy(), g_p3d[f"{name}_pts"])
+
+
+# ---- kNN ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["knn_patch", "knn_dupq", "knn_ties", "knn_self", "knn_kgtn"])
+def test_knn_golden(pcc, g_p3d, name):
+    r = pcc.knn_points(cu(g_p3d[f"{name}_q"]), cu(g_p3d[f"{name}_p"]), K=int(g_p3d[f"{name}_K"]), return_nn=True)
+    dists, idx, nn = r  # the reference unpacks the namedtuple as a 3-tuple (train.py:185)
+    assert np.array_equal(r.idx.cpu().numpy(), g_p3d[f"{name}_i"])
+    assert np.array_equal(dists.cpu().numpy(), g_p3d[f"{name}_d"])
+    assert np.array_equal(nn.cpu().numpy(), g_p3d[f"{name}_nn"])
+
+
+@pytest.mark.parametrize("B,P1,P2,K", [(1, 1, 5, 3), (2, 64, 8192, 256), (3, 33, 1500, 100), (2, 7, 5000, 1024),
+                                       (1, 1, 8192, 1024), (2, 512, 2048, 16), (2, 512, 2048, 32), (2, 100, 40, 64),
+                                       (1, 9, 3000, 1), (4, 130, 1025, 17)])
+def test_knn_warp_kernel_vs_oracle(pcc, orc, B, P1, P2, K):
+    p = synth.grid_quantised(B, P2, depth=4, seed=P2) if (P1 + K) % 2 else synth.uniform_cube(B, P2, seed=P2)
+    q = synth.uniform_cube(B, P1, seed=P1 + 1)
+    d, i, nn = pcc.ops.knn(cu(q), cu(p), K, return_nn=True, centre_sub=True, nn_scale=2.0)
+    od, oi, onn = orc.knn_points(q, p, K, True, threads=8)
+    assert np.array_equal(i.cpu().numpy(), oi) and np.array_equal(d.cpu().numpy(), od)
+    want = (onn - q[:, :, None, :]) * np.float32(2.0)
+    if P2 >= K:
+        assert np.array_equal(nn.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("BS,P,K", [(200, 256, 16), (300, 128, 8), (150, 256, 32), (140, 250, 20), (600, 64, 3)])
+def test_knn_thread_kernel_in_patch_vs_oracle(pcc, orc, BS, P, K):
+    """Many small self-searches (the pn_kit.SetAbstraction K=16 case) -> thread-per-query kernel."""
+    x = synth.grid_quantised(BS, P, depth=3, seed=K) if K == 16 else synth.uniform_cube(BS, P, seed=K)
+    d, i, nn = pcc.ops.knn(cu(x), cu(x), K, return_nn=True, centre_sub=True)
+    od, oi, onn = orc.knn_points(x, x, K, True, threads=8)
+    assert np.array_equal(i.cpu().numpy(), oi) and np.array_equal(d.cpu().numpy(), od)
+    assert np.array_equal(nn.cpu().numpy(), onn - x[:, :, None, :])
+
+
+def test_knn_patching_full_size_properties(pcc):
+    """BASELINE size (32 clouds x 64 centres x 8192 points, K=256): size-independent properties."""
+    xyz = cu(synth.modelnet_like(32, 8192, seed=3))
+    centres = pcc.index_points(xyz, pcc.ops.fps(xyz, 64, None, 1e10))
+    d, i, nn = pcc.ops.knn(centres, xyz, 256, return_nn=True)
+    assert bool((d[:, :, 1:] >= d[:, :, :-1]).all())  # ascending
+    same = d[:, :, 1:] == d[:, :, :-1]
+    assert bool((i[:, :, 1:][same] > i[:, :, :-1][same]).all())  # ties ordered by index
+    assert bool((d[:, :, 0] == 0).all()) and bool((nn[:, :, 0] == centres).all())  # a centre is its own 1st NN
+    assert torch.equal(nn, pcc.index_points(xyz, i))  # gathered neighbours == gather(idx)
+    d2 = ((nn - centres[:, :, None, :]) ** 2)
+    assert torch.equal(d, (d2[..., 0] + d2[..., 1]) + d2[..., 2])  # distances re-derivable, un-fused
+    d1, i1 = pcc.ops.nn1(centres, xyz)
+    assert torch.equal(d1, d[:, :, 0]) and torch.equal(i1, i[:, :, 0])  # K=1 search agrees with the K=256 head
+
+
+# ---- ball query / gather ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["ball_sa1", "ball_edge", "ball_few"])
+def test_ball_query_golden(pcc, g_p3d, name):
+    r = pcc.ball_query(cu(g_p3d[f"{name}_q"]), cu(g_p3d[f"{name}_p"]), K=int(g_p3d[f"{name}_K"]),
+                       radius=float(g_p3d[f"{name}_r"]))
+    assert np.array_equal(r.idx.cpu().numpy(), g_p3d[f"{name}_i"])
+    assert np.array_equal(r.dists.cpu().numpy(), g_p3d[f"{name}_d"])
+    want = g_p3d[f"{name}_p"][np.arange(r.idx.shape[0])[:, None, None], np.maximum(g_p3d[f"{name}_i"], 0)]
+    want[g_p3d[f"{name}_i"] < 0] = 0
+    assert np.array_equal(r.knn.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("B,P1,P2,K,r", [(4, 512, 2048, 32, 0.2), (4, 128, 512, 64, 0.4), (4, 32, 128, 128, 0.8),
+                                         (2, 5, 3000, 7, 0.05), (1, 1, 1, 4, 1.0)])
+def test_ball_query_pointnetpp_shapes_vs_oracle(pcc, orc, B, P1, P2, K, r):
+    p = synth.shapenet_like(B, P2, seed=P2)
+    q = p[:, :P1] if P1 <= P2 else synth.uniform_cube(B, P1)
+    idx = pcc.PointnetPPOps.ball_query(r, K, cu(p), cu(q))  # (radius, nsample, xyz, new_xyz) as the reference
+    od, oi = orc.ball_query(q, p, K, r, threads=8)
+    assert np.array_equal(idx.idx.cpu().numpy(), oi) and np.array_equal(idx.dists.cpu().numpy(), od)
+    feats = synth.uniform_cube(B, P2 * 16, seed=1).reshape(B, P2, 48)
+    grouped = pcc.PointnetPPOps.group_points(cu(feats), idx)  # -1 pads clamp to point 0 (pointnet_sa_module.py:27)
+    assert np.array_equal(grouped.cpu().numpy(), orc.gather(feats, np.maximum(oi, 0)))
+
+
+def test_gather_backward_is_scatter_add(pcc):
+    feat = torch.rand(2, 50, 8, device="cuda", requires_grad=True)
+    idx = torch.randint(0, 50, (2, 30, 4), device="cuda")
+    out = pcc.knn_gather(feat, idx)
+    w = torch.rand_like(out)
+    (out * w).sum().backward()
+    ref = torch.zeros(2, 50, 8, device="cuda")
+    ref.scatter_add_(1, idx.reshape(2, -1, 1).expand(-1, -1, 8), w.reshape(2, -1, 8))
+    assert torch.allclose(feat.grad, ref, atol=1e-6)
+
+
+# ---- Chamfer / D1 -----------------------------------------------------------------------------------------------
+def test_chamfer_golden(pcc, g_p3d):
+    x, y = cu(g_p3d["cham_x"]), cu(g_p3d["cham_y"])
+    r = pcc.ops.chamfer_forward(x, y)
+    assert np.array_equal(r["dx"].cpu().numpy(), g_p3d["cham_dx"]) and np.array_equal(r["ix"].cpu().numpy(), g_p3d["cham_ix"])
+    assert np.array_equal(r["dy"].cpu().numpy(), g_p3d["cham_dy"]) and np.array_equal(r["iy"].cpu().numpy(), g_p3d["cham_iy"])
+    want = float(g_p3d["cham_loss"])
+    assert abs(r["loss"].item() - want) <= CHAMFER_RTOL * abs(want)
+    assert np.allclose(r["per_cloud"].cpu().numpy(), g_p3d["cham_pc"], rtol=CHAMFER_RTOL, atol=0)
+    xg, yg = x.clone().requires_grad_(), y.clone().requires_grad_()
+    loss, normals = pcc.chamfer_distance(xg, yg)
+    assert normals is None
+    loss.backward()
+    assert np.allclose(xg.grad.cpu().numpy(), g_p3d["cham_gx"], rtol=1e-5, atol=1e-9)
+    assert np.allclose(yg.grad.cpu().numpy(), g_p3d["cham_gy"], rtol=1e-5, atol=1e-9)
+
+
+@pytest.mark.parametrize("B,P1,P2", [(1, 8192, 8192), (3, 1000, 777), (2, 16384, 8192), (1, 1, 1), (5, 9, 2050)])
+def test_chamfer_vs_oracle(pcc, orc, B, P1, P2):
+    x = synth.modelnet_like(B, max(P1, P2), seed=P1)
+    y = synth.decompressed_like(x, seed=P2)[:, :P2]
+    x = x[:, :P1]
+    if P1 == 1000:  # tie-heavy
+        x, y = synth.grid_quantised(B, P1, depth=3, seed=1), synth.grid_quantised(B, P2, depth=3, seed=2)
+    r = pcc.ops.chamfer_forward(cu(x), cu(y))
+    loss, pc, dx, ix, dy, iy = orc.chamfer(x, y, threads=8)
+    assert np.array_equal(r["dx"].cpu().numpy(), dx) and np.array_equal(r["dy"].cpu().numpy(), dy)
+    assert np.array_equal(r["ix"].cpu().numpy(), ix) and np.array_equal(r["iy"].cpu().numpy(), iy)
+    assert abs(r["loss"].item() - loss) <= CHAMFER_RTOL * abs(loss) + 1e-30
+
+
+def test_chamfer_full_batch_properties(pcc):
+    """BASELINE size (32 x 8192 x 8192): symmetry, zero self-distance, agreement with the 1-NN entry point."""
+    x = cu(synth.modelnet_like(32, 8192, seed=7))
+    y = cu(synth.decompressed_like(x.cpu().numpy(), seed=8))
+    a = pcc.ops.chamfer_forward(x, y)
+    b = pcc.ops.chamfer_forward(y, x)
+    assert torch.equal(a["dx"], b["dy"]) and torch.equal(a["ix"], b["iy"]) and torch.equal(a["per_cloud"], b["per_cloud"])
+    z = pcc.ops.chamfer_forward(x, x)
+    assert float(z["loss"]) == 0.0 and torch.equal(z["ix"], torch.arange(8192, device="cuda").expand(32, -1))
+    d, i = pcc.ops.nn1(x, y)
+    assert torch.equal(d, a["dx"]) and torch.equal(i, a["ix"])
+    assert abs(a["per_cloud"].double().mean().item() - a["loss"].item()) <= 1e-6 * a["loss"].item()
+
+
+def test_d1_psnr_inner_step(pcc, orc, g_p3d):
+    """eval.py:68-92: PSNR from the one-directional 1-NN (recon -> original); fp32 device NN vs the float64 oracle."""
+    orig, recon = g_p3d["cham_x"][0], g_p3d["cham_y"][0]
+    d, _ = pcc.ops.nn1(cu(recon[None]), cu(orig[None]))
+    mse = d.double().mean().item()
+    diag2 = float(((orig.max(0) - orig.min(0)).astype(np.float64) ** 2).sum())
+    psnr = 10 * np.log10(diag2 / mse)
+    assert abs(psnr - float(g_p3d["d1_psnr"])) < 1e-4  # dB

@@ -1,0 +1,109 @@
+"""CPU tests of the oracle: against the committed golden vectors (minted from the reference's own code, see
+tests/golden/make_golden.py), against the live reference when /root/reference is present, and against an
+independent torch statement of the PyTorch3D semantics."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as orc
+from oracle import ref_loader
+from tools import synth
+
+
+@pytest.fixture(scope="module")
+def g_ref(golden_dir):
+    return np.load(os.path.join(golden_dir, "ref_fps_gather.npz"))
+
+
+@pytest.fixture(scope="module")
+def g_p3d(golden_dir):
+    return np.load(os.path.join(golden_dir, "p3d_ops.npz"))
+
+
+@pytest.mark.parametrize("name", ["modelnet", "grid", "perm", "tiny"])
+def test_fps_and_gather_match_reference_golden(g_ref, name):
+    xyz = g_ref[f"{name}_xyz"]
+    idx = orc.fps(xyz, int(g_ref[f"{name}_npoint"]), g_ref[f"{name}_start"], 1e10)
+    assert np.array_equal(idx, g_ref[f"{name}_idx"])
+    assert np.array_equal(orc.gather(xyz, idx), g_ref[f"{name}_gather"])
+    assert np.array_equal(orc.gather(xyz, g_ref[f"{name}_idx3"]), g_ref[f"{name}_gather3"])
+
+
+def test_synth_generators_are_stable(g_ref, g_p3d):
+    assert np.array_equal(synth.modelnet_like(2, 8192, seed=11), g_ref["modelnet_xyz"])
+    assert np.array_equal(synth.grid_quantised(3, 1000, depth=3, seed=12), g_ref["grid_xyz"])
+    assert np.array_equal(synth.modelnet_like(2, 2048, seed=21), g_p3d["knn_patch_p"])
+
+
+@pytest.mark.parametrize("name", ["knn_patch", "knn_dupq", "knn_ties", "knn_self", "knn_kgtn"])
+def test_knn_golden(g_p3d, name):
+    d, i, nn = orc.knn_points(g_p3d[f"{name}_q"], g_p3d[f"{name}_p"], int(g_p3d[f"{name}_K"]), True)
+    assert np.array_equal(d, g_p3d[f"{name}_d"]) and np.array_equal(i, g_p3d[f"{name}_i"])
+    assert np.array_equal(nn, g_p3d[f"{name}_nn"])
+
+
+@pytest.mark.parametrize("name", ["ball_sa1", "ball_edge", "ball_few"])
+def test_ball_query_golden(g_p3d, name):
+    d, i = orc.ball_query(g_p3d[f"{name}_q"], g_p3d[f"{name}_p"], int(g_p3d[f"{name}_K"]), float(g_p3d[f"{name}_r"]))
+    assert np.array_equal(i, g_p3d[f"{name}_i"]) and np.array_equal(d, g_p3d[f"{name}_d"])
+
+
+@pytest.mark.parametrize("name", ["sfp", "sfp_pad", "sfp_ties"])
+def test_sample_farthest_points_golden(g_p3d, name):
+    pts, idx = orc.sample_farthest_points(g_p3d[f"{name}_x"], int(g_p3d[f"{name}_K"]))
+    assert np.array_equal(idx, g_p3d[f"{name}_idx"]) and np.array_equal(pts, g_p3d[f"{name}_pts"])
+
+
+def test_chamfer_golden_and_threads(g_p3d):
+    x, y = g_p3d["cham_x"], g_p3d["cham_y"]
+    for threads in (1, 4):
+        loss, pc, dx, ix, dy, iy = orc.chamfer(x, y, threads=threads)
+        assert loss == float(g_p3d["cham_loss"])
+        assert np.array_equal(dx, g_p3d["cham_dx"]) and np.array_equal(iy, g_p3d["cham_iy"])
+    gx, gy = orc.chamfer_bwd(x, y, ix, iy, 1.0)
+    assert np.array_equal(gx, g_p3d["cham_gx"]) and np.array_equal(gy, g_p3d["cham_gy"])
+    psnr, mse = orc.d1_psnr(x[0], y[0])
+    assert psnr == float(g_p3d["d1_psnr"])
+
+
+def test_knn_matches_torch_bruteforce_random():
+    rng = np.random.default_rng(0)
+    for trial in range(5):
+        B, P1, P2, K = int(rng.integers(1, 4)), int(rng.integers(1, 40)), int(rng.integers(40, 300)), int(rng.integers(1, 40))
+        q = rng.random((B, P1, 3), dtype=np.float32)
+        p = synth.grid_quantised(B, P2, depth=2, seed=trial) if trial % 2 else rng.random((B, P2, 3), dtype=np.float32)
+        d, i, _ = orc.knn_points(q, p, K)
+        D = ((torch.from_numpy(q)[:, :, None] - torch.from_numpy(p)[:, None]) ** 2).sum(-1)
+        ds, js = torch.sort(D, dim=2, stable=True)
+        assert np.array_equal(ds[:, :, :K].numpy(), d) and np.array_equal(js[:, :, :K].numpy(), i)
+
+
+def test_chamfer_backward_matches_autograd():
+    rng = np.random.default_rng(1)
+    x = torch.from_numpy(rng.random((2, 50, 3), dtype=np.float32)).requires_grad_()
+    y = torch.from_numpy(rng.random((2, 70, 3), dtype=np.float32)).requires_grad_()
+    D = ((x[:, :, None] - y[:, None]) ** 2).sum(-1)
+    loss = (D.min(2)[0].mean(1) + D.min(1)[0].mean(1)).mean()
+    loss.backward()
+    l, _, _, ix, _, iy = orc.chamfer(x.detach().numpy(), y.detach().numpy())
+    gx, gy = orc.chamfer_bwd(x.detach().numpy(), y.detach().numpy(), ix, iy, 1.0)
+    assert abs(l - loss.item()) < 1e-6
+    assert np.allclose(gx, x.grad.numpy(), atol=1e-7) and np.allclose(gy, y.grad.numpy(), atol=1e-7)
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not present (GPU box)")
+def test_fps_matches_live_reference():
+    pn = ref_loader.load("pn_kit")
+    torch.manual_seed(3)
+    for B, N, S in [(2, 500, 33), (1, 2048, 128), (3, 64, 64)]:
+        xyz = torch.rand(B, N, 3)
+        if N == 500:
+            xyz = (torch.floor(xyz * 4) + 0.5) / 4
+        state = torch.get_rng_state()
+        ref = pn.farthest_point_sample_batch(xyz, S)
+        torch.set_rng_state(state)
+        start = torch.randint(0, N, (B,), dtype=torch.long)
+        assert np.array_equal(orc.fps(xyz.numpy(), S, start.numpy(), 1e10), ref.numpy())
+        assert np.array_equal(orc.gather(xyz.numpy(), ref.numpy()), pn.index_points(xyz, ref).numpy())

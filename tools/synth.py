@@ -1,0 +1,114 @@
+"""Seeded synthetic point clouds shaped like the reference's datasets.  No dataset is
+available offline, so tests and bench.py use these.  Pure numpy, deterministic for a given seed."""
+import numpy as np
+
+
+def _surface_points(rng, n):
+    """n points uniformly on the surface of a random union of 3-6 boxes / cylinders / spheres."""
+    nprim = int(rng.integers(3, 7))
+    kinds = rng.integers(0, 3, nprim)
+    centres = rng.uniform(-1.0, 1.0, (nprim, 3))
+    sizes = rng.uniform(0.2, 0.8, (nprim, 3))
+    areas = np.empty(nprim)
+    for i in range(nprim):
+        a, b, c = sizes[i]
+        if kinds[i] == 0:
+            areas[i] = 2 * (a * b + b * c + a * c) * 4
+        elif kinds[i] == 1:
+            areas[i] = 2 * np.pi * a * (2 * c) + 2 * np.pi * a * a
+        else:
+            areas[i] = 4 * np.pi * a * a
+    counts = rng.multinomial(n, areas / areas.sum())
+    out = []
+    for i in range(nprim):
+        m = int(counts[i])
+        if m == 0:
+            continue
+        a, b, c = sizes[i]
+        if kinds[i] == 0:  # box: pick a face by area, then uniform on it
+            fa = np.array([b * c, b * c, a * c, a * c, a * b, a * b])
+            face = rng.choice(6, m, p=fa / fa.sum())
+            u = rng.uniform(-1, 1, (m, 3)) * sizes[i]
+            axis = face // 2
+            sign = (face % 2) * 2.0 - 1.0
+            u[np.arange(m), axis] = sign * sizes[i][axis]
+            pts = u
+        elif kinds[i] == 1:  # cylinder radius a, half height c
+            side = 2 * np.pi * a * 2 * c
+            cap = np.pi * a * a
+            which = rng.choice(3, m, p=np.array([side, cap, cap]) / (side + 2 * cap))
+            th = rng.uniform(0, 2 * np.pi, m)
+            r = np.where(which == 0, a, a * np.sqrt(rng.uniform(0, 1, m)))
+            z = np.where(which == 0, rng.uniform(-c, c, m), np.where(which == 1, c, -c))
+            pts = np.stack([r * np.cos(th), r * np.sin(th), z], 1)
+        else:  # sphere radius a
+            v = rng.normal(size=(m, 3))
+            pts = a * v / np.linalg.norm(v, axis=1, keepdims=True)
+        out.append(pts + centres[i])
+    pts = np.concatenate(out, 0)
+    return pts[rng.permutation(pts.shape[0])]
+
+
+def modelnet_like(n_clouds, n_points=8192, seed=11):
+    """[n_clouds, n_points, 3] float32 in [0,1], scaled exactly like sample_modelnet.py:47-48."""
+    rng = np.random.default_rng(seed)
+    out = np.empty((n_clouds, n_points, 3), dtype=np.float32)
+    for i in range(n_clouds):
+        p = _surface_points(rng, n_points).astype(np.float32)
+        p -= p.min()
+        p /= p.max()
+        out[i] = p
+    return out
+
+
+def uniform_cube(n_clouds, n_points, seed=11):
+    return np.random.default_rng(seed).random((n_clouds, n_points, 3), dtype=np.float32)
+
+
+def grid_quantised(n_clouds, n_points, depth=4, seed=11):
+    """Points on the octree grid (i+1/2)/2^depth: exact distance ties are everywhere."""
+    rng = np.random.default_rng(seed)
+    cells = rng.integers(0, 2 ** depth, (n_clouds, n_points, 3))
+    return ((cells + 0.5) / 2 ** depth).astype(np.float32)
+
+
+def shapenet_like(n_clouds, n_points=2048, seed=11):
+    """2048-point clouds shifted by +0.5 as sample_shapenet.py:161 does."""
+    p = modelnet_like(n_clouds, n_points, seed) - 0.5
+    return (p + 0.5).astype(np.float32)
+
+
+def decompressed_like(clouds, sigma=2e-3, seed=12):
+    """A 'decoded' cloud for eval: original + N(0, sigma) noise, points re-ordered."""
+    rng = np.random.default_rng(seed)
+    out = clouds + rng.normal(0, sigma, clouds.shape).astype(np.float32)
+    for i in range(out.shape[0]):
+        out[i] = out[i][rng.permutation(out.shape[1])]
+    return out.astype(np.float32)
+
+
+def scene_like(n_points=1_000_000, seed=11):
+    """S3DIS-shaped room: 8 x 6 x 3 m, 6 planes + 20 boxes, surface-uniform + 1 cm noise, metres."""
+    rng = np.random.default_rng(seed)
+    room = np.array([8.0, 6.0, 3.0])
+    n_planes = n_points // 2
+    pts = []
+    face = rng.integers(0, 6, n_planes)
+    u = rng.uniform(0, 1, (n_planes, 3)) * room
+    axis = face // 2
+    u[np.arange(n_planes), axis] = (face % 2) * room[axis]
+    pts.append(u)
+    n_box = n_points - n_planes
+    per = np.full(20, n_box // 20)
+    per[: n_box - per.sum()] += 1
+    for i in range(20):
+        size = rng.uniform(0.2, 1.2, 3)
+        c = rng.uniform(size, room - size)
+        m = int(per[i])
+        f = rng.integers(0, 6, m)
+        v = rng.uniform(-1, 1, (m, 3)) * size
+        ax = f // 2
+        v[np.arange(m), ax] = ((f % 2) * 2.0 - 1.0) * size[ax]
+        pts.append(v + c)
+    p = np.concatenate(pts, 0) + rng.normal(0, 0.01, (n_points, 3))
+    return p[rng.permutation(n_points)].astype(np.float32)[None]
