@@ -36,6 +36,8 @@ extern "C" {
 /* Library version (major*10000 + minor*100 + patch) and the last error text of the calling thread. */
 int pcc_version(void);
 const char *pcc_last_error_string(void);
+/* Number of kernels this library has enqueued so far in the process (every launch is counted once). */
+int64_t pcc_launch_count(void);
 
 /*
  * Farthest point sampling of `npoint` indices from each of B clouds of N points.

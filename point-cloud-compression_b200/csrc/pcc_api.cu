@@ -14,9 +14,14 @@ void set_error(const char *fmt, ...) {
     va_end(ap);
 }
 
+static unsigned long long g_launches = 0;  // kernels enqueued through check_launch (bench.py's gpu_launches)
+
 int check_launch(const char *what) {
     const cudaError_t e = cudaGetLastError();
-    if (e == cudaSuccess) return 0;
+    if (e == cudaSuccess) {
+        __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED);
+        return 0;
+    }
     set_error("%s: %s", what, cudaGetErrorString(e));
     return static_cast<int>(e);
 }
@@ -38,3 +43,5 @@ int num_sms() {
 PCC_API int pcc_version(void) { return 100; /* 0.1.0 */ }
 
 PCC_API const char *pcc_last_error_string(void) { return pcc::g_err; }
+
+PCC_API int64_t pcc_launch_count(void) { return static_cast<int64_t>(__atomic_load_n(&pcc::g_launches, __ATOMIC_RELAXED)); }

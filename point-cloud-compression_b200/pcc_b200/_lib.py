@@ -18,6 +18,7 @@ _f = ctypes.c_float
 SIGNATURES = {
     "pcc_version": (_i, []),
     "pcc_last_error_string": (ctypes.c_char_p, []),
+    "pcc_launch_count": (_i64, []),
     "pcc_fps_workspace_bytes": (_i64, [_i, _i, _i]),
     "pcc_fps_f32": (_i, [_vp, _i, _i, _i, _vp, _f, _vp, _vp, _vp]),
     "pcc_knn_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _f, _vp]),

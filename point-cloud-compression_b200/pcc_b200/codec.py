@@ -1,0 +1,100 @@
+"""Batched compress / decompress / eval drivers for the IPDAE patch codec: the hot path of the reference's
+compress.py:78-127, decompress.py:96-116 and eval.py:180,199-205 run for many clouds per launch.
+
+Only the data-parallel hot path is here.  Octree centre coding and the entropy coder stay on the reference path
+(north_star); where the reference round-trips the FPS centres through its octree coder on the host
+(compress.py:98-101) this driver applies the coder's quantisation rule (octree_np.getDecodeFromPc:
+floor(c / cube) * cube + cube / 2) on the device at a fixed depth, keeping the FPS order -- SURVEY.md 8d
+"intended" centres (ii).
+"""
+import math
+
+import torch
+
+from . import ops
+from .modules import AE
+from .pn_kit_ops import farthest_point_sample_batch, index_points
+
+
+def normalize_batch(pc, margin=0.01):
+    """pn_kit.normalize (/root/reference/pn_kit.py:47-60) applied per cloud (the reference is called with B=1 in
+    compress.py:90): returns (pc in [margin, 1-margin], center [B,3], longest [B])."""
+    mx, mn = pc.max(dim=1)[0], pc.min(dim=1)[0]
+    center = (mx + mn) / 2
+    longest = (mx - mn).max(dim=1)[0]
+    out = pc - center[:, None, :]
+    out = out * (1 - margin) / longest[:, None, None]
+    return out + 0.5, center, longest
+
+
+def denormalize_batch(pc, center, longest, margin=0.01):
+    """pn_kit.denormalize (/root/reference/pn_kit.py:62-66), per cloud."""
+    out = pc - 0.5
+    out = out * longest[:, None, None] / (1 - margin)
+    return out + center[:, None, :]
+
+
+def quantise_centres(centres, depth, resolution=1.0):
+    """octree_np.getDecodeFromPc's rule (/root/reference/octree_np.py:114-133) without the np.unique re-ordering."""
+    cube = float(resolution) / max(1.0, math.pow(2.0, min(depth, 30)))
+    return torch.floor(centres / cube) * cube + cube / 2
+
+
+class PatchCodec:
+    def __init__(self, ae: AE, N0=1024, alpha=2, centre_depth=6):
+        self.ae, self.N0, self.alpha, self.centre_depth = ae, N0, alpha, centre_depth
+
+    def patch_scale(self, N):
+        return (N / self.N0) ** (1 / 3)  # compress.py:108
+
+    @torch.no_grad()
+    def compress(self, xyz, start_idx=None):
+        """xyz [B,N,3] on the device -> dict(latent_q [B,S,d], centres [B,S,3], center, longest, patches)."""
+        B, N, _ = xyz.shape
+        K = self.ae.K
+        S = int(N * self.alpha // K)                                              # compress.py:93
+        pc, center, longest = normalize_batch(xyz)                                # compress.py:90
+        if start_idx is None:
+            idx = farthest_point_sample_batch(pc, S)                              # compress.py:96 (CPU RNG draw)
+        else:
+            idx = ops.fps(pc, S, start_idx, 1e10)
+        rec_centres = quantise_centres(index_points(pc, idx), self.centre_depth)  # compress.py:98-101
+        _, _, patches = ops.knn(rec_centres, pc, K, return_nn=True, centre_sub=True,
+                                nn_scale=self.patch_scale(N))                     # compress.py:105-108
+        latent, latent_q = self.ae.encode_patches(patches.view(B * S, K, 3))      # compress.py:113-127
+        return dict(latent_q=latent_q.view(B, S, -1), latent=latent.view(B, S, -1), centres=rec_centres, center=center,
+                    longest=longest, pc=pc)
+
+    @torch.no_grad()
+    def decompress(self, latent_q, centres, N, center=None, longest=None):
+        """latent_q [B,S,d], centres [B,S,3] -> reconstructed cloud [B, S*k, 3] (decompress.py:96-116)."""
+        B, S, d = latent_q.shape
+        patches = self.ae.decode_patches(latent_q.reshape(B * S, d))              # decompress.py:96-102
+        patches = patches / self.patch_scale(N)                                   # decompress.py:105
+        pc = (patches.view(B, S, -1, 3) + centres.view(B, S, 1, 3)).reshape(B, -1, 3)
+        if center is not None:
+            pc = denormalize_batch(pc, center, longest)                           # decompress.py:113-116
+        return pc
+
+    @torch.no_grad()
+    def evaluate(self, decomp, original):
+        """Per-cloud metrics of eval.py: normalised Chamfer distance (eval.py:199-205, pred first) and D1 PSNR
+        (eval.py:68-92: recon -> original 1-NN, peak = bbox diagonal of the original).  Returns [B,3]
+        (chamfer, d1_psnr_db, d1_mse).  The 1-NN distances of both metrics come from ONE Chamfer launch: the
+        normalisation is a uniform scale, so d2_original = d2_normalised * (max-min)^2."""
+        mn = original.amin(dim=(1, 2), keepdim=True)
+        mx = original.amax(dim=(1, 2), keepdim=True)
+        scale = mx - mn
+        r = ops.chamfer_forward((decomp - mn) / scale, (original - mn) / scale, want_idx=False)
+        mse = r["dx"].double().mean(dim=1) * scale.view(-1).double() ** 2
+        ext = original.amax(dim=1) - original.amin(dim=1)
+        diag2 = (ext.double() ** 2).sum(dim=1)
+        psnr = 10.0 * torch.log10(diag2 / mse)
+        return torch.stack((r["per_cloud"].double(), psnr, mse), dim=1)
+
+    @torch.no_grad()
+    def roundtrip(self, xyz, start_idx=None):
+        """compress -> decompress -> eval for a batch; returns (latent_q int8 [B,S,d], centres, metrics [B,3])."""
+        c = self.compress(xyz, start_idx)
+        rec = self.decompress(c["latent_q"], c["centres"], xyz.shape[1], c["center"], c["longest"])
+        return c["latent_q"].to(torch.int8), c["centres"], self.evaluate(rec, xyz), rec

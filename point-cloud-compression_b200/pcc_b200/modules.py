@@ -1,0 +1,147 @@
+"""Parameter containers with the reference's state_dict keys, and the batched device forward of the IPDAE patch
+auto-encoder (/root/reference/AE.py:12-55) built on the pcc_b200 kernels.
+
+The containers mirror the reference classes only as far as names, constructor arguments and parameter keys /
+shapes go, so `ae.pkl` checkpoints written by the reference's train.py load unchanged:
+    sa.conv{0,1,2}.{weight,bias}                 pn_kit.SetAbstraction   (pn_kit.py:146-162)
+    pn.mlp_Modules.{0..3}.0.{weight,bias}        pn_kit.PointNet         (pn_kit.py:98-121)
+    inv_pool.{0,2,4}.{weight,bias}               AE.inv_pool             (AE.py:19-26)
+    inv_mlp.mlp_Modules.{0..3}.0.{weight,bias}   pn_kit.MLP              (pn_kit.py:263-287)
+The forward bodies are NOT the reference's: they run channel-last on flattened [rows, C] activations and call the
+fused kernels (in-patch kNN -> shared MLP -> max over neighbours, ...).
+"""
+import torch
+import torch.nn as nn
+
+from . import mlp_ops, ops
+
+
+class STEQuantize(torch.autograd.Function):
+    """Round in the forward pass, identity gradient (AE.STEQuantize, /root/reference/AE.py:72-85)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.round()
+
+    @staticmethod
+    def backward(ctx, grad_outputs):
+        return grad_outputs
+
+
+def _conv_stack(channels):
+    mods = nn.ModuleList()
+    for cin, cout in zip(channels[:-1], channels[1:]):
+        mods.append(nn.Sequential(nn.Conv2d(cin, cout, 1)))  # key "<i>.0.weight", ReLU has no parameters
+    return mods
+
+
+class SetAbstraction(nn.Module):
+    """pn_kit.SetAbstraction(npoint, K, in_channel, mlp, bn=False, finalRelu=True) with S == N (no FPS)."""
+
+    def __init__(self, npoint, K, in_channel, mlp, bn=False, finalRelu=True):
+        super().__init__()
+        if bn:
+            raise NotImplementedError("pcc_b200.SetAbstraction: bn=True is not used by the reference AE")
+        self.npoint, self.K, self.finalRelu = npoint, K, finalRelu
+        self.conv0 = nn.Conv2d(in_channel + 3, mlp[0], 1)
+        self.conv1 = nn.Conv2d(mlp[0], mlp[1], 1)
+        self.conv2 = nn.Conv2d(mlp[1], mlp[2], 1)
+
+    def layers(self):
+        return [(self.conv0.weight.flatten(1), self.conv0.bias, True), (self.conv1.weight.flatten(1), self.conv1.bias, True),
+                (self.conv2.weight.flatten(1), self.conv2.bias, self.finalRelu)]
+
+    def forward_points(self, xyz):
+        """xyz [BS, P, 3] (channel-last) -> per-point features [BS, P, C_out] (channel-last).
+        pn_kit.py:164-211: kNN(K) in the patch, recentre on the query, shared MLP, max over the K neighbours."""
+        BS, P, _ = xyz.shape
+        if self.npoint != P:
+            raise NotImplementedError("pcc_b200.SetAbstraction: only the S == N configuration of AE.py:16 is built")
+        _, _, grouped = ops.knn(xyz, xyz, self.K, return_nn=True, centre_sub=True)  # [BS,P,K,3]
+        return mlp_ops.mlp_chain_groupmax(grouped.reshape(BS * P * self.K, 3), self.layers(), group=self.K).reshape(BS, P, -1)
+
+    def forward(self, xyz):
+        """Reference signature: xyz [B, 3, N] -> (new_xyz [B, 3, S], new_points [B, D', S])."""
+        feat = self.forward_points(xyz.permute(0, 2, 1).contiguous())
+        return xyz, feat.permute(0, 2, 1)
+
+
+class PointNet(nn.Module):
+    """pn_kit.PointNet(in_channel, mlps, relu, bn): shared MLP then max over the points."""
+
+    def __init__(self, in_channel, mlps, relu, bn=False):
+        super().__init__()
+        if bn:
+            raise NotImplementedError("pcc_b200.PointNet: bn=True is not used by the reference AE")
+        self.relu = list(relu)
+        self.mlp_Modules = _conv_stack([in_channel] + list(mlps))
+
+    def layers(self):
+        return [(m[0].weight.flatten(1), m[0].bias, r) for m, r in zip(self.mlp_Modules, self.relu)]
+
+    def forward_points(self, x):
+        """x [BS, P, C] channel-last -> [BS, D]."""
+        BS, P, C = x.shape
+        return mlp_ops.mlp_chain_groupmax(x.reshape(BS * P, C), self.layers(), group=P)
+
+    def forward(self, points):
+        """Reference signature: points [B, C, N] -> [B, D]."""
+        return self.forward_points(points.permute(0, 2, 1).contiguous())
+
+
+class MLP(nn.Module):
+    """pn_kit.MLP(in_channel, mlps, relu, bn): shared MLP, no pooling."""
+
+    def __init__(self, in_channel, mlps, relu, bn=False):
+        super().__init__()
+        if bn:
+            raise NotImplementedError("pcc_b200.MLP: bn=True is not used by the reference AE")
+        self.relu = list(relu)
+        self.mlp_Modules = _conv_stack([in_channel] + list(mlps))
+
+    def layers(self):
+        return [(m[0].weight.flatten(1), m[0].bias, r) for m, r in zip(self.mlp_Modules, self.relu)]
+
+    def forward_points(self, x):
+        BS, P, C = x.shape
+        return mlp_ops.mlp_chain(x.reshape(BS * P, C), self.layers()).reshape(BS, P, -1)
+
+    def forward(self, points):
+        return self.forward_points(points.permute(0, 2, 1).contiguous()).permute(0, 2, 1)
+
+
+class AE(nn.Module):
+    """AE.AE(K, k, d, L) (/root/reference/AE.py:12-55): IPDAE patch auto-encoder, same parameters, batched forward."""
+
+    def __init__(self, K, k, d, L):
+        super().__init__()
+        self.sa = SetAbstraction(npoint=K, K=16, in_channel=0, mlp=[32, 64, 128], bn=False)
+        self.pn = PointNet(in_channel=3 + 128, mlps=[128, 256, 512, d], relu=[True, True, True, False], bn=False)
+        self.inv_pool = nn.Sequential(nn.Linear(d, 256), nn.ReLU(), nn.Linear(256, 1024), nn.ReLU(),
+                                      nn.Linear(1024, k * 128), nn.ReLU())
+        self.inv_mlp = MLP(in_channel=d + 128, mlps=[128, 64, 32, 3], relu=[True, True, True, False], bn=False)
+        self.K, self.k, self.d, self.L = K, k, d, L
+        self.quantize = STEQuantize.apply
+
+    # -- the two halves the scripts use separately (compress.py:113-127, decompress.py:96-102) --
+    def encode_patches(self, patches):
+        """patches [BS, K, 3] (recentred, scaled) -> (latent [BS, d] after the sigmoid spread, rounded latent)."""
+        feat = self.sa.forward_points(patches)                                    # AE.py:38
+        latent = self.pn.forward_points(torch.cat((patches, feat), dim=2))        # AE.py:39 (xyz first)
+        spread = self.L - 0.2                                                     # AE.py:42-45
+        latent = torch.sigmoid(latent) * spread - spread / 2
+        return latent, STEQuantize.apply(latent)
+
+    def decode_patches(self, latent_q):
+        """latent_q [BS, d] -> patches [BS, k, 3]   (AE.py:48-53)."""
+        BS = latent_q.shape[0]
+        lin = mlp_ops.mlp_chain(latent_q, [(m.weight, m.bias, True) for m in (self.inv_pool[0], self.inv_pool[2],
+                                                                               self.inv_pool[4])])
+        lin = lin.view(BS, 128, self.k).permute(0, 2, 1)                          # [BS, k, 128] channel-last
+        x = torch.cat((lin, latent_q.unsqueeze(1).expand(-1, self.k, -1)), dim=2)  # 128 features then d latent
+        return self.inv_mlp.forward_points(x.contiguous())
+
+    def forward(self, xyz):
+        """Reference signature (AE.py:34-55): xyz [BS, K, 3] -> (new_xyz [BS, k, 3], latent, latent_quantized)."""
+        latent, latent_q = self.encode_patches(xyz.contiguous())
+        return self.decode_patches(latent_q), latent, latent_q

@@ -112,3 +112,34 @@ def scene_like(n_points=1_000_000, seed=11):
         pts.append(v + c)
     p = np.concatenate(pts, 0) + rng.normal(0, 0.01, (n_points, 3))
     return p[rng.permutation(n_points)].astype(np.float32)[None]
+
+
+def ae_shapes(k=128, d=16, L=7):
+    """Parameter keys / shapes of the reference AE.AE(K, k, d, L) state_dict (/root/reference/AE.py:12-32)."""
+    del L
+    shapes = {}
+    for i, (cin, cout) in enumerate([(3, 32), (32, 64), (64, 128)]):
+        shapes[f"sa.conv{i}.weight"], shapes[f"sa.conv{i}.bias"] = (cout, cin, 1, 1), (cout,)
+    for i, (cin, cout) in enumerate([(131, 128), (128, 256), (256, 512), (512, d)]):
+        shapes[f"pn.mlp_Modules.{i}.0.weight"], shapes[f"pn.mlp_Modules.{i}.0.bias"] = (cout, cin, 1, 1), (cout,)
+    for i, (cin, cout) in zip((0, 2, 4), [(d, 256), (256, 1024), (1024, k * 128)]):
+        shapes[f"inv_pool.{i}.weight"], shapes[f"inv_pool.{i}.bias"] = (cout, cin), (cout,)
+    for i, (cin, cout) in enumerate([(d + 128, 128), (128, 64), (64, 32), (32, 3)]):
+        shapes[f"inv_mlp.mlp_Modules.{i}.0.weight"], shapes[f"inv_mlp.mlp_Modules.{i}.0.bias"] = (cout, cin, 1, 1), (cout,)
+    return shapes
+
+
+def seeded_state_dict(shapes, seed=11):
+    """Deterministic PyTorch-default-like init (U(-1/sqrt(fan_in), 1/sqrt(fan_in))) for a dict of shapes, so tests,
+    bench and the CPU baseline on any machine use identical weights without shipping a checkpoint."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    fan_in = 1
+    for key in sorted(shapes):
+        shape = shapes[key]
+        if key.endswith("weight"):
+            fan_in = int(np.prod(shape[1:]))
+        bound = 1.0 / np.sqrt(fan_in) if key.endswith(("weight", "bias")) else 1.0
+        sd[key] = (torch.rand(shape, generator=g) * 2 - 1) * bound
+    return sd
