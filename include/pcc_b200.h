@@ -117,6 +117,33 @@ int pcc_chamfer_fwd_f32(const float *x, const float *y, int B, int P1, int P2, f
 int pcc_chamfer_bwd_f32(const float *x, const float *y, const int64_t *ix, const int64_t *iy, int B, int P1,
                         int P2, const float *grad_loss, float *gx, float *gy, void *stream);
 
+/*
+ * Fused shared-MLP chain on the tensor cores (tcgen05, bf16 operands, fp32 accumulation):
+ *     y = act_L(W_L . ... act_1(W_1 . x + b_1) ... + b_L)      per row of x [rows, ldx] (first cin columns used),
+ * optionally followed by a max over every run of `group` consecutive rows (group <= 1: none).
+ * Replaces the 1x1-conv stacks (+ max-pool) of pn_kit.SetAbstraction / PointNet / MLP
+ * (/root/reference/pn_kit.py:196-207, 124-144, 289-305) and PointnetSAModule.mlp
+ * (/root/reference/pointnet_sa_module.py:87-91).  Intermediate activations stay in shared memory / TMEM.
+ *   - weights are packed once per layer with pcc_mlp_pack_weights_f32 from the reference's [cout, cin] fp32 tensor
+ *     (Conv2d weight flattened) into pcc_mlp_packed_bytes(cin, cout) bytes of device memory;
+ *   - `layers` is a HOST array; every layer's weights must fit in shared memory together (otherwise
+ *     PCC_ERR_UNSUPPORTED, never a fallback); group must divide 32, or be a multiple of 32 dividing 128, or be a
+ *     multiple of 128, and rows % group == 0;
+ *   - out: fp32 [rows, cout_L] or [rows / group, cout_L], channel-last.
+ * Numerics: operands rounded to bf16, products accumulated in fp32 (tolerance stated in tests/test_gpu_mlp.py).
+ */
+#define PCC_MLP_MAX_LAYERS 6
+typedef struct PccMlpLayer {
+    const void *packed_w; /* device, from pcc_mlp_pack_weights_f32 */
+    const float *bias;    /* device, [cout] fp32 */
+    int cin, cout;
+    int relu;             /* apply max(x, 0) after this layer */
+} PccMlpLayer;
+int64_t pcc_mlp_packed_bytes(int cin, int cout);
+int pcc_mlp_pack_weights_f32(const float *w, int cin, int cout, void *packed, void *stream);
+int pcc_mlp_chain_f32(const float *x, int64_t rows, int ldx, const PccMlpLayer *layers, int n_layers, int group,
+                      float *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,407 @@
+// Fused shared-MLP chain on the 5th-gen tensor cores (tcgen05 + TMEM), sm_100a.
+//
+// Replaces the 1x1-convolution stacks + max-pool of the reference's point-set blocks, whose intermediates the
+// reference materialises in HBM ([B*S,128,16,256] fp32 per SetAbstraction call):
+//   pn_kit.SetAbstraction  conv0/1/2 + ReLU + max over K   /root/reference/pn_kit.py:196-207
+//   pn_kit.PointNet        4 convs + max over points        /root/reference/pn_kit.py:124-144
+//   pn_kit.MLP             4 convs                          /root/reference/pn_kit.py:289-305
+//   PointnetSAModule.mlp   Conv2d+BN(folded)+ReLU + max     /root/reference/pointnet_sa_module.py:87-91
+//
+// Formulation: "channels on lanes".  For a tile of P = 128 positions the kernel computes, layer by layer,
+//     D^T[Cout, P] = W[Cout, Cin] . X^T[Cin, P]        (bf16 operands, fp32 accumulation in TMEM)
+// i.e. the WEIGHTS are the MMA A operand (M = 128 output channels per tcgen05.mma, K-major, pre-packed on the
+// device into the canonical no-swizzle core-matrix layout) and the ACTIVATIONS are the B operand (N = positions).
+// A TMEM lane is an output channel, a TMEM column is a position, so in the epilogue each thread owns one channel:
+// bias is one register, ReLU and the max over G consecutive positions (neighbours / points of a group) are
+// plain in-register ops on consecutive columns, and the next layer's B operand is written back to shared memory as
+// 16-byte chunks (8 consecutive positions of one channel = one row of an MN-major core matrix), 512 contiguous
+// bytes per warp.  Activations never leave the SM between layers; only the pooled result is written to HBM.
+//
+// One CTA = 128 threads, sequential per tile (load -> [mma -> commit -> epilogue] x layers); MMA/epilogue overlap
+// comes from several co-resident CTAs per SM (each owns <= 256 TMEM columns).  tcgen05.mma is issued by thread 0;
+// completion is tracked with tcgen05.commit on an mbarrier.
+#include <cuda_bf16.h>
+
+#include "pcc_common.cuh"
+
+namespace pcc {
+
+constexpr int MLP_P = 128;  // positions per tile == MMA N
+constexpr int MLP_THREADS = 128;
+constexpr int MLP_MAX_LAYERS = PCC_MLP_MAX_LAYERS;
+
+struct MlpChainParams {
+    int n_layers;
+    int cin[MLP_MAX_LAYERS], cout[MLP_MAX_LAYERS], kp[MLP_MAX_LAYERS], mt[MLP_MAX_LAYERS], relu[MLP_MAX_LAYERS];
+    int w_off[MLP_MAX_LAYERS];    // shared-memory byte offset of the packed weights of layer l
+    int w_bytes[MLP_MAX_LAYERS];
+    int x_off[MLP_MAX_LAYERS];    // shared-memory byte offset of the INPUT activations of layer l
+    const void *w[MLP_MAX_LAYERS];
+    const float *bias[MLP_MAX_LAYERS];
+    int tmem_cols;
+    int ctrl_off;                 // mbarrier + TMEM base address slot
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+// Shared-memory matrix descriptor, SWIZZLE_NONE, version 1 (sm_100): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = static_cast<uint64_t>((saddr & 0x3ffffu) >> 4);
+    d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3fffu) << 16;
+    d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3fffu) << 32;
+    d |= 1ull << 46;
+    return d;
+}
+
+// Instruction descriptor for kind::f16: D=f32, A=B=bf16, A K-major, B K- or MN-major, shape M x N.
+__device__ __forceinline__ uint32_t umma_idesc(int M, int N, int b_mn_major) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(b_mn_major) << 16) |
+           (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+
+__device__ __forceinline__ void umma_commit(uint32_t mbar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+    uint32_t ok;
+    uint32_t spins = 0;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(ok)
+            : "r"(mbar), "r"(parity)
+            : "memory");
+        if (!ok && ++spins > (1u << 26)) __trap();  // a lost completion must fail loudly, never hang the GPU
+    } while (!ok);
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t *>(&h);
+}
+
+// ---- weight packing -------------------------------------------------------------------------------------------
+// Packed layer = mt tiles of [128 channels x kp] bf16 in the K-major no-swizzle core-matrix layout:
+//   offset(ch, k) = tile * 128*kp*2 + (ch_local / 8) * (kp * 16) + (k / 8) * 128 + (ch_local % 8) * 16 + (k % 8) * 2
+// (SBO = kp*16 bytes between 8-channel groups, LBO = 128 bytes between 8-wide k chunks); zero beyond cout / cin.
+__global__ void __launch_bounds__(256)
+mlp_pack_kernel(const float *__restrict__ w, int cin, int cout, int kp, int mt, __nv_bfloat16 *__restrict__ packed) {
+    const long long total = static_cast<long long>(mt) * 128 * kp;
+    for (long long e = blockIdx.x * 256ll + threadIdx.x; e < total; e += static_cast<long long>(gridDim.x) * 256ll) {
+        const int tile = static_cast<int>(e / (128ll * kp));
+        const int r = static_cast<int>(e - static_cast<long long>(tile) * 128 * kp);
+        const int grp = r / (kp * 8);       // 8-channel group
+        const int r2 = r - grp * kp * 8;
+        const int kc = r2 / 64;             // 8-wide k chunk
+        const int r3 = r2 - kc * 64;
+        const int chl = r3 / 8, kl = r3 - chl * 8;
+        const int ch = tile * 128 + grp * 8 + chl, k = kc * 8 + kl;
+        const float v = (ch < cout && k < cin) ? w[static_cast<size_t>(ch) * cin + k] : 0.0f;
+        packed[e] = __float2bfloat16_rn(v);
+    }
+}
+
+// ---- the chain kernel -------------------------------------------------------------------------------------------
+// x: fp32 [rows, ldx] row-major (first cin[0] columns used).  Work unit = max(1, group / P) consecutive tiles.
+// out: fp32 [rows, CL] (group <= 1) or [rows / group, CL] (max over each run of `group` consecutive rows).
+__global__ void __launch_bounds__(MLP_THREADS)
+mlp_chain_kernel(const __grid_constant__ MlpChainParams prm, const float *__restrict__ x, long long rows, int ldx,
+                 int group, float *__restrict__ out, long long n_units, int tiles_per_unit) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t mbar = smem_base + prm.ctrl_off;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + prm.ctrl_off + 8);
+
+    // ---- prologue: weights -> shared memory, barrier init, TMEM allocation ----
+    for (int l = 0; l < prm.n_layers; ++l) {
+        const int4 *src = static_cast<const int4 *>(prm.w[l]);
+        int4 *dst = reinterpret_cast<int4 *>(smem + prm.w_off[l]);
+        for (int i = tid; i < prm.w_bytes[l] / 16; i += MLP_THREADS) dst[i] = src[i];
+    }
+    if (tid == 0) mbar_init(mbar, 1);
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(static_cast<uint32_t>(prm.tmem_cols))
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    uint32_t phase = 0;
+
+    const int L = prm.n_layers;
+    const int CL = prm.cout[L - 1];
+    const int kp0 = prm.kp[0], c0 = prm.cin[0];
+
+    for (long long unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        float run_max[8];  // running max across the tiles of one unit (one per M-tile of the last layer)
+#pragma unroll
+        for (int t = 0; t < 8; ++t) run_max[t] = -INFINITY;
+
+        for (int sub = 0; sub < tiles_per_unit; ++sub) {
+            const long long row0 = (unit * tiles_per_unit + sub) * MLP_P;
+
+            // ---- load the input tile: thread p owns position p; K-major core matrices (8 channels = 16 bytes) ----
+            {
+                unsigned char *x0 = smem + prm.x_off[0];
+                const long long r = row0 + tid;
+                const float *xr = x + r * ldx;
+                const bool ok = r < rows;
+                for (int c8 = 0; c8 < kp0 / 8; ++c8) {
+                    float f[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int c = c8 * 8 + i;
+                        f[i] = (ok && c < c0) ? __ldg(xr + c) : 0.0f;
+                    }
+                    uint4 pk = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                                          pack_bf16x2(f[6], f[7]));
+                    // (p/8)*SBO + c8*LBO + (p%8)*16 with SBO = 128, LBO = (P/8)*128
+                    *reinterpret_cast<uint4 *>(x0 + (tid >> 3) * 128 + c8 * (MLP_P / 8) * 128 + (tid & 7) * 16) = pk;
+                }
+            }
+            fence_async_smem();
+            __syncthreads();
+
+            for (int l = 0; l < L; ++l) {
+                const int kp = prm.kp[l], mt = prm.mt[l];
+                // ---- MMA: one elected thread ----
+                if (tid == 0) {
+                    tc_fence_after();
+                    const uint32_t a_base = smem_base + prm.w_off[l];
+                    const uint32_t b_base = smem_base + prm.x_off[l];
+                    const uint32_t idesc = umma_idesc(128, MLP_P, l == 0 ? 0 : 1);
+                    for (int t = 0; t < mt; ++t) {
+                        for (int ks = 0; ks < kp / 16; ++ks) {
+                            const uint64_t a_desc = umma_desc(a_base + t * 128 * kp * 2 + ks * 256, 128, kp * 16);
+                            uint64_t b_desc;
+                            if (l == 0)  // K-major input tile: LBO = (P/8)*128 between k chunks, SBO = 128
+                                b_desc = umma_desc(b_base + ks * 2 * (MLP_P / 8) * 128, (MLP_P / 8) * 128, 128);
+                            else         // MN-major activations: LBO = 128 between k groups, SBO = kp*16 between position groups
+                                b_desc = umma_desc(b_base + ks * 256, 128, kp * 16);
+                            umma_bf16(tmem_base + t * MLP_P, a_desc, b_desc, idesc, ks > 0 ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(mbar);
+                }
+                mbar_wait(mbar, phase);
+                phase ^= 1u;
+                tc_fence_after();
+
+                // ---- epilogue: thread = output channel (TMEM lane), registers = positions (TMEM columns) ----
+                const bool last = (l == L - 1);
+                const int cout = prm.cout[l];
+                const int relu = prm.relu[l];
+                const float *bias = prm.bias[l];
+                unsigned char *xn = last ? nullptr : smem + prm.x_off[l + 1];
+                const int kpn = last ? 0 : prm.kp[l + 1];
+                for (int t = 0; t < mt; ++t) {
+                    if (t * 128 + warp * 32 >= (last ? cout : kpn)) break;  // warp-uniform: nothing real in this quadrant
+                    const int c = t * 128 + warp * 32 + lane;
+                    const bool real = c < cout;
+                    const float b = real ? __ldg(bias + c) : 0.0f;
+                    float gmax = run_max[t & 7];
+                    for (int j = 0; j < MLP_P / 32; ++j) {
+                        uint32_t v[32];
+                        tmem_ld32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + t * MLP_P + j * 32, v);
+                        float f[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            float a = real ? __uint_as_float(v[i]) + b : 0.0f;  // padded channels feed exact zeros
+                            f[i] = relu ? fmaxf(a, 0.0f) : a;
+                        }
+                        if (!last) {
+                            if (c < kpn) {
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    const uint4 pk = make_uint4(pack_bf16x2(f[q * 8 + 0], f[q * 8 + 1]),
+                                                                pack_bf16x2(f[q * 8 + 2], f[q * 8 + 3]),
+                                                                pack_bf16x2(f[q * 8 + 4], f[q * 8 + 5]),
+                                                                pack_bf16x2(f[q * 8 + 6], f[q * 8 + 7]));
+                                    const int pg = j * 4 + q;  // position group (8 positions)
+                                    *reinterpret_cast<uint4 *>(xn + pg * (kpn * 16) + (c >> 3) * 128 + (c & 7) * 16) = pk;
+                                }
+                            }
+                        } else if (real) {
+                            if (group <= 1) {
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) {
+                                    const long long r = row0 + j * 32 + i;
+                                    if (r < rows) out[r * CL + c] = f[i];
+                                }
+                            } else if (group <= 32) {
+                                const int per = 32 / group;  // groups inside this 32-column chunk
+                                for (int g = 0; g < per; ++g) {
+                                    float m = -INFINITY;
+#pragma unroll
+                                    for (int i = 0; i < 32; ++i)
+                                        if (i / group == g) m = fmaxf(m, f[i]);
+                                    const long long r = row0 + j * 32 + g * group;
+                                    if (r < rows) out[(r / group) * CL + c] = m;
+                                }
+                            } else {
+                                float m = f[0];
+#pragma unroll
+                                for (int i = 1; i < 32; ++i) m = fmaxf(m, f[i]);
+                                gmax = fmaxf(gmax, m);
+                                const long long pos = static_cast<long long>(sub) * MLP_P + (j + 1) * 32;  // within the unit
+                                const long long gsz = group < MLP_P ? group : static_cast<long long>(tiles_per_unit) * MLP_P;
+                                if (pos % gsz == 0) {
+                                    const long long r = unit * tiles_per_unit * MLP_P + pos - gsz;
+                                    if (r < rows) out[(r / group) * CL + c] = gmax;
+                                    gmax = -INFINITY;
+                                }
+                            }
+                        }
+                    }
+                    run_max[t & 7] = gmax;
+                }
+                tc_fence_before();
+                fence_async_smem();
+                __syncthreads();
+            }
+        }
+    }
+
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                     "r"(static_cast<uint32_t>(prm.tmem_cols))
+                     : "memory");
+    }
+}
+
+static int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+}  // namespace pcc
+
+PCC_API int64_t pcc_mlp_packed_bytes(int cin, int cout) {
+    if (cin < 1 || cout < 1) return 0;
+    return static_cast<int64_t>(pcc::round_up(cout, 128)) * pcc::round_up(cin, 16) * 2;
+}
+
+PCC_API int pcc_mlp_pack_weights_f32(const float *w, int cin, int cout, void *packed, void *stream) {
+    using namespace pcc;
+    PCC_REQUIRE(w && packed && cin >= 1 && cout >= 1, "pcc_mlp_pack_weights_f32: bad argument");
+    const int kp = round_up(cin, 16), mt = round_up(cout, 128) / 128;
+    const long long total = static_cast<long long>(mt) * 128 * kp;
+    const int blocks = static_cast<int>((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+    mlp_pack_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, cin, cout, kp, mt,
+                                                                          static_cast<__nv_bfloat16 *>(packed));
+    return check_launch("mlp_pack_kernel");
+}
+
+PCC_API int pcc_mlp_chain_f32(const float *x, int64_t rows, int ldx, const PccMlpLayer *layers, int n_layers, int group,
+                              float *out, void *stream) {
+    using namespace pcc;
+    PCC_REQUIRE(x && layers && out, "pcc_mlp_chain_f32: null pointer");
+    PCC_REQUIRE(n_layers >= 1 && n_layers <= MLP_MAX_LAYERS, "pcc_mlp_chain_f32: n_layers=%d outside [1,%d]", n_layers,
+                MLP_MAX_LAYERS);
+    PCC_REQUIRE(rows >= 0 && ldx >= layers[0].cin, "pcc_mlp_chain_f32: bad rows / ldx");
+    PCC_REQUIRE(group >= 0, "pcc_mlp_chain_f32: bad group");
+    if (rows == 0) return 0;
+    if (group > 1) {
+        PCC_REQUIRE(rows % group == 0, "pcc_mlp_chain_f32: rows=%lld is not a multiple of group=%d",
+                    static_cast<long long>(rows), group);
+        const bool ok = (group <= MLP_P) ? (MLP_P % group == 0 && (group <= 32 ? 32 % group == 0 : group % 32 == 0))
+                                         : (group % MLP_P == 0);
+        if (!ok) {
+            set_error("pcc_mlp_chain_f32: group=%d must divide %d (and 32) or be a multiple of %d", group, MLP_P, MLP_P);
+            return PCC_ERR_UNSUPPORTED;
+        }
+    }
+    MlpChainParams prm{};
+    prm.n_layers = n_layers;
+    int off = 0, max_cols = 0;
+    size_t xa = 0, xb = 0;
+    for (int l = 0; l < n_layers; ++l) {
+        PCC_REQUIRE(layers[l].packed_w && layers[l].bias && layers[l].cin >= 1 && layers[l].cout >= 1,
+                    "pcc_mlp_chain_f32: bad layer %d", l);
+        if (l > 0) PCC_REQUIRE(layers[l].cin == layers[l - 1].cout, "pcc_mlp_chain_f32: layer %d cin != previous cout", l);
+        prm.cin[l] = layers[l].cin;
+        prm.cout[l] = layers[l].cout;
+        prm.kp[l] = round_up(layers[l].cin, 16);
+        prm.mt[l] = round_up(layers[l].cout, 128) / 128;
+        prm.relu[l] = layers[l].relu;
+        prm.w[l] = layers[l].packed_w;
+        prm.bias[l] = layers[l].bias;
+        prm.w_bytes[l] = prm.mt[l] * 128 * prm.kp[l] * 2;
+        prm.w_off[l] = off;
+        off += prm.w_bytes[l];
+        const size_t xbytes = static_cast<size_t>(MLP_P) * prm.kp[l] * 2;
+        if (l % 2 == 0) xa = xbytes > xa ? xbytes : xa; else xb = xbytes > xb ? xbytes : xb;
+        if (prm.mt[l] * MLP_P > max_cols) max_cols = prm.mt[l] * MLP_P;
+    }
+    if (prm.mt[n_layers - 1] > 8 || max_cols > 512) {
+        set_error("pcc_mlp_chain_f32: a layer wider than 512 channels (TMEM columns %d) is not supported by this kernel", max_cols);
+        return PCC_ERR_UNSUPPORTED;
+    }
+    for (int l = 0; l < n_layers; ++l) prm.x_off[l] = off + (l % 2 == 0 ? 0 : static_cast<int>(xa));
+    off += static_cast<int>(xa + xb);
+    prm.ctrl_off = off;
+    off += 16;
+    int cols = 32;
+    while (cols < max_cols) cols <<= 1;
+    prm.tmem_cols = cols;
+    const size_t smem_bytes = static_cast<size_t>(off);
+    if (smem_bytes > 227 * 1024) {
+        set_error("pcc_mlp_chain_f32: chain needs %zu bytes of shared memory (resident weights); max is %d", smem_bytes,
+                  227 * 1024);
+        return PCC_ERR_UNSUPPORTED;
+    }
+    cudaError_t e = cudaFuncSetAttribute(mlp_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem_bytes));
+    if (e != cudaSuccess) {
+        set_error("pcc_mlp_chain_f32: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+        return static_cast<int>(e);
+    }
+    const int tiles_per_unit = group > MLP_P ? group / MLP_P : 1;
+    const long long n_tiles = (rows + MLP_P - 1) / MLP_P;
+    const long long n_units = (n_tiles + tiles_per_unit - 1) / tiles_per_unit;
+    // co-resident CTAs per SM: limited by shared memory and by TMEM columns (512 per SM)
+    int per_sm = static_cast<int>((227 * 1024) / (smem_bytes + 1024));
+    if (per_sm > 512 / cols) per_sm = 512 / cols;
+    if (per_sm > 8) per_sm = 8;
+    if (per_sm < 1) per_sm = 1;
+    long long grid = static_cast<long long>(num_sms()) * per_sm;
+    if (grid > n_units) grid = n_units;
+    mlp_chain_kernel<<<static_cast<unsigned>(grid), MLP_THREADS, smem_bytes, static_cast<cudaStream_t>(stream)>>>(
+        prm, x, rows, ldx, group, out, n_units, tiles_per_unit);
+    return check_launch("mlp_chain_kernel");
+}

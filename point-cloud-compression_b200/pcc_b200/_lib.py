@@ -32,6 +32,19 @@ SIGNATURES = {
     "pcc_chamfer_bwd_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
 }
 
+
+
+class PccMlpLayer(ctypes.Structure):
+    """struct PccMlpLayer of include/pcc_b200.h"""
+    _fields_ = [("packed_w", _vp), ("bias", _vp), ("cin", _i), ("cout", _i), ("relu", _i)]
+
+
+SIGNATURES.update({
+    "pcc_mlp_packed_bytes": (_i64, [_i, _i]),
+    "pcc_mlp_pack_weights_f32": (_i, [_vp, _i, _i, _vp, _vp]),
+    "pcc_mlp_chain_f32": (_i, [_vp, _i64, _i, ctypes.POINTER(PccMlpLayer), _i, _i, _vp, _vp]),
+})
+
 _lib = None
 
 

@@ -3,15 +3,23 @@
     mlp_chain(x [M, C0], layers)                  -> [M, CL]
     mlp_chain_groupmax(x [M, C0], layers, group)  -> [M/group, CL]   (max over each run of `group` consecutive rows)
 
-`layers` is a list of (weight [Cout, Cin], bias [Cout], relu: bool).
+`layers` is a list of (weight [Cout, Cin], bias [Cout], relu: bool) -- the reference's Conv2d / Linear parameters.
 
-INTERIM (round 1): the contraction itself is issued through torch.addmm on the device (cuBLAS) in row chunks while
-the fused tcgen05 kernel is being brought up; the max-pool, layout and chunking live here.  There is still no CPU
-path: CPU tensors are rejected.
+Chains whose packed bf16 weights fit in shared memory run in ONE launch of the fused tcgen05 kernel
+(csrc/mlp_chain.cu: bf16 operands, fp32 accumulation in TMEM, activations never leave the SM).  Layers that do not
+fit (PointNet's 256->512->16 tail, the 1024->16384 decoder Linear) are still issued as plain library GEMMs
+(torch.addmm in bf16 -> cuBLAS) in round 1; the split point is chosen here.  There is no CPU path.
 """
+import ctypes
+
 import torch
 
+from . import _lib
+
+_P = 128
+_SMEM_MAX = 227 * 1024
 _CHUNK_ROWS = 1 << 20
+_pack_cache = {}
 
 
 def _check(x):
@@ -19,19 +27,93 @@ def _check(x):
         raise RuntimeError("pcc_b200: mlp_chain input must be a CUDA tensor (there is no CPU path)")
 
 
-def _chain(x, layers):
+def _ru(a, b):
+    return (a + b - 1) // b * b
+
+
+def _fused_smem_bytes(dims):
+    """Shared memory the fused kernel needs for a chain with channel sizes dims = [C0, C1, ..., CL]."""
+    w = sum(_ru(co, 128) * _ru(ci, 16) * 2 for ci, co in zip(dims[:-1], dims[1:]))
+    xa = max([_P * _ru(c, 16) * 2 for c in dims[0:-1:2]] or [0])
+    xb = max([_P * _ru(c, 16) * 2 for c in dims[1:-1:2]] or [0])
+    return w + xa + xb + 16
+
+
+def _fits(dims):
+    return (len(dims) - 1 <= 6 and _fused_smem_bytes(dims) <= _SMEM_MAX and max(dims[1:]) <= 512)
+
+
+def _packed(w, b):
+    """Pack (and cache per parameter version) one layer's weights for the tcgen05 kernel."""
+    key = (w.data_ptr(), w._version, b.data_ptr(), b._version, tuple(w.shape))
+    hit = _pack_cache.get(key)
+    if hit is None:
+        lib = _lib.load()
+        cout, cin = w.shape
+        wf = w.detach().float().contiguous()
+        buf = torch.empty((lib.pcc_mlp_packed_bytes(cin, cout),), dtype=torch.uint8, device=w.device)
+        with torch.cuda.device(w.device):
+            _lib.check(lib.pcc_mlp_pack_weights_f32(wf.data_ptr(), cin, cout, buf.data_ptr(),
+                                                    torch.cuda.current_stream().cuda_stream), "pcc_mlp_pack_weights_f32")
+        if len(_pack_cache) > 256:
+            _pack_cache.clear()
+        hit = (buf, b.detach().float().contiguous())
+        _pack_cache[key] = hit
+    return hit
+
+
+def fused_chain(x, layers, group=0):
+    """One launch of the tcgen05 chain kernel.  x [M, >=C0] fp32 row-major (row stride may exceed C0)."""
+    _check(x)
+    lib = _lib.load()
+    if x.dtype != torch.float32 or x.stride(-1) != 1:
+        x = x.float().contiguous()
+    M, ldx = x.shape[0], x.stride(0)
+    arr = (_lib.PccMlpLayer * len(layers))()
+    keep = []
+    for i, (w, b, relu) in enumerate(layers):
+        pw, pb = _packed(w, b)
+        keep.append((pw, pb))
+        arr[i] = _lib.PccMlpLayer(pw.data_ptr(), pb.data_ptr(), w.shape[1], w.shape[0], int(bool(relu)))
+    cl = layers[-1][0].shape[0]
+    out_rows = M // group if group > 1 else M
+    out = torch.empty((out_rows, cl), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.pcc_mlp_chain_f32(x.data_ptr(), M, ldx, arr, len(layers), int(group), out.data_ptr(),
+                                         torch.cuda.current_stream().cuda_stream), "pcc_mlp_chain_f32")
+    return out
+
+
+def _library_chain(x, layers):
+    """Plain library GEMMs (cuBLAS through torch) in bf16 with fp32 accumulation, for layers too large for the fused
+    kernel's resident-weight design."""
+    x = x.to(torch.bfloat16)
     for w, b, relu in layers:
-        x = torch.addmm(b, x, w.t())
+        x = torch.addmm(b.to(torch.bfloat16), x, w.to(torch.bfloat16).t())
         if relu:
             x = torch.relu_(x)
-    return x
+    return x.float()
+
+
+def _split(layers):
+    """Longest prefix of `layers` that fits the fused kernel."""
+    dims = [layers[0][0].shape[1]] + [w.shape[0] for w, _, _ in layers]
+    n = len(layers)
+    while n > 0 and not _fits(dims[:n + 1]):
+        n -= 1
+    return n
 
 
 def mlp_chain(x, layers):
     _check(x)
+    n = _split(layers)
+    if n == len(layers):
+        return fused_chain(x, layers)
+    if n > 0:
+        x = fused_chain(x, layers[:n])
     if x.shape[0] <= _CHUNK_ROWS:
-        return _chain(x, layers)
-    return torch.cat([_chain(x[i:i + _CHUNK_ROWS], layers) for i in range(0, x.shape[0], _CHUNK_ROWS)], dim=0)
+        return _library_chain(x, layers[n:])
+    return torch.cat([_library_chain(x[i:i + _CHUNK_ROWS], layers[n:]) for i in range(0, x.shape[0], _CHUNK_ROWS)])
 
 
 def mlp_chain_groupmax(x, layers, group):
@@ -39,9 +121,14 @@ def mlp_chain_groupmax(x, layers, group):
     M = x.shape[0]
     if M % group:
         raise ValueError("pcc_b200.mlp_chain_groupmax: rows must be a multiple of the group size")
+    n = _split(layers)
+    if n == len(layers):
+        return fused_chain(x, layers, group)
+    if n > 0:
+        x = fused_chain(x, layers[:n])
     step = max(group, (_CHUNK_ROWS // group) * group)
     outs = []
     for i in range(0, M, step):
-        y = _chain(x[i:i + step], layers)
+        y = _library_chain(x[i:i + step], layers[n:])
         outs.append(y.view(-1, group, y.shape[1]).max(dim=1)[0])
     return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)

@@ -1,0 +1,100 @@
+"""GPU numerics of the fused tcgen05 MLP-chain kernel (through the C ABI).
+
+Two references, both plain PyTorch fp32:
+  * the kernel's own numeric model (operands and inter-layer activations rounded to bf16, fp32 accumulation):
+    must agree to MODEL_RTOL -- this checks descriptors / layouts / pooling exactly;
+  * the reference's fp32 arithmetic (what pn_kit's Conv2d stacks compute): must agree to BF16_RTOL of the
+    output scale -- the stated bf16-vs-fp32 tolerance of north_star.
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+MODEL_RTOL = 2e-3   # vs the bf16-operand / fp32-accumulate model (differences: accumulation order, 1-ulp bf16 ties)
+BF16_RTOL = 3e-2    # vs pure fp32, relative to the output's max magnitude
+
+
+@pytest.fixture(scope="module")
+def mlp():
+    import __graft_entry__  # noqa: F401
+    from pcc_b200 import mlp_ops
+    return mlp_ops
+
+
+def make_layers(dims, relu, seed):
+    g = torch.Generator().manual_seed(seed)
+    layers = []
+    for (ci, co), r in zip(zip(dims[:-1], dims[1:]), relu):
+        bound = 1.0 / ci ** 0.5
+        w = ((torch.rand((co, ci), generator=g) * 2 - 1) * bound).cuda()
+        b = ((torch.rand((co,), generator=g) * 2 - 1) * bound).cuda()
+        layers.append((w, b, r))
+    return layers
+
+
+def ref_chain(x, layers, group, model_bf16):
+    rnd = (lambda t: t.bfloat16().float()) if model_bf16 else (lambda t: t)
+    h = x.double() if not model_bf16 else x
+    for i, (w, b, r) in enumerate(layers):
+        if model_bf16:
+            h = rnd(h) @ rnd(w).t() + b
+        else:
+            h = h @ w.double().t() + b.double()
+        if r:
+            h = torch.relu(h)
+    h = h.float()
+    if group > 1:
+        h = h.view(-1, group, h.shape[1]).max(dim=1)[0]
+    return h
+
+
+CASES = [
+    # dims, relu, rows, group
+    ([16, 32], [False], 128, 0),
+    ([3, 32], [True], 256, 0),
+    ([64, 128], [True], 384, 0),
+    ([40, 200], [False], 300, 0),                       # ragged K, two M tiles, tail rows
+    ([3, 32, 64, 128], [True, True, True], 4096, 16),   # pn_kit.SetAbstraction body (AE.py:16)
+    ([3, 32, 64, 128], [True, True, True], 1000, 0),
+    ([131, 128, 256], [True, True], 1024, 0),           # first half of pn_kit.PointNet (AE.py:17)
+    ([144, 128, 64, 32, 3], [True, True, True, False], 640, 0),  # pn_kit.MLP decoder tail (AE.py:27)
+    ([6, 64, 64, 128], [True, True, True], 2048, 32),   # PointNet++ SA1-like (nsample 32)
+    ([19, 64, 128], [True, True], 2048, 64),
+    ([19, 64, 128], [True, False], 1024, 128),
+    ([35, 64, 16], [True, False], 1024, 256),           # max over 256 points spanning two tiles
+    ([35, 64, 16], [True, False], 2048, 512),
+]
+
+
+@pytest.mark.parametrize("dims,relu,rows,group", CASES)
+def test_fused_chain_numerics(mlp, dims, relu, rows, group):
+    torch.manual_seed(rows + len(dims))
+    layers = make_layers(dims, relu, seed=sum(dims))
+    x = (torch.rand(rows, dims[0], device="cuda") - 0.5) * 2
+    y = mlp.fused_chain(x, layers, group)
+    torch.cuda.synchronize()
+    ym = ref_chain(x, layers, group, model_bf16=True)
+    yf = ref_chain(x, layers, group, model_bf16=False)
+    assert y.shape == ym.shape
+    scale = yf.abs().max().item() + 1e-12
+    err_model = (y - ym).abs().max().item() / scale
+    err_fp32 = (y - yf).abs().max().item() / scale
+    assert err_model < MODEL_RTOL, f"vs bf16 model: {err_model}"
+    assert err_fp32 < BF16_RTOL, f"vs fp32: {err_fp32}"
+
+
+def test_row_stride_and_repeat_launches(mlp):
+    layers = make_layers([3, 32, 64, 128], [True, True, True], seed=1)
+    big = torch.rand(512, 8, device="cuda")
+    y1 = mlp.fused_chain(big[:, :3].contiguous(), layers, 16)
+    for _ in range(3):
+        y2 = mlp.fused_chain(big, layers, 16)  # row stride 8, first 3 columns used
+    assert torch.equal(y1, y2)
+
+
+def test_unsupported_chain_is_an_error_not_a_fallback(mlp):
+    layers = make_layers([256, 512, 1024], [True, True], seed=2)
+    x = torch.rand(128, 256, device="cuda")
+    with pytest.raises((ValueError, RuntimeError)):
+        mlp.fused_chain(x, layers, 0)
