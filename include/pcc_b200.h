@@ -57,7 +57,8 @@ int pcc_fps_f32(const float *xyz, int B, int N, int npoint, const int64_t *start
  * K nearest neighbours of every q[b, i] among p[b, :], ascending in (d2, idx).
  * Replaces pytorch3d.ops.knn_points (call sites /root/reference/train.py:185, compress.py:71, pn_kit.py:190,
  * pppe_pcd_ae.py:599, eval.py:132).  1 <= K <= PCC_MAX_KNN_K.
- *   out_d2 [B,P1,K] float32, out_idx [B,P1,K] int64; slots k >= P2 hold d2 = 0, idx = 0.
+ *   out_d2 [B,P1,K] float32, out_idx [B,P1,K] int64 (either may be NULL when only out_nn is wanted);
+ *   slots k >= P2 hold d2 = 0, idx = 0.
  *   out_nn (nullable) [B,P1,K,3]: the gathered neighbours (return_nn=True); with centre_sub != 0 the query is
  *   subtracted (the `grouped_xyz -= centre` that follows every reference call: train.py:188, compress.py:72,
  *   pn_kit.py:191) and the result is multiplied by nn_scale (train.py:192, compress.py:108; pass 1.0f to
@@ -139,10 +140,24 @@ typedef struct PccMlpLayer {
     int cin, cout;
     int relu;             /* apply max(x, 0) after this layer */
 } PccMlpLayer;
+/* One input segment: rows of `channels` values taken from ptr[(row / row_div) * ld + 0..channels), fp32 (dtype 0) or
+ * bf16 (dtype 1).  Segments are concatenated along the channel axis in order (the torch.cat of AE.py:39,51 without
+ * materialising it); row_div > 1 broadcasts one source row over row_div consecutive positions (AE.py:50). */
+#define PCC_MLP_MAX_INPUTS 3
+typedef struct PccMlpInput {
+    const void *ptr;
+    int dtype;
+    int channels;
+    int64_t ld;
+    int row_div;
+} PccMlpInput;
 int64_t pcc_mlp_packed_bytes(int cin, int cout);
 int pcc_mlp_pack_weights_f32(const float *w, int cin, int cout, void *packed, void *stream);
 int pcc_mlp_chain_f32(const float *x, int64_t rows, int ldx, const PccMlpLayer *layers, int n_layers, int group,
                       float *out, void *stream);
+/* General form: several input segments, output fp32 (out_dtype 0) or bf16 (out_dtype 1). */
+int pcc_mlp_chain(const PccMlpInput *inputs, int n_inputs, int64_t rows, const PccMlpLayer *layers, int n_layers,
+                  int group, void *out, int out_dtype, void *stream);
 
 #ifdef __cplusplus
 }

@@ -119,8 +119,8 @@ knn_warp_kernel(const float *__restrict__ q, const float *__restrict__ p, int P1
             d = key_d2(key);
             idx = key_idx(key);
         }
-        out_d2[obase + k] = d;
-        out_idx[obase + k] = static_cast<int64_t>(idx);
+        if (out_d2) out_d2[obase + k] = d;
+        if (out_idx) out_idx[obase + k] = static_cast<int64_t>(idx);
         if (out_nn) {
             float nx = pc[static_cast<size_t>(idx) * 3 + 0], ny = pc[static_cast<size_t>(idx) * 3 + 1],
                   nz = pc[static_cast<size_t>(idx) * 3 + 2];
@@ -140,6 +140,137 @@ knn_warp_kernel(const float *__restrict__ q, const float *__restrict__ p, int P1
             o[2] = nz;
         }
     }
+}
+
+// ---- CTA-per-query kernel (P2 <= 8192) ---------------------------------------------------------------------------------
+// One CTA (512 threads) per query; every thread keeps the d2 bit patterns of its CPT candidates in registers (candidate
+// s*512 + tid).  The K-th smallest (d2, idx) key is found WITHOUT sorting: a bisection on the 32-bit pattern of d2 (each
+// step = CPT compares per thread + one redux.sync.add per warp + one __syncthreads, double-buffered partials), stopping
+// early when a threshold selects exactly K; exact distance ties at the K-th value are resolved by a second bisection on
+// the index.  The K selected keys are compacted into shared memory, ranked by counting (K broadcast compares per key, no
+// barriers) and written out in order.  Cost per query ~ 6-8 k cycles regardless of K, against ~0.3 ms of dependent warp
+// bitonic sorts in knn_warp_kernel -- this is what makes the B=1 compress latency and the K=256 patching cheap.
+constexpr int KB_THREADS = 512;
+constexpr int KB_WARPS = KB_THREADS / 32;
+
+__device__ __forceinline__ int block_sum(int v, int (*part)[KB_WARPS], int &buf) {
+    const int w = __reduce_add_sync(FULL_MASK, v);
+    if (lane_id() == 0) part[buf][threadIdx.x >> 5] = w;
+    __syncthreads();
+    const int r = lane_id() < KB_WARPS ? part[buf][lane_id()] : 0;
+    buf ^= 1;
+    return __reduce_add_sync(FULL_MASK, r);
+}
+
+template <int CPT>
+__global__ void __launch_bounds__(KB_THREADS)
+knn_block_kernel(const float *__restrict__ q, const float *__restrict__ p, int P1, int P2, int K,
+                 float *__restrict__ out_d2, int64_t *__restrict__ out_idx, float *__restrict__ out_nn, int centre_sub,
+                 float nn_scale) {
+    __shared__ unsigned long long sel[PCC_MAX_KNN_K];
+    __shared__ unsigned long long sorted[PCC_MAX_KNN_K];
+    __shared__ int part[2][KB_WARPS];
+    __shared__ int sel_count;
+    const int b = blockIdx.y, qi = blockIdx.x, tid = threadIdx.x;
+    const float *pc = p + static_cast<size_t>(b) * P2 * 3;
+    const float *qp = q + (static_cast<size_t>(b) * P1 + qi) * 3;
+    const float qx = qp[0], qy = qp[1], qz = qp[2];
+    if (tid == 0) sel_count = 0;
+
+    unsigned d[CPT];
+#pragma unroll
+    for (int s = 0; s < CPT; ++s) {
+        const int j = s * KB_THREADS + tid;
+        d[s] = 0xffffffffu;  // beyond P2: above every real pattern (finite d2 and +inf are <= 0x7f800000)
+        if (j < P2) d[s] = __float_as_uint(dist2_rn(qx, qy, qz, pc[static_cast<size_t>(j) * 3 + 0],
+                                                    pc[static_cast<size_t>(j) * 3 + 1], pc[static_cast<size_t>(j) * 3 + 2]));
+    }
+    const int Keff = K < P2 ? K : P2;
+    int buf = 0;
+    // bisection on the distance pattern: smallest v with count(d <= v) >= Keff
+    unsigned lo = 0u, hi = 0xfffffffeu;
+    bool exact = false;
+    while (lo < hi) {
+        const unsigned mid = lo + ((hi - lo) >> 1);
+        int c = 0;
+#pragma unroll
+        for (int s = 0; s < CPT; ++s) c += d[s] <= mid ? 1 : 0;
+        c = block_sum(c, part, buf);
+        if (c == Keff) {
+            lo = mid;
+            exact = true;
+            break;
+        }
+        if (c > Keff) hi = mid; else lo = mid + 1u;
+    }
+    const unsigned v = lo;
+    unsigned tie_max = 0xffffffffu;  // candidates with d == v are taken while idx <= tie_max
+    if (!exact) {
+        int c = 0;
+#pragma unroll
+        for (int s = 0; s < CPT; ++s) c += d[s] < v ? 1 : 0;
+        const int need = Keff - block_sum(c, part, buf);  // >= 1 ties to take, lowest indices first
+        unsigned tlo = 0u, thi = static_cast<unsigned>(P2 - 1);
+        while (tlo < thi) {
+            const unsigned mid = tlo + ((thi - tlo) >> 1);
+            int t = 0;
+#pragma unroll
+            for (int s = 0; s < CPT; ++s) t += (d[s] == v && static_cast<unsigned>(s * KB_THREADS + tid) <= mid) ? 1 : 0;
+            t = block_sum(t, part, buf);
+            if (t >= need) thi = mid; else tlo = mid + 1u;
+        }
+        tie_max = tlo;
+    }
+    // compaction of exactly Keff keys (unordered), one shared atomic per warp and slot
+#pragma unroll
+    for (int s = 0; s < CPT; ++s) {
+        const unsigned j = static_cast<unsigned>(s * KB_THREADS + tid);
+        const bool take = d[s] < v || (d[s] == v && j <= tie_max);
+        const unsigned m = __ballot_sync(FULL_MASK, take);
+        if (m) {
+            int base = 0;
+            if (lane_id() == static_cast<unsigned>(__ffs(m) - 1)) base = atomicAdd(&sel_count, __popc(m));
+            base = __shfl_sync(FULL_MASK, base, __ffs(m) - 1);
+            if (take) sel[base + __popc(m & ((1u << lane_id()) - 1u))] = (static_cast<unsigned long long>(d[s]) << 32) | j;
+        }
+    }
+    __syncthreads();
+    // rank by counting: keys are unique, so ranks are a permutation of 0..Keff-1
+    for (int e = tid; e < Keff; e += KB_THREADS) {
+        const unsigned long long key = sel[e];
+        int rank = 0;
+        for (int o = 0; o < Keff; ++o) rank += sel[o] < key ? 1 : 0;
+        sorted[rank] = key;
+    }
+    __syncthreads();
+    const size_t obase = (static_cast<size_t>(b) * P1 + qi) * K;
+    for (int k = tid; k < K; k += KB_THREADS) {
+        float dd = 0.0f;
+        unsigned idx = 0u;
+        if (k < Keff) {
+            dd = key_d2(sorted[k]);
+            idx = key_idx(sorted[k]);
+        }
+        if (out_d2) out_d2[obase + k] = dd;
+        if (out_idx) out_idx[obase + k] = static_cast<int64_t>(idx);
+    }
+    if (out_nn) {
+        for (int e = tid; e < K * 3; e += KB_THREADS) {
+            const int k = e / 3, c = e - k * 3;
+            const unsigned idx = k < Keff ? key_idx(sorted[k]) : 0u;
+            float val = pc[static_cast<size_t>(idx) * 3 + c];
+            if (centre_sub) val = __fsub_rn(val, c == 0 ? qx : (c == 1 ? qy : qz));
+            if (nn_scale != 1.0f) val = __fmul_rn(val, nn_scale);
+            out_nn[obase * 3 + e] = val;
+        }
+    }
+}
+
+template <int CPT>
+static int launch_block(const float *q, const float *p, int B, int P1, int P2, int K, float *out_d2, int64_t *out_idx,
+                        float *out_nn, int centre_sub, float nn_scale, cudaStream_t st) {
+    knn_block_kernel<CPT><<<dim3(P1, B), KB_THREADS, 0, st>>>(q, p, P1, P2, K, out_d2, out_idx, out_nn, centre_sub, nn_scale);
+    return check_launch("knn_block_kernel");
 }
 
 // ---- thread-per-query kernel ---------------------------------------------------------------------------------
@@ -219,18 +350,22 @@ knn_thread_kernel(const float *__restrict__ q, const float *__restrict__ p, int 
 #pragma unroll
     for (int s = 0; s < KT; ++s) stage[threadIdx.x * STAGE_LD + s] = s < valid ? __float_as_uint(dl[s]) : 0u;
     __syncthreads();
-    for (int e = threadIdx.x; e < nq * K; e += KT_THREADS) {
-        const int ql = e / K, k = e - ql * K;
-        out_d2[obase + e] = __uint_as_float(stage[ql * STAGE_LD + k]);
+    if (out_d2) {
+        for (int e = threadIdx.x; e < nq * K; e += KT_THREADS) {
+            const int ql = e / K, k = e - ql * K;
+            out_d2[obase + e] = __uint_as_float(stage[ql * STAGE_LD + k]);
+        }
     }
     __syncthreads();
     // indices (+ gathered neighbours)
 #pragma unroll
     for (int s = 0; s < KT; ++s) stage[threadIdx.x * STAGE_LD + s] = s < valid ? il[s] : 0u;
     __syncthreads();
-    for (int e = threadIdx.x; e < nq * K; e += KT_THREADS) {
-        const int ql = e / K, k = e - ql * K;
-        out_idx[obase + e] = static_cast<int64_t>(stage[ql * STAGE_LD + k]);
+    if (out_idx) {
+        for (int e = threadIdx.x; e < nq * K; e += KT_THREADS) {
+            const int ql = e / K, k = e - ql * K;
+            out_idx[obase + e] = static_cast<int64_t>(stage[ql * STAGE_LD + k]);
+        }
     }
     if (out_nn) {
         for (int e = threadIdx.x; e < nq * K * 3; e += KT_THREADS) {
@@ -257,7 +392,7 @@ static int launch_thread(const float *q, const float *p, int B, int P1, int P2, 
 PCC_API int pcc_knn_f32(const float *q, const float *p, int B, int P1, int P2, int K, float *out_d2, int64_t *out_idx,
                         float *out_nn, int centre_sub, float nn_scale, void *stream) {
     using namespace pcc;
-    PCC_REQUIRE(q && p && out_d2 && out_idx, "pcc_knn_f32: null pointer");
+    PCC_REQUIRE(q && p && (out_d2 || out_idx || out_nn), "pcc_knn_f32: null pointer");
     PCC_REQUIRE(B >= 0 && P1 >= 0 && P2 >= 1, "pcc_knn_f32: bad shape B=%d P1=%d P2=%d", B, P1, P2);
     PCC_REQUIRE(K >= 1 && K <= PCC_MAX_KNN_K, "pcc_knn_f32: K=%d outside [1,%d]", K, PCC_MAX_KNN_K);
     PCC_REQUIRE(B <= 65535, "pcc_knn_f32: B=%d exceeds 65535", B);
@@ -269,6 +404,14 @@ PCC_API int pcc_knn_f32(const float *q, const float *p, int B, int P1, int P2, i
         if (K <= 8) return launch_thread<8>(q, p, B, P1, P2, K, out_d2, out_idx, out_nn, centre_sub, nn_scale, st);
         if (K <= 16) return launch_thread<16>(q, p, B, P1, P2, K, out_d2, out_idx, out_nn, centre_sub, nn_scale, st);
         return launch_thread<32>(q, p, B, P1, P2, K, out_d2, out_idx, out_nn, centre_sub, nn_scale, st);
+    }
+
+    if (P2 <= 16 * KB_THREADS && P1 <= 65535) {
+        if (P2 <= 1 * KB_THREADS) return launch_block<1>(q, p, B, P1, P2, K, out_d2, out_idx, out_nn, centre_sub, nn_scale, st);
+        if (P2 <= 2 * KB_THREADS) return launch_block<2>(q, p, B, P1, P2, K, out_d2, out_idx, out_nn, centre_sub, nn_scale, st);
+        if (P2 <= 4 * KB_THREADS) return launch_block<4>(q, p, B, P1, P2, K, out_d2, out_idx, out_nn, centre_sub, nn_scale, st);
+        if (P2 <= 8 * KB_THREADS) return launch_block<8>(q, p, B, P1, P2, K, out_d2, out_idx, out_nn, centre_sub, nn_scale, st);
+        return launch_block<16>(q, p, B, P1, P2, K, out_d2, out_idx, out_nn, centre_sub, nn_scale, st);
     }
 
     int kp = 32;

@@ -134,17 +134,50 @@ mlp_pack_kernel(const float *__restrict__ w, int cin, int cout, int kp, int mt, 
 }
 
 // ---- the chain kernel -------------------------------------------------------------------------------------------
-// x: fp32 [rows, ldx] row-major (first cin[0] columns used).  Work unit = max(1, group / P) consecutive tiles.
-// out: fp32 [rows, CL] (group <= 1) or [rows / group, CL] (max over each run of `group` consecutive rows).
+struct MlpSeg {
+    const void *ptr;   // [rows / row_div, ld] row-major
+    long long ld;
+    int dtype;         // 0 = fp32, 1 = bf16
+    int ch;            // channels taken from this segment (they are concatenated in segment order)
+    int row_div;       // source row = position row / row_div (broadcast of a per-group vector, e.g. the latent)
+    int vec;           // 1: bf16 rows can be moved as 16-byte chunks (8 channels)
+};
+
+struct MlpIo {
+    MlpSeg seg[PCC_MLP_MAX_INPUTS];
+    int n_seg;
+    int out_bf16;
+};
+
+template <int G>
+__device__ __forceinline__ void pool_store_small(const float (&f)[32], float *__restrict__ out_f, __nv_bfloat16 *__restrict__ out_h,
+                                                 long long row_base, long long rows, int CL, int c) {
+#pragma unroll
+    for (int g = 0; g < 32 / G; ++g) {
+        float m = f[g * G];
+#pragma unroll
+        for (int i = 1; i < G; ++i) m = fmaxf(m, f[g * G + i]);
+        const long long r = row_base + g * G;
+        if (r < rows) {
+            const long long o = (r / G) * CL + c;
+            if (out_h) out_h[o] = __float2bfloat16_rn(m); else out_f[o] = m;
+        }
+    }
+}
+
+// Work unit = max(1, group / P) consecutive tiles of P positions.
+// out: [rows, CL] (group <= 1) or [rows / group, CL] (max over each run of `group` consecutive rows), fp32 or bf16.
 __global__ void __launch_bounds__(MLP_THREADS)
-mlp_chain_kernel(const __grid_constant__ MlpChainParams prm, const float *__restrict__ x, long long rows, int ldx,
-                 int group, float *__restrict__ out, long long n_units, int tiles_per_unit) {
+mlp_chain_kernel(const __grid_constant__ MlpChainParams prm, const __grid_constant__ MlpIo io, long long rows, int group,
+                 void *__restrict__ out, long long n_units, int tiles_per_unit) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t mbar = smem_base + prm.ctrl_off;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + prm.ctrl_off + 8);
+    float *out_f = io.out_bf16 ? nullptr : static_cast<float *>(out);
+    __nv_bfloat16 *out_h = io.out_bf16 ? static_cast<__nv_bfloat16 *>(out) : nullptr;
 
     // ---- prologue: weights -> shared memory, barrier init, TMEM allocation ----
     for (int l = 0; l < prm.n_layers; ++l) {
@@ -168,7 +201,7 @@ mlp_chain_kernel(const __grid_constant__ MlpChainParams prm, const float *__rest
 
     const int L = prm.n_layers;
     const int CL = prm.cout[L - 1];
-    const int kp0 = prm.kp[0], c0 = prm.cin[0];
+    const int kp0 = prm.kp[0];
 
     for (long long unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
         float run_max[8];  // running max across the tiles of one unit (one per M-tile of the last layer)
@@ -178,24 +211,52 @@ mlp_chain_kernel(const __grid_constant__ MlpChainParams prm, const float *__rest
         for (int sub = 0; sub < tiles_per_unit; ++sub) {
             const long long row0 = (unit * tiles_per_unit + sub) * MLP_P;
 
-            // ---- load the input tile: thread p owns position p; K-major core matrices (8 channels = 16 bytes) ----
+            // ---- load the input tile into K-major core matrices: element (p, c) at
+            //      (p/8)*128 + (c/8)*(P/8)*128 + (p%8)*16 + (c%8)*2     (SBO = 128, LBO = (P/8)*128) ----
             {
                 unsigned char *x0 = smem + prm.x_off[0];
-                const long long r = row0 + tid;
-                const float *xr = x + r * ldx;
-                const bool ok = r < rows;
-                for (int c8 = 0; c8 < kp0 / 8; ++c8) {
-                    float f[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int c = c8 * 8 + i;
-                        f[i] = (ok && c < c0) ? __ldg(xr + c) : 0.0f;
+                int coff = 0;
+                for (int s = 0; s < io.n_seg; ++s) {
+                    const MlpSeg sg = io.seg[s];
+                    if (sg.vec) {  // bf16 rows, 16-byte chunks: thread p owns position p
+                        const long long r = row0 + tid;
+                        const uint4 *src = reinterpret_cast<const uint4 *>(static_cast<const __nv_bfloat16 *>(sg.ptr) +
+                                                                           (r / sg.row_div) * sg.ld);
+                        const bool ok = r < rows;
+                        unsigned char *dst = x0 + (tid >> 3) * 128 + (tid & 7) * 16 + (coff >> 3) * (MLP_P / 8) * 128;
+                        for (int c8 = 0; c8 < sg.ch / 8; ++c8) {
+                            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                            if (ok) v = __ldg(src + c8);
+                            *reinterpret_cast<uint4 *>(dst + c8 * (MLP_P / 8) * 128) = v;
+                        }
+                    } else {       // element-wise, coalesced along the channels of a row
+                        const int total = MLP_P * sg.ch;
+                        int p = tid / sg.ch, c = tid - p * sg.ch;
+                        const int dp = MLP_THREADS / sg.ch, dc = MLP_THREADS - dp * sg.ch;
+                        for (int e = tid; e < total; e += MLP_THREADS) {
+                            const long long r = row0 + p;
+                            float v = 0.0f;
+                            if (r < rows) {
+                                const long long o = (r / sg.row_div) * sg.ld + c;
+                                v = sg.dtype == 0 ? __ldg(static_cast<const float *>(sg.ptr) + o)
+                                                  : __bfloat162float(static_cast<const __nv_bfloat16 *>(sg.ptr)[o]);
+                            }
+                            const int cc = coff + c;
+                            *reinterpret_cast<__nv_bfloat16 *>(x0 + (p >> 3) * 128 + (cc >> 3) * (MLP_P / 8) * 128 + (p & 7) * 16 +
+                                                               (cc & 7) * 2) = __float2bfloat16_rn(v);
+                            p += dp;
+                            c += dc;
+                            if (c >= sg.ch) {
+                                c -= sg.ch;
+                                ++p;
+                            }
+                        }
                     }
-                    uint4 pk = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
-                                          pack_bf16x2(f[6], f[7]));
-                    // (p/8)*SBO + c8*LBO + (p%8)*16 with SBO = 128, LBO = (P/8)*128
-                    *reinterpret_cast<uint4 *>(x0 + (tid >> 3) * 128 + c8 * (MLP_P / 8) * 128 + (tid & 7) * 16) = pk;
+                    coff += sg.ch;
                 }
+                for (int cc = coff; cc < kp0; ++cc)  // zero the K padding
+                    *reinterpret_cast<__nv_bfloat16 *>(x0 + (tid >> 3) * 128 + (cc >> 3) * (MLP_P / 8) * 128 + (tid & 7) * 16 +
+                                                       (cc & 7) * 2) = __float2bfloat16_rn(0.0f);
             }
             fence_async_smem();
             __syncthreads();
@@ -237,14 +298,19 @@ mlp_chain_kernel(const __grid_constant__ MlpChainParams prm, const float *__rest
                     const int c = t * 128 + warp * 32 + lane;
                     const bool real = c < cout;
                     const float b = real ? __ldg(bias + c) : 0.0f;
-                    float gmax = run_max[t & 7];
+                    float gmax = -INFINITY;
+                    if (last && group > 32) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            if (q == t) gmax = run_max[q];
+                    }
                     for (int j = 0; j < MLP_P / 32; ++j) {
                         uint32_t v[32];
                         tmem_ld32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + t * MLP_P + j * 32, v);
                         float f[32];
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
-                            float a = real ? __uint_as_float(v[i]) + b : 0.0f;  // padded channels feed exact zeros
+                            const float a = real ? __uint_as_float(v[i]) + b : 0.0f;  // padded channels feed exact zeros
                             f[i] = relu ? fmaxf(a, 0.0f) : a;
                         }
                         if (!last) {
@@ -260,22 +326,25 @@ mlp_chain_kernel(const __grid_constant__ MlpChainParams prm, const float *__rest
                                 }
                             }
                         } else if (real) {
+                            const long long rb = row0 + j * 32;
                             if (group <= 1) {
 #pragma unroll
                                 for (int i = 0; i < 32; ++i) {
-                                    const long long r = row0 + j * 32 + i;
-                                    if (r < rows) out[r * CL + c] = f[i];
+                                    const long long r = rb + i;
+                                    if (r < rows) {
+                                        if (out_h) out_h[r * CL + c] = __float2bfloat16_rn(f[i]); else out_f[r * CL + c] = f[i];
+                                    }
                                 }
-                            } else if (group <= 32) {
-                                const int per = 32 / group;  // groups inside this 32-column chunk
-                                for (int g = 0; g < per; ++g) {
-                                    float m = -INFINITY;
-#pragma unroll
-                                    for (int i = 0; i < 32; ++i)
-                                        if (i / group == g) m = fmaxf(m, f[i]);
-                                    const long long r = row0 + j * 32 + g * group;
-                                    if (r < rows) out[(r / group) * CL + c] = m;
-                                }
+                            } else if (group == 2) {
+                                pool_store_small<2>(f, out_f, out_h, rb, rows, CL, c);
+                            } else if (group == 4) {
+                                pool_store_small<4>(f, out_f, out_h, rb, rows, CL, c);
+                            } else if (group == 8) {
+                                pool_store_small<8>(f, out_f, out_h, rb, rows, CL, c);
+                            } else if (group == 16) {
+                                pool_store_small<16>(f, out_f, out_h, rb, rows, CL, c);
+                            } else if (group == 32) {
+                                pool_store_small<32>(f, out_f, out_h, rb, rows, CL, c);
                             } else {
                                 float m = f[0];
 #pragma unroll
@@ -285,13 +354,20 @@ mlp_chain_kernel(const __grid_constant__ MlpChainParams prm, const float *__rest
                                 const long long gsz = group < MLP_P ? group : static_cast<long long>(tiles_per_unit) * MLP_P;
                                 if (pos % gsz == 0) {
                                     const long long r = unit * tiles_per_unit * MLP_P + pos - gsz;
-                                    if (r < rows) out[(r / group) * CL + c] = gmax;
+                                    if (r < rows) {
+                                        const long long o = (r / group) * CL + c;
+                                        if (out_h) out_h[o] = __float2bfloat16_rn(gmax); else out_f[o] = gmax;
+                                    }
                                     gmax = -INFINITY;
                                 }
                             }
                         }
                     }
-                    run_max[t & 7] = gmax;
+                    if (last && group > 32) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            if (q == t) run_max[q] = gmax;
+                    }
                 }
                 tc_fence_before();
                 fence_async_smem();
@@ -327,22 +403,42 @@ PCC_API int pcc_mlp_pack_weights_f32(const float *w, int cin, int cout, void *pa
     return check_launch("mlp_pack_kernel");
 }
 
-PCC_API int pcc_mlp_chain_f32(const float *x, int64_t rows, int ldx, const PccMlpLayer *layers, int n_layers, int group,
-                              float *out, void *stream) {
+PCC_API int pcc_mlp_chain(const PccMlpInput *inputs, int n_inputs, int64_t rows, const PccMlpLayer *layers, int n_layers,
+                          int group, void *out, int out_dtype, void *stream) {
     using namespace pcc;
-    PCC_REQUIRE(x && layers && out, "pcc_mlp_chain_f32: null pointer");
-    PCC_REQUIRE(n_layers >= 1 && n_layers <= MLP_MAX_LAYERS, "pcc_mlp_chain_f32: n_layers=%d outside [1,%d]", n_layers,
+    PCC_REQUIRE(inputs && layers && out, "pcc_mlp_chain: null pointer");
+    PCC_REQUIRE(n_inputs >= 1 && n_inputs <= PCC_MLP_MAX_INPUTS, "pcc_mlp_chain: n_inputs=%d outside [1,%d]", n_inputs,
+                PCC_MLP_MAX_INPUTS);
+    PCC_REQUIRE(n_layers >= 1 && n_layers <= MLP_MAX_LAYERS, "pcc_mlp_chain: n_layers=%d outside [1,%d]", n_layers,
                 MLP_MAX_LAYERS);
-    PCC_REQUIRE(rows >= 0 && ldx >= layers[0].cin, "pcc_mlp_chain_f32: bad rows / ldx");
-    PCC_REQUIRE(group >= 0, "pcc_mlp_chain_f32: bad group");
+    PCC_REQUIRE(rows >= 0 && group >= 0 && (out_dtype == 0 || out_dtype == 1), "pcc_mlp_chain: bad rows / group / out_dtype");
     if (rows == 0) return 0;
+    MlpIo io{};
+    io.n_seg = n_inputs;
+    io.out_bf16 = out_dtype;
+    int ctot = 0;
+    for (int s = 0; s < n_inputs; ++s) {
+        const PccMlpInput &in = inputs[s];
+        PCC_REQUIRE(in.ptr && in.channels >= 1 && in.ld >= in.channels && in.row_div >= 1 && (in.dtype == 0 || in.dtype == 1),
+                    "pcc_mlp_chain: bad input segment %d", s);
+        io.seg[s].ptr = in.ptr;
+        io.seg[s].ld = in.ld;
+        io.seg[s].dtype = in.dtype;
+        io.seg[s].ch = in.channels;
+        io.seg[s].row_div = in.row_div;
+        io.seg[s].vec = (in.dtype == 1 && in.channels % 8 == 0 && ctot % 8 == 0 && in.ld % 8 == 0 &&
+                         reinterpret_cast<uintptr_t>(in.ptr) % 16 == 0) ? 1 : 0;
+        ctot += in.channels;
+    }
+    PCC_REQUIRE(ctot == layers[0].cin, "pcc_mlp_chain: input segments carry %d channels, layer 0 expects %d", ctot,
+                layers[0].cin);
     if (group > 1) {
-        PCC_REQUIRE(rows % group == 0, "pcc_mlp_chain_f32: rows=%lld is not a multiple of group=%d",
+        PCC_REQUIRE(rows % group == 0, "pcc_mlp_chain: rows=%lld is not a multiple of group=%d",
                     static_cast<long long>(rows), group);
         const bool ok = (group <= MLP_P) ? (MLP_P % group == 0 && (group <= 32 ? 32 % group == 0 : group % 32 == 0))
                                          : (group % MLP_P == 0);
         if (!ok) {
-            set_error("pcc_mlp_chain_f32: group=%d must divide %d (and 32) or be a multiple of %d", group, MLP_P, MLP_P);
+            set_error("pcc_mlp_chain: group=%d must divide %d (and 32) or be a multiple of %d", group, MLP_P, MLP_P);
             return PCC_ERR_UNSUPPORTED;
         }
     }
@@ -352,8 +448,8 @@ PCC_API int pcc_mlp_chain_f32(const float *x, int64_t rows, int ldx, const PccMl
     size_t xa = 0, xb = 0;
     for (int l = 0; l < n_layers; ++l) {
         PCC_REQUIRE(layers[l].packed_w && layers[l].bias && layers[l].cin >= 1 && layers[l].cout >= 1,
-                    "pcc_mlp_chain_f32: bad layer %d", l);
-        if (l > 0) PCC_REQUIRE(layers[l].cin == layers[l - 1].cout, "pcc_mlp_chain_f32: layer %d cin != previous cout", l);
+                    "pcc_mlp_chain: bad layer %d", l);
+        if (l > 0) PCC_REQUIRE(layers[l].cin == layers[l - 1].cout, "pcc_mlp_chain: layer %d cin != previous cout", l);
         prm.cin[l] = layers[l].cin;
         prm.cout[l] = layers[l].cout;
         prm.kp[l] = round_up(layers[l].cin, 16);
@@ -369,7 +465,7 @@ PCC_API int pcc_mlp_chain_f32(const float *x, int64_t rows, int ldx, const PccMl
         if (prm.mt[l] * MLP_P > max_cols) max_cols = prm.mt[l] * MLP_P;
     }
     if (prm.mt[n_layers - 1] > 8 || max_cols > 512) {
-        set_error("pcc_mlp_chain_f32: a layer wider than 512 channels (TMEM columns %d) is not supported by this kernel", max_cols);
+        set_error("pcc_mlp_chain: a layer wider than 512 channels (TMEM columns %d) is not supported by this kernel", max_cols);
         return PCC_ERR_UNSUPPORTED;
     }
     for (int l = 0; l < n_layers; ++l) prm.x_off[l] = off + (l % 2 == 0 ? 0 : static_cast<int>(xa));
@@ -381,14 +477,14 @@ PCC_API int pcc_mlp_chain_f32(const float *x, int64_t rows, int ldx, const PccMl
     prm.tmem_cols = cols;
     const size_t smem_bytes = static_cast<size_t>(off);
     if (smem_bytes > 227 * 1024) {
-        set_error("pcc_mlp_chain_f32: chain needs %zu bytes of shared memory (resident weights); max is %d", smem_bytes,
+        set_error("pcc_mlp_chain: chain needs %zu bytes of shared memory (resident weights); max is %d", smem_bytes,
                   227 * 1024);
         return PCC_ERR_UNSUPPORTED;
     }
     cudaError_t e = cudaFuncSetAttribute(mlp_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem_bytes));
     if (e != cudaSuccess) {
-        set_error("pcc_mlp_chain_f32: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+        set_error("pcc_mlp_chain: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
         return static_cast<int>(e);
     }
     const int tiles_per_unit = group > MLP_P ? group / MLP_P : 1;
@@ -402,6 +498,13 @@ PCC_API int pcc_mlp_chain_f32(const float *x, int64_t rows, int ldx, const PccMl
     long long grid = static_cast<long long>(num_sms()) * per_sm;
     if (grid > n_units) grid = n_units;
     mlp_chain_kernel<<<static_cast<unsigned>(grid), MLP_THREADS, smem_bytes, static_cast<cudaStream_t>(stream)>>>(
-        prm, x, rows, ldx, group, out, n_units, tiles_per_unit);
+        prm, io, rows, group, out, n_units, tiles_per_unit);
     return check_launch("mlp_chain_kernel");
+}
+
+PCC_API int pcc_mlp_chain_f32(const float *x, int64_t rows, int ldx, const PccMlpLayer *layers, int n_layers, int group,
+                              float *out, void *stream) {
+    PCC_REQUIRE(x && layers && n_layers >= 1, "pcc_mlp_chain_f32: null pointer");
+    PccMlpInput in{x, 0, layers[0].cin, ldx, 1};
+    return pcc_mlp_chain(&in, 1, rows, layers, n_layers, group, out, 0, stream);
 }

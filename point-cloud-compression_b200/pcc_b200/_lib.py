@@ -39,7 +39,13 @@ class PccMlpLayer(ctypes.Structure):
     _fields_ = [("packed_w", _vp), ("bias", _vp), ("cin", _i), ("cout", _i), ("relu", _i)]
 
 
+class PccMlpInput(ctypes.Structure):
+    """struct PccMlpInput of include/pcc_b200.h"""
+    _fields_ = [("ptr", _vp), ("dtype", _i), ("channels", _i), ("ld", _i64), ("row_div", _i)]
+
+
 SIGNATURES.update({
+    "pcc_mlp_chain": (_i, [ctypes.POINTER(PccMlpInput), _i, _i64, ctypes.POINTER(PccMlpLayer), _i, _i, _vp, _i, _vp]),
     "pcc_mlp_packed_bytes": (_i64, [_i, _i]),
     "pcc_mlp_pack_weights_f32": (_i, [_vp, _i, _i, _vp, _vp]),
     "pcc_mlp_chain_f32": (_i, [_vp, _i64, _i, ctypes.POINTER(PccMlpLayer), _i, _i, _vp, _vp]),

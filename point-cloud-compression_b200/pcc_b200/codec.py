@@ -60,7 +60,7 @@ class PatchCodec:
             idx = ops.fps(pc, S, start_idx, 1e10)
         rec_centres = quantise_centres(index_points(pc, idx), self.centre_depth)  # compress.py:98-101
         _, _, patches = ops.knn(rec_centres, pc, K, return_nn=True, centre_sub=True,
-                                nn_scale=self.patch_scale(N))                     # compress.py:105-108
+                                nn_scale=self.patch_scale(N), nn_only=True)       # compress.py:105-108
         latent, latent_q = self.ae.encode_patches(patches.view(B * S, K, 3))      # compress.py:113-127
         return dict(latent_q=latent_q.view(B, S, -1), latent=latent.view(B, S, -1), centres=rec_centres, center=center,
                     longest=longest, pc=pc)

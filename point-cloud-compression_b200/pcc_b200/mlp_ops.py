@@ -62,37 +62,72 @@ def _packed(w, b):
     return hit
 
 
-def fused_chain(x, layers, group=0):
-    """One launch of the tcgen05 chain kernel.  x [M, >=C0] fp32 row-major (row stride may exceed C0)."""
-    _check(x)
+def fused_chain(inputs, layers, group=0, out_dtype=torch.float32):
+    """One launch of the tcgen05 chain kernel.
+
+    inputs: a [M, C0] tensor, or a list of segments `(tensor [R, C], row_div)` concatenated along the channel axis
+    (segment row used for position r is r // row_div); fp32 or bf16, unit stride along channels.
+    Returns [M, CL] (group <= 1) or [M / group, CL], fp32 or bf16."""
     lib = _lib.load()
-    if x.dtype != torch.float32 or x.stride(-1) != 1:
-        x = x.float().contiguous()
-    M, ldx = x.shape[0], x.stride(0)
-    arr = (_lib.PccMlpLayer * len(layers))()
+    if isinstance(inputs, torch.Tensor):
+        inputs = [(inputs, 1)]
+    segs = (_lib.PccMlpInput * len(inputs))()
     keep = []
+    M = None
+    for i, (t, div) in enumerate(inputs):
+        _check(t)
+        if t.dtype not in (torch.float32, torch.bfloat16):
+            t = t.float()
+        if t.dim() != 2 or t.stride(1) != 1:
+            t = t.reshape(-1, t.shape[-1]).contiguous()
+        keep.append(t)
+        rows_here = t.shape[0] * div
+        M = rows_here if M is None else M
+        if rows_here != M:
+            raise ValueError("pcc_b200.fused_chain: input segments disagree on the number of rows")
+        segs[i] = _lib.PccMlpInput(t.data_ptr(), 0 if t.dtype == torch.float32 else 1, t.shape[1], t.stride(0), div)
+    arr = (_lib.PccMlpLayer * len(layers))()
     for i, (w, b, relu) in enumerate(layers):
         pw, pb = _packed(w, b)
         keep.append((pw, pb))
         arr[i] = _lib.PccMlpLayer(pw.data_ptr(), pb.data_ptr(), w.shape[1], w.shape[0], int(bool(relu)))
     cl = layers[-1][0].shape[0]
     out_rows = M // group if group > 1 else M
-    out = torch.empty((out_rows, cl), dtype=torch.float32, device=x.device)
-    with torch.cuda.device(x.device):
-        _lib.check(lib.pcc_mlp_chain_f32(x.data_ptr(), M, ldx, arr, len(layers), int(group), out.data_ptr(),
-                                         torch.cuda.current_stream().cuda_stream), "pcc_mlp_chain_f32")
+    dev = keep[0].device
+    out = torch.empty((out_rows, cl), dtype=out_dtype, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.pcc_mlp_chain(segs, len(inputs), M, arr, len(layers), int(group), out.data_ptr(),
+                                     0 if out_dtype == torch.float32 else 1, torch.cuda.current_stream().cuda_stream),
+                   "pcc_mlp_chain")
     return out
 
 
-def _library_chain(x, layers):
+_bf16_cache = {}
+
+
+def _bf16(t):
+    key = (t.data_ptr(), t._version, tuple(t.shape))
+    hit = _bf16_cache.get(key)
+    if hit is None:
+        if len(_bf16_cache) > 256:
+            _bf16_cache.clear()
+        hit = t.detach().to(torch.bfloat16).contiguous()
+        _bf16_cache[key] = hit
+    return hit
+
+
+def library_chain(x, layers, out_dtype=torch.float32):
     """Plain library GEMMs (cuBLAS through torch) in bf16 with fp32 accumulation, for layers too large for the fused
     kernel's resident-weight design."""
     x = x.to(torch.bfloat16)
     for w, b, relu in layers:
-        x = torch.addmm(b.to(torch.bfloat16), x, w.to(torch.bfloat16).t())
+        x = torch.addmm(_bf16(b), x, _bf16(w).t())
         if relu:
             x = torch.relu_(x)
-    return x.float()
+    return x.to(out_dtype)
+
+
+_library_chain = library_chain
 
 
 def _split(layers):

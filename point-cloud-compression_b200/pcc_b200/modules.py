@@ -51,14 +51,15 @@ class SetAbstraction(nn.Module):
         return [(self.conv0.weight.flatten(1), self.conv0.bias, True), (self.conv1.weight.flatten(1), self.conv1.bias, True),
                 (self.conv2.weight.flatten(1), self.conv2.bias, self.finalRelu)]
 
-    def forward_points(self, xyz):
+    def forward_points(self, xyz, out_dtype=torch.float32):
         """xyz [BS, P, 3] (channel-last) -> per-point features [BS, P, C_out] (channel-last).
         pn_kit.py:164-211: kNN(K) in the patch, recentre on the query, shared MLP, max over the K neighbours."""
         BS, P, _ = xyz.shape
         if self.npoint != P:
             raise NotImplementedError("pcc_b200.SetAbstraction: only the S == N configuration of AE.py:16 is built")
-        _, _, grouped = ops.knn(xyz, xyz, self.K, return_nn=True, centre_sub=True)  # [BS,P,K,3]
-        return mlp_ops.mlp_chain_groupmax(grouped.reshape(BS * P * self.K, 3), self.layers(), group=self.K).reshape(BS, P, -1)
+        _, _, grouped = ops.knn(xyz, xyz, self.K, return_nn=True, centre_sub=True, nn_only=True)  # [BS,P,K,3]
+        return mlp_ops.fused_chain(grouped.reshape(BS * P * self.K, 3), self.layers(), group=self.K,
+                                   out_dtype=out_dtype).reshape(BS, P, -1)
 
     def forward(self, xyz):
         """Reference signature: xyz [B, 3, N] -> (new_xyz [B, 3, S], new_points [B, D', S])."""
@@ -83,6 +84,29 @@ class PointNet(nn.Module):
         """x [BS, P, C] channel-last -> [BS, D]."""
         BS, P, C = x.shape
         return mlp_ops.mlp_chain_groupmax(x.reshape(BS * P, C), self.layers(), group=P)
+
+    def forward_xyz_feat(self, xyz, feat):
+        """The AE.py:39 call `pn(cat((xyz, feat)))` without materialising the concatenation: xyz [BS,P,3] fp32 and
+        feat [BS,P,F] (bf16 from the SetAbstraction kernel) are two input segments of the fused chain; the first
+        layer's weight columns are rotated once so the 16-byte aligned feature block comes first."""
+        BS, P, F = feat.shape
+        layers = self.layers()
+        w0 = layers[0][0]
+        key = (w0.data_ptr(), w0._version)
+        if getattr(self, "_rot_key", None) != key:
+            self._rot_w0 = torch.cat((w0[:, 3:], w0[:, :3]), dim=1).detach().contiguous()
+            self._rot_key = key
+        layers[0] = (self._rot_w0, layers[0][1], layers[0][2])
+        n = mlp_ops._split(layers)
+        if n == 0:
+            raise RuntimeError("pcc_b200.PointNet: first layer does not fit the fused kernel")
+        h = mlp_ops.fused_chain([(feat.reshape(BS * P, F), 1), (xyz.reshape(BS * P, 3), 1)], layers[:n],
+                                group=P if n == len(layers) else 0,
+                                out_dtype=torch.float32 if n == len(layers) else torch.bfloat16)
+        if n == len(layers):
+            return h
+        h = mlp_ops.library_chain(h, layers[n:])
+        return h.view(BS, P, -1).max(dim=1)[0]
 
     def forward(self, points):
         """Reference signature: points [B, C, N] -> [B, D]."""
@@ -126,8 +150,8 @@ class AE(nn.Module):
     # -- the two halves the scripts use separately (compress.py:113-127, decompress.py:96-102) --
     def encode_patches(self, patches):
         """patches [BS, K, 3] (recentred, scaled) -> (latent [BS, d] after the sigmoid spread, rounded latent)."""
-        feat = self.sa.forward_points(patches)                                    # AE.py:38
-        latent = self.pn.forward_points(torch.cat((patches, feat), dim=2))        # AE.py:39 (xyz first)
+        feat = self.sa.forward_points(patches, out_dtype=torch.bfloat16)          # AE.py:38
+        latent = self.pn.forward_xyz_feat(patches, feat)                          # AE.py:39
         spread = self.L - 0.2                                                     # AE.py:42-45
         latent = torch.sigmoid(latent) * spread - spread / 2
         return latent, STEQuantize.apply(latent)
@@ -135,11 +159,21 @@ class AE(nn.Module):
     def decode_patches(self, latent_q):
         """latent_q [BS, d] -> patches [BS, k, 3]   (AE.py:48-53)."""
         BS = latent_q.shape[0]
-        lin = mlp_ops.mlp_chain(latent_q, [(m.weight, m.bias, True) for m in (self.inv_pool[0], self.inv_pool[2],
-                                                                               self.inv_pool[4])])
-        lin = lin.view(BS, 128, self.k).permute(0, 2, 1)                          # [BS, k, 128] channel-last
-        x = torch.cat((lin, latent_q.unsqueeze(1).expand(-1, self.k, -1)), dim=2)  # 128 features then d latent
-        return self.inv_mlp.forward_points(x.contiguous())
+        # inv_pool's last Linear emits [128 channels, k points] per patch (AE.py:49 `view(BS, -1, k)`); permuting its
+        # rows once makes the GEMM write [k points, 128 channels] (channel-last) directly.
+        w4, b4 = self.inv_pool[4].weight, self.inv_pool[4].bias
+        key = (w4.data_ptr(), w4._version, b4._version)
+        if getattr(self, "_perm_key", None) != key:
+            self._perm_w4 = w4.detach().view(128, self.k, -1).permute(1, 0, 2).reshape(128 * self.k, -1).contiguous()
+            self._perm_b4 = b4.detach().view(128, self.k).t().reshape(-1).contiguous()
+            self._perm_key = key
+        lin = mlp_ops.library_chain(latent_q.detach(), [(self.inv_pool[0].weight, self.inv_pool[0].bias, True),
+                                                        (self.inv_pool[2].weight, self.inv_pool[2].bias, True),
+                                                        (self._perm_w4, self._perm_b4, True)], out_dtype=torch.bfloat16)
+        # AE.py:50-52: cat(features, tiled latent) -> inv_mlp, as two input segments of the fused chain
+        out = mlp_ops.fused_chain([(lin.view(BS * self.k, 128), 1), (latent_q.detach().float().contiguous(), self.k)],
+                                  self.inv_mlp.layers())
+        return out.view(BS, self.k, 3)
 
     def forward(self, xyz):
         """Reference signature (AE.py:34-55): xyz [BS, K, 3] -> (new_xyz [BS, k, 3], latent, latent_quantized)."""

@@ -57,15 +57,19 @@ def fps(xyz, npoint, start_idx=None, init_dist=1e10):
     return out
 
 
-def knn(p1, p2, K, return_nn=False, centre_sub=False, nn_scale=1.0):
-    """K nearest neighbours: (dists [B,P1,K] squared, idx int64 [B,P1,K], nn [B,P1,K,3] or None)."""
+def knn(p1, p2, K, return_nn=False, centre_sub=False, nn_scale=1.0, nn_only=False):
+    """K nearest neighbours: (dists [B,P1,K] squared, idx int64 [B,P1,K], nn [B,P1,K,3] or None).
+    nn_only=True skips the distance / index outputs (returns None for them): the grouping calls of the network bodies
+    use only the gathered, recentred neighbours."""
     lib = _lib.load()
     p1, p2 = _cuda_f32(p1, "p1"), _cuda_f32(p2, "p2")
     _check_pair(p1, p2)
     B, P1, _ = p1.shape
     P2 = p2.shape[1]
-    d = torch.empty((B, P1, K), dtype=torch.float32, device=p1.device)
-    i = torch.empty((B, P1, K), dtype=torch.int64, device=p1.device)
+    if nn_only and not return_nn:
+        raise ValueError("pcc_b200.knn: nn_only requires return_nn")
+    d = None if nn_only else torch.empty((B, P1, K), dtype=torch.float32, device=p1.device)
+    i = None if nn_only else torch.empty((B, P1, K), dtype=torch.int64, device=p1.device)
     nn = torch.empty((B, P1, K, 3), dtype=torch.float32, device=p1.device) if return_nn else None
     with torch.cuda.device(p1.device):
         _lib.check(lib.pcc_knn_f32(_ptr(p1), _ptr(p2), B, P1, P2, K, _ptr(d), _ptr(i), _ptr(nn), int(centre_sub),

@@ -8,9 +8,14 @@ from tools import synth
 
 pytestmark = pytest.mark.gpu
 
-# fp32 network bodies on both sides; the device GEMMs sum in a different order than the CPU convolutions.
-LATENT_ATOL = 2e-4
-REC_ATOL = 2e-4
+# The device network bodies run on the tensor cores with bf16 operands / fp32 accumulation (north_star: "within a
+# bf16/fp32 tolerance"); the CPU reference flow is fp32.  The latent lives in [-3.4, 3.4] before rounding.
+# Measured on B200 with the seeded weights: latent 6e-4, decoded coordinates 2.5e-4, Chamfer 2e-4 relative, PSNR 0.01 dB.
+LATENT_ATOL = 5e-3      # absolute, on the pre-rounding latent
+SYMBOL_MATCH_MIN = 0.98  # fraction of rounded symbols identical to the fp32 flow (the rest sit near a .5 boundary)
+REC_ATOL = 2e-3         # absolute, decoded coordinates (unit cube) for identical symbols
+CHAMFER_RTOL = 2e-3     # end-to-end metric of the bf16 network vs the fp32 flow
+PSNR_ATOL_DB = 0.05
 
 
 @pytest.fixture(scope="module")
@@ -41,15 +46,16 @@ def test_roundtrip_matches_cpu_reference_flow(setup):
         lat = c["latent"][b].cpu().numpy()
         assert np.abs(lat - ref["latent"]).max() < LATENT_ATOL
         lq, rq = c["latent_q"][b].cpu().numpy(), ref["latent_q"]
-        near_half = np.abs(np.abs(ref["latent"] - np.floor(ref["latent"])) - 0.5) < 1e-3
+        near_half = np.abs(np.abs(ref["latent"] - np.floor(ref["latent"])) - 0.5) < LATENT_ATOL
         assert np.array_equal(lq[~near_half], rq[~near_half])
+        assert (lq == rq).mean() >= SYMBOL_MATCH_MIN
         # decoder parity on identical symbols
         rec_b = codec.decompress(torch.from_numpy(rq)[None].cuda(), c["centres"][b:b + 1], 8192, c["center"][b:b + 1],
                                  c["longest"][b:b + 1])
         assert np.abs(rec_b[0].cpu().numpy() - ref["rec"]).max() < REC_ATOL
         if np.array_equal(lq, rq):
-            assert abs(met[b, 0] - ref["chamfer"]) <= 1e-4 * ref["chamfer"]
-            assert abs(met[b, 1] - ref["d1_psnr"]) < 1e-2  # dB
+            assert abs(met[b, 0] - ref["chamfer"]) <= CHAMFER_RTOL * ref["chamfer"]
+            assert abs(met[b, 1] - ref["d1_psnr"]) < PSNR_ATOL_DB
 
 
 def test_ae_forward_signature_and_shapes(setup):

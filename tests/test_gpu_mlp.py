@@ -89,8 +89,29 @@ def test_row_stride_and_repeat_launches(mlp):
     big = torch.rand(512, 8, device="cuda")
     y1 = mlp.fused_chain(big[:, :3].contiguous(), layers, 16)
     for _ in range(3):
-        y2 = mlp.fused_chain(big, layers, 16)  # row stride 8, first 3 columns used
+        y2 = mlp.fused_chain(big[:, :3], layers, 16)  # a strided view: row stride 8, 3 channels
     assert torch.equal(y1, y2)
+
+
+def test_input_segments_bf16_and_broadcast(mlp):
+    """cat((xyz, feat)) of AE.py:39 and cat((features, tiled latent)) of AE.py:50-51 as input segments."""
+    torch.manual_seed(3)
+    layers = make_layers([144, 128, 64, 32, 3], [True, True, True, False], seed=9)
+    k = 128
+    lin = (torch.rand(5 * k, 128, device="cuda") - 0.5).bfloat16()
+    lat = torch.randint(-3, 4, (5, 16), device="cuda").float()
+    y = mlp.fused_chain([(lin, 1), (lat, k)], layers)
+    x = torch.cat((lin.float(), lat.repeat_interleave(k, dim=0)), dim=1)
+    ym = ref_chain(x, layers, 0, model_bf16=True)
+    assert (y - ym).abs().max().item() / ym.abs().max().item() < MODEL_RTOL
+    # bf16 output + group max, fp32 segment that is not 8-aligned comes second
+    layers2 = make_layers([131, 128, 256], [True, True], seed=10)
+    feat = (torch.rand(512, 128, device="cuda") - 0.5).bfloat16()
+    xyz = torch.rand(512, 3, device="cuda") - 0.5
+    yb = mlp.fused_chain([(feat, 1), (xyz, 1)], layers2, group=0, out_dtype=torch.bfloat16)
+    ym2 = ref_chain(torch.cat((feat.float(), xyz), dim=1), layers2, 0, model_bf16=True)
+    assert yb.dtype == torch.bfloat16
+    assert (yb.float() - ym2).abs().max().item() / ym2.abs().max().item() < 1e-2  # one extra bf16 rounding of the output
 
 
 def test_unsupported_chain_is_an_error_not_a_fallback(mlp):
