@@ -126,17 +126,17 @@ int pcc_chamfer_bwd_f32(const float *x, const float *y, const int64_t *ix, const
  * (/root/reference/pn_kit.py:196-207, 124-144, 289-305) and PointnetSAModule.mlp
  * (/root/reference/pointnet_sa_module.py:87-91).  Intermediate activations stay in shared memory / TMEM.
  *   - weights are packed once per layer with pcc_mlp_pack_weights_f32 from the reference's [cout, cin] fp32 tensor
- *     (Conv2d weight flattened) into pcc_mlp_packed_bytes(cin, cout) bytes of device memory;
+ *     (Conv2d weight flattened) and [cout] bias into pcc_mlp_packed_bytes(cin, cout) bytes of device memory (bf16; the
+ *     bias becomes an extra K column that multiplies a constant-one input channel, so it is rounded to bf16 too);
  *   - `layers` is a HOST array; every layer's weights must fit in shared memory together (otherwise
  *     PCC_ERR_UNSUPPORTED, never a fallback); group must divide 32, or be a multiple of 32 dividing 128, or be a
- *     multiple of 128, and rows % group == 0;
+ *     multiple of 128 (then cout_L <= 128), and rows % group == 0;
  *   - out: fp32 [rows, cout_L] or [rows / group, cout_L], channel-last.
  * Numerics: operands rounded to bf16, products accumulated in fp32 (tolerance stated in tests/test_gpu_mlp.py).
  */
 #define PCC_MLP_MAX_LAYERS 6
 typedef struct PccMlpLayer {
-    const void *packed_w; /* device, from pcc_mlp_pack_weights_f32 */
-    const float *bias;    /* device, [cout] fp32 */
+    const void *packed_w; /* device, from pcc_mlp_pack_weights_f32 (weights and bias) */
     int cin, cout;
     int relu;             /* apply max(x, 0) after this layer */
 } PccMlpLayer;
@@ -152,7 +152,7 @@ typedef struct PccMlpInput {
     int row_div;
 } PccMlpInput;
 int64_t pcc_mlp_packed_bytes(int cin, int cout);
-int pcc_mlp_pack_weights_f32(const float *w, int cin, int cout, void *packed, void *stream);
+int pcc_mlp_pack_weights_f32(const float *w, const float *bias, int cin, int cout, void *packed, void *stream);
 int pcc_mlp_chain_f32(const float *x, int64_t rows, int ldx, const PccMlpLayer *layers, int n_layers, int group,
                       float *out, void *stream);
 /* General form: several input segments, output fp32 (out_dtype 0) or bf16 (out_dtype 1). */

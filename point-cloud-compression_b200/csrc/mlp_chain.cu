@@ -7,37 +7,42 @@
 //   pn_kit.MLP             4 convs                          /root/reference/pn_kit.py:289-305
 //   PointnetSAModule.mlp   Conv2d+BN(folded)+ReLU + max     /root/reference/pointnet_sa_module.py:87-91
 //
-// Formulation: "channels on lanes".  For a tile of P = 128 positions the kernel computes, layer by layer,
-//     D^T[Cout, P] = W[Cout, Cin] . X^T[Cin, P]        (bf16 operands, fp32 accumulation in TMEM)
-// i.e. the WEIGHTS are the MMA A operand (M = 128 output channels per tcgen05.mma, K-major, pre-packed on the
-// device into the canonical no-swizzle core-matrix layout) and the ACTIVATIONS are the B operand (N = positions).
-// A TMEM lane is an output channel, a TMEM column is a position, so in the epilogue each thread owns one channel:
-// bias is one register, ReLU and the max over G consecutive positions (neighbours / points of a group) are
-// plain in-register ops on consecutive columns, and the next layer's B operand is written back to shared memory as
-// 16-byte chunks (8 consecutive positions of one channel = one row of an MN-major core matrix), 512 contiguous
-// bytes per warp.  Activations never leave the SM between layers; only the pooled result is written to HBM.
+// A CTA (128 threads) walks tiles of P = 128 positions (rows).  Weights are packed once (bf16, canonical no-swizzle
+// K-major core matrices, the bias folded in as an extra K column that multiplies a constant-one input channel) and stay
+// resident in shared memory; activations live in ONE shared buffer, K-major ([8-channel chunk][position][8] bf16), that
+// each epilogue overwrites in place (the MMA that read it has completed); accumulators live in TMEM.
 //
-// One CTA = 128 threads, sequential per tile (load -> [mma -> commit -> epilogue] x layers); MMA/epilogue overlap
-// comes from several co-resident CTAs per SM (each owns <= 256 TMEM columns).  tcgen05.mma is issued by thread 0;
-// completion is tracked with tcgen05.commit on an mbarrier.
+// Two MMA orientations, chosen per layer:
+//   N-form (every layer but a pooled last one):   D[128 positions, Cout] = X[128, K] . W[Cout, K]^T
+//       activations are the A operand (M = 128), weights the B operand (N = Cout <= 256 per instruction).  A TMEM lane is
+//       a position, so all 128 epilogue threads are busy whatever Cout is (32-channel layers included) and each thread
+//       writes its position's next-layer channels as 16-byte chunks (8 channels), 512 contiguous bytes per warp.
+//   T-form (last layer when a max over G consecutive positions follows):   D^T[Cout, 128] = W . X^T
+//       weights are the A operand (M = 128 channels per instruction), activations the B operand.  A TMEM lane is a channel
+//       and the columns are positions, so the max over a group is a plain in-register reduction over consecutive columns
+//       and the pooled row is written coalesced across the warp's 32 channels.
+// The epilogue is ReLU + bf16 pack only (bias rides in the MMA).  tcgen05.mma is issued by thread 0; completion is
+// tracked with tcgen05.commit on an mbarrier; MMA/epilogue overlap comes from the co-resident CTAs of an SM.
 #include <cuda_bf16.h>
 
 #include "pcc_common.cuh"
 
 namespace pcc {
 
-constexpr int MLP_P = 128;  // positions per tile == MMA N
+constexpr int MLP_P = 128;  // positions per tile
 constexpr int MLP_THREADS = 128;
 constexpr int MLP_MAX_LAYERS = PCC_MLP_MAX_LAYERS;
+constexpr int MLP_CHUNK = (MLP_P / 8) * 128;  // bytes between 8-channel chunks of the activation buffer (LBO)
 
 struct MlpChainParams {
     int n_layers;
-    int cin[MLP_MAX_LAYERS], cout[MLP_MAX_LAYERS], kp[MLP_MAX_LAYERS], mt[MLP_MAX_LAYERS], relu[MLP_MAX_LAYERS];
+    int cin[MLP_MAX_LAYERS], cout[MLP_MAX_LAYERS], kp[MLP_MAX_LAYERS], relu[MLP_MAX_LAYERS];
+    int tform[MLP_MAX_LAYERS];    // 1: channels on lanes (pooled last layer)
+    int ncol[MLP_MAX_LAYERS];     // TMEM columns the layer's accumulator uses
+    int w_rows[MLP_MAX_LAYERS];   // weight rows kept in shared memory (Cout rounded to 16, or to 128 for T-form)
     int w_off[MLP_MAX_LAYERS];    // shared-memory byte offset of the packed weights of layer l
-    int w_bytes[MLP_MAX_LAYERS];
-    int x_off[MLP_MAX_LAYERS];    // shared-memory byte offset of the INPUT activations of layer l
     const void *w[MLP_MAX_LAYERS];
-    const float *bias[MLP_MAX_LAYERS];
+    int x_off;                    // the activation buffer
     int tmem_cols;
     int ctrl_off;                 // mbarrier + TMEM base address slot
 };
@@ -54,10 +59,9 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
     return d;
 }
 
-// Instruction descriptor for kind::f16: D=f32, A=B=bf16, A K-major, B K- or MN-major, shape M x N.
-__device__ __forceinline__ uint32_t umma_idesc(int M, int N, int b_mn_major) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(b_mn_major) << 16) |
-           (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+// Instruction descriptor for kind::f16: D=f32, A=B=bf16, both operands K-major, shape M x N.
+__device__ __forceinline__ uint32_t umma_idesc(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
@@ -113,22 +117,26 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 
 // ---- weight packing -------------------------------------------------------------------------------------------
-// Packed layer = mt tiles of [128 channels x kp] bf16 in the K-major no-swizzle core-matrix layout:
-//   offset(ch, k) = tile * 128*kp*2 + (ch_local / 8) * (kp * 16) + (k / 8) * 128 + (ch_local % 8) * 16 + (k % 8) * 2
-// (SBO = kp*16 bytes between 8-channel groups, LBO = 128 bytes between 8-wide k chunks); zero beyond cout / cin.
+// Packed layer = [rows128 x kp] bf16, kp = roundup(cin + 1, 16), in the K-major no-swizzle core-matrix layout:
+//   offset(ch, k) = (ch / 8) * (kp * 16) + (k / 8) * 128 + (ch % 8) * 16 + (k % 8) * 2        bytes
+// (SBO = kp*16 between 8-channel groups, LBO = 128 between 8-wide k chunks).  Column k = cin holds the bias (it
+// multiplies the constant-one channel the kernel appends to every activation tile); everything else is zero padded.
 __global__ void __launch_bounds__(256)
-mlp_pack_kernel(const float *__restrict__ w, int cin, int cout, int kp, int mt, __nv_bfloat16 *__restrict__ packed) {
-    const long long total = static_cast<long long>(mt) * 128 * kp;
+mlp_pack_kernel(const float *__restrict__ w, const float *__restrict__ bias, int cin, int cout, int kp, int rows128,
+                __nv_bfloat16 *__restrict__ packed) {
+    const long long total = static_cast<long long>(rows128) * kp;
     for (long long e = blockIdx.x * 256ll + threadIdx.x; e < total; e += static_cast<long long>(gridDim.x) * 256ll) {
-        const int tile = static_cast<int>(e / (128ll * kp));
-        const int r = static_cast<int>(e - static_cast<long long>(tile) * 128 * kp);
-        const int grp = r / (kp * 8);       // 8-channel group
-        const int r2 = r - grp * kp * 8;
-        const int kc = r2 / 64;             // 8-wide k chunk
+        const int grp = static_cast<int>(e / (kp * 8));  // 8-channel group
+        const int r2 = static_cast<int>(e - static_cast<long long>(grp) * kp * 8);
+        const int kc = r2 / 64;                          // 8-wide k chunk
         const int r3 = r2 - kc * 64;
         const int chl = r3 / 8, kl = r3 - chl * 8;
-        const int ch = tile * 128 + grp * 8 + chl, k = kc * 8 + kl;
-        const float v = (ch < cout && k < cin) ? w[static_cast<size_t>(ch) * cin + k] : 0.0f;
+        const int ch = grp * 8 + chl, k = kc * 8 + kl;
+        float v = 0.0f;
+        if (ch < cout) {
+            if (k < cin) v = w[static_cast<size_t>(ch) * cin + k];
+            else if (k == cin) v = bias[ch];
+        }
         packed[e] = __float2bfloat16_rn(v);
     }
 }
@@ -147,21 +155,30 @@ struct MlpIo {
     MlpSeg seg[PCC_MLP_MAX_INPUTS];
     int n_seg;
     int out_bf16;
+    long long *timing;  // bring-up aid (NULL in production): CTA 0 / thread 0 stores clock64() at phase boundaries
 };
 
+#define MLP_TICK(slot)                                                                   \
+    do {                                                                                 \
+        if (io.timing && blockIdx.x == 0 && tid == 0 && tick < 256) io.timing[tick++] = clock64(); \
+    } while (0)
+
+__device__ __forceinline__ void store_out(float *__restrict__ out_f, __nv_bfloat16 *__restrict__ out_h, long long o, float v) {
+    if (out_h) out_h[o] = __float2bfloat16_rn(v); else out_f[o] = v;
+}
+
 template <int G>
-__device__ __forceinline__ void pool_store_small(const float (&f)[32], float *__restrict__ out_f, __nv_bfloat16 *__restrict__ out_h,
-                                                 long long row_base, long long rows, int CL, int c) {
+__device__ __forceinline__ void pool_store_small(const uint32_t (&v)[32], int relu, float *__restrict__ out_f,
+                                                 __nv_bfloat16 *__restrict__ out_h, long long row_base, long long rows,
+                                                 int CL, int c) {
 #pragma unroll
     for (int g = 0; g < 32 / G; ++g) {
-        float m = f[g * G];
+        float m = __uint_as_float(v[g * G]);
 #pragma unroll
-        for (int i = 1; i < G; ++i) m = fmaxf(m, f[g * G + i]);
+        for (int i = 1; i < G; ++i) m = fmaxf(m, __uint_as_float(v[g * G + i]));
+        if (relu) m = fmaxf(m, 0.0f);  // ReLU commutes with max
         const long long r = row_base + g * G;
-        if (r < rows) {
-            const long long o = (r / G) * CL + c;
-            if (out_h) out_h[o] = __float2bfloat16_rn(m); else out_f[o] = m;
-        }
+        if (r < rows) store_out(out_f, out_h, (r / G) * CL + c, m);
     }
 }
 
@@ -178,12 +195,16 @@ mlp_chain_kernel(const __grid_constant__ MlpChainParams prm, const __grid_consta
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + prm.ctrl_off + 8);
     float *out_f = io.out_bf16 ? nullptr : static_cast<float *>(out);
     __nv_bfloat16 *out_h = io.out_bf16 ? static_cast<__nv_bfloat16 *>(out) : nullptr;
+    unsigned char *xbuf = smem + prm.x_off;
+    unsigned char *xrow = xbuf + (tid >> 3) * 128 + (tid & 7) * 16;  // this thread's position inside every chunk
+    const uint32_t ONE_BF16 = 0x3f80u;
 
     // ---- prologue: weights -> shared memory, barrier init, TMEM allocation ----
     for (int l = 0; l < prm.n_layers; ++l) {
         const int4 *src = static_cast<const int4 *>(prm.w[l]);
         int4 *dst = reinterpret_cast<int4 *>(smem + prm.w_off[l]);
-        for (int i = tid; i < prm.w_bytes[l] / 16; i += MLP_THREADS) dst[i] = src[i];
+        const int n16 = prm.w_rows[l] * prm.kp[l] * 2 / 16;
+        for (int i = tid; i < n16; i += MLP_THREADS) dst[i] = src[i];
     }
     if (tid == 0) mbar_init(mbar, 1);
     if (warp == 0) {
@@ -198,36 +219,49 @@ mlp_chain_kernel(const __grid_constant__ MlpChainParams prm, const __grid_consta
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     uint32_t phase = 0;
+    int tick = 0;
 
     const int L = prm.n_layers;
     const int CL = prm.cout[L - 1];
-    const int kp0 = prm.kp[0];
+    const int kp0 = prm.kp[0], c0 = prm.cin[0];
 
     for (long long unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-        float run_max[8];  // running max across the tiles of one unit (one per M-tile of the last layer)
-#pragma unroll
-        for (int t = 0; t < 8; ++t) run_max[t] = -INFINITY;
+        float run_max = -INFINITY;  // running max across the tiles of one unit (pooled last layer, group > P, Cout <= 128)
 
         for (int sub = 0; sub < tiles_per_unit; ++sub) {
             const long long row0 = (unit * tiles_per_unit + sub) * MLP_P;
+            MLP_TICK(0);
 
-            // ---- load the input tile into K-major core matrices: element (p, c) at
-            //      (p/8)*128 + (c/8)*(P/8)*128 + (p%8)*16 + (c%8)*2     (SBO = 128, LBO = (P/8)*128) ----
+            // ---- load the input tile: element (p, c) at (p/8)*128 + (c/8)*MLP_CHUNK + (p%8)*16 + (c%8)*2 ----
             {
-                unsigned char *x0 = smem + prm.x_off[0];
                 int coff = 0;
                 for (int s = 0; s < io.n_seg; ++s) {
                     const MlpSeg sg = io.seg[s];
                     if (sg.vec) {  // bf16 rows, 16-byte chunks: thread p owns position p
                         const long long r = row0 + tid;
-                        const uint4 *src = reinterpret_cast<const uint4 *>(static_cast<const __nv_bfloat16 *>(sg.ptr) +
-                                                                           (r / sg.row_div) * sg.ld);
+                        const long long sr = sg.row_div == 1 ? r : r / sg.row_div;
+                        const uint4 *src = reinterpret_cast<const uint4 *>(static_cast<const __nv_bfloat16 *>(sg.ptr) + sr * sg.ld);
                         const bool ok = r < rows;
-                        unsigned char *dst = x0 + (tid >> 3) * 128 + (tid & 7) * 16 + (coff >> 3) * (MLP_P / 8) * 128;
-                        for (int c8 = 0; c8 < sg.ch / 8; ++c8) {
+                        unsigned char *dst = xrow + (coff >> 3) * MLP_CHUNK;
+                        const int n8 = sg.ch >> 3;
+                        int c8 = 0;
+                        for (; c8 + 4 <= n8; c8 += 4) {  // 4 loads in flight
+                            uint4 v0 = make_uint4(0u, 0u, 0u, 0u), v1 = v0, v2 = v0, v3 = v0;
+                            if (ok) {
+                                v0 = __ldg(src + c8);
+                                v1 = __ldg(src + c8 + 1);
+                                v2 = __ldg(src + c8 + 2);
+                                v3 = __ldg(src + c8 + 3);
+                            }
+                            *reinterpret_cast<uint4 *>(dst + (c8 + 0) * MLP_CHUNK) = v0;
+                            *reinterpret_cast<uint4 *>(dst + (c8 + 1) * MLP_CHUNK) = v1;
+                            *reinterpret_cast<uint4 *>(dst + (c8 + 2) * MLP_CHUNK) = v2;
+                            *reinterpret_cast<uint4 *>(dst + (c8 + 3) * MLP_CHUNK) = v3;
+                        }
+                        for (; c8 < n8; ++c8) {
                             uint4 v = make_uint4(0u, 0u, 0u, 0u);
                             if (ok) v = __ldg(src + c8);
-                            *reinterpret_cast<uint4 *>(dst + c8 * (MLP_P / 8) * 128) = v;
+                            *reinterpret_cast<uint4 *>(dst + c8 * MLP_CHUNK) = v;
                         }
                     } else {       // element-wise, coalesced along the channels of a row
                         const int total = MLP_P * sg.ch;
@@ -237,12 +271,12 @@ mlp_chain_kernel(const __grid_constant__ MlpChainParams prm, const __grid_consta
                             const long long r = row0 + p;
                             float v = 0.0f;
                             if (r < rows) {
-                                const long long o = (r / sg.row_div) * sg.ld + c;
+                                const long long o = (sg.row_div == 1 ? r : r / sg.row_div) * sg.ld + c;
                                 v = sg.dtype == 0 ? __ldg(static_cast<const float *>(sg.ptr) + o)
                                                   : __bfloat162float(static_cast<const __nv_bfloat16 *>(sg.ptr)[o]);
                             }
                             const int cc = coff + c;
-                            *reinterpret_cast<__nv_bfloat16 *>(x0 + (p >> 3) * 128 + (cc >> 3) * (MLP_P / 8) * 128 + (p & 7) * 16 +
+                            *reinterpret_cast<__nv_bfloat16 *>(xbuf + (p >> 3) * 128 + (cc >> 3) * MLP_CHUNK + (p & 7) * 16 +
                                                                (cc & 7) * 2) = __float2bfloat16_rn(v);
                             p += dp;
                             c += dc;
@@ -254,124 +288,176 @@ mlp_chain_kernel(const __grid_constant__ MlpChainParams prm, const __grid_consta
                     }
                     coff += sg.ch;
                 }
-                for (int cc = coff; cc < kp0; ++cc)  // zero the K padding
-                    *reinterpret_cast<__nv_bfloat16 *>(x0 + (tid >> 3) * 128 + (cc >> 3) * (MLP_P / 8) * 128 + (tid & 7) * 16 +
-                                                       (cc & 7) * 2) = __float2bfloat16_rn(0.0f);
+                // the constant-one channel (multiplies the folded bias) and the zero K padding
+                int cc = c0;
+                for (; (cc & 7) != 0 && cc < kp0; ++cc)
+                    *reinterpret_cast<unsigned short *>(xrow + (cc >> 3) * MLP_CHUNK + (cc & 7) * 2) =
+                        static_cast<unsigned short>(cc == c0 ? ONE_BF16 : 0u);
+                for (; cc < kp0; cc += 8)
+                    *reinterpret_cast<uint4 *>(xrow + (cc >> 3) * MLP_CHUNK) = make_uint4(cc == c0 ? ONE_BF16 : 0u, 0u, 0u, 0u);
             }
+            MLP_TICK(1);
             fence_async_smem();
             __syncthreads();
+            MLP_TICK(2);
 
             for (int l = 0; l < L; ++l) {
-                const int kp = prm.kp[l], mt = prm.mt[l];
+                const int kp = prm.kp[l];
+                const int tform = prm.tform[l];
+                const int ncol = prm.ncol[l];
                 // ---- MMA: one elected thread ----
                 if (tid == 0) {
                     tc_fence_after();
-                    const uint32_t a_base = smem_base + prm.w_off[l];
-                    const uint32_t b_base = smem_base + prm.x_off[l];
-                    const uint32_t idesc = umma_idesc(128, MLP_P, l == 0 ? 0 : 1);
-                    for (int t = 0; t < mt; ++t) {
-                        for (int ks = 0; ks < kp / 16; ++ks) {
-                            const uint64_t a_desc = umma_desc(a_base + t * 128 * kp * 2 + ks * 256, 128, kp * 16);
-                            uint64_t b_desc;
-                            if (l == 0)  // K-major input tile: LBO = (P/8)*128 between k chunks, SBO = 128
-                                b_desc = umma_desc(b_base + ks * 2 * (MLP_P / 8) * 128, (MLP_P / 8) * 128, 128);
-                            else         // MN-major activations: LBO = 128 between k groups, SBO = kp*16 between position groups
-                                b_desc = umma_desc(b_base + ks * 256, 128, kp * 16);
-                            umma_bf16(tmem_base + t * MLP_P, a_desc, b_desc, idesc, ks > 0 ? 1u : 0u);
+                    const uint32_t w_base = smem_base + prm.w_off[l];
+                    const uint32_t x_base = smem_base + prm.x_off;
+                    if (tform) {   // D^T[128 channels, P] per M tile: A = weights, B = activations
+                        const uint32_t idesc = umma_idesc(128, MLP_P);
+                        for (int t = 0; t < ncol / MLP_P; ++t)
+                            for (int ks = 0; ks < kp / 16; ++ks)
+                                umma_bf16(tmem_base + t * MLP_P, umma_desc(w_base + t * 128 * kp * 2 + ks * 256, 128, kp * 16),
+                                          umma_desc(x_base + ks * 2 * MLP_CHUNK, MLP_CHUNK, 128), idesc, ks > 0 ? 1u : 0u);
+                    } else {       // D[P positions, Cout]: A = activations, B = weights (N <= 256 per instruction)
+                        for (int n0 = 0; n0 < ncol; n0 += 256) {
+                            const int n = ncol - n0 < 256 ? ncol - n0 : 256;
+                            const uint32_t idesc = umma_idesc(128, n);
+                            for (int ks = 0; ks < kp / 16; ++ks)
+                                umma_bf16(tmem_base + n0, umma_desc(x_base + ks * 2 * MLP_CHUNK, MLP_CHUNK, 128),
+                                          umma_desc(w_base + n0 * kp * 2 + ks * 256, 128, kp * 16), idesc, ks > 0 ? 1u : 0u);
                         }
                     }
                     umma_commit(mbar);
                 }
+                MLP_TICK(3);
                 mbar_wait(mbar, phase);
                 phase ^= 1u;
                 tc_fence_after();
+                MLP_TICK(4);
 
-                // ---- epilogue: thread = output channel (TMEM lane), registers = positions (TMEM columns) ----
                 const bool last = (l == L - 1);
                 const int cout = prm.cout[l];
                 const int relu = prm.relu[l];
-                const float *bias = prm.bias[l];
-                unsigned char *xn = last ? nullptr : smem + prm.x_off[l + 1];
-                const int kpn = last ? 0 : prm.kp[l + 1];
-                for (int t = 0; t < mt; ++t) {
-                    if (t * 128 + warp * 32 >= (last ? cout : kpn)) break;  // warp-uniform: nothing real in this quadrant
-                    const int c = t * 128 + warp * 32 + lane;
-                    const bool real = c < cout;
-                    const float b = real ? __ldg(bias + c) : 0.0f;
-                    float gmax = -INFINITY;
-                    if (last && group > 32) {
+                const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+                if (!tform) {
+                    // ---- N-form epilogue: thread = position (TMEM lane), columns = channels ----
+                    if (!last) {
+                        const int kpn = prm.kp[l + 1];
+                        for (int j = 0; j < ncol / 32 + (ncol % 32 ? 1 : 0); ++j) {
+                            uint32_t v[32];
+                            tmem_ld32(lane_addr + j * 32, v);  // columns past ncol (< 32 over) are stale but never stored
 #pragma unroll
-                        for (int q = 0; q < 8; ++q)
-                            if (q == t) gmax = run_max[q];
-                    }
-                    for (int j = 0; j < MLP_P / 32; ++j) {
-                        uint32_t v[32];
-                        tmem_ld32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + t * MLP_P + j * 32, v);
-                        float f[32];
+                            for (int q = 0; q < 4; ++q) {
+                                if (j * 32 + q * 8 < ncol) {
+                                    uint32_t pk[4];
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const float a = real ? __uint_as_float(v[i]) + b : 0.0f;  // padded channels feed exact zeros
-                            f[i] = relu ? fmaxf(a, 0.0f) : a;
-                        }
-                        if (!last) {
-                            if (c < kpn) {
-#pragma unroll
-                                for (int q = 0; q < 4; ++q) {
-                                    const uint4 pk = make_uint4(pack_bf16x2(f[q * 8 + 0], f[q * 8 + 1]),
-                                                                pack_bf16x2(f[q * 8 + 2], f[q * 8 + 3]),
-                                                                pack_bf16x2(f[q * 8 + 4], f[q * 8 + 5]),
-                                                                pack_bf16x2(f[q * 8 + 6], f[q * 8 + 7]));
-                                    const int pg = j * 4 + q;  // position group (8 positions)
-                                    *reinterpret_cast<uint4 *>(xn + pg * (kpn * 16) + (c >> 3) * 128 + (c & 7) * 16) = pk;
+                                    for (int h = 0; h < 4; ++h) {
+                                        float a = __uint_as_float(v[q * 8 + 2 * h]), b = __uint_as_float(v[q * 8 + 2 * h + 1]);
+                                        if (relu) {
+                                            a = fmaxf(a, 0.0f);
+                                            b = fmaxf(b, 0.0f);
+                                        }
+                                        pk[h] = pack_bf16x2(a, b);
+                                    }
+                                    *reinterpret_cast<uint4 *>(xrow + (j * 4 + q) * MLP_CHUNK) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                                 }
                             }
-                        } else if (real) {
-                            const long long rb = row0 + j * 32;
-                            if (group <= 1) {
+                        }
+                        // constant-one channel at index cout, zero chunks up to the next layer's padded K
+                        if (cout < ncol)
+                            *reinterpret_cast<unsigned short *>(xrow + (cout >> 3) * MLP_CHUNK + (cout & 7) * 2) =
+                                static_cast<unsigned short>(ONE_BF16);
+                        for (int cc = ncol; cc < kpn; cc += 8)
+                            *reinterpret_cast<uint4 *>(xrow + (cc >> 3) * MLP_CHUNK) = make_uint4(cc == cout ? ONE_BF16 : 0u, 0u, 0u, 0u);
+                    } else {
+                        const long long r = row0 + tid;
+                        for (int j = 0; j < (cout + 31) / 32; ++j) {
+                            uint32_t v[32];
+                            tmem_ld32(lane_addr + j * 32, v);
+                            if (r < rows) {
+                                const long long o = r * CL + j * 32;
+                                if (out_h && (CL & 7) == 0) {
 #pragma unroll
-                                for (int i = 0; i < 32; ++i) {
-                                    const long long r = rb + i;
-                                    if (r < rows) {
-                                        if (out_h) out_h[r * CL + c] = __float2bfloat16_rn(f[i]); else out_f[r * CL + c] = f[i];
+                                    for (int q = 0; q < 4; ++q) {
+                                        if (j * 32 + q * 8 < cout) {
+                                            uint32_t pk[4];
+#pragma unroll
+                                            for (int h = 0; h < 4; ++h) {
+                                                float a = __uint_as_float(v[q * 8 + 2 * h]), b = __uint_as_float(v[q * 8 + 2 * h + 1]);
+                                                if (relu) {
+                                                    a = fmaxf(a, 0.0f);
+                                                    b = fmaxf(b, 0.0f);
+                                                }
+                                                pk[h] = pack_bf16x2(a, b);
+                                            }
+                                            *reinterpret_cast<uint4 *>(out_h + o + q * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                                        }
+                                    }
+                                } else if (out_f && (CL & 3) == 0) {
+#pragma unroll
+                                    for (int q = 0; q < 8; ++q) {
+                                        if (j * 32 + q * 4 < cout) {
+                                            float4 f = make_float4(__uint_as_float(v[q * 4]), __uint_as_float(v[q * 4 + 1]),
+                                                                   __uint_as_float(v[q * 4 + 2]), __uint_as_float(v[q * 4 + 3]));
+                                            if (relu) f = make_float4(fmaxf(f.x, 0.f), fmaxf(f.y, 0.f), fmaxf(f.z, 0.f), fmaxf(f.w, 0.f));
+                                            *reinterpret_cast<float4 *>(out_f + o + q * 4) = f;
+                                        }
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int i = 0; i < 32; ++i) {
+                                        if (j * 32 + i < cout) {
+                                            float a = __uint_as_float(v[i]);
+                                            if (relu) a = fmaxf(a, 0.0f);
+                                            store_out(out_f, out_h, o + i, a);
+                                        }
                                     }
                                 }
-                            } else if (group == 2) {
-                                pool_store_small<2>(f, out_f, out_h, rb, rows, CL, c);
+                            }
+                        }
+                    }
+                } else {
+                    // ---- T-form epilogue (pooled last layer): thread = channel (TMEM lane), columns = positions ----
+                    for (int t = 0; t < ncol / MLP_P; ++t) {
+                        if (t * 128 + warp * 32 >= cout) break;  // warp-uniform: no real channel in this quadrant
+                        const int c = t * 128 + warp * 32 + lane;
+                        const bool real = c < cout;
+                        float gmax = (group > 32 && t == 0) ? run_max : -INFINITY;
+                        for (int j = 0; j < MLP_P / 32; ++j) {
+                            uint32_t v[32];
+                            tmem_ld32(lane_addr + t * MLP_P + j * 32, v);
+                            if (!real) continue;
+                            const long long rb = row0 + j * 32;
+                            if (group == 2) {
+                                pool_store_small<2>(v, relu, out_f, out_h, rb, rows, CL, c);
                             } else if (group == 4) {
-                                pool_store_small<4>(f, out_f, out_h, rb, rows, CL, c);
+                                pool_store_small<4>(v, relu, out_f, out_h, rb, rows, CL, c);
                             } else if (group == 8) {
-                                pool_store_small<8>(f, out_f, out_h, rb, rows, CL, c);
+                                pool_store_small<8>(v, relu, out_f, out_h, rb, rows, CL, c);
                             } else if (group == 16) {
-                                pool_store_small<16>(f, out_f, out_h, rb, rows, CL, c);
+                                pool_store_small<16>(v, relu, out_f, out_h, rb, rows, CL, c);
                             } else if (group == 32) {
-                                pool_store_small<32>(f, out_f, out_h, rb, rows, CL, c);
+                                pool_store_small<32>(v, relu, out_f, out_h, rb, rows, CL, c);
                             } else {
-                                float m = f[0];
+                                float m = __uint_as_float(v[0]);
 #pragma unroll
-                                for (int i = 1; i < 32; ++i) m = fmaxf(m, f[i]);
+                                for (int i = 1; i < 32; ++i) m = fmaxf(m, __uint_as_float(v[i]));
                                 gmax = fmaxf(gmax, m);
                                 const long long pos = static_cast<long long>(sub) * MLP_P + (j + 1) * 32;  // within the unit
                                 const long long gsz = group < MLP_P ? group : static_cast<long long>(tiles_per_unit) * MLP_P;
                                 if (pos % gsz == 0) {
                                     const long long r = unit * tiles_per_unit * MLP_P + pos - gsz;
-                                    if (r < rows) {
-                                        const long long o = (r / group) * CL + c;
-                                        if (out_h) out_h[o] = __float2bfloat16_rn(gmax); else out_f[o] = gmax;
-                                    }
+                                    if (r < rows) store_out(out_f, out_h, (r / group) * CL + c, relu ? fmaxf(gmax, 0.0f) : gmax);
                                     gmax = -INFINITY;
                                 }
                             }
                         }
-                    }
-                    if (last && group > 32) {
-#pragma unroll
-                        for (int q = 0; q < 8; ++q)
-                            if (q == t) run_max[q] = gmax;
+                        if (group > 32 && t == 0) run_max = gmax;
                     }
                 }
+                MLP_TICK(5);
                 tc_fence_before();
                 fence_async_smem();
                 __syncthreads();
+                MLP_TICK(6);
             }
         }
     }
@@ -387,18 +473,22 @@ static int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
 }  // namespace pcc
 
+static long long *g_mlp_timing = nullptr;
+/* bring-up aid, not part of the public header: device buffer of 256 int64 that CTA 0 fills with clock64() ticks */
+PCC_API void pcc_debug_mlp_timing(long long *buf) { g_mlp_timing = buf; }
+
 PCC_API int64_t pcc_mlp_packed_bytes(int cin, int cout) {
     if (cin < 1 || cout < 1) return 0;
-    return static_cast<int64_t>(pcc::round_up(cout, 128)) * pcc::round_up(cin, 16) * 2;
+    return static_cast<int64_t>(pcc::round_up(cout, 128)) * pcc::round_up(cin + 1, 16) * 2;
 }
 
-PCC_API int pcc_mlp_pack_weights_f32(const float *w, int cin, int cout, void *packed, void *stream) {
+PCC_API int pcc_mlp_pack_weights_f32(const float *w, const float *bias, int cin, int cout, void *packed, void *stream) {
     using namespace pcc;
-    PCC_REQUIRE(w && packed && cin >= 1 && cout >= 1, "pcc_mlp_pack_weights_f32: bad argument");
-    const int kp = round_up(cin, 16), mt = round_up(cout, 128) / 128;
-    const long long total = static_cast<long long>(mt) * 128 * kp;
+    PCC_REQUIRE(w && bias && packed && cin >= 1 && cout >= 1, "pcc_mlp_pack_weights_f32: bad argument");
+    const int kp = round_up(cin + 1, 16), rows128 = round_up(cout, 128);
+    const long long total = static_cast<long long>(rows128) * kp;
     const int blocks = static_cast<int>((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
-    mlp_pack_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, cin, cout, kp, mt,
+    mlp_pack_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, bias, cin, cout, kp, rows128,
                                                                           static_cast<__nv_bfloat16 *>(packed));
     return check_launch("mlp_pack_kernel");
 }
@@ -416,6 +506,7 @@ PCC_API int pcc_mlp_chain(const PccMlpInput *inputs, int n_inputs, int64_t rows,
     MlpIo io{};
     io.n_seg = n_inputs;
     io.out_bf16 = out_dtype;
+    io.timing = g_mlp_timing;
     int ctot = 0;
     for (int s = 0; s < n_inputs; ++s) {
         const PccMlpInput &in = inputs[s];
@@ -432,7 +523,8 @@ PCC_API int pcc_mlp_chain(const PccMlpInput *inputs, int n_inputs, int64_t rows,
     }
     PCC_REQUIRE(ctot == layers[0].cin, "pcc_mlp_chain: input segments carry %d channels, layer 0 expects %d", ctot,
                 layers[0].cin);
-    if (group > 1) {
+    const bool pooled = group > 1;
+    if (pooled) {
         PCC_REQUIRE(rows % group == 0, "pcc_mlp_chain: rows=%lld is not a multiple of group=%d",
                     static_cast<long long>(rows), group);
         const bool ok = (group <= MLP_P) ? (MLP_P % group == 0 && (group <= 32 ? 32 % group == 0 : group % 32 == 0))
@@ -441,35 +533,37 @@ PCC_API int pcc_mlp_chain(const PccMlpInput *inputs, int n_inputs, int64_t rows,
             set_error("pcc_mlp_chain: group=%d must divide %d (and 32) or be a multiple of %d", group, MLP_P, MLP_P);
             return PCC_ERR_UNSUPPORTED;
         }
+        if (group > MLP_P && layers[n_layers - 1].cout > 128) {
+            set_error("pcc_mlp_chain: a max over more than %d rows needs the last layer to have <= 128 channels", MLP_P);
+            return PCC_ERR_UNSUPPORTED;
+        }
     }
     MlpChainParams prm{};
     prm.n_layers = n_layers;
-    int off = 0, max_cols = 0;
-    size_t xa = 0, xb = 0;
+    int off = 0, max_cols = 0, max_kp = 0;
     for (int l = 0; l < n_layers; ++l) {
-        PCC_REQUIRE(layers[l].packed_w && layers[l].bias && layers[l].cin >= 1 && layers[l].cout >= 1,
-                    "pcc_mlp_chain: bad layer %d", l);
+        PCC_REQUIRE(layers[l].packed_w && layers[l].cin >= 1 && layers[l].cout >= 1, "pcc_mlp_chain: bad layer %d", l);
         if (l > 0) PCC_REQUIRE(layers[l].cin == layers[l - 1].cout, "pcc_mlp_chain: layer %d cin != previous cout", l);
         prm.cin[l] = layers[l].cin;
         prm.cout[l] = layers[l].cout;
-        prm.kp[l] = round_up(layers[l].cin, 16);
-        prm.mt[l] = round_up(layers[l].cout, 128) / 128;
+        prm.kp[l] = round_up(layers[l].cin + 1, 16);
         prm.relu[l] = layers[l].relu;
+        prm.tform[l] = (pooled && l == n_layers - 1) ? 1 : 0;
+        prm.w_rows[l] = prm.tform[l] ? round_up(layers[l].cout, 128) : round_up(layers[l].cout, 16);
+        prm.ncol[l] = prm.w_rows[l];
         prm.w[l] = layers[l].packed_w;
-        prm.bias[l] = layers[l].bias;
-        prm.w_bytes[l] = prm.mt[l] * 128 * prm.kp[l] * 2;
         prm.w_off[l] = off;
-        off += prm.w_bytes[l];
-        const size_t xbytes = static_cast<size_t>(MLP_P) * prm.kp[l] * 2;
-        if (l % 2 == 0) xa = xbytes > xa ? xbytes : xa; else xb = xbytes > xb ? xbytes : xb;
-        if (prm.mt[l] * MLP_P > max_cols) max_cols = prm.mt[l] * MLP_P;
+        off += prm.w_rows[l] * prm.kp[l] * 2;
+        if (prm.ncol[l] > max_cols) max_cols = prm.ncol[l];
+        if (prm.kp[l] > max_kp) max_kp = prm.kp[l];
     }
-    if (prm.mt[n_layers - 1] > 8 || max_cols > 512) {
+    if (max_cols > 512) {
         set_error("pcc_mlp_chain: a layer wider than 512 channels (TMEM columns %d) is not supported by this kernel", max_cols);
         return PCC_ERR_UNSUPPORTED;
     }
-    for (int l = 0; l < n_layers; ++l) prm.x_off[l] = off + (l % 2 == 0 ? 0 : static_cast<int>(xa));
-    off += static_cast<int>(xa + xb);
+    off = round_up(off, 128);
+    prm.x_off = off;
+    off += MLP_P * max_kp * 2;
     prm.ctrl_off = off;
     off += 16;
     int cols = 32;

@@ -36,7 +36,7 @@ SIGNATURES = {
 
 class PccMlpLayer(ctypes.Structure):
     """struct PccMlpLayer of include/pcc_b200.h"""
-    _fields_ = [("packed_w", _vp), ("bias", _vp), ("cin", _i), ("cout", _i), ("relu", _i)]
+    _fields_ = [("packed_w", _vp), ("cin", _i), ("cout", _i), ("relu", _i)]
 
 
 class PccMlpInput(ctypes.Structure):
@@ -47,7 +47,7 @@ class PccMlpInput(ctypes.Structure):
 SIGNATURES.update({
     "pcc_mlp_chain": (_i, [ctypes.POINTER(PccMlpInput), _i, _i64, ctypes.POINTER(PccMlpLayer), _i, _i, _vp, _i, _vp]),
     "pcc_mlp_packed_bytes": (_i64, [_i, _i]),
-    "pcc_mlp_pack_weights_f32": (_i, [_vp, _i, _i, _vp, _vp]),
+    "pcc_mlp_pack_weights_f32": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "pcc_mlp_chain_f32": (_i, [_vp, _i64, _i, ctypes.POINTER(PccMlpLayer), _i, _i, _vp, _vp]),
 })
 

@@ -11,6 +11,7 @@ fit (PointNet's 256->512->16 tail, the 1024->16384 decoder Linear) are still iss
 (torch.addmm in bf16 -> cuBLAS) in round 1; the split point is chosen here.  There is no CPU path.
 """
 import ctypes
+import weakref
 
 import torch
 
@@ -31,35 +32,43 @@ def _ru(a, b):
     return (a + b - 1) // b * b
 
 
-def _fused_smem_bytes(dims):
-    """Shared memory the fused kernel needs for a chain with channel sizes dims = [C0, C1, ..., CL]."""
-    w = sum(_ru(co, 128) * _ru(ci, 16) * 2 for ci, co in zip(dims[:-1], dims[1:]))
-    xa = max([_P * _ru(c, 16) * 2 for c in dims[0:-1:2]] or [0])
-    xb = max([_P * _ru(c, 16) * 2 for c in dims[1:-1:2]] or [0])
-    return w + xa + xb + 16
+def _fused_smem_bytes(dims, pooled=False):
+    """Shared memory the fused kernel needs for a chain with channel sizes dims = [C0, C1, ..., CL]
+    (mirrors pcc_mlp_chain: resident packed weights + one activation buffer)."""
+    n = len(dims) - 1
+    w = 0
+    for l, (ci, co) in enumerate(zip(dims[:-1], dims[1:])):
+        rows = _ru(co, 128) if (pooled and l == n - 1) else _ru(co, 16)
+        w += rows * _ru(ci + 1, 16) * 2
+    x = _P * max(_ru(c + 1, 16) for c in dims[:-1]) * 2
+    return _ru(w, 128) + x + 16
 
 
-def _fits(dims):
-    return (len(dims) - 1 <= 6 and _fused_smem_bytes(dims) <= _SMEM_MAX and max(dims[1:]) <= 512)
+def _fits(dims, pooled=False):
+    return (len(dims) - 1 <= 6 and _fused_smem_bytes(dims, pooled) <= _SMEM_MAX and max(dims[1:]) <= 512)
 
 
 def _packed(w, b):
-    """Pack (and cache per parameter version) one layer's weights for the tcgen05 kernel."""
-    key = (w.data_ptr(), w._version, b.data_ptr(), b._version, tuple(w.shape))
+    """Pack (and cache per parameter tensor + version) one layer's weights and bias for the tcgen05 kernel.  The cache
+    entry holds weak references to the tensors, so a recycled address or id can never alias a stale entry."""
+    key = (id(w), id(b))
     hit = _pack_cache.get(key)
-    if hit is None:
-        lib = _lib.load()
-        cout, cin = w.shape
-        wf = w.detach().float().contiguous()
-        buf = torch.empty((lib.pcc_mlp_packed_bytes(cin, cout),), dtype=torch.uint8, device=w.device)
-        with torch.cuda.device(w.device):
-            _lib.check(lib.pcc_mlp_pack_weights_f32(wf.data_ptr(), cin, cout, buf.data_ptr(),
-                                                    torch.cuda.current_stream().cuda_stream), "pcc_mlp_pack_weights_f32")
-        if len(_pack_cache) > 256:
-            _pack_cache.clear()
-        hit = (buf, b.detach().float().contiguous())
-        _pack_cache[key] = hit
-    return hit
+    if hit is not None:
+        rw, rb, vw, vb, buf = hit
+        if rw() is w and rb() is b and vw == w._version and vb == b._version:
+            return buf, None
+    lib = _lib.load()
+    cout, cin = w.shape
+    wf = w.detach().float().contiguous()
+    bf = b.detach().float().contiguous()
+    buf = torch.empty((lib.pcc_mlp_packed_bytes(cin, cout),), dtype=torch.uint8, device=w.device)
+    with torch.cuda.device(w.device):
+        _lib.check(lib.pcc_mlp_pack_weights_f32(wf.data_ptr(), bf.data_ptr(), cin, cout, buf.data_ptr(),
+                                                torch.cuda.current_stream().cuda_stream), "pcc_mlp_pack_weights_f32")
+    if len(_pack_cache) > 256:
+        _pack_cache.clear()
+    _pack_cache[key] = (weakref.ref(w), weakref.ref(b), w._version, b._version, buf)
+    return buf, None
 
 
 def fused_chain(inputs, layers, group=0, out_dtype=torch.float32):
@@ -90,7 +99,7 @@ def fused_chain(inputs, layers, group=0, out_dtype=torch.float32):
     for i, (w, b, relu) in enumerate(layers):
         pw, pb = _packed(w, b)
         keep.append((pw, pb))
-        arr[i] = _lib.PccMlpLayer(pw.data_ptr(), pb.data_ptr(), w.shape[1], w.shape[0], int(bool(relu)))
+        arr[i] = _lib.PccMlpLayer(pw.data_ptr(), w.shape[1], w.shape[0], int(bool(relu)))
     cl = layers[-1][0].shape[0]
     out_rows = M // group if group > 1 else M
     dev = keep[0].device
@@ -106,14 +115,15 @@ _bf16_cache = {}
 
 
 def _bf16(t):
-    key = (t.data_ptr(), t._version, tuple(t.shape))
+    key = id(t)
     hit = _bf16_cache.get(key)
-    if hit is None:
-        if len(_bf16_cache) > 256:
-            _bf16_cache.clear()
-        hit = t.detach().to(torch.bfloat16).contiguous()
-        _bf16_cache[key] = hit
-    return hit
+    if hit is not None and hit[0]() is t and hit[1] == t._version:
+        return hit[2]
+    if len(_bf16_cache) > 256:
+        _bf16_cache.clear()
+    val = t.detach().to(torch.bfloat16).contiguous()
+    _bf16_cache[key] = (weakref.ref(t), t._version, val)
+    return val
 
 
 def library_chain(x, layers, out_dtype=torch.float32):
@@ -130,11 +140,11 @@ def library_chain(x, layers, out_dtype=torch.float32):
 _library_chain = library_chain
 
 
-def _split(layers):
+def _split(layers, pooled=False):
     """Longest prefix of `layers` that fits the fused kernel."""
     dims = [layers[0][0].shape[1]] + [w.shape[0] for w, _, _ in layers]
     n = len(layers)
-    while n > 0 and not _fits(dims[:n + 1]):
+    while n > 0 and not _fits(dims[:n + 1], pooled and n == len(layers)):
         n -= 1
     return n
 

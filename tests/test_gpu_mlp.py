@@ -38,7 +38,7 @@ def ref_chain(x, layers, group, model_bf16):
     h = x.double() if not model_bf16 else x
     for i, (w, b, r) in enumerate(layers):
         if model_bf16:
-            h = rnd(h) @ rnd(w).t() + b
+            h = rnd(h) @ rnd(w).t() + rnd(b)  # the bias is folded into the MMA as a bf16 column
         else:
             h = h @ w.double().t() + b.double()
         if r:
@@ -64,6 +64,10 @@ CASES = [
     ([19, 64, 128], [True, False], 1024, 128),
     ([35, 64, 16], [True, False], 1024, 256),           # max over 256 points spanning two tiles
     ([35, 64, 16], [True, False], 2048, 512),
+    ([20, 100, 48], [True, True], 512, 0),              # Cout not a multiple of 16: ones channel inside a TMEM chunk
+    ([64, 256, 200], [True, False], 512, 0),            # two N chunks? no: N=256 single instruction, ragged last Cout
+    ([30, 300, 8], [True, False], 384, 0),              # Cout > 256: two MMA N chunks
+    ([30, 64, 300], [True, True], 1024, 64),            # pooled last layer with three M tiles
 ]
 
 
