@@ -46,12 +46,15 @@ int64_t pcc_launch_count(void);
  * and pytorch3d.ops.sample_farthest_points (/root/reference/pointnet_sa_module.py:10-13): start_idx = NULL
  * (start at index 0), init_dist = FLT_MAX.
  * out_idx[B, npoint] int64; entries k >= N are -1 (PyTorch3D padding when npoint > N).
+ * out_xyz (nullable) [B, npoint, 3]: the sampled points themselves -- the index_points / gather call that follows every
+ * reference FPS call (compress.py:96, pointnet_sa_module.py:68) -- snapped to the octree grid when quant_cube > 0
+ * (floor(c / cube) * cube + cube / 2, octree_np.py:114-133); padded entries are 0.
  * Clouds with N > 8192 are spread over several co-resident CTAs and need a device `workspace` of
  * pcc_fps_workspace_bytes(B, N, npoint) bytes (0 for N <= 8192 -> NULL allowed).
  */
 int64_t pcc_fps_workspace_bytes(int B, int N, int npoint);
 int pcc_fps_f32(const float *xyz, int B, int N, int npoint, const int64_t *start_idx, float init_dist,
-                int64_t *out_idx, void *workspace, void *stream);
+                int64_t *out_idx, float *out_xyz, float quant_cube, void *workspace, void *stream);
 
 /*
  * K nearest neighbours of every q[b, i] among p[b, :], ascending in (d2, idx).
@@ -119,6 +122,18 @@ int pcc_chamfer_bwd_f32(const float *x, const float *y, const int64_t *ix, const
                         int P2, const float *grad_loss, float *gx, float *gy, void *stream);
 
 /*
+ * Element-wise glue of the batched codec driver.
+ * pcc_normalize_f32: pn_kit.normalize (/root/reference/pn_kit.py:47-60) per cloud: out = (p - center) * (1 - margin) /
+ *   longest + 0.5; center [B,3], longest [B], bbox [B,6] (min xyz, max xyz) are optional outputs.
+ * pcc_assemble_f32: decompress.py:104-116 -- patches [B*S,k,3] / patch_scale + centres [B,S,3], then pn_kit.denormalize
+ *   with center / longest (both NULL: skip the de-normalisation); out [B, S*k, 3].
+ */
+int pcc_normalize_f32(const float *xyz, int B, int N, float margin, float *out, float *center, float *longest, float *bbox,
+                      void *stream);
+int pcc_assemble_f32(const float *patches, const float *centres, const float *center, const float *longest, int B, int S,
+                     int k, float patch_scale, float margin, float *out, void *stream);
+
+/*
  * Fused shared-MLP chain on the tensor cores (tcgen05, bf16 operands, fp32 accumulation):
  *     y = act_L(W_L . ... act_1(W_1 . x + b_1) ... + b_L)      per row of x [rows, ldx] (first cin columns used),
  * optionally followed by a max over every run of `group` consecutive rows (group <= 1: none).
@@ -139,6 +154,8 @@ typedef struct PccMlpLayer {
     const void *packed_w; /* device, from pcc_mlp_pack_weights_f32 (weights and bias) */
     int cin, cout;
     int relu;             /* apply max(x, 0) after this layer */
+    const float *w_f32;   /* optional: the raw [cout, cin] fp32 weights and [cout] bias (device).  When layer 0 has  */
+    const float *b_f32;   /* cin <= 8 and these are given, it runs in fp32 on the CUDA cores (inputs not rounded).   */
 } PccMlpLayer;
 /* One input segment: rows of `channels` values taken from ptr[(row / row_div) * ld + 0..channels), fp32 (dtype 0) or
  * bf16 (dtype 1).  Segments are concatenated along the channel axis in order (the torch.cat of AE.py:39,51 without

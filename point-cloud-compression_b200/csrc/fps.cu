@@ -93,10 +93,24 @@ __device__ __forceinline__ void select_slot(const float (&px)[PPT], const float 
         }
 }
 
+// Optional fused epilogue: the sampled point itself (the index_points gather that follows every FPS call), optionally
+// snapped to the octree grid: floor(c / cube) * cube + cube / 2 (octree_np.getDecodeFromPc, octree_np.py:114-133).
+__device__ __forceinline__ void store_centre(float *o, float x, float y, float z, float cube) {
+    if (cube > 0.0f) {
+        const float h = __fmul_rn(cube, 0.5f);
+        x = __fadd_rn(__fmul_rn(floorf(__fdiv_rn(x, cube)), cube), h);
+        y = __fadd_rn(__fmul_rn(floorf(__fdiv_rn(y, cube)), cube), h);
+        z = __fadd_rn(__fmul_rn(floorf(__fdiv_rn(z, cube)), cube), h);
+    }
+    o[0] = x;
+    o[1] = y;
+    o[2] = z;
+}
+
 template <int THREADS, int PPT>
 __global__ void __launch_bounds__(THREADS, 1)
 fps_block_kernel(const float *__restrict__ xyz, int N, int npoint, const int64_t *__restrict__ start_idx,
-                 float init_dist, int64_t *__restrict__ out_idx) {
+                 float init_dist, int64_t *__restrict__ out_idx, float *__restrict__ out_xyz, float quant_cube) {
     constexpr int NWARPS = THREADS / 32;
     __shared__ FpsSlots slots;
     const int b = blockIdx.x;
@@ -119,12 +133,21 @@ fps_block_kernel(const float *__restrict__ xyz, int N, int npoint, const int64_t
         }
     }
     const int k_n = npoint < N ? npoint : N;
-    for (int k = k_n + tid; k < npoint; k += THREADS) out[k] = -1;  // PyTorch3D padding when npoint > N
+    for (int k = k_n + tid; k < npoint; k += THREADS) {  // PyTorch3D padding when npoint > N
+        out[k] = -1;
+        if (out_xyz) {
+            float *o = out_xyz + (static_cast<size_t>(b) * npoint + k) * 3;
+            o[0] = o[1] = o[2] = 0.0f;
+        }
+    }
 
     int far = start_idx ? static_cast<int>(start_idx[b]) : 0;
     float cx = pc[far * 3 + 0], cy = pc[far * 3 + 1], cz = pc[far * 3 + 2];
     for (int i = 0; i < k_n; ++i) {
-        if (tid == 0) out[i] = far;
+        if (tid == 0) {
+            out[i] = far;
+            if (out_xyz) store_centre(out_xyz + (static_cast<size_t>(b) * npoint + i) * 3, cx, cy, cz, quant_cube);
+        }
         if (i == k_n - 1) break;
         unsigned bits;
         int slot;
@@ -151,7 +174,8 @@ constexpr int GRID_PTS_PER_CTA = GRID_THREADS * GRID_PPT;
 
 __global__ void __launch_bounds__(GRID_THREADS, 1)
 fps_grid_kernel(const float *__restrict__ xyz, int N, int npoint, const int64_t *__restrict__ start_idx,
-                float init_dist, int64_t *__restrict__ out_idx, FpsGridWs *ws, int ctas_per_cloud, int cloud0) {
+                float init_dist, int64_t *__restrict__ out_idx, FpsGridWs *ws, int ctas_per_cloud, int cloud0,
+                float *__restrict__ out_xyz, float quant_cube) {
     constexpr int NWARPS = GRID_THREADS / 32;
     __shared__ FpsSlots slots;
     __shared__ unsigned long long s_win;
@@ -180,13 +204,22 @@ fps_grid_kernel(const float *__restrict__ xyz, int N, int npoint, const int64_t 
     }
     const int k_n = npoint < N ? npoint : N;
     if (part == 0)
-        for (int k = k_n + tid; k < npoint; k += GRID_THREADS) out[k] = -1;
+        for (int k = k_n + tid; k < npoint; k += GRID_THREADS) {
+            out[k] = -1;
+            if (out_xyz) {
+                float *o = out_xyz + (static_cast<size_t>(b) * npoint + k) * 3;
+                o[0] = o[1] = o[2] = 0.0f;
+            }
+        }
 
     int far = start_idx ? static_cast<int>(start_idx[b]) : 0;
     float cx = pc[static_cast<size_t>(far) * 3 + 0], cy = pc[static_cast<size_t>(far) * 3 + 1],
           cz = pc[static_cast<size_t>(far) * 3 + 2];
     for (int i = 0; i < k_n; ++i) {
-        if (part == 0 && tid == 0) out[i] = far;
+        if (part == 0 && tid == 0) {
+            out[i] = far;
+            if (out_xyz) store_centre(out_xyz + (static_cast<size_t>(b) * npoint + i) * 3, cx, cy, cz, quant_cube);
+        }
         if (i == k_n - 1) break;
         unsigned bits;
         int slot;
@@ -223,8 +256,8 @@ fps_grid_kernel(const float *__restrict__ xyz, int N, int npoint, const int64_t 
 
 template <int THREADS, int PPT>
 static int launch_block(const float *xyz, int B, int N, int npoint, const int64_t *start_idx, float init_dist,
-                        int64_t *out_idx, cudaStream_t st) {
-    fps_block_kernel<THREADS, PPT><<<B, THREADS, 0, st>>>(xyz, N, npoint, start_idx, init_dist, out_idx);
+                        int64_t *out_idx, float *out_xyz, float quant_cube, cudaStream_t st) {
+    fps_block_kernel<THREADS, PPT><<<B, THREADS, 0, st>>>(xyz, N, npoint, start_idx, init_dist, out_idx, out_xyz, quant_cube);
     return check_launch("fps_block_kernel");
 }
 
@@ -237,19 +270,19 @@ PCC_API int64_t pcc_fps_workspace_bytes(int B, int N, int npoint) {
 }
 
 PCC_API int pcc_fps_f32(const float *xyz, int B, int N, int npoint, const int64_t *start_idx, float init_dist,
-                        int64_t *out_idx, void *workspace, void *stream) {
+                        int64_t *out_idx, float *out_xyz, float quant_cube, void *workspace, void *stream) {
     using namespace pcc;
     PCC_REQUIRE(xyz && out_idx, "pcc_fps_f32: null pointer");
     PCC_REQUIRE(B >= 0 && N >= 1 && npoint >= 0, "pcc_fps_f32: bad shape B=%d N=%d npoint=%d", B, N, npoint);
     if (B == 0 || npoint == 0) return 0;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (N <= 128) return launch_block<128, 1>(xyz, B, N, npoint, start_idx, init_dist, out_idx, st);
-    if (N <= 256) return launch_block<128, 2>(xyz, B, N, npoint, start_idx, init_dist, out_idx, st);
-    if (N <= 512) return launch_block<128, 4>(xyz, B, N, npoint, start_idx, init_dist, out_idx, st);
-    if (N <= 1024) return launch_block<256, 4>(xyz, B, N, npoint, start_idx, init_dist, out_idx, st);
-    if (N <= 2048) return launch_block<512, 4>(xyz, B, N, npoint, start_idx, init_dist, out_idx, st);
-    if (N <= 4096) return launch_block<1024, 4>(xyz, B, N, npoint, start_idx, init_dist, out_idx, st);
-    if (N <= 8192) return launch_block<1024, 8>(xyz, B, N, npoint, start_idx, init_dist, out_idx, st);
+    if (N <= 128) return launch_block<128, 1>(xyz, B, N, npoint, start_idx, init_dist, out_idx, out_xyz, quant_cube, st);
+    if (N <= 256) return launch_block<128, 2>(xyz, B, N, npoint, start_idx, init_dist, out_idx, out_xyz, quant_cube, st);
+    if (N <= 512) return launch_block<128, 4>(xyz, B, N, npoint, start_idx, init_dist, out_idx, out_xyz, quant_cube, st);
+    if (N <= 1024) return launch_block<256, 4>(xyz, B, N, npoint, start_idx, init_dist, out_idx, out_xyz, quant_cube, st);
+    if (N <= 2048) return launch_block<512, 4>(xyz, B, N, npoint, start_idx, init_dist, out_idx, out_xyz, quant_cube, st);
+    if (N <= 4096) return launch_block<1024, 4>(xyz, B, N, npoint, start_idx, init_dist, out_idx, out_xyz, quant_cube, st);
+    if (N <= 8192) return launch_block<1024, 8>(xyz, B, N, npoint, start_idx, init_dist, out_idx, out_xyz, quant_cube, st);
 
     // multi-CTA path: C co-resident CTAs per cloud, as many clouds per cooperative launch as fit.
     PCC_REQUIRE(workspace, "pcc_fps_f32: N=%d needs a workspace of pcc_fps_workspace_bytes()", N);
@@ -269,7 +302,7 @@ PCC_API int pcc_fps_f32(const float *xyz, int B, int N, int npoint, const int64_
             return static_cast<int>(e);
         }
         int ctas = C, cloud0 = c0;
-        void *args[] = {&xyz, &N, &npoint, &start_idx, &init_dist, &out_idx, &ws, &ctas, &cloud0};
+        void *args[] = {&xyz, &N, &npoint, &start_idx, &init_dist, &out_idx, &ws, &ctas, &cloud0, &out_xyz, &quant_cube};
         e = cudaLaunchCooperativeKernel(reinterpret_cast<void *>(fps_grid_kernel), dim3(nc * C), dim3(GRID_THREADS),
                                         args, 0, st);
         if (e != cudaSuccess) {

@@ -286,6 +286,9 @@ knn_thread_kernel(const float *__restrict__ q, const float *__restrict__ p, int 
     constexpr int STAGE_BYTES = KT_THREADS * STAGE_LD * 4;
     __shared__ __align__(16) unsigned char smem_raw[TILE_BYTES > STAGE_BYTES ? TILE_BYTES : STAGE_BYTES];
     __shared__ float sq[KT_THREADS * 3];
+    constexpr int PB = KT <= 16 ? 8 : 4;  // pending queue depth (shared memory budget)
+    __shared__ float pend_d[PB][KT_THREADS];
+    __shared__ unsigned pend_i[PB][KT_THREADS];
     float4 *tile = reinterpret_cast<float4 *>(smem_raw);
     unsigned *stage = reinterpret_cast<unsigned *>(smem_raw);
 
@@ -293,7 +296,7 @@ knn_thread_kernel(const float *__restrict__ q, const float *__restrict__ p, int 
     const int q0 = blockIdx.x * KT_THREADS;
     const int qi = q0 + threadIdx.x;
     const bool active = qi < P1;
-    const float *pc = p + static_cast<size_t>(b) * P2 * 3;
+    const float *pc_ = p + static_cast<size_t>(b) * P2 * 3;
 
     float qx = 0.f, qy = 0.f, qz = 0.f;
     if (active) {
@@ -314,33 +317,57 @@ knn_thread_kernel(const float *__restrict__ q, const float *__restrict__ p, int 
         il[s] = 0u;
     }
 
+    // Sorted insertion costs ~5 instructions per list slot and, thread-per-query, a warp pays it whenever ANY lane
+    // inserts -- i.e. for almost every candidate.  Candidates that beat the (possibly stale) K-th best are therefore only
+    // parked in a per-thread shared-memory queue (2 predicated stores); the warp drains all queues, in candidate order,
+    // when one of them is full.  The result is identical to immediate insertion: the list changes only through the same
+    // insertions in the same order, and a stale threshold only lets extra candidates through to the exact re-test.
+    int pc = 0;
+    float worst = __int_as_float(0x7f800000);
+    auto insert = [&](float d, unsigned j) {
+        if (d < dl[KT - 1]) {  // strict: an equal distance with a larger index never displaces
+            dl[KT - 1] = d;
+            il[KT - 1] = j;
+#pragma unroll
+            for (int s = KT - 1; s > 0; --s) {
+                const bool sw = dl[s] < dl[s - 1];  // strict keeps earlier (lower) indices first on ties
+                const float dlo = sw ? dl[s] : dl[s - 1], dhi = sw ? dl[s - 1] : dl[s];
+                const unsigned ilo = sw ? il[s] : il[s - 1], ihi = sw ? il[s - 1] : il[s];
+                dl[s - 1] = dlo;
+                dl[s] = dhi;
+                il[s - 1] = ilo;
+                il[s] = ihi;
+            }
+        }
+    };
+    auto drain = [&]() {
+        const int n = __reduce_max_sync(FULL_MASK, pc);
+        for (int s = 0; s < n; ++s)
+            if (s < pc) insert(pend_d[s][threadIdx.x], pend_i[s][threadIdx.x]);
+        pc = 0;
+        worst = dl[KT - 1];
+    };
+
     for (int t0 = 0; t0 < P2; t0 += KNN_TILE) {
         const int tn = min(KNN_TILE, P2 - t0);
         __syncthreads();
         for (int pt = threadIdx.x; pt < tn; pt += KT_THREADS) {
-            const float *s = pc + static_cast<size_t>(t0 + pt) * 3;
+            const float *s = pc_ + static_cast<size_t>(t0 + pt) * 3;
             tile[pt] = make_float4(s[0], s[1], s[2], 0.f);
         }
         __syncthreads();
         for (int j = 0; j < tn; ++j) {
             const float4 c = tile[j];
             const float d = dist2_rn(qx, qy, qz, c.x, c.y, c.z);
-            if (d < dl[KT - 1]) {  // strict: an equal distance with a larger index never displaces
-                dl[KT - 1] = d;
-                il[KT - 1] = static_cast<unsigned>(t0 + j);
-#pragma unroll
-                for (int s = KT - 1; s > 0; --s) {
-                    const bool sw = dl[s] < dl[s - 1];  // strict keeps earlier (lower) indices first on ties
-                    const float dlo = sw ? dl[s] : dl[s - 1], dhi = sw ? dl[s - 1] : dl[s];
-                    const unsigned ilo = sw ? il[s] : il[s - 1], ihi = sw ? il[s - 1] : il[s];
-                    dl[s - 1] = dlo;
-                    dl[s] = dhi;
-                    il[s - 1] = ilo;
-                    il[s] = ihi;
-                }
+            if (d < worst) {
+                pend_d[pc][threadIdx.x] = d;
+                pend_i[pc][threadIdx.x] = static_cast<unsigned>(t0 + j);
+                ++pc;
             }
+            if (__any_sync(FULL_MASK, pc == PB)) drain();
         }
     }
+    drain();
     __syncthreads();  // tile no longer needed: reuse as output staging
 
     const int nq = min(KT_THREADS, P1 - q0);
@@ -371,7 +398,7 @@ knn_thread_kernel(const float *__restrict__ q, const float *__restrict__ p, int 
         for (int e = threadIdx.x; e < nq * K * 3; e += KT_THREADS) {
             const int pk = e / 3, c = e - pk * 3;
             const int ql = pk / K, k = pk - ql * K;
-            float v = pc[static_cast<size_t>(stage[ql * STAGE_LD + k]) * 3 + c];
+            float v = pc_[static_cast<size_t>(stage[ql * STAGE_LD + k]) * 3 + c];
             if (centre_sub) v = __fsub_rn(v, sq[ql * 3 + c]);
             if (nn_scale != 1.0f) v = __fmul_rn(v, nn_scale);
             out_nn[obase * 3 + e] = v;

@@ -20,7 +20,7 @@ SIGNATURES = {
     "pcc_last_error_string": (ctypes.c_char_p, []),
     "pcc_launch_count": (_i64, []),
     "pcc_fps_workspace_bytes": (_i64, [_i, _i, _i]),
-    "pcc_fps_f32": (_i, [_vp, _i, _i, _i, _vp, _f, _vp, _vp, _vp]),
+    "pcc_fps_f32": (_i, [_vp, _i, _i, _i, _vp, _f, _vp, _vp, _f, _vp, _vp]),
     "pcc_knn_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _f, _vp]),
     "pcc_ball_query_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
     "pcc_gather_f32": (_i, [_vp, _vp, _i, _i, _i, _i64, _vp, _vp]),
@@ -36,7 +36,7 @@ SIGNATURES = {
 
 class PccMlpLayer(ctypes.Structure):
     """struct PccMlpLayer of include/pcc_b200.h"""
-    _fields_ = [("packed_w", _vp), ("cin", _i), ("cout", _i), ("relu", _i)]
+    _fields_ = [("packed_w", _vp), ("cin", _i), ("cout", _i), ("relu", _i), ("w_f32", _vp), ("b_f32", _vp)]
 
 
 class PccMlpInput(ctypes.Structure):
@@ -45,6 +45,8 @@ class PccMlpInput(ctypes.Structure):
 
 
 SIGNATURES.update({
+    "pcc_normalize_f32": (_i, [_vp, _i, _i, _f, _vp, _vp, _vp, _vp, _vp]),
+    "pcc_assemble_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _vp, _vp]),
     "pcc_mlp_chain": (_i, [ctypes.POINTER(PccMlpInput), _i, _i64, ctypes.POINTER(PccMlpLayer), _i, _i, _vp, _i, _vp]),
     "pcc_mlp_packed_bytes": (_i64, [_i, _i]),
     "pcc_mlp_pack_weights_f32": (_i, [_vp, _vp, _i, _i, _vp, _vp]),

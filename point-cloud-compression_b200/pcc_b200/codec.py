@@ -13,7 +13,6 @@ import torch
 
 from . import ops
 from .modules import AE
-from .pn_kit_ops import farthest_point_sample_batch, index_points
 
 
 def normalize_batch(pc, margin=0.01):
@@ -49,52 +48,49 @@ class PatchCodec:
 
     @torch.no_grad()
     def compress(self, xyz, start_idx=None):
-        """xyz [B,N,3] on the device -> dict(latent_q [B,S,d], centres [B,S,3], center, longest, patches)."""
+        """xyz [B,N,3] on the device -> dict(latent_q [B,S,d], centres [B,S,3], center, longest, bbox, ...)."""
         B, N, _ = xyz.shape
         K = self.ae.K
         S = int(N * self.alpha // K)                                              # compress.py:93
-        pc, center, longest = normalize_batch(xyz)                                # compress.py:90
-        if start_idx is None:
-            idx = farthest_point_sample_batch(pc, S)                              # compress.py:96 (CPU RNG draw)
-        else:
-            idx = ops.fps(pc, S, start_idx, 1e10)
-        rec_centres = quantise_centres(index_points(pc, idx), self.centre_depth)  # compress.py:98-101
+        pc, center, longest, bbox = ops.normalize(xyz)                            # compress.py:90 (one fused kernel)
+        if start_idx is None:                                                     # compress.py:96 (CPU RNG draw, pn_kit.py:321)
+            start_idx = torch.randint(0, N, (B,), dtype=torch.long).to(xyz.device)
+        cube = 1.0 / max(1.0, math.pow(2.0, min(self.centre_depth, 30)))
+        _, rec_centres = ops.fps(pc, S, start_idx, 1e10, return_xyz=True, quant_cube=cube)  # compress.py:96-101
         _, _, patches = ops.knn(rec_centres, pc, K, return_nn=True, centre_sub=True,
                                 nn_scale=self.patch_scale(N), nn_only=True)       # compress.py:105-108
         latent, latent_q = self.ae.encode_patches(patches.view(B * S, K, 3))      # compress.py:113-127
         return dict(latent_q=latent_q.view(B, S, -1), latent=latent.view(B, S, -1), centres=rec_centres, center=center,
-                    longest=longest, pc=pc)
+                    longest=longest, bbox=bbox, pc=pc)
 
     @torch.no_grad()
     def decompress(self, latent_q, centres, N, center=None, longest=None):
         """latent_q [B,S,d], centres [B,S,3] -> reconstructed cloud [B, S*k, 3] (decompress.py:96-116)."""
         B, S, d = latent_q.shape
         patches = self.ae.decode_patches(latent_q.reshape(B * S, d))              # decompress.py:96-102
-        patches = patches / self.patch_scale(N)                                   # decompress.py:105
-        pc = (patches.view(B, S, -1, 3) + centres.view(B, S, 1, 3)).reshape(B, -1, 3)
-        if center is not None:
-            pc = denormalize_batch(pc, center, longest)                           # decompress.py:113-116
-        return pc
+        return ops.assemble(patches, centres, self.patch_scale(N), center, longest)  # decompress.py:104-116
 
     @torch.no_grad()
-    def evaluate(self, decomp, original):
+    def evaluate(self, decomp, original, bbox=None):
         """Per-cloud metrics of eval.py: normalised Chamfer distance (eval.py:199-205, pred first) and D1 PSNR
         (eval.py:68-92: recon -> original 1-NN, peak = bbox diagonal of the original).  Returns [B,3]
-        (chamfer, d1_psnr_db, d1_mse).  The 1-NN distances of both metrics come from ONE Chamfer launch: the
-        normalisation is a uniform scale, so d2_original = d2_normalised * (max-min)^2."""
-        mn = original.amin(dim=(1, 2), keepdim=True)
-        mx = original.amax(dim=(1, 2), keepdim=True)
-        scale = mx - mn
-        r = ops.chamfer_forward((decomp - mn) / scale, (original - mn) / scale, want_idx=False)
-        mse = r["dx"].double().mean(dim=1) * scale.view(-1).double() ** 2
-        ext = original.amax(dim=1) - original.amin(dim=1)
-        diag2 = (ext.double() ** 2).sum(dim=1)
+        (chamfer, d1_psnr_db, d1_mse).  Both metrics come from ONE Chamfer launch on the raw clouds: eval.py's
+        normalisation (p - min) / (max - min) is a uniform scale + shift, so the normalised squared distances are the
+        raw ones divided by (max - min)^2, and the 1-NN assignment does not change."""
+        if bbox is None:
+            bbox = torch.cat((original.amin(dim=1), original.amax(dim=1)), dim=1)
+        bbox = bbox.double()
+        scale = bbox[:, 3:].amax(dim=1) - bbox[:, :3].amin(dim=1)                 # global max - global min (eval.py:199-200)
+        diag2 = ((bbox[:, 3:] - bbox[:, :3]) ** 2).sum(dim=1)                     # eval.py:88-89
+        r = ops.chamfer_forward(decomp, original, want_idx=False)
+        mse = r["dx"].double().mean(dim=1)                                        # eval.py:84 (recon -> original)
+        cham = r["per_cloud"].double() / (scale * scale)
         psnr = 10.0 * torch.log10(diag2 / mse)
-        return torch.stack((r["per_cloud"].double(), psnr, mse), dim=1)
+        return torch.stack((cham, psnr, mse), dim=1)
 
     @torch.no_grad()
     def roundtrip(self, xyz, start_idx=None):
-        """compress -> decompress -> eval for a batch; returns (latent_q int8 [B,S,d], centres, metrics [B,3])."""
+        """compress -> decompress -> eval for a batch; returns (latent_q int8 [B,S,d], centres, metrics [B,3], rec)."""
         c = self.compress(xyz, start_idx)
         rec = self.decompress(c["latent_q"], c["centres"], xyz.shape[1], c["center"], c["longest"])
-        return c["latent_q"].to(torch.int8), c["centres"], self.evaluate(rec, xyz), rec
+        return c["latent_q"].to(torch.int8), c["centres"], self.evaluate(rec, xyz, c["bbox"]), rec

@@ -40,23 +40,30 @@ def _fused_smem_bytes(dims, pooled=False):
     for l, (ci, co) in enumerate(zip(dims[:-1], dims[1:])):
         rows = _ru(co, 128) if (pooled and l == n - 1) else _ru(co, 16)
         w += rows * _ru(ci + 1, 16) * 2
-    x = _P * max(_ru(c + 1, 16) for c in dims[:-1]) * 2
-    return _ru(w, 128) + x + 16
+    x0 = _P * _ru(dims[0] + 1, 16) * 2
+    x = _P * max([_ru(c + 1, 16) for c in dims[1:-1]] or [0]) * 2
+    return _ru(w, 128) + x0 + x + 32 + 4096  # + first-layer fp32 weights when that layer runs on the CUDA cores
 
 
 def _fits(dims, pooled=False):
     return (len(dims) - 1 <= 6 and _fused_smem_bytes(dims, pooled) <= _SMEM_MAX and max(dims[1:]) <= 512)
 
 
+def _base(t):
+    return t._base if t._base is not None else t
+
+
 def _packed(w, b):
-    """Pack (and cache per parameter tensor + version) one layer's weights and bias for the tcgen05 kernel.  The cache
-    entry holds weak references to the tensors, so a recycled address or id can never alias a stale entry."""
-    key = (id(w), id(b))
+    """Pack (and cache) one layer's weights and bias for the tcgen05 kernel.  The cache is keyed on the parameter
+    tensors that own the storage (`w` is usually a fresh `.flatten(1)` view of a Conv2d weight on every call) plus the
+    view geometry, and holds weak references + version counters, so an in-place update or a recycled id re-packs."""
+    bw, bb = _base(w), _base(b)
+    key = (id(bw), id(bb), w.data_ptr(), tuple(w.shape), tuple(w.stride()), b.data_ptr())
     hit = _pack_cache.get(key)
     if hit is not None:
-        rw, rb, vw, vb, buf = hit
-        if rw() is w and rb() is b and vw == w._version and vb == b._version:
-            return buf, None
+        rw, rb, vw, vb, val = hit
+        if rw() is bw and rb() is bb and vw == bw._version and vb == bb._version:
+            return val
     lib = _lib.load()
     cout, cin = w.shape
     wf = w.detach().float().contiguous()
@@ -67,8 +74,9 @@ def _packed(w, b):
                                                 torch.cuda.current_stream().cuda_stream), "pcc_mlp_pack_weights_f32")
     if len(_pack_cache) > 256:
         _pack_cache.clear()
-    _pack_cache[key] = (weakref.ref(w), weakref.ref(b), w._version, b._version, buf)
-    return buf, None
+    val = (buf, wf, bf)
+    _pack_cache[key] = (weakref.ref(bw), weakref.ref(bb), bw._version, bb._version, val)
+    return val
 
 
 def fused_chain(inputs, layers, group=0, out_dtype=torch.float32):
@@ -97,9 +105,9 @@ def fused_chain(inputs, layers, group=0, out_dtype=torch.float32):
         segs[i] = _lib.PccMlpInput(t.data_ptr(), 0 if t.dtype == torch.float32 else 1, t.shape[1], t.stride(0), div)
     arr = (_lib.PccMlpLayer * len(layers))()
     for i, (w, b, relu) in enumerate(layers):
-        pw, pb = _packed(w, b)
-        keep.append((pw, pb))
-        arr[i] = _lib.PccMlpLayer(pw.data_ptr(), w.shape[1], w.shape[0], int(bool(relu)))
+        pw, wf, bf = _packed(w, b)
+        keep.append((pw, wf, bf))
+        arr[i] = _lib.PccMlpLayer(pw.data_ptr(), w.shape[1], w.shape[0], int(bool(relu)), wf.data_ptr(), bf.data_ptr())
     cl = layers[-1][0].shape[0]
     out_rows = M // group if group > 1 else M
     dev = keep[0].device
@@ -115,14 +123,15 @@ _bf16_cache = {}
 
 
 def _bf16(t):
-    key = id(t)
+    bt = _base(t)
+    key = (id(bt), t.data_ptr(), tuple(t.shape), tuple(t.stride()))
     hit = _bf16_cache.get(key)
-    if hit is not None and hit[0]() is t and hit[1] == t._version:
+    if hit is not None and hit[0]() is bt and hit[1] == bt._version:
         return hit[2]
     if len(_bf16_cache) > 256:
         _bf16_cache.clear()
     val = t.detach().to(torch.bfloat16).contiguous()
-    _bf16_cache[key] = (weakref.ref(t), t._version, val)
+    _bf16_cache[key] = (weakref.ref(bt), bt._version, val)
     return val
 
 
@@ -149,31 +158,45 @@ def _split(layers, pooled=False):
     return n
 
 
+def _materialise(inputs):
+    """Concatenate input segments into one [M, C] tensor (only needed in front of a library GEMM)."""
+    if isinstance(inputs, torch.Tensor):
+        return inputs
+    parts = []
+    for t, div in inputs:
+        t = t.reshape(-1, t.shape[-1])
+        parts.append(t.repeat_interleave(div, dim=0) if div > 1 else t)
+    return parts[0] if len(parts) == 1 else torch.cat([p.float() for p in parts], dim=1)
+
+
+def run_chain(inputs, layers, group=0, out_dtype=torch.float32):
+    """Shared-MLP chain of any size: greedy runs of layers that fit the fused tcgen05 kernel (activations stay on the
+    SM inside a run, bf16 in HBM between runs); a layer whose weights alone exceed shared memory is a library GEMM."""
+    L = len(layers)
+    cur, i = inputs, 0
+    pooled_done = False
+    while i < L:
+        n = _split(layers[i:], pooled=group > 1)
+        if n > 0:
+            last = i + n == L
+            cur = fused_chain(cur, layers[i:i + n], group if last else 0, out_dtype if last else torch.bfloat16)
+            pooled_done = last and group > 1
+            i += n
+        else:
+            cur = library_chain(_materialise(cur), layers[i:i + 1], out_dtype if i + 1 == L else torch.bfloat16)
+            i += 1
+    if group > 1 and not pooled_done:
+        cur = cur.view(-1, group, cur.shape[1]).max(dim=1)[0]
+    return cur
+
+
 def mlp_chain(x, layers):
     _check(x)
-    n = _split(layers)
-    if n == len(layers):
-        return fused_chain(x, layers)
-    if n > 0:
-        x = fused_chain(x, layers[:n])
-    if x.shape[0] <= _CHUNK_ROWS:
-        return _library_chain(x, layers[n:])
-    return torch.cat([_library_chain(x[i:i + _CHUNK_ROWS], layers[n:]) for i in range(0, x.shape[0], _CHUNK_ROWS)])
+    return run_chain(x, layers, 0)
 
 
 def mlp_chain_groupmax(x, layers, group):
     _check(x)
-    M = x.shape[0]
-    if M % group:
+    if x.shape[0] % group:
         raise ValueError("pcc_b200.mlp_chain_groupmax: rows must be a multiple of the group size")
-    n = _split(layers)
-    if n == len(layers):
-        return fused_chain(x, layers, group)
-    if n > 0:
-        x = fused_chain(x, layers[:n])
-    step = max(group, (_CHUNK_ROWS // group) * group)
-    outs = []
-    for i in range(0, M, step):
-        y = _library_chain(x[i:i + step], layers[n:])
-        outs.append(y.view(-1, group, y.shape[1]).max(dim=1)[0])
-    return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
+    return run_chain(x, layers, group)

@@ -39,21 +39,53 @@ def _check_pair(p1, p2):
         raise ValueError("pcc_b200: only 3-D points are supported (pts1 and pts2 must have the same point dimension 3).")
 
 
-def fps(xyz, npoint, start_idx=None, init_dist=1e10):
-    """Farthest point sampling.  start_idx [B] int64 (device) or None (= start at 0).  Returns int64 [B,npoint]."""
+def fps(xyz, npoint, start_idx=None, init_dist=1e10, return_xyz=False, quant_cube=0.0):
+    """Farthest point sampling.  start_idx [B] int64 (device) or None (= start at 0).  Returns int64 [B,npoint];
+    with return_xyz also the sampled points [B,npoint,3] (snapped to the octree grid when quant_cube > 0)."""
     lib = _lib.load()
     xyz = _cuda_f32(xyz, "xyz")
     B, N, C = xyz.shape
     if C != 3:
         raise ValueError("pcc_b200.fps: xyz must be [B, N, 3]")
     out = torch.empty((B, npoint), dtype=torch.int64, device=xyz.device)
+    out_xyz = torch.empty((B, npoint, 3), dtype=torch.float32, device=xyz.device) if return_xyz else None
     if start_idx is not None:
         start_idx = start_idx.to(device=xyz.device, dtype=torch.int64).contiguous()
     with torch.cuda.device(xyz.device):
         ws_bytes = lib.pcc_fps_workspace_bytes(B, N, npoint)
         ws = torch.empty((max(ws_bytes, 1),), dtype=torch.uint8, device=xyz.device) if ws_bytes else None
-        _lib.check(lib.pcc_fps_f32(_ptr(xyz), B, N, npoint, _ptr(start_idx), init_dist, _ptr(out), _ptr(ws), _stream()),
-                   "pcc_fps_f32")
+        _lib.check(lib.pcc_fps_f32(_ptr(xyz), B, N, npoint, _ptr(start_idx), init_dist, _ptr(out), _ptr(out_xyz),
+                                   float(quant_cube), _ptr(ws), _stream()), "pcc_fps_f32")
+    return (out, out_xyz) if return_xyz else out
+
+
+def normalize(xyz, margin=0.01):
+    """pn_kit.normalize per cloud (pn_kit.py:47-60): (normalised [B,N,3], center [B,3], longest [B], bbox [B,6])."""
+    lib = _lib.load()
+    xyz = _cuda_f32(xyz, "xyz")
+    B, N, _ = xyz.shape
+    out = torch.empty_like(xyz)
+    center = torch.empty((B, 3), dtype=torch.float32, device=xyz.device)
+    longest = torch.empty((B,), dtype=torch.float32, device=xyz.device)
+    bbox = torch.empty((B, 6), dtype=torch.float32, device=xyz.device)
+    with torch.cuda.device(xyz.device):
+        _lib.check(lib.pcc_normalize_f32(_ptr(xyz), B, N, float(margin), _ptr(out), _ptr(center), _ptr(longest), _ptr(bbox),
+                                         _stream()), "pcc_normalize_f32")
+    return out, center, longest, bbox
+
+
+def assemble(patches, centres, patch_scale, center=None, longest=None, margin=0.01):
+    """decompress.py:104-116: patches [B*S,k,3] / patch_scale + centres [B,S,3] (+ denormalise) -> [B, S*k, 3]."""
+    lib = _lib.load()
+    patches, centres = _cuda_f32(patches, "patches"), _cuda_f32(centres, "centres")
+    B, S, _ = centres.shape
+    k = patches.shape[1]
+    out = torch.empty((B, S * k, 3), dtype=torch.float32, device=patches.device)
+    if center is not None:
+        center, longest = _cuda_f32(center, "center"), _cuda_f32(longest, "longest")
+    with torch.cuda.device(patches.device):
+        _lib.check(lib.pcc_assemble_f32(_ptr(patches), _ptr(centres), _ptr(center), _ptr(longest), B, S, k,
+                                        float(patch_scale), float(margin), _ptr(out), _stream()), "pcc_assemble_f32")
     return out
 
 

@@ -116,6 +116,43 @@ def p3d_ops():
     print("p3d_ops.npz written:", len(out), "arrays")
 
 
+
+
+def pppf_modules():
+    """Outputs of the REFERENCE's PPPF_AE (PointnetSAModule x3 + FoldingNet) in eval mode on CPU, PyTorch3D ops served by
+    the oracle, with the seeded state of tools/synth.seeded_module_state (regenerated, not stored, by the tests)."""
+    ref = ref_loader.load("PPPF_AE")
+    model = ref.PPPF_AE(K=512, k=0, d=16, L=7)
+    model.load_state_dict(synth.seeded_module_state(model, 17))
+    model.eval()
+    x = torch.from_numpy(synth.shapenet_like(2, 2048, seed=51))
+    with torch.no_grad():
+        xyz1, f1 = model.encoder.sa1(x, None)
+        xyz2, f2 = model.encoder.sa2(xyz1, f1)
+        xyz3, f3 = model.encoder.sa3(xyz2, f2)
+        recon, latent, lq = model(x)
+    np.savez_compressed(os.path.join(HERE, "pppf_modules.npz"), x=x.numpy(), xyz1=xyz1.numpy(), f1=f1.numpy(), xyz2=xyz2.numpy(),
+                        f2=f2.numpy(), xyz3=xyz3.numpy(), f3=f3.numpy(), recon=recon.numpy(), latent=latent.numpy(), lq=lq.numpy())
+    print("pppf_modules.npz:", {k: tuple(v.shape) for k, v in dict(f1=f1, f2=f2, f3=f3, recon=recon, latent=latent).items()})
+
+
+def ae_modules():
+    """Outputs of the REFERENCE's AE.AE (SetAbstraction + PointNet encoder, inv_pool + MLP decoder) on CPU."""
+    ref = ref_loader.load("AE")
+    model = ref.AE(K=256, k=128, d=16, L=7)
+    model.load_state_dict(synth.seeded_state_dict(synth.ae_shapes(128, 16, 7), 11))
+    model.eval()
+    x = torch.from_numpy(synth.uniform_cube(6, 256, seed=52)) - 0.5
+    with torch.no_grad():
+        new_xyz, latent, lq = model(x)
+        _, feat = model.sa(x.transpose(2, 1))
+    np.savez_compressed(os.path.join(HERE, "ae_modules.npz"), x=x.numpy(), new_xyz=new_xyz.numpy(), latent=latent.numpy(),
+                        lq=lq.numpy(), sa_feat=feat.numpy())
+    print("ae_modules.npz:", tuple(new_xyz.shape), tuple(latent.shape))
+
+
 if __name__ == "__main__":
     ref_fps_gather()
     p3d_ops()
+    pppf_modules()
+    ae_modules()

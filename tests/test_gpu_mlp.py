@@ -33,11 +33,17 @@ def make_layers(dims, relu, seed):
     return layers
 
 
-def ref_chain(x, layers, group, model_bf16):
+def ref_chain(x, layers, group, model_bf16, first_fp32=None):
+    """model_bf16: the kernel's numeric model -- operands, bias and inter-layer activations rounded to bf16, fp32
+    accumulation; a first layer with <= 7 input channels (multi-layer chain, one fp32 input) runs in plain fp32."""
     rnd = (lambda t: t.bfloat16().float()) if model_bf16 else (lambda t: t)
     h = x.double() if not model_bf16 else x
+    if first_fp32 is None:
+        first_fp32 = len(layers) >= 2 and layers[0][0].shape[1] <= 7
     for i, (w, b, r) in enumerate(layers):
-        if model_bf16:
+        if model_bf16 and i == 0 and first_fp32:
+            h = h @ w.t() + b
+        elif model_bf16:
             h = rnd(h) @ rnd(w).t() + rnd(b)  # the bias is folded into the MMA as a bf16 column
         else:
             h = h @ w.double().t() + b.double()
@@ -65,7 +71,7 @@ CASES = [
     ([35, 64, 16], [True, False], 1024, 256),           # max over 256 points spanning two tiles
     ([35, 64, 16], [True, False], 2048, 512),
     ([20, 100, 48], [True, True], 512, 0),              # Cout not a multiple of 16: ones channel inside a TMEM chunk
-    ([64, 256, 200], [True, False], 512, 0),            # two N chunks? no: N=256 single instruction, ragged last Cout
+    ([64, 128, 200], [True, False], 512, 0),            # ragged last Cout, vector fp32 store path
     ([30, 300, 8], [True, False], 384, 0),              # Cout > 256: two MMA N chunks
     ([30, 64, 300], [True, True], 1024, 64),            # pooled last layer with three M tiles
 ]

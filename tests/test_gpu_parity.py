@@ -224,3 +224,45 @@ def test_d1_psnr_inner_step(pcc, orc, g_p3d):
     diag2 = float(((orig.max(0) - orig.min(0)).astype(np.float64) ** 2).sum())
     psnr = 10 * np.log10(diag2 / mse)
     assert abs(psnr - float(g_p3d["d1_psnr"])) < 1e-4  # dB
+
+
+# ---- fused glue kernels of the batched driver -------------------------------------------------------------------------
+def test_normalize_matches_pn_kit_formula(pcc):
+    """pcc_normalize_f32 vs the reference op order of pn_kit.normalize (pn_kit.py:47-60), applied per cloud."""
+    x = cu(synth.modelnet_like(3, 8192, seed=41) * np.float32(3.7) - np.float32(1.2))
+    out, center, longest, bbox = pcc.ops.normalize(x)
+    for b in range(3):
+        pc = x[b:b + 1]
+        xs, ys, zs = pc[0, :, 0], pc[0, :, 1], pc[0, :, 2]
+        c = torch.stack(((xs.max() + xs.min()) / 2, (ys.max() + ys.min()) / 2, (zs.max() + zs.min()) / 2))
+        l = torch.max(torch.stack((xs.max() - xs.min(), ys.max() - ys.min(), zs.max() - zs.min())))
+        ref = (pc - c) * (1 - 0.01) / l + 0.5
+        assert torch.equal(center[b], c) and torch.equal(longest[b], l)
+        assert torch.equal(out[b:b + 1], ref)
+        assert torch.equal(bbox[b], torch.cat((pc[0].amin(0), pc[0].amax(0))))
+
+
+def test_fps_fused_centres_and_quantisation(pcc, orc):
+    xyz = synth.modelnet_like(2, 8192, seed=43)
+    start = np.array([11, 4000])
+    idx, cen = pcc.ops.fps(cu(xyz), 64, cu(start), 1e10, return_xyz=True)
+    assert np.array_equal(idx.cpu().numpy(), orc.fps(xyz, 64, start, 1e10))
+    assert np.array_equal(cen.cpu().numpy(), orc.gather(xyz, idx.cpu().numpy()))
+    _, q = pcc.ops.fps(cu(xyz), 64, cu(start), 1e10, return_xyz=True, quant_cube=1.0 / 64)
+    cube = np.float32(1.0 / 64)
+    want = (orc.gather(xyz, idx.cpu().numpy()) // cube * cube) + cube / 2   # octree_np.getDecodeFromPc's rule
+    assert np.array_equal(q.cpu().numpy(), want.astype(np.float32))
+
+
+def test_assemble_matches_reference_ops(pcc):
+    B, S, k = 2, 64, 128
+    patches = torch.rand(B * S, k, 3, device="cuda") - 0.5
+    centres = torch.rand(B, S, 3, device="cuda")
+    center = torch.rand(B, 3, device="cuda")
+    longest = torch.rand(B, device="cuda") + 0.5
+    got = pcc.ops.assemble(patches, centres, 2.0, center, longest)
+    pc = (patches / 2.0).view(B, S, k, 3) + centres.view(B, S, 1, 3)   # decompress.py:105-110
+    pc = pc.reshape(B, -1, 3)
+    ref = (pc - 0.5) * longest[:, None, None] / (1 - 0.01) + center[:, None, :]  # pn_kit.denormalize
+    assert torch.allclose(got, ref, rtol=0, atol=1e-6)
+    assert torch.equal(pcc.ops.assemble(patches, centres, 2.0), pc)

@@ -143,3 +143,29 @@ def seeded_state_dict(shapes, seed=11):
         bound = 1.0 / np.sqrt(fan_in) if key.endswith(("weight", "bias")) else 1.0
         sd[key] = (torch.rand(shape, generator=g) * 2 - 1) * bound
     return sd
+
+
+def seeded_module_state(module, seed=11):
+    """Deterministic parameters AND buffers for any nn.Module (BatchNorm running statistics included, so that eval-mode
+    folding is exercised): same values on every machine, keyed only by the module's own state_dict shapes."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    fan_in = 1
+    for key, ref in module.state_dict().items():
+        shape = tuple(ref.shape)
+        leaf = key.rsplit(".", 1)[-1]
+        if leaf == "num_batches_tracked":
+            sd[key] = torch.zeros(shape, dtype=ref.dtype)
+        elif leaf == "running_var":
+            sd[key] = torch.rand(shape, generator=g) + 0.5
+        elif leaf == "running_mean":
+            sd[key] = (torch.rand(shape, generator=g) - 0.5) * 0.2
+        elif leaf == "weight" and len(shape) == 1:   # BatchNorm gamma
+            sd[key] = torch.rand(shape, generator=g) + 0.5
+        elif leaf == "weight":
+            fan_in = int(np.prod(shape[1:]))
+            sd[key] = (torch.rand(shape, generator=g) * 2 - 1) / np.sqrt(fan_in)
+        else:                                        # biases / BatchNorm beta
+            sd[key] = (torch.rand(shape, generator=g) * 2 - 1) / np.sqrt(max(fan_in, 1))
+    return sd

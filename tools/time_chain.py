@@ -25,11 +25,12 @@ for name, (mk, layers, group, od) in cases.items():
     dbg(None)
     t = buf.cpu().tolist()
     n = max(i for i, v in enumerate(t) if v) + 1
+    f32 = 1 if (len(layers) >= 2 and layers[0][0].shape[1] <= 7) else 0
     L = len(layers)
-    per = 3 + 4 * L
+    per = 4 + 7 * (L - f32)
     print(name, "ticks per tile:", per)
     for tile in range(2, min(8, n // per)):
         seg = t[tile * per:(tile + 1) * per + 1]
         d = [seg[i + 1] - seg[i] for i in range(len(seg) - 1)]
-        labels = ["load", "fence+sync"] + sum([[f"L{l} issue", f"L{l} wait", f"L{l} epi", f"L{l} fence+sync"] for l in range(L)], []) + ["loop"]
+        labels = ["stage", "cpwait", "prefetch"] + sum([[f"L{l} pre", f"L{l} mma", f"L{l} commit", f"L{l} wait", f"L{l} cpissue", f"L{l} epi", f"L{l} sync"] for l in range(f32, L)], []) + ["loop"]
         print(f" tile {tile}: total {seg[-1] - seg[0]:6d} | " + " ".join(f"{a}={b}" for a, b in zip(labels, d)))
