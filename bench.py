@@ -40,8 +40,8 @@ WORKLOAD = ("cfg2-shape batch: 32 synthetic ModelNet40-shaped clouds x 8192 pts,
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -267,20 +267,27 @@ def run_b200(args):
         peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
         roofline = None
         if cham_ms:
-            # dominant kernel = nn1_kernel inside the Chamfer call.  Algorithmic bytes: 12*(P1+P2) per
-            # cloud pair in + 4*(P1+P2) per-point minima + 8 out.
-            alg_bytes = BATCH * (12 * 2 * N_POINTS + 4 * 2 * N_POINTS + 8)
-            pair_evals = 2.0 * BATCH * N_POINTS * N_POINTS  # as launched: both directions
+            # Dominant kernel = chamfer_onepass_kernel inside the Chamfer call (profiles/r01_launch_shares.txt).
+            # Algorithmic bytes per launch: 12*(P1+P2) in + 4*(P1+P2) per-point minima out, per cloud pair.
+            # It is FP32-issue bound, not HBM bound: every (x_i, y_j) pair is evaluated once (8 un-fused FP32 ops) and
+            # feeds both directions; 11.8 warp-level instructions per pair measured with ncu
+            # (profiles/r01_chamfer_ncu_full.txt: smsp__inst_executed.sum / (B*P1*P2)).
+            alg_bytes = BATCH * (12 * 2 * N_POINTS + 4 * 2 * N_POINTS)
+            pair_evals = 1.0 * BATCH * N_POINTS * N_POINTS
             achieved = alg_bytes / (cham_ms / 1e3) / 1e9
-            fp32_peak = 34.4e12  # measured with tools/ubench.cu (profiles/r01_ubench_fp32_pipes.txt), lane-instr/s
-            roofline = {"kernel": "nn1_kernel (Chamfer, both directions)", "bound": "hbm", "achieved": achieved,
-                        "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
-                        "peak_source": peak_src, "ms_per_launch": cham_ms,
-                        "note": "FP32-issue bound, not HBM bound: see fp32_issue",
-                        "fp32_issue": {"pair_evals_per_launch": pair_evals, "instr_per_pair": 9.25,
-                                       "achieved_lane_instr_per_s": pair_evals * 9.25 / (cham_ms / 1e3),
+            fp32_peak = 34.4e12  # lane-instr/s measured with tools/ubench.cu (profiles/r01_ubench_fp32_pipes.txt)
+            instr_per_pair = 11.8
+            roofline = {"kernel": "chamfer_onepass_kernel (+ finalize) -- Chamfer, both directions from one pass",
+                        "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                        "traffic": 10.5e6, "peak_source": peak_src, "ms_per_launch": cham_ms,
+                        "note": "the schema offers hbm|tensor; this kernel is FP32-issue bound (196 KB of input per "
+                                "67 M pair evaluations): see fp32_issue. traffic = dram read+write of one launch from "
+                                "profiles/r01_chamfer_ncu_full.txt",
+                        "fp32_issue": {"pair_evals_per_launch": pair_evals, "instr_per_pair": instr_per_pair,
+                                       "achieved_lane_instr_per_s": pair_evals * instr_per_pair / (cham_ms / 1e3),
                                        "peak_lane_instr_per_s": fp32_peak,
-                                       "frac": pair_evals * 9.25 / (cham_ms / 1e3) / fp32_peak}}
+                                       "frac": pair_evals * instr_per_pair / (cham_ms / 1e3) / fp32_peak,
+                                       "useful_frac": pair_evals * 8.0 / (cham_ms / 1e3) / fp32_peak}}
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -288,7 +295,9 @@ def run_b200(args):
             "config": {"workload": WORKLOAD, "clouds_per_step_per_gpu": BATCH, "points": N_POINTS, "K": K_PATCH,
                        "parallelism": f"dp{world} (whole clouds sharded by rank, metrics all_gather only)",
                        "l2": f"rotating pool of {POOL_BATCHES} distinct input batches (138 MB > 126 MB L2), no flush",
-                       "mlp": "interim torch.addmm (cuBLAS) while the fused tcgen05 kernel is brought up"},
+                       "mlp": "fused tcgen05 chains (SetAbstraction 3-32-64-128+max16, PointNet 131-128-256, decoder "
+                              "144-128-64-32-3); layers whose weights exceed shared memory (256-512-16, inv_pool) are "
+                              "library GEMMs"},
             "clocks": clk, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "roofline": roofline, "cpu_baseline": cpu_base,

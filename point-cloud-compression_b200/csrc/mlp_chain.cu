@@ -639,7 +639,24 @@ mlp_chain_kernel(const __grid_constant__ MlpChainParams prm, const __grid_consta
                                 }
                             } else if (!row_ok) {
                                 return;
-                            } else if (out_h && (CL & 7) == 0) {                            } else {
+                            } else if (out_h && (CL & 7) == 0) {  // no staging space (single-layer chain): direct 16-byte stores
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    if (j * 32 + q * 8 < cout) {
+                                        uint32_t pk[4];
+#pragma unroll
+                                        for (int h = 0; h < 4; ++h) {
+                                            float a = __uint_as_float(v[q * 8 + 2 * h]), b = __uint_as_float(v[q * 8 + 2 * h + 1]);
+                                            if (relu) {
+                                                a = fmaxf(a, 0.0f);
+                                                b = fmaxf(b, 0.0f);
+                                            }
+                                            pk[h] = pack_bf16x2(a, b);
+                                        }
+                                        *reinterpret_cast<uint4 *>(out_h + o + q * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                                    }
+                                }
+                            } else {
 #pragma unroll
                                 for (int i = 0; i < 32; ++i) {
                                     if (j * 32 + i < cout) {

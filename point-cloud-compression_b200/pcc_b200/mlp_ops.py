@@ -140,9 +140,10 @@ def library_chain(x, layers, out_dtype=torch.float32):
     kernel's resident-weight design."""
     x = x.to(torch.bfloat16)
     for w, b, relu in layers:
-        x = torch.addmm(_bf16(b), x, _bf16(w).t())
-        if relu:
-            x = torch.relu_(x)
+        if relu:  # bias + ReLU in the GEMM epilogue (cuBLASLt), no separate element-wise pass
+            x = torch._addmm_activation(_bf16(b), x, _bf16(w).t(), use_gelu=False)
+        else:
+            x = torch.addmm(_bf16(b), x, _bf16(w).t())
     return x.to(out_dtype)
 
 

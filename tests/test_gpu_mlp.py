@@ -124,6 +124,25 @@ def test_input_segments_bf16_and_broadcast(mlp):
     assert (yb.float() - ym2).abs().max().item() / ym2.abs().max().item() < 1e-2  # one extra bf16 rounding of the output
 
 
+def test_wide_fp32_segment_single_layer_and_run_chain_planner(mlp):
+    """PointnetSAModule SA3-like: [gathered features fp32 256ch | xyz 3ch] -> 256 -> 256 -> 512 -> 1024, max over 128.
+    The planner runs the layers that fit as fused launches and the rest as library GEMMs."""
+    torch.manual_seed(5)
+    rows = 128 * 16
+    feat = torch.rand(rows, 256, device="cuda") - 0.5
+    xyz = torch.rand(rows, 3, device="cuda") - 0.5
+    layers1 = make_layers([259, 256], [True], seed=21)
+    y1 = mlp.fused_chain([(feat, 1), (xyz, 1)], layers1, 0, torch.bfloat16)
+    ym1 = ref_chain(torch.cat((feat, xyz), 1), layers1, 0, model_bf16=True)
+    assert not torch.isnan(y1.float()).any()
+    assert (y1.float() - ym1).abs().max().item() / ym1.abs().max().item() < 1e-2
+    layers = make_layers([259, 256, 256, 512, 1024], [True] * 4, seed=22)
+    y = mlp.run_chain([(feat, 1), (xyz, 1)], layers, group=128)
+    yf = ref_chain(torch.cat((feat, xyz), 1), layers, 128, model_bf16=False)
+    assert y.shape == (16, 1024)
+    assert (y - yf).abs().max().item() / yf.abs().max().item() < BF16_RTOL
+
+
 def test_unsupported_chain_is_an_error_not_a_fallback(mlp):
     layers = make_layers([256, 512, 1024], [True, True], seed=2)
     x = torch.rand(128, 256, device="cuda")
