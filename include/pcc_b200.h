@@ -176,6 +176,12 @@ int pcc_mlp_chain_f32(const float *x, int64_t rows, int ldx, const PccMlpLayer *
 int pcc_mlp_chain(const PccMlpInput *inputs, int n_inputs, int64_t rows, const PccMlpLayer *layers, int n_layers,
                   int group, void *out, int out_dtype, void *stream);
 
+/*
+ * Diagnostics (tools/time_chain.py): when given a device buffer of 256 int64, CTA 0 / thread 0 of the next
+ * pcc_mlp_chain launches stores clock64() at its phase boundaries; pass NULL to switch it off (the default).
+ */
+void pcc_debug_mlp_timing(long long *device_buf);
+
 #ifdef __cplusplus
 }
 #endif

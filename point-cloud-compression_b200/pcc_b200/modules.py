@@ -61,6 +61,18 @@ class SetAbstraction(nn.Module):
         return mlp_ops.fused_chain(grouped.reshape(BS * P * self.K, 3), self.layers(), group=self.K,
                                    out_dtype=out_dtype).reshape(BS, P, -1)
 
+    def forward_points_train(self, xyz):
+        """Differentiable body (training): the kNN grouping runs on the pcc kernel (no gradient flows into it, SURVEY.md
+        3.3), the shared MLP is issued as fp32 library GEMMs under autograd, like the reference's default fp32 training."""
+        BS, P, _ = xyz.shape
+        _, _, grouped = ops.knn(xyz.detach(), xyz.detach(), self.K, return_nn=True, centre_sub=True, nn_only=True)
+        h = grouped.reshape(BS * P * self.K, 3)
+        for w, b, relu in self.layers():
+            h = torch.addmm(b, h, w.t())
+            if relu:
+                h = torch.relu(h)
+        return h.view(BS * P, self.K, -1).max(dim=1)[0].view(BS, P, -1)
+
     def forward(self, xyz):
         """Reference signature: xyz [B, 3, N] -> (new_xyz [B, 3, S], new_points [B, D', S])."""
         feat = self.forward_points(xyz.permute(0, 2, 1).contiguous())
@@ -175,7 +187,59 @@ class AE(nn.Module):
                                   self.inv_mlp.layers())
         return out.view(BS, self.k, 3)
 
+    def forward_train(self, xyz):
+        """AE.forward (AE.py:34-55) under autograd: fp32 library GEMMs for the network bodies, pcc kernels for the
+        grouping; gradients reach every parameter through the STE quantiser exactly as in the reference."""
+        BS = xyz.shape[0]
+        feat = self.sa.forward_points_train(xyz)
+        h = torch.cat((xyz, feat), dim=2).reshape(BS * xyz.shape[1], -1)          # AE.py:39
+        for w, b, relu in self.pn.layers():
+            h = torch.addmm(b, h, w.t())
+            if relu:
+                h = torch.relu(h)
+        latent = h.view(BS, xyz.shape[1], -1).max(dim=1)[0]
+        spread = self.L - 0.2
+        latent = torch.sigmoid(latent) * spread - spread / 2                      # AE.py:42-44
+        latent_q = STEQuantize.apply(latent)                                      # AE.py:45
+        lin = self.inv_pool(latent_q).view(BS, -1, self.k)                        # AE.py:48-49  [BS,128,k]
+        x = torch.cat((lin, latent_q.unsqueeze(-1).repeat((1, 1, self.k))), dim=1)  # AE.py:50-51 [BS,144,k]
+        h = x.permute(0, 2, 1).reshape(BS * self.k, -1)
+        for w, b, relu in self.inv_mlp.layers():
+            h = torch.addmm(b, h, w.t())
+            if relu:
+                h = torch.relu(h)
+        return h.view(BS, self.k, 3), latent, latent_q
+
     def forward(self, xyz):
-        """Reference signature (AE.py:34-55): xyz [BS, K, 3] -> (new_xyz [BS, k, 3], latent, latent_quantized)."""
+        """Reference signature (AE.py:34-55): xyz [BS, K, 3] -> (new_xyz [BS, k, 3], latent, latent_quantized).
+        With autograd enabled and trainable parameters the differentiable body runs; otherwise the fused inference path."""
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            return self.forward_train(xyz.contiguous())
         latent, latent_q = self.encode_patches(xyz.contiguous())
         return self.decode_patches(latent_q), latent, latent_q
+
+
+class ConditionalProbabilityModel(nn.Module):
+    """AE.ConditionalProbabilityModel(L, d) (/root/reference/AE.py:87-123): PMF of every latent symbol given the patch
+    centres.  Tiny (0.5 M parameters, 63 MFLOP per cloud): plain library GEMMs, same parameter keys."""
+
+    def __init__(self, L, d):
+        super().__init__()
+        self.L, self.d = L, d
+        self.model_pn = PointNet(in_channel=3, mlps=[64, 128, 256], relu=[True, True, True], bn=False)
+        self.model_mlp = nn.Sequential(nn.Conv2d(3 + 256, 512, 1), nn.ReLU(), nn.Conv2d(512, 512, 1), nn.ReLU(),
+                                       nn.Conv2d(512, d * L, 1))
+
+    def forward(self, sampled_xyz):
+        B, S, _ = sampled_xyz.shape
+        h = sampled_xyz.reshape(B * S, 3)
+        for w, b, relu in self.model_pn.layers():
+            h = torch.relu(torch.addmm(b, h, w.t())) if relu else torch.addmm(b, h, w.t())
+        feature = h.view(B, S, -1).max(dim=1)[0]                                  # AE.py:112
+        x = torch.cat((sampled_xyz, feature[:, None, :].expand(-1, S, -1)), dim=2).reshape(B * S, -1)  # AE.py:115
+        for i in (0, 2, 4):
+            m = self.model_mlp[i]
+            x = torch.addmm(m.bias, x, m.weight.flatten(1).t())
+            if i < 4:
+                x = torch.relu(x)
+        return torch.softmax(x.view(B, S, self.d, self.L), dim=3)                 # AE.py:118-121

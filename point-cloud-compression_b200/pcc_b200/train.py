@@ -1,0 +1,81 @@
+"""Training step of the IPDAE patch auto-encoder on the B200 ops: the body of train.py:148-247 for one batch.
+
+The data-parallel geometric stages (normalise, FPS, kNN patching, in-patch kNN, Chamfer forward / backward) are the pcc
+kernels; the network bodies run as fp32 library GEMMs under autograd (the reference trains in fp32 by default, SURVEY.md
+appendix B-6).  Multi-GPU: one process per GPU, whole clouds per rank, gradients all-reduced by DistributedDataParallel
+over NCCL -- the only collective of the path.  The octree centre coder stays on the reference path; the step applies its
+quantisation rule on the device (see codec.py).
+"""
+import math
+
+import torch
+
+from . import ops
+from .modules import AE, ConditionalProbabilityModel
+from .pytorch3d_compat import chamfer_distance
+
+
+def estimate_bits_from_pmf(pmf, sym):
+    """pn_kit.estimate_bits_from_pmf (/root/reference/pn_kit.py:439-450)."""
+    L = pmf.shape[-1]
+    p = torch.gather(pmf.reshape(-1, L), dim=1, index=sym.reshape(-1, 1))
+    return torch.sum(-torch.log2(p.clamp(min=1e-3)))
+
+
+class Trainer:
+    def __init__(self, K=256, k=128, d=16, L=7, N0=1024, alpha=2, lr=0.0005, lamda=1e-6, rate_loss_enable_step=40000,
+                 centre_depth=6, device="cuda", ddp=False, state_dict=None):
+        self.K, self.k, self.d, self.L, self.N0, self.alpha = K, k, d, L, N0, alpha
+        self.lamda, self.rate_loss_enable_step, self.centre_depth = lamda, rate_loss_enable_step, centre_depth
+        self.ae = AE(K, k, d, L).to(device)
+        if state_dict is not None:
+            self.ae.load_state_dict(state_dict)
+        self.prob = ConditionalProbabilityModel(L, d).to(device)
+        self.ae_fwd, self.prob_fwd = self.ae.forward_train, self.prob
+        if ddp:  # gradients of both models are all-reduced over NCCL, bucketed and overlapped with the backward pass
+            from torch.nn.parallel import DistributedDataParallel as DDP
+
+            class _Train(torch.nn.Module):
+                def __init__(self, ae):
+                    super().__init__()
+                    self.ae = ae
+
+                def forward(self, x):
+                    return self.ae.forward_train(x)
+
+            self._ddp_ae, self._ddp_prob = DDP(_Train(self.ae)), DDP(self.prob)
+            self.ae_fwd, self.prob_fwd = self._ddp_ae, self._ddp_prob
+        self.optimizer = torch.optim.Adam(list(self.ae.parameters()) + list(self.prob.parameters()), lr=lr)  # train.py:132-135
+        self.global_step = 0
+
+    def step(self, batch_x, start_idx=None):
+        """One optimisation step on batch_x [B,N,3] (device).  Returns dict(loss, chamfer, fbpp)."""
+        self.ae.train()
+        self.prob.train()
+        B, N, _ = batch_x.shape
+        S = N * self.alpha // self.K
+        # train.py:164 -- pn_kit.normalize takes the bounding box of cloud 0 for the whole batch (appendix B-5)
+        _, center, longest, _ = ops.normalize(batch_x[:1])
+        x = (batch_x - center.view(1, 1, 3)) * (1 - 0.01) / longest.view(1, 1, 1) + 0.5
+        self.optimizer.zero_grad(set_to_none=True)
+        if start_idx is None:                                                     # pn_kit.py:321 (CPU RNG)
+            start_idx = torch.randint(0, N, (B,), dtype=torch.long).to(x.device)
+        cube = 1.0 / max(1.0, math.pow(2.0, min(self.centre_depth, 30)))
+        _, rec_centres = ops.fps(x, S, start_idx, 1e10, return_xyz=True, quant_cube=cube)          # train.py:171-179
+        scale = (N / self.N0) ** (1 / 3)
+        _, _, patches = ops.knn(rec_centres, x, self.K, return_nn=True, centre_sub=True, nn_scale=scale,
+                                nn_only=True)                                     # train.py:185-192
+        patches_pred, _, latent_q = self.ae_fwd(patches.view(B * S, self.K, 3))   # train.py:193
+        patches_pred = patches_pred / scale                                       # train.py:194
+        pmf = self.prob_fwd(rec_centres)                                          # train.py:197
+        sym = (latent_q.view(B, S, self.d) + self.L // 2).long().clamp(0, self.L - 1)
+        feature_bits = estimate_bits_from_pmf(pmf, sym) / (B * N)                 # train.py:201
+        fbpp = feature_bits / (B * N)                                             # train.py:205 (divided twice, appendix B-7)
+        pc_pred = (patches_pred.view(B, S, -1, 3) + rec_centres.view(B, S, 1, 3)).reshape(B, -1, 3)  # train.py:207-209
+        cham, _ = chamfer_distance(pc_pred, x)                                    # AE.get_loss, AE.py:67
+        lam = 0.0 if self.global_step < self.rate_loss_enable_step else self.lamda
+        loss = cham + lam * fbpp                                                  # AE.py:68-69
+        loss.backward()                                                           # train.py:221
+        self.optimizer.step()
+        self.global_step += 1
+        return dict(loss=loss.detach(), chamfer=cham.detach(), fbpp=fbpp.detach())

@@ -6,8 +6,7 @@ sys.path[:0] = [ROOT, os.path.join(ROOT, "point-cloud-compression_b200"), os.pat
 from pcc_b200 import mlp_ops, _lib
 from test_gpu_mlp import make_layers
 lib = _lib.load()
-dbg = ctypes.CDLL(_lib.LIB_PATH).pcc_debug_mlp_timing
-dbg.argtypes = [ctypes.c_void_p]
+dbg = lib.pcc_debug_mlp_timing
 BS = 2048
 cases = {
     "sa": (lambda: (torch.rand(BS * 256 * 16, 3, device="cuda") - 0.5), make_layers([3, 32, 64, 128], [True] * 3, 1), 16, torch.bfloat16),
