@@ -117,6 +117,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ uint32_t relu_bf16x2(uint32_t v) {
+    uint32_t r;
+    asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(0u));
+    return r;
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<const uint32_t *>(&h);
@@ -164,27 +170,28 @@ struct MlpIo {
     long long *timing;  // bring-up aid (NULL in production): CTA 0 / thread 0 stores clock64() at phase boundaries
 };
 
-#define MLP_TICK(slot)                                                                   \
-    do {                                                                                 \
-        if (io.timing && blockIdx.x == 0 && tid == 0 && tick < 128) io.timing[tick++] = clock64(); \
+#define MLP_TICK(slot)                                                                                 \
+    do {                                                                                               \
+        if constexpr (TIMED) {                                                                         \
+            if (io.timing && blockIdx.x == 0 && tid == 0 && tick < 128) io.timing[tick++] = clock64(); \
+        }                                                                                              \
     } while (0)
 
 __device__ __forceinline__ void store_out(float *__restrict__ out_f, __nv_bfloat16 *__restrict__ out_h, long long o, float v) {
     if (out_h) out_h[o] = __float2bfloat16_rn(v); else out_f[o] = v;
 }
 
+// v = 32 consecutive positions of one channel; writes the 32 / G pooled values.  `o` = output offset of the first group.
 template <int G>
 __device__ __forceinline__ void pool_store_small(const uint32_t (&v)[32], int relu, float *__restrict__ out_f,
-                                                 __nv_bfloat16 *__restrict__ out_h, long long row_base, long long rows,
-                                                 int CL, int c) {
+                                                 __nv_bfloat16 *__restrict__ out_h, long long o, int groups_left, int CL) {
 #pragma unroll
     for (int g = 0; g < 32 / G; ++g) {
         float m = __uint_as_float(v[g * G]);
 #pragma unroll
         for (int i = 1; i < G; ++i) m = fmaxf(m, __uint_as_float(v[g * G + i]));
         if (relu) m = fmaxf(m, 0.0f);  // ReLU commutes with max
-        const long long r = row_base + g * G;
-        if (r < rows) store_out(out_f, out_h, (r / G) * CL + c, m);
+        if (g < groups_left) store_out(out_f, out_h, o + g * CL, m);
     }
 }
 
@@ -427,7 +434,7 @@ __device__ __forceinline__ void stage_tile(const MlpIo &io, const MlpChainParams
 // Work unit = max(1, group / P) consecutive tiles of P positions.
 // out: [rows, CL] (group <= 1) or [rows / group, CL] (max over each run of `group` consecutive rows), fp32 or bf16.
 // POOL: 0 = no pooling, 2..32 = max over that many consecutive rows (in-register), 64 = any larger group.
-template <int POOL, int MINB>
+template <int POOL, int MINB, bool TIMED>
 __global__ void __launch_bounds__(MLP_THREADS, MINB)
 mlp_chain_kernel(const __grid_constant__ MlpChainParams prm, const __grid_constant__ MlpIo io, long long rows, int group,
                  void *__restrict__ out, long long n_units, int tiles_per_unit) {
@@ -564,13 +571,9 @@ mlp_chain_kernel(const __grid_constant__ MlpChainParams prm, const __grid_consta
                                 if (j * 32 + q * 8 < ncol) {  // columns past ncol are stale and never stored
                                     uint32_t pk[4];
 #pragma unroll
-                                    for (int h = 0; h < 4; ++h) {
-                                        float a = __uint_as_float(v[q * 8 + 2 * h]), b = __uint_as_float(v[q * 8 + 2 * h + 1]);
-                                        if (relu) {
-                                            a = fmaxf(a, 0.0f);
-                                            b = fmaxf(b, 0.0f);
-                                        }
-                                        pk[h] = pack_bf16x2(a, b);
+                                    for (int h = 0; h < 4; ++h) {  // ReLU after the (monotone) bf16 rounding: one packed max
+                                        pk[h] = pack_bf16x2(__uint_as_float(v[q * 8 + 2 * h]), __uint_as_float(v[q * 8 + 2 * h + 1]));
+                                        if (relu) pk[h] = relu_bf16x2(pk[h]);
                                     }
                                     *reinterpret_cast<uint4 *>(xrow + (j * 4 + q) * MLP_CHUNK) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                                 }
@@ -677,9 +680,11 @@ mlp_chain_kernel(const __grid_constant__ MlpChainParams prm, const __grid_consta
                         float gmax = (group > 32 && t == 0) ? run_max : -INFINITY;
                         for_each_chunk(lane_addr + t * MLP_P, MLP_P / 32, [&](const uint32_t (&v)[32], int j) {
                             if (!real) return;
-                            const long long rb = row0 + j * 32;
                             if constexpr (POOL >= 2 && POOL <= 32) {
-                                pool_store_small<POOL>(v, relu, out_f, out_h, rb, rows, CL, c);
+                                // rows % POOL == 0 (checked by the host): whole groups only
+                                const long long g0 = (row0 + j * 32) / POOL;
+                                const long long gl = rows / POOL - g0;
+                                pool_store_small<POOL>(v, relu, out_f, out_h, g0 * CL + c, gl > 32 ? 32 : static_cast<int>(gl), CL);
                             } else {
                                 float m = __uint_as_float(v[0]);
 #pragma unroll
@@ -818,13 +823,24 @@ PCC_API int pcc_mlp_chain(const PccMlpInput *inputs, int n_inputs, int64_t rows,
     prm.w0f_off = off;
     if (prm.first_fp32) off += round_up(round_up(layers[0].cout, 8) * 8 * 4, 128);
     const int lfirst = prm.first_fp32;  // first layer that runs as an MMA; its operand is the producer's buffer
-    prm.x0_off = off;
-    off += MLP_P * prm.kp[lfirst] * 2;
+    // Without cp.async segments nothing lands in the input buffer while a tile is being computed (the next tile waits in
+    // registers), so the activation buffer may alias it: one buffer of the larger size, and room for a 4th CTA per SM.
+    bool any_vec = false;
+    for (int s = 0; s < n_inputs; ++s) any_vec = any_vec || io.seg[s].vec;
     int max_kp_rest = 0;
     for (int l = lfirst + 1; l < n_layers; ++l) max_kp_rest = prm.kp[l] > max_kp_rest ? prm.kp[l] : max_kp_rest;
-    prm.x_off = off;
-    prm.x_bytes = MLP_P * max_kp_rest * 2;
-    off += prm.x_bytes;
+    prm.x0_off = off;
+    if (any_vec) {
+        off += MLP_P * prm.kp[lfirst] * 2;
+        prm.x_off = off;
+        prm.x_bytes = MLP_P * max_kp_rest * 2;
+        off += prm.x_bytes;
+    } else {
+        const int kp_max = prm.kp[lfirst] > max_kp_rest ? prm.kp[lfirst] : max_kp_rest;
+        prm.x_off = off;
+        prm.x_bytes = max_kp_rest > 0 ? MLP_P * kp_max * 2 : 0;
+        off += MLP_P * kp_max * 2;
+    }
     prm.ctrl_off = off;
     off += 16;
     int cols = 32;
@@ -851,10 +867,10 @@ PCC_API int pcc_mlp_chain(const PccMlpInput *inputs, int n_inputs, int64_t rows,
     cudaError_t e = cudaSuccess;
 #define PCC_MLP_LAUNCH(POOL, MINB)                                                                                      \
     do {                                                                                                                \
-        e = cudaFuncSetAttribute(mlp_chain_kernel<POOL, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,             \
+        e = cudaFuncSetAttribute(mlp_chain_kernel<POOL, MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
                                  static_cast<int>(smem_bytes));                                                         \
         if (e == cudaSuccess)                                                                                           \
-            mlp_chain_kernel<POOL, MINB><<<static_cast<unsigned>(grid), MLP_THREADS, smem_bytes, st>>>(                 \
+            mlp_chain_kernel<POOL, MINB, false><<<static_cast<unsigned>(grid), MLP_THREADS, smem_bytes, st>>>(          \
                 prm, io, rows, group, out, n_units, tiles_per_unit);                                                    \
     } while (0)
 #define PCC_MLP_LAUNCH_POOL(MINB)                                                                                       \
@@ -867,7 +883,20 @@ PCC_API int pcc_mlp_chain(const PccMlpInput *inputs, int n_inputs, int64_t rows,
         case 32: PCC_MLP_LAUNCH(32, MINB); break;                                                                       \
         default: PCC_MLP_LAUNCH(64, MINB); break;                                                                       \
     }
-    if (per_sm >= 3) { PCC_MLP_LAUNCH_POOL(4) } else { PCC_MLP_LAUNCH_POOL(2) }
+    if (io.timing) {  // bring-up instantiations with clock64() ticks (tools/time_chain.py): pool 16 / none only
+        if (pool == 16) {
+            e = cudaFuncSetAttribute(mlp_chain_kernel<16, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes));
+            if (e == cudaSuccess)
+                mlp_chain_kernel<16, 4, true><<<static_cast<unsigned>(grid), MLP_THREADS, smem_bytes, st>>>(prm, io, rows, group, out, n_units, tiles_per_unit);
+        } else if (pool == 0) {
+            e = cudaFuncSetAttribute(mlp_chain_kernel<0, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes));
+            if (e == cudaSuccess)
+                mlp_chain_kernel<0, 2, true><<<static_cast<unsigned>(grid), MLP_THREADS, smem_bytes, st>>>(prm, io, rows, group, out, n_units, tiles_per_unit);
+        } else {
+            set_error("pcc_mlp_chain: timing instantiation exists for group 16 or none only");
+            return PCC_ERR_UNSUPPORTED;
+        }
+    } else if (per_sm >= 3) { PCC_MLP_LAUNCH_POOL(4) } else { PCC_MLP_LAUNCH_POOL(2) }
     if (e != cudaSuccess) {
         set_error("pcc_mlp_chain: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
         return static_cast<int>(e);
