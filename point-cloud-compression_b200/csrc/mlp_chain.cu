@@ -25,7 +25,9 @@
 // tracked with tcgen05.commit on an mbarrier; MMA/epilogue overlap comes from the co-resident CTAs of an SM.
 #include <cuda_bf16.h>
 
+#include "chain_ws.h"
 #include "pcc_common.cuh"
+#include "tc_ptx.cuh"
 
 namespace pcc {
 
@@ -52,81 +54,6 @@ struct MlpChainParams {
     int tmem_cols;
     int ctrl_off;                 // mbarrier + TMEM base address slot
 };
-
-// ---- PTX wrappers ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-
-// Shared-memory matrix descriptor, SWIZZLE_NONE, version 1 (sm_100): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46).
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    uint64_t d = static_cast<uint64_t>((saddr & 0x3ffffu) >> 4);
-    d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3fffu) << 16;
-    d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3fffu) << 32;
-    d |= 1ull << 46;
-    return d;
-}
-
-// Instruction descriptor for kind::f16: D=f32, A=B=bf16, both operands K-major, shape M x N.
-__device__ __forceinline__ uint32_t umma_idesc(int M, int N) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
-}
-
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
-        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
-        : "memory");
-}
-
-__device__ __forceinline__ void umma_commit(uint32_t mbar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
-}
-
-__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
-}
-
-__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
-    uint32_t ok;
-    uint32_t spins = 0;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-            : "=r"(ok)
-            : "r"(mbar), "r"(parity)
-            : "memory");
-        if (!ok && ++spins > (1u << 26)) __trap();  // a lost completion must fail loudly, never hang the GPU
-    } while (!ok);
-}
-
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-__device__ __forceinline__ uint32_t relu_bf16x2(uint32_t v) {
-    uint32_t r;
-    asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(0u));
-    return r;
-}
-
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-    const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
-    return *reinterpret_cast<const uint32_t *>(&h);
-}
 
 // ---- weight packing -------------------------------------------------------------------------------------------
 // Packed layer = [rows128 x kp] bf16, kp = roundup(cin + 1, 16), in the K-major no-swizzle core-matrix layout:
@@ -193,30 +120,6 @@ __device__ __forceinline__ void pool_store_small(const uint32_t (&v)[32], int re
         if (relu) m = fmaxf(m, 0.0f);  // ReLU commutes with max
         if (g < groups_left) store_out(out_f, out_h, o + g * CL, m);
     }
-}
-
-// Issue / wait halves of a 32-column TMEM load so the next chunk's load overlaps the current chunk's arithmetic.
-__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr)
-        : "memory");
-}
-// The registers are listed as in/out operands so the compiler cannot move their uses above the wait.
-__device__ __forceinline__ void tmem_ld32_wait(uint32_t (&v)[32]) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
-                   "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]),
-                   "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]),
-                   "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
-                 :
-                 : "memory");
 }
 
 // for (j = 0; j < nj; ++j) body(v_j, j)   with the TMEM load of chunk j+1 in flight while chunk j is processed
@@ -787,6 +690,12 @@ PCC_API int pcc_mlp_chain(const PccMlpInput *inputs, int n_inputs, int64_t rows,
             set_error("pcc_mlp_chain: a max over more than %d rows needs the last layer to have <= 128 channels", MLP_P);
             return PCC_ERR_UNSUPPORTED;
         }
+    }
+    if (!g_mlp_timing) {  // the AE's three chains have compile-time-shaped, warp-specialised kernels (chain_ws.cu)
+        bool handled = false;
+        const int r = ws_dispatch(inputs, n_inputs, rows, layers, n_layers, group, out, out_dtype,
+                                  static_cast<cudaStream_t>(stream), &handled);
+        if (handled || r != 0) return r;
     }
     MlpChainParams prm{};
     prm.n_layers = n_layers;
