@@ -182,6 +182,16 @@ int pcc_mlp_chain(const PccMlpInput *inputs, int n_inputs, int64_t rows, const P
  */
 void pcc_debug_mlp_timing(long long *device_buf);
 
+/*
+ * Fused tail of pn_kit.PointNet (/root/reference/pn_kit.py:136-143 as configured by AE.py:17): per position
+ *     y = W3 . relu(W2 . x + b2) + b3   (256 -> 512 -> cout <= 16),   then max over every run of 256 positions.
+ * x [rows, 256] bf16 (row pitch ldx elements; rows % 256 == 0), w2 [512, 256] bf16 row-major, b2 [512] fp32,
+ * w3_packed = pcc_mlp_pack_weights_f32(cin = 512, cout), out [rows / 256, cout] fp32.  The 512-wide activation stays on
+ * the SM (TMEM / shared memory); W2 is streamed from L2 by TMA.
+ */
+int pcc_pn_tail_bf16(const void *x, int64_t rows, int64_t ldx, const void *w2_bf16, const float *b2, const void *w3_packed,
+                     int cout, int relu3, float *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

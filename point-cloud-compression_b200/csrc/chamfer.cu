@@ -14,6 +14,8 @@
 //   When a launch would leave SMs idle the candidate range is split over several CTAs, which merge through
 //   atomicMin on the packed (d2, idx) key.
 // chamfer_finalize_kernel: unpacks keys, reduces the means in double (fixed order -> run-to-run deterministic).
+#include <stdlib.h>
+
 #include "pcc_common.cuh"
 
 namespace pcc {
@@ -387,8 +389,25 @@ PCC_API int64_t pcc_nn1_workspace_bytes(int B, int P1, int P2) {
     return static_cast<int64_t>(sizeof(unsigned long long)) * B * P1;
 }
 
+namespace pcc {
+// chamfer_grid.cu: exact grid-pruned search for large clouds
+int64_t chamfer_grid_extra_bytes(int B, int P1, int P2, int G);
+int chamfer_grid_pick(int P1, int P2);
+int chamfer_grid_run(const float *x, const float *y, int B, int P1, int P2, int G, unsigned long long *kx,
+                     unsigned long long *ky, void *extra, cudaStream_t st);
+static int chamfer_path() {   // PCC_CHAMFER_PATH=brute forces the brute-force kernels (A/B measurements)
+    static const int v = [] {
+        const char *e = getenv("PCC_CHAMFER_PATH");
+        return (e && e[0] == 'b') ? 1 : 0;
+    }();
+    return v;
+}
+}  // namespace pcc
+
 PCC_API int64_t pcc_chamfer_workspace_bytes(int B, int P1, int P2) {
-    return static_cast<int64_t>(sizeof(unsigned long long)) * B * (static_cast<int64_t>(P1) + P2);
+    const int64_t keys = static_cast<int64_t>(sizeof(unsigned long long)) * B * (static_cast<int64_t>(P1) + P2);
+    const int G = pcc::chamfer_grid_pick(P1, P2);
+    return keys + (G ? 16 + pcc::chamfer_grid_extra_bytes(B, P1, P2, G) : 0);   // + 16: the grid region is 16-byte aligned
 }
 
 PCC_API int pcc_nn1_f32(const float *q, const float *p, int B, int P1, int P2, float *out_d2, int64_t *out_idx,
@@ -416,7 +435,12 @@ PCC_API int pcc_chamfer_fwd_f32(const float *x, const float *y, int B, int P1, i
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     unsigned long long *kx = static_cast<unsigned long long *>(workspace);
     unsigned long long *ky = kx + static_cast<size_t>(B) * P1;
-    {
+    const int G = chamfer_path() ? 0 : chamfer_grid_pick(P1, P2);
+    if (G) {
+        const uintptr_t extra = (reinterpret_cast<uintptr_t>(ky + static_cast<size_t>(B) * P2) + 15) & ~static_cast<uintptr_t>(15);
+        const int rc = chamfer_grid_run(x, y, B, P1, P2, G, kx, ky, reinterpret_cast<void *>(extra), st);
+        if (rc) return rc;
+    } else {
         // one-pass kernel: pick the column split that balances the grid over the SMs (~4 resident CTAs each)
         const int row_blocks = (P1 + CH_RB - 1) / CH_RB;
         const int max_s = (P2 + 255) / 256;  // at least 256 columns per split

@@ -1,0 +1,309 @@
+// Exact nearest-neighbour search through a uniform grid, for the Chamfer distance / D1 PSNR of clouds with 1024..2^24 points.
+//
+// Same results as the brute-force kernels of chamfer.cu, bit for bit: every candidate that is evaluated goes through the
+// same un-fused d2 (dist2_rn) and the same (d2, original index) key, and a cell (or a row of cells) is skipped only when
+// its distance to the query provably exceeds the best d2 found so far (with explicit margins against the rounding of the
+// cell assignment and of the bound itself), so the minimum over the visited candidates is the minimum over all of them
+// and ties still go to the lowest original index.  What changes is the work: 30-1000 candidates per query instead of P2
+// (8192): the algorithmic P1*P2 pair evaluations of SURVEY.md 8(d) are mostly pruned.  Replaces the two
+// knn_points(K=1) passes of pytorch3d.loss.chamfer_distance (/root/reference/AE.py:67, eval.py:204) and the KD-tree loop
+// of eval.py:68-81.  (A variant that culled dense 128-point Morton tiles against 256-query blocks was measured 2x slower
+// than brute force: bounding boxes of Morton runs are too loose, and two directions cost two passes.)
+//
+//   grid_build_kernel   one CTA per (cloud, side): bounding box, G^3 cell histogram in shared memory, exclusive scan,
+//                       counting-sort scatter of (x, y, z, original index) -> points sorted by cell (x fastest)
+//   grid_nn_kernel      one thread per query, queries taken in *their own* sorted order so a warp's queries are
+//                       neighbours in space and walk the same cells.  Step 1: the 3x3x3 block of cells around the query,
+//                       which settles it when the best d2 is closer than the block's faces.  Step 2 (far neighbours),
+//                       warp-cooperative: an upper bound from a strided sample of the candidates if nothing was found,
+//                       then the warp walks the union of its unsettled queries' balls with uniform control flow
+#include "pcc_common.cuh"
+
+namespace pcc {
+
+struct GridInfo {
+    float mnx, mny, mnz, h, inv_h;
+    int G;
+    float margin;   // slack taken off every face / gap distance before it is trusted (rounding of cell assignment / faces)
+    int pad;
+};
+
+constexpr int GRID_BUILD_THREADS = 1024;
+
+__device__ __forceinline__ int cell_coord(float p, float mn, float inv_h, int G) {
+    const int c = static_cast<int>((p - mn) * inv_h);
+    return c < 0 ? 0 : (c >= G ? G - 1 : c);
+}
+
+// grid (B, 2); dynamic smem: (G^3 + 1) u32
+__global__ void __launch_bounds__(GRID_BUILD_THREADS)
+grid_build_kernel(const float *__restrict__ x, const float *__restrict__ y, int P1, int P2, int G, float4 *__restrict__ sorted,
+                  unsigned *__restrict__ starts, GridInfo *__restrict__ info) {
+    extern __shared__ unsigned cnt[];
+    __shared__ float red[6][32];
+    __shared__ unsigned wsum[32];
+    __shared__ GridInfo gi;
+    const int b = blockIdx.x, side = blockIdx.y, B = gridDim.x;
+    const int P = side ? P2 : P1;
+    const float *pts = side ? y + static_cast<size_t>(b) * P2 * 3 : x + static_cast<size_t>(b) * P1 * 3;
+    float4 *out = sorted + (side ? static_cast<size_t>(B) * P1 + static_cast<size_t>(b) * P2 : static_cast<size_t>(b) * P1);
+    const int ncell = G * G * G;
+    unsigned *st_out = starts + (static_cast<size_t>(side) * B + b) * (ncell + 1);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    // ---- bounding box ----
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int i = tid; i < P; i += GRID_BUILD_THREADS) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float v = pts[static_cast<size_t>(i) * 3 + a];
+            mn[a] = fminf(mn[a], v);
+            mx[a] = fmaxf(mx[a], v);
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[a] = fminf(mn[a], __shfl_xor_sync(FULL_MASK, mn[a], o));
+            mx[a] = fmaxf(mx[a], __shfl_xor_sync(FULL_MASK, mx[a], o));
+        }
+        if (lane == 0) {
+            red[a][warp] = mn[a];
+            red[3 + a][warp] = mx[a];
+        }
+    }
+    for (int i = tid; i <= ncell; i += GRID_BUILD_THREADS) cnt[i] = 0u;
+    __syncthreads();
+    if (warp == 0) {
+        float ext = 0.0f, lo[3], maxabs = 0.0f;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            float m0 = red[a][lane], m1 = red[3 + a][lane];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                m0 = fminf(m0, __shfl_xor_sync(FULL_MASK, m0, o));
+                m1 = fmaxf(m1, __shfl_xor_sync(FULL_MASK, m1, o));
+            }
+            lo[a] = m0;
+            ext = fmaxf(ext, m1 - m0);
+            maxabs = fmaxf(maxabs, fmaxf(fabsf(m0), fabsf(m1)));
+        }
+        if (lane == 0) {
+            // non-finite or zero extent: a cell size of 1 keeps every formula finite (all points land in clamped cells)
+            const bool ok = ext > 0.0f && ext < 3.0e38f;
+            gi.h = ok ? ext / static_cast<float>(G) : 1.0f;
+            gi.inv_h = ok ? static_cast<float>(G) / ext : 1.0f;
+            gi.mnx = lo[0];
+            gi.mny = lo[1];
+            gi.mnz = lo[2];
+            gi.G = G;
+            gi.margin = 1e-4f * gi.h + 1e-6f * maxabs;
+            info[static_cast<size_t>(side) * B + b] = gi;
+        }
+    }
+    __syncthreads();
+    const GridInfo g = gi;
+
+    // ---- histogram ----
+    for (int i = tid; i < P; i += GRID_BUILD_THREADS) {
+        const int cx = cell_coord(pts[static_cast<size_t>(i) * 3], g.mnx, g.inv_h, G);
+        const int cy = cell_coord(pts[static_cast<size_t>(i) * 3 + 1], g.mny, g.inv_h, G);
+        const int cz = cell_coord(pts[static_cast<size_t>(i) * 3 + 2], g.mnz, g.inv_h, G);
+        atomicAdd(&cnt[(cz * G + cy) * G + cx], 1u);
+    }
+    __syncthreads();
+
+    // ---- exclusive scan of cnt[0 .. ncell): warp w owns a contiguous segment, 32 entries per step ----
+    const int seg = (ncell + 31) / 32;
+    const int s0 = warp * seg, s1 = min(ncell, s0 + seg);
+    unsigned carry = 0u;
+    for (int base = s0; base < s1; base += 32) {
+        const int i = base + lane;
+        const unsigned v = i < s1 ? cnt[i] : 0u;
+        unsigned inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(FULL_MASK, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (i < s1) cnt[i] = carry + inc - v;   // exclusive, relative to the segment
+        carry += __shfl_sync(FULL_MASK, inc, 31);
+    }
+    if (lane == 0) wsum[warp] = carry;
+    __syncthreads();
+    if (warp == 0) {
+        const unsigned v = wsum[lane];
+        unsigned inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(FULL_MASK, inc, o);
+            if (lane >= o) inc += t;
+        }
+        wsum[lane] = inc - v;
+    }
+    __syncthreads();
+    const unsigned off = wsum[warp];
+    for (int i = s0 + lane; i < s1; i += 32) {
+        const unsigned v = cnt[i] + off;
+        cnt[i] = v;
+        st_out[i] = v;
+    }
+    if (tid == 0) st_out[ncell] = static_cast<unsigned>(P);
+    __syncthreads();
+
+    // ---- scatter (cnt now holds the running cursor of every cell; the order inside a cell does not affect any result) ----
+    for (int i = tid; i < P; i += GRID_BUILD_THREADS) {
+        const float px = pts[static_cast<size_t>(i) * 3], py = pts[static_cast<size_t>(i) * 3 + 1], pz = pts[static_cast<size_t>(i) * 3 + 2];
+        const int cx = cell_coord(px, g.mnx, g.inv_h, G), cy = cell_coord(py, g.mny, g.inv_h, G), cz = cell_coord(pz, g.mnz, g.inv_h, G);
+        const unsigned pos = atomicAdd(&cnt[(cz * G + cy) * G + cx], 1u);
+        out[pos] = make_float4(px, py, pz, __uint_as_float(static_cast<unsigned>(i)));
+    }
+}
+
+__device__ __forceinline__ void scan_range(const float4 *__restrict__ cand, unsigned a, unsigned e, float qx, float qy, float qz,
+                                           unsigned long long &best) {
+    for (unsigned j = a; j < e; ++j) {
+        const float4 c = __ldg(cand + j);
+        const unsigned long long k = pack_key(dist2_rn(qx, qy, qz, c.x, c.y, c.z), __float_as_uint(c.w));
+        best = k < best ? k : best;
+    }
+}
+
+// distance from q to the slab [mn + c*h, mn + (c+1)*h] along one axis, made safe (never over-estimated) by the margin
+__device__ __forceinline__ float slab_gap(float q, float mn, float h, int c, float margin) {
+    const float lo = mn + static_cast<float>(c) * h;
+    const float g = fmaxf(lo - q, q - (lo + h)) - margin;
+    return g > 0.0f ? g : 0.0f;
+}
+
+// grid (ceil(max(P1,P2) / 128), B, n_dir): direction 0 = x queries against y's grid -> kx; direction 1 = y against x -> ky
+__global__ void __launch_bounds__(128)
+grid_nn_kernel(int P1, int P2, const float4 *__restrict__ sorted, const unsigned *__restrict__ starts,
+               const GridInfo *__restrict__ info, unsigned long long *__restrict__ kx, unsigned long long *__restrict__ ky) {
+    const int b = blockIdx.y, dir = blockIdx.z, B = gridDim.y;
+    const int Pq = dir ? P2 : P1, Pc = dir ? P1 : P2;
+    if (blockIdx.x * 128 >= Pq) return;
+    const int qi_raw = blockIdx.x * 128 + threadIdx.x;
+    const int qi = qi_raw < Pq ? qi_raw : Pq - 1;   // lanes past the end replay the last query (warp-uniform step 2) and do not store
+    const float4 *qpts = sorted + (dir ? static_cast<size_t>(B) * P1 + static_cast<size_t>(b) * P2 : static_cast<size_t>(b) * P1);
+    const float4 *cand = sorted + (dir ? static_cast<size_t>(b) * P1 : static_cast<size_t>(B) * P1 + static_cast<size_t>(b) * P2);
+    const int cside = dir ? 0 : 1;
+    const GridInfo g = info[static_cast<size_t>(cside) * B + b];
+    const int G = g.G;
+    const unsigned *st = starts + (static_cast<size_t>(cside) * B + b) * (G * G * G + 1);
+    unsigned long long *keys = dir ? ky + static_cast<size_t>(b) * P2 : kx + static_cast<size_t>(b) * P1;
+
+    const float4 q = qpts[qi];
+    const int cx = cell_coord(q.x, g.mnx, g.inv_h, G), cy = cell_coord(q.y, g.mny, g.inv_h, G), cz = cell_coord(q.z, g.mnz, g.inv_h, G);
+    unsigned long long best = KEY_MAX;
+    // ---- step 1: the 3x3x3 block around the query's cell ----
+    {
+        const int z0 = max(cz - 1, 0), z1 = min(cz + 1, G - 1), y0 = max(cy - 1, 0), y1 = min(cy + 1, G - 1);
+        const int xa = max(cx - 1, 0), xb = min(cx + 1, G - 1);
+        for (int z = z0; z <= z1; ++z)
+            for (int yy = y0; yy <= y1; ++yy) {
+                const unsigned row = static_cast<unsigned>((z * G + yy) * G);
+                scan_range(cand, __ldg(st + row + xa), __ldg(st + row + xb + 1), q.x, q.y, q.z, best);
+            }
+    }
+    // every unvisited point lies beyond one of the block's faces that are inside the grid.  Cell boundaries computed here
+    // and the cell assignment of the build differ by rounding (~1e-6 cells + a few ulp of the coordinates): the bound is
+    // shrunk by GridInfo::margin and compared with a 2e-5 relative slack on the square
+    float bound = INFINITY;
+    if (cx - 1 > 0) bound = fminf(bound, q.x - (g.mnx + static_cast<float>(cx - 1) * g.h));
+    if (cx + 2 < G) bound = fminf(bound, (g.mnx + static_cast<float>(cx + 2) * g.h) - q.x);
+    if (cy - 1 > 0) bound = fminf(bound, q.y - (g.mny + static_cast<float>(cy - 1) * g.h));
+    if (cy + 2 < G) bound = fminf(bound, (g.mny + static_cast<float>(cy + 2) * g.h) - q.y);
+    if (cz - 1 > 0) bound = fminf(bound, q.z - (g.mnz + static_cast<float>(cz - 1) * g.h));
+    if (cz + 2 < G) bound = fminf(bound, (g.mnz + static_cast<float>(cz + 2) * g.h) - q.z);
+    bound -= g.margin;
+    const bool done = bound == INFINITY || (best != KEY_MAX && bound > 0.0f && key_d2(best) < bound * bound * 0.99998f);
+    // ---- step 2 (warp-cooperative): some neighbour is farther than a cell.  Per-thread cell walks would make every load
+    // a 32-way scattered access; instead the warp walks ONE region - the union of its unsettled queries' balls - with
+    // uniform control flow, so every candidate is one broadcast load and 32 dense distance evaluations.
+    const bool need = !done;
+    if (__any_sync(FULL_MASK, need)) {
+        if (__any_sync(FULL_MASK, need && best == KEY_MAX)) {
+            // upper bound from a strided sample of the candidates (<= 128 points, the same for every lane)
+            const unsigned stride = static_cast<unsigned>(Pc) / 128u + 1u;
+            for (unsigned j = 0; j < static_cast<unsigned>(Pc); j += stride) {
+                const float4 c = __ldg(cand + j);
+                const unsigned long long k = pack_key(dist2_rn(q.x, q.y, q.z, c.x, c.y, c.z), __float_as_uint(c.w));
+                best = k < best ? k : best;
+            }
+        }
+        const float R = need ? sqrtf(key_d2(best)) * 1.0001f + g.margin : 0.0f;
+        float lo[3] = {need ? q.x - R : INFINITY, need ? q.y - R : INFINITY, need ? q.z - R : INFINITY};
+        float hi[3] = {need ? q.x + R : -INFINITY, need ? q.y + R : -INFINITY, need ? q.z + R : -INFINITY};
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                lo[a] = fminf(lo[a], __shfl_xor_sync(FULL_MASK, lo[a], o));
+                hi[a] = fmaxf(hi[a], __shfl_xor_sync(FULL_MASK, hi[a], o));
+            }
+        }
+        const int xa = max(cell_coord(lo[0], g.mnx, g.inv_h, G) - 1, 0), xb = min(cell_coord(hi[0], g.mnx, g.inv_h, G) + 1, G - 1);
+        const int ya = max(cell_coord(lo[1], g.mny, g.inv_h, G) - 1, 0), yb = min(cell_coord(hi[1], g.mny, g.inv_h, G) + 1, G - 1);
+        const int za = max(cell_coord(lo[2], g.mnz, g.inv_h, G) - 1, 0), zb = min(cell_coord(hi[2], g.mnz, g.inv_h, G) + 1, G - 1);
+        for (int z = za; z <= zb; ++z) {
+            const float gz = slab_gap(q.z, g.mnz, g.h, z, g.margin);
+            if (__all_sync(FULL_MASK, !need || gz * gz * 0.9999f > key_d2(best))) continue;
+            for (int yy = ya; yy <= yb; ++yy) {
+                const float gy = slab_gap(q.y, g.mny, g.h, yy, g.margin);
+                // a row is skipped only if it lies outside the ball of every unsettled query of the warp
+                if (__all_sync(FULL_MASK, !need || (gz * gz + gy * gy) * 0.9999f > key_d2(best))) continue;
+                const unsigned row = static_cast<unsigned>((z * G + yy) * G);
+                const unsigned a = __ldg(st + row + xa), e = __ldg(st + row + xb + 1);
+                for (unsigned j = a; j < e; ++j) {
+                    const float4 c = __ldg(cand + j);
+                    const unsigned long long k = pack_key(dist2_rn(q.x, q.y, q.z, c.x, c.y, c.z), __float_as_uint(c.w));
+                    best = k < best ? k : best;
+                }
+            }
+        }
+    }
+    if (qi_raw >= Pq) return;
+    keys[__float_as_uint(q.w)] = best;
+}
+
+int64_t chamfer_grid_extra_bytes(int B, int P1, int P2, int G) {
+    const int64_t pts = static_cast<int64_t>(B) * (static_cast<int64_t>(P1) + P2) * 16;
+    const int64_t tab = 2ll * B * (static_cast<int64_t>(G) * G * G + 1) * 4;
+    return pts + ((tab + 15) / 16) * 16 + 2ll * B * static_cast<int64_t>(sizeof(GridInfo));
+}
+
+int chamfer_grid_pick(int P1, int P2) {   // grid resolution, or 0: use the brute-force kernels
+    const int lo = P1 < P2 ? P1 : P2, hi = P1 < P2 ? P2 : P1;
+    if (lo < 1024 || hi > (1 << 24)) return 0;
+    return lo >= 4096 ? 32 : 16;
+}
+
+// extra = 16-byte aligned workspace region behind the two key arrays (chamfer_grid_extra_bytes); fills kx and (if ky) ky
+int chamfer_grid_run(const float *x, const float *y, int B, int P1, int P2, int G, unsigned long long *kx,
+                     unsigned long long *ky, void *extra, cudaStream_t st) {
+    float4 *sorted = static_cast<float4 *>(extra);
+    const int64_t pts = static_cast<int64_t>(B) * (static_cast<int64_t>(P1) + P2) * 16;
+    const int64_t tab = 2ll * B * (static_cast<int64_t>(G) * G * G + 1) * 4;
+    unsigned *starts = reinterpret_cast<unsigned *>(static_cast<char *>(extra) + pts);
+    GridInfo *info = reinterpret_cast<GridInfo *>(static_cast<char *>(extra) + pts + ((tab + 15) / 16) * 16);
+    const size_t smem = static_cast<size_t>(G) * G * G * 4 + 4;
+    static bool attr_done = false;
+    if (!attr_done) {
+        const cudaError_t e = cudaFuncSetAttribute(grid_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 32 * 32 * 4 + 4);
+        if (e != cudaSuccess) {
+            set_error("chamfer grid: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+            return static_cast<int>(e);
+        }
+        attr_done = true;
+    }
+    grid_build_kernel<<<dim3(B, 2), GRID_BUILD_THREADS, smem, st>>>(x, y, P1, P2, G, sorted, starts, info);
+    int rc = check_launch("grid_build_kernel");
+    if (rc) return rc;
+    const int pmax = P1 > P2 ? P1 : P2;
+    grid_nn_kernel<<<dim3((pmax + 127) / 128, B, ky ? 2 : 1), 128, 0, st>>>(P1, P2, sorted, starts, info, kx, ky);
+    return check_launch("grid_nn_kernel");
+}
+
+}  // namespace pcc

@@ -150,6 +150,29 @@ def library_chain(x, layers, out_dtype=torch.float32):
 _library_chain = library_chain
 
 
+def pn_tail_supported(x, layers, group):
+    """The fused PointNet tail kernel: [M, 256] bf16 -> 512 (ReLU) -> cout <= 16, max over runs of 256 rows."""
+    return (len(layers) == 2 and group == 256 and x.dtype == torch.bfloat16 and x.dim() == 2 and x.shape[1] == 256 and
+            x.stride(1) == 1 and x.stride(0) % 8 == 0 and x.data_ptr() % 16 == 0 and x.shape[0] % 256 == 0 and
+            tuple(layers[0][0].shape) == (512, 256) and layers[0][2] and layers[1][0].shape[1] == 512 and
+            layers[1][0].shape[0] <= 16)
+
+
+def pn_tail(x, layers):
+    """relu(W2 x + b2) -> W3 . + b3 -> max over each run of 256 rows, in one launch (csrc/pn_tail.cu)."""
+    lib = _lib.load()
+    (w2, b2, _), (w3, b3, relu3) = layers
+    w2h = _bf16(w2)
+    b2f = b2.detach().float().contiguous()
+    pw3, _, _ = _packed(w3, b3)
+    out = torch.empty((x.shape[0] // 256, w3.shape[0]), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.pcc_pn_tail_bf16(x.data_ptr(), x.shape[0], x.stride(0), w2h.data_ptr(), b2f.data_ptr(), pw3.data_ptr(),
+                                        w3.shape[0], int(bool(relu3)), out.data_ptr(), torch.cuda.current_stream().cuda_stream),
+                   "pcc_pn_tail_bf16")
+    return out
+
+
 def _split(layers, pooled=False):
     """Longest prefix of `layers` that fits the fused kernel."""
     dims = [layers[0][0].shape[1]] + [w.shape[0] for w, _, _ in layers]

@@ -117,6 +117,8 @@ class PointNet(nn.Module):
                                 out_dtype=torch.float32 if n == len(layers) else torch.bfloat16)
         if n == len(layers):
             return h
+        if mlp_ops.pn_tail_supported(h, layers[n:], P):   # 256 -> 512 -> d + max over the patch, one launch
+            return mlp_ops.pn_tail(h, layers[n:])
         h = mlp_ops.library_chain(h, layers[n:])
         return h.view(BS, P, -1).max(dim=1)[0]
 

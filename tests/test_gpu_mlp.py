@@ -148,3 +148,23 @@ def test_unsupported_chain_is_an_error_not_a_fallback(mlp):
     x = torch.rand(128, 256, device="cuda")
     with pytest.raises((ValueError, RuntimeError)):
         mlp.fused_chain(x, layers, 0)
+
+
+@pytest.mark.parametrize("patches,cout", [(1, 16), (5, 16), (300, 16), (3, 7)])
+def test_pn_tail_fused_kernel(mlp, patches, cout):
+    """pn_kit.PointNet tail 256 -> 512 (ReLU) -> d, max over the patch's 256 points, in one launch (csrc/pn_tail.cu)."""
+    torch.manual_seed(patches)
+    layers = make_layers([256, 512, cout], [True, False], seed=31)
+    x = ((torch.rand(patches * 256, 256, device="cuda") - 0.3)).bfloat16()
+    assert mlp.pn_tail_supported(x, layers, 256)
+    y = mlp.pn_tail(x, layers)
+    torch.cuda.synchronize()
+    rnd = lambda t: t.bfloat16().float()  # noqa: E731
+    (w2, b2, _), (w3, b3, _) = layers
+    h = torch.relu(x.float() @ rnd(w2).t() + b2)                   # fp32 bias in the epilogue of the streamed layer
+    ym = (rnd(h) @ rnd(w3).t() + rnd(b3)).view(patches, 256, cout).max(dim=1)[0]
+    yf = (torch.relu(x.double() @ w2.double().t() + b2.double()) @ w3.double().t() + b3.double()).view(patches, 256, cout).max(dim=1)[0]
+    scale = yf.abs().max().item() + 1e-12
+    assert y.shape == ym.shape
+    assert (y - ym).abs().max().item() / scale < MODEL_RTOL
+    assert (y - yf.float()).abs().max().item() / scale < BF16_RTOL

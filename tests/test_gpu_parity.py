@@ -202,6 +202,48 @@ def test_chamfer_vs_oracle(pcc, orc, B, P1, P2):
     assert abs(r["loss"].item() - loss) <= CHAMFER_RTOL * abs(loss) + 1e-30
 
 
+def _adversarial_pair(kind, P1, P2, seed):
+    rng = np.random.default_rng(seed)
+    if kind == "ties":          # octree-grid points: exact ties and duplicates everywhere
+        return synth.grid_quantised(1, P1, depth=4, seed=seed), synth.grid_quantised(1, P2, depth=4, seed=seed + 1)
+    if kind == "identical":     # zero-extent clouds
+        x = np.full((1, P1, 3), 0.25, np.float32)
+        y = np.full((1, P2, 3), 0.25, np.float32)
+        y[0, 7] = (0.5, 0.25, 0.25)
+        return x, y
+    if kind == "outliers":      # a tight cluster plus a few far points: almost every point in one cell
+        x = (rng.normal(0, 1e-3, (1, P1, 3)) + 0.5).astype(np.float32)
+        y = (rng.normal(0, 1e-3, (1, P2, 3)) + 0.5).astype(np.float32)
+        x[0, :5] = rng.uniform(-50, 50, (5, 3))
+        y[0, :3] = rng.uniform(-50, 50, (3, 3))
+        return x, y
+    if kind == "offset":        # large common offset: coordinates ~1000, extent ~1 (face rounding vs the margin)
+        x = synth.modelnet_like(1, P1, seed=seed) + np.float32(1000.0)
+        y = synth.decompressed_like(x, seed=seed + 1)[:, :P2]
+        return x.astype(np.float32), y.astype(np.float32)
+    if kind == "disjoint":      # the two clouds do not overlap at all: every query leaves the other grid
+        x = synth.modelnet_like(1, P1, seed=seed)
+        y = synth.modelnet_like(1, P2, seed=seed + 1) + np.array([3.0, -2.0, 0.5], np.float32)
+        return x, y.astype(np.float32)
+    if kind == "line":          # points on a segment (one occupied row of cells) against a surface
+        t = rng.uniform(0, 1, (1, P1, 1)).astype(np.float32)
+        x = np.concatenate((t, 0.3 * t + 0.1, 0.5 - 0.2 * t), axis=2).astype(np.float32)
+        return x, synth.modelnet_like(1, P2, seed=seed)
+    raise ValueError(kind)
+
+
+@pytest.mark.parametrize("kind", ["ties", "identical", "outliers", "offset", "disjoint", "line"])
+@pytest.mark.parametrize("P1,P2", [(4096, 4096), (1024, 2500)])
+def test_chamfer_grid_path_adversarial_vs_oracle(pcc, orc, kind, P1, P2):
+    """The grid-pruned search (clouds >= 1024 points) must return exactly what the exhaustive search returns."""
+    x, y = _adversarial_pair(kind, P1, P2, seed=P1 + len(kind))
+    r = pcc.ops.chamfer_forward(cu(x), cu(y))
+    loss, pc, dx, ix, dy, iy = orc.chamfer(x, y, threads=8)
+    assert np.array_equal(r["dx"].cpu().numpy(), dx) and np.array_equal(r["dy"].cpu().numpy(), dy)
+    assert np.array_equal(r["ix"].cpu().numpy(), ix) and np.array_equal(r["iy"].cpu().numpy(), iy)
+    assert abs(r["loss"].item() - loss) <= CHAMFER_RTOL * abs(loss) + 1e-30
+
+
 def test_chamfer_full_batch_properties(pcc):
     """BASELINE size (32 x 8192 x 8192): symmetry, zero self-distance, agreement with the 1-NN entry point."""
     x = cu(synth.modelnet_like(32, 8192, seed=7))

@@ -20,6 +20,10 @@ cases = {
     "pnf 131-128-256": (lambda: mlp_ops.fused_chain([(feat, 1), (xyz, 1)], pna, out_dtype=torch.bfloat16), BS * 256 * 2 * (131 * 128 + 128 * 256)),
     "dec 144-128-64-32-3": (lambda: mlp_ops.fused_chain([(lin, 1), (lat, 128)], dec), BS * 128 * 2 * (144 * 128 + 128 * 64 + 64 * 32 + 32 * 3)),
 }
+tail = make_layers([256, 512, 16], [True, False], 4)
+h256 = mlp_ops.fused_chain([(feat, 1), (xyz, 1)], pna, out_dtype=torch.bfloat16)
+cases["pn tail 256-512-16 max256"] = (lambda: mlp_ops.pn_tail(h256, tail), BS * 256 * 2 * (256 * 512 + 512 * 16))
+cases["pn tail (library GEMMs)"] = (lambda: mlp_ops.library_chain(h256, tail).view(BS, 256, -1).max(dim=1)[0], BS * 256 * 2 * (256 * 512 + 512 * 16))
 for name, (fn, flop) in cases.items():
     for _ in range(3):
         fn()
