@@ -181,6 +181,8 @@ int pcc_mlp_chain(const PccMlpInput *inputs, int n_inputs, int64_t rows, const P
  * pcc_mlp_chain launches stores clock64() at its phase boundaries; pass NULL to switch it off (the default).
  */
 void pcc_debug_mlp_timing(long long *device_buf);
+/* same for the warp-specialised SetAbstraction chain (chain_ws.cu): 1024 int64, MMA warp ticks at [512..) */
+void pcc_debug_ws_timing(long long *device_buf);
 
 /*
  * Fused tail of pn_kit.PointNet (/root/reference/pn_kit.py:136-143 as configured by AE.py:17): per position

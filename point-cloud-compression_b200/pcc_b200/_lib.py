@@ -46,6 +46,7 @@ class PccMlpInput(ctypes.Structure):
 
 SIGNATURES.update({
     "pcc_debug_mlp_timing": (None, [_vp]),
+    "pcc_debug_ws_timing": (None, [_vp]),
     "pcc_normalize_f32": (_i, [_vp, _i, _i, _f, _vp, _vp, _vp, _vp, _vp]),
     "pcc_assemble_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _vp, _vp]),
     "pcc_mlp_chain": (_i, [ctypes.POINTER(PccMlpInput), _i, _i64, ctypes.POINTER(PccMlpLayer), _i, _i, _vp, _i, _vp]),
