@@ -32,6 +32,7 @@ METRIC = "point clouds/sec (8192 pts, K=256) compress+Chamfer eval"
 UNIT = "clouds/s"
 N_POINTS, K_PATCH, K_OUT, D_LATENT, L_LEVELS, N0, ALPHA = 8192, 256, 128, 16, 7, 1024, 2
 BATCH = 32
+SA_DRAM_BYTES = 189.16e6  # dram read+write of one sa_chain_kernel launch (profiles/r01_step_kernels_ncu_full.txt: 100.72 + 88.44 MB)
 POOL_BATCHES = 44  # 44 x 3.1 MB = 138 MB of distinct inputs > 126 MB L2 (no L2 flush needed between steps)
 WORKLOAD = ("cfg2-shape batch: 32 synthetic ModelNet40-shaped clouds x 8192 pts, K=256, S=64, d=16; "
             "compress -> decompress -> Chamfer + D1-PSNR eval (forward)")
@@ -165,22 +166,31 @@ def run_b200(args):
     start_idx = torch.zeros(BATCH, dtype=torch.int64, device=dev)
     batch_of = lambda t, s: t[(s % POOL_BATCHES) * BATCH:(s % POOL_BATCHES + 1) * BATCH]  # noqa: E731
 
-    # per-kernel timing hook: CUDA events around the Chamfer launch (the dominant kernel), recorded live
-    cham_events = []
-    orig_chamfer = pcc_b200.ops.chamfer_forward
+    # per-kernel timing hooks: CUDA events around the launches of the kernels that dominate the step, recorded live on
+    # torch's current stream (the stream every pcc kernel is launched on)
+    events = {"sa_chain": [], "knn_in_patch": [], "chamfer": [], "pn_tail": []}
     record = {"on": False}
 
-    def timed_chamfer(*a, **kw):
-        if not record["on"]:
-            return orig_chamfer(*a, **kw)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        out = orig_chamfer(*a, **kw)
-        e1.record()
-        cham_events.append((e0, e1))
-        return out
+    def timed(name, fn):
+        def wrapper(*a, **kw):
+            if not record["on"]:
+                return fn(*a, **kw)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = fn(*a, **kw)
+            e1.record()
+            events[name].append((e0, e1))
+            return out
+        return wrapper
 
-    pcc_b200.ops.chamfer_forward = timed_chamfer
+    from pcc_b200 import mlp_ops
+    orig_fused, orig_knn = mlp_ops.fused_chain, pcc_b200.ops.knn
+    sa_timed, knn_timed = timed("sa_chain", orig_fused), timed("knn_in_patch", orig_knn)
+    mlp_ops.fused_chain = lambda inputs, layers, group=0, out_dtype=torch.float32: (
+        sa_timed if group == 16 else orig_fused)(inputs, layers, group, out_dtype)
+    pcc_b200.ops.knn = lambda q, p, K, *a, **kw: (knn_timed if K == 16 else orig_knn)(q, p, K, *a, **kw)
+    pcc_b200.ops.chamfer_forward = timed("chamfer", pcc_b200.ops.chamfer_forward)
+    mlp_ops.pn_tail = timed("pn_tail", mlp_ops.pn_tail)
 
     def barrier():
         if dist is not None:
@@ -220,7 +230,7 @@ def run_b200(args):
     launches = lib.pcc_launch_count() - launches0
     clk = clocks.stop() if rank == 0 else None
     value = world * BATCH * args.steps / (dev_ms / 1e3)
-    cham_ms = float(np.mean([a.elapsed_time(b) for a, b in cham_events])) if cham_events else None
+    kernel_ms = {k: float(np.mean([a.elapsed_time(b) for a, b in v])) for k, v in events.items() if v}
 
     # ---- end to end from pinned host buffers ----
     out_lat = torch.empty((BATCH, N_POINTS * ALPHA // K_PATCH, D_LATENT), dtype=torch.int8).pin_memory()
@@ -266,28 +276,42 @@ def run_b200(args):
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
         roofline = None
-        if cham_ms:
-            # Dominant kernel = chamfer_onepass_kernel inside the Chamfer call (profiles/r01_launch_shares.txt).
-            # Algorithmic bytes per launch: 12*(P1+P2) in + 4*(P1+P2) per-point minima out, per cloud pair.
-            # It is FP32-issue bound, not HBM bound: every (x_i, y_j) pair is evaluated once (8 un-fused FP32 ops) and
-            # feeds both directions; 11.8 warp-level instructions per pair measured with ncu
-            # (profiles/r01_chamfer_ncu_full.txt: smsp__inst_executed.sum / (B*P1*P2)).
-            alg_bytes = BATCH * (12 * 2 * N_POINTS + 4 * 2 * N_POINTS)
-            pair_evals = 1.0 * BATCH * N_POINTS * N_POINTS
-            achieved = alg_bytes / (cham_ms / 1e3) / 1e9
+        if "sa_chain" in kernel_ms:
+            # Dominant kernel of the step = ws::sa_chain_kernel (pn_kit.SetAbstraction's 3-32-64-128 shared MLP + max over the
+            # 16 neighbours): tensor-pipe work.  Algorithmic FLOP per launch: 2 * MACs =
+            # 2 * (3*32 + 32*64 + 64*128) = 20,672 FLOP per (patch point, neighbour) position, B*S*K*16 positions per launch.
+            # (The 3 -> 32 layer runs in fp32 on the CUDA cores; it is 0.9 % of the FLOP and is counted.)
+            tf_peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
+            positions = BATCH * (N_POINTS * ALPHA // K_PATCH) * K_PATCH * 16
+            flop = positions * 2.0 * (3 * 32 + 32 * 64 + 64 * 128)
+            ms = kernel_ms["sa_chain"]
+            achieved = flop / (ms / 1e3) / 1e12
             fp32_peak = 34.4e12  # lane-instr/s measured with tools/ubench.cu (profiles/r01_ubench_fp32_pipes.txt)
-            instr_per_pair = 11.8
-            roofline = {"kernel": "chamfer_onepass_kernel (+ finalize) -- Chamfer, both directions from one pass",
-                        "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                        "traffic": 10.5e6, "peak_source": peak_src, "ms_per_launch": cham_ms,
-                        "note": "the schema offers hbm|tensor; this kernel is FP32-issue bound (196 KB of input per "
-                                "67 M pair evaluations): see fp32_issue. traffic = dram read+write of one launch from "
-                                "profiles/r01_chamfer_ncu_full.txt",
-                        "fp32_issue": {"pair_evals_per_launch": pair_evals, "instr_per_pair": instr_per_pair,
-                                       "achieved_lane_instr_per_s": pair_evals * instr_per_pair / (cham_ms / 1e3),
-                                       "peak_lane_instr_per_s": fp32_peak,
-                                       "frac": pair_evals * instr_per_pair / (cham_ms / 1e3) / fp32_peak,
-                                       "useful_frac": pair_evals * 8.0 / (cham_ms / 1e3) / fp32_peak}}
+            others = {}
+            if "knn_in_patch" in kernel_ms:  # in-patch kNN (K=16 of 256): 8 un-fused FP32 ops per pair
+                pairs = BATCH * (N_POINTS * ALPHA // K_PATCH) * K_PATCH * K_PATCH
+                others["knn_thread_kernel"] = {"ms_per_launch": kernel_ms["knn_in_patch"], "pair_evals": pairs, "bound": "fp32 issue",
+                                               "useful_frac": pairs * 8.0 / (kernel_ms["knn_in_patch"] / 1e3) / fp32_peak}
+            if "chamfer" in kernel_ms:       # exact grid-pruned Chamfer: algorithmic pairs = P1 * P2 per cloud, mostly culled
+                pairs = 1.0 * BATCH * N_POINTS * N_POINTS
+                others["grid_nn_kernel (+ build, finalize)"] = {
+                    "ms_per_launch": kernel_ms["chamfer"], "algorithmic_pair_evals": pairs, "bound": "L1 / FP32 issue",
+                    "algorithmic_gpairs_per_s": pairs / (kernel_ms["chamfer"] / 1e3) / 1e9,
+                    "note": "pairs evaluated << algorithmic pairs (culling); the brute-force kernel it replaces ran at 0.90 of the "
+                            "FP32 issue roof (profiles/r01_chamfer_ncu_full.txt)"}
+            if "pn_tail" in kernel_ms:       # 256-512-16 + max: tensor pipe, weights streamed from L2
+                fl = BATCH * (N_POINTS * ALPHA // K_PATCH) * K_PATCH * 2.0 * (256 * 512 + 512 * D_LATENT)
+                others["pn_tail_kernel"] = {"ms_per_launch": kernel_ms["pn_tail"], "bound": "tensor",
+                                            "achieved_tflops": fl / (kernel_ms["pn_tail"] / 1e3) / 1e12,
+                                            "frac": fl / (kernel_ms["pn_tail"] / 1e3) / 1e12 / tf_peak}
+            roofline = {"kernel": "ws::sa_chain_kernel -- SetAbstraction shared MLP 3-32-64-128 + max over 16 neighbours (tcgen05)",
+                        "bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
+                        "traffic": SA_DRAM_BYTES, "peak_source": peak_src + " bf16_tflops_sustained (kernel timed inside a long step)",
+                        "ms_per_launch": ms, "flop_per_launch": flop,
+                        "note": "K is 32..64 per layer, so the kernel is paced by the MMA -> epilogue -> MMA hand-offs of its four "
+                                "tiles in flight per SM (TMEM: 128 accumulator columns per tile), not by the tensor pipe; see "
+                                "DESIGN.md 4 and profiles/",
+                        "other_kernels": others}
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -295,9 +319,9 @@ def run_b200(args):
             "config": {"workload": WORKLOAD, "clouds_per_step_per_gpu": BATCH, "points": N_POINTS, "K": K_PATCH,
                        "parallelism": f"dp{world} (whole clouds sharded by rank, metrics all_gather only)",
                        "l2": f"rotating pool of {POOL_BATCHES} distinct input batches (138 MB > 126 MB L2), no flush",
-                       "mlp": "fused tcgen05 chains (SetAbstraction 3-32-64-128+max16, PointNet 131-128-256, decoder "
-                              "144-128-64-32-3); layers whose weights exceed shared memory (256-512-16, inv_pool) are "
-                              "library GEMMs"},
+                       "mlp": "hand-written tcgen05 kernels: SetAbstraction 3-32-64-128+max16, PointNet 131-128-256 and its "
+                              "256-512-16+max tail (W2 streamed by TMA), decoder 144-128-64-32-3; only inv_pool's three "
+                              "Linear layers (16-256-1024-16384, 4 % of the step) are still library GEMMs"},
             "clocks": clk, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "roofline": roofline, "cpu_baseline": cpu_base,

@@ -194,6 +194,13 @@ void pcc_debug_ws_timing(long long *device_buf);
 int pcc_pn_tail_bf16(const void *x, int64_t rows, int64_t ldx, const void *w2_bf16, const float *b2, const void *w3_packed,
                      int cout, int relu3, float *out, void *stream);
 
+/*
+ * Per-cloud eval.py metrics from the by-products of pcc_chamfer_fwd_f32(decompressed, original): out [B,3] float64 =
+ * (Chamfer on the (p - min) / (max - min) normalised clouds, eval.py:199-205; D1 PSNR in dB, eval.py:68-92; D1 MSE).
+ * dx [B,P1] = recon -> original squared distances, per_cloud [B], bbox [B,6] = (min xyz, max xyz) of the original.
+ */
+int pcc_eval_metrics_f32(const float *dx, const float *per_cloud, const float *bbox, int B, int P1, double *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -95,6 +95,40 @@ assemble_kernel(const float *__restrict__ patches, const float *__restrict__ cen
     }
 }
 
+// eval.py's per-cloud metrics from the Chamfer by-products, one CTA per cloud (all arithmetic in double, fixed order):
+//   chamfer = per_cloud / (max - min)^2                  eval.py:199-205 (the scale + shift normalisation divides d2)
+//   d1 mse  = mean_i dx[i]                               eval.py:84 (recon -> original)
+//   d1 psnr = 10 log10(|bbox diagonal|^2 / mse)          eval.py:88-92
+__global__ void __launch_bounds__(256)
+eval_metrics_kernel(const float *__restrict__ dx, const float *__restrict__ per_cloud, const float *__restrict__ bbox, int P1,
+                    double *__restrict__ out) {
+    __shared__ double red[8];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    double s = 0.0;
+    for (int i = tid; i < P1; i += 256) s += static_cast<double>(dx[static_cast<size_t>(b) * P1 + i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL_MASK, s, o);
+    if ((tid & 31) == 0) red[tid >> 5] = s;
+    __syncthreads();
+    if (tid == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        const double mse = t / static_cast<double>(P1);
+        const float *bb = bbox + static_cast<size_t>(b) * 6;
+        const double lo = fmin(fmin(static_cast<double>(bb[0]), static_cast<double>(bb[1])), static_cast<double>(bb[2]));
+        const double hi = fmax(fmax(static_cast<double>(bb[3]), static_cast<double>(bb[4])), static_cast<double>(bb[5]));
+        const double scale = hi - lo;
+        double diag2 = 0.0;
+        for (int a = 0; a < 3; ++a) {
+            const double e = static_cast<double>(bb[3 + a]) - static_cast<double>(bb[a]);
+            diag2 += e * e;
+        }
+        out[static_cast<size_t>(b) * 3 + 0] = static_cast<double>(per_cloud[b]) / (scale * scale);
+        out[static_cast<size_t>(b) * 3 + 1] = 10.0 * log10(diag2 / mse);
+        out[static_cast<size_t>(b) * 3 + 2] = mse;
+    }
+}
+
 }  // namespace pcc
 
 PCC_API int pcc_normalize_f32(const float *xyz, int B, int N, float margin, float *out, float *center, float *longest,
@@ -121,4 +155,13 @@ PCC_API int pcc_assemble_f32(const float *patches, const float *centres, const f
     assemble_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         patches, centres, center, longest, S, k, 1.0f / patch_scale, one_minus, total, out);
     return check_launch("assemble_kernel");
+}
+
+PCC_API int pcc_eval_metrics_f32(const float *dx, const float *per_cloud, const float *bbox, int B, int P1, double *out,
+                                 void *stream) {
+    using namespace pcc;
+    PCC_REQUIRE(dx && per_cloud && bbox && out, "pcc_eval_metrics_f32: null pointer");
+    PCC_REQUIRE(B >= 1 && P1 >= 1, "pcc_eval_metrics_f32: bad shape B=%d P1=%d", B, P1);
+    eval_metrics_kernel<<<B, 256, 0, static_cast<cudaStream_t>(stream)>>>(dx, per_cloud, bbox, P1, out);
+    return check_launch("eval_metrics_kernel");
 }

@@ -53,6 +53,7 @@ SIGNATURES.update({
     "pcc_mlp_packed_bytes": (_i64, [_i, _i]),
     "pcc_mlp_pack_weights_f32": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "pcc_mlp_chain_f32": (_i, [_vp, _i64, _i, ctypes.POINTER(PccMlpLayer), _i, _i, _vp, _vp]),
+    "pcc_eval_metrics_f32": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),
     "pcc_pn_tail_bf16": (_i, [_vp, _i64, _i64, _vp, _vp, _vp, _i, _i, _vp, _vp]),
 })
 

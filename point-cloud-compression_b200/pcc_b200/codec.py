@@ -79,14 +79,8 @@ class PatchCodec:
         raw ones divided by (max - min)^2, and the 1-NN assignment does not change."""
         if bbox is None:
             bbox = torch.cat((original.amin(dim=1), original.amax(dim=1)), dim=1)
-        bbox = bbox.double()
-        scale = bbox[:, 3:].amax(dim=1) - bbox[:, :3].amin(dim=1)                 # global max - global min (eval.py:199-200)
-        diag2 = ((bbox[:, 3:] - bbox[:, :3]) ** 2).sum(dim=1)                     # eval.py:88-89
         r = ops.chamfer_forward(decomp, original, want_idx=False)
-        mse = r["dx"].double().mean(dim=1)                                        # eval.py:84 (recon -> original)
-        cham = r["per_cloud"].double() / (scale * scale)
-        psnr = 10.0 * torch.log10(diag2 / mse)
-        return torch.stack((cham, psnr, mse), dim=1)
+        return ops.eval_metrics(r["dx"], r["per_cloud"], bbox)                    # eval.py:84,88-92,199-205 in one kernel
 
     @torch.no_grad()
     def roundtrip(self, xyz, start_idx=None):

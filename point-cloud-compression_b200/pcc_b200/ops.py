@@ -194,6 +194,19 @@ def chamfer_forward(x, y, want_idx=True):
     return dict(loss=loss.reshape(()), per_cloud=per_cloud, dx=dx, ix=ix, dy=dy, iy=iy)
 
 
+def eval_metrics(dx, per_cloud, bbox):
+    """[B,3] float64 (normalised Chamfer, D1 PSNR dB, D1 MSE) from chamfer_forward's dx / per_cloud and the original's
+    bbox [B,6] (eval.py:84,88-92,199-205)."""
+    lib = _lib.load()
+    B, P1 = dx.shape
+    bbox = bbox.detach().float().contiguous()
+    out = torch.empty((B, 3), dtype=torch.float64, device=dx.device)
+    with torch.cuda.device(dx.device):
+        _lib.check(lib.pcc_eval_metrics_f32(_ptr(dx), _ptr(per_cloud), _ptr(bbox), B, P1, _ptr(out), _stream()),
+                   "pcc_eval_metrics_f32")
+    return out
+
+
 class _Chamfer(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, y):
