@@ -275,9 +275,10 @@ static int launch_block(const float *q, const float *p, int B, int P1, int P2, i
 
 // ---- thread-per-query kernel ---------------------------------------------------------------------------------
 constexpr int KT_THREADS = 256;
+constexpr int KT_PENDING = 32;
 
 template <int KT>
-__global__ void __launch_bounds__(KT_THREADS)
+__global__ void __launch_bounds__(KT_THREADS, KT <= 16 ? 4 : 2)
 knn_thread_kernel(const float *__restrict__ q, const float *__restrict__ p, int P1, int P2, int K,
                   float *__restrict__ out_d2, int64_t *__restrict__ out_idx, float *__restrict__ out_nn,
                   int centre_sub, float nn_scale) {
@@ -286,9 +287,8 @@ knn_thread_kernel(const float *__restrict__ q, const float *__restrict__ p, int 
     constexpr int STAGE_BYTES = KT_THREADS * STAGE_LD * 4;
     __shared__ __align__(16) unsigned char smem_raw[TILE_BYTES > STAGE_BYTES ? TILE_BYTES : STAGE_BYTES];
     __shared__ float sq[KT_THREADS * 3];
-    constexpr int PB = KT <= 16 ? 8 : 4;  // pending queue depth (shared memory budget)
-    __shared__ float pend_d[PB][KT_THREADS];
-    __shared__ unsigned pend_i[PB][KT_THREADS];
+    constexpr int PB = KT <= 16 ? KT_PENDING : KT_PENDING / 2;  // pending queue depth: candidate indices only (the distance is re-evaluated when drained)
+    __shared__ unsigned short pend_i[PB][KT_THREADS];
     float4 *tile = reinterpret_cast<float4 *>(smem_raw);
     unsigned *stage = reinterpret_cast<unsigned *>(smem_raw);
 
@@ -309,6 +309,57 @@ knn_thread_kernel(const float *__restrict__ q, const float *__restrict__ p, int 
     sq[threadIdx.x * 3 + 1] = qy;
     sq[threadIdx.x * 3 + 2] = qz;
 
+
+    // the candidate set is one shared-memory tile (the dispatch guarantees P2 <= KNN_TILE)
+    const int tn = P2;
+    __syncthreads();
+    for (int pt = threadIdx.x; pt < tn; pt += KT_THREADS) {
+        const float *s = pc_ + static_cast<size_t>(pt) * 3;
+        tile[pt] = make_float4(s[0], s[1], s[2], 0.f);
+    }
+    __syncthreads();
+    float worst = __int_as_float(0x7f800000);
+    {
+        if (tn >= 64) {
+            // A-priori threshold: the KT-th smallest of G >= KT group minima is >= the KT-th smallest distance overall (KT
+            // distinct candidates are <= it).  With 32 strided groups of 8 only ~8 % of the candidates pass it (rank ~21 of
+            // 256 for K = 16), so one extra pass of 9 instructions per pair + a 32-value register sort replaces the whole
+            // threshold warm-up and most of its ~85-instruction sorted insertions.  Groups are strided (j mod 32): the
+            // callers' candidates are often ordered (kNN patches come sorted by distance from the patch centre), and
+            // contiguous groups would then be radial shells with useless minima.
+            constexpr int G = 32;
+            float m[G];
+#pragma unroll
+            for (int g0 = 0; g0 < G; ++g0) m[g0] = __int_as_float(0x7f800000);
+            const int full = tn / G * G;
+            for (int j0 = 0; j0 < full; j0 += G) {
+#pragma unroll
+                for (int g0 = 0; g0 < G; ++g0) {
+                    const float4 c = tile[j0 + g0];
+                    m[g0] = fminf(m[g0], dist2_rn(qx, qy, qz, c.x, c.y, c.z));
+                }
+            }
+            // bitonic sort of the 32 minima in registers (values only: one FMNMX pair per compare-exchange)
+#pragma unroll
+            for (int k = 2; k <= G; k <<= 1) {
+#pragma unroll
+                for (int jj = k >> 1; jj > 0; jj >>= 1) {
+#pragma unroll
+                    for (int i = 0; i < G; ++i) {
+                        const int l = i ^ jj;
+                        if (l > i) {
+                            const float lo = fminf(m[i], m[l]), hi = fmaxf(m[i], m[l]);
+                            const bool up = (i & k) == 0;
+                            m[i] = up ? lo : hi;
+                            m[l] = up ? hi : lo;
+                        }
+                    }
+                }
+            }
+            const float tau = m[KT - 1 < G ? KT - 1 : G - 1];   // KT-th smallest (KT <= 32)
+            worst = __uint_as_float(__float_as_uint(tau) + 1u);   // next float up: `d < worst` admits d == tau (d2 >= +0)
+        }
+    }
     float dl[KT];
     unsigned il[KT];
 #pragma unroll
@@ -316,14 +367,13 @@ knn_thread_kernel(const float *__restrict__ q, const float *__restrict__ p, int 
         dl[s] = __int_as_float(0x7f800000);  // +inf: unfilled
         il[s] = 0u;
     }
-
+    int pc = 0;
+    unsigned short *pq = &pend_i[0][threadIdx.x];
     // Sorted insertion costs ~5 instructions per list slot and, thread-per-query, a warp pays it whenever ANY lane
     // inserts -- i.e. for almost every candidate.  Candidates that beat the (possibly stale) K-th best are therefore only
     // parked in a per-thread shared-memory queue (2 predicated stores); the warp drains all queues, in candidate order,
     // when one of them is full.  The result is identical to immediate insertion: the list changes only through the same
     // insertions in the same order, and a stale threshold only lets extra candidates through to the exact re-test.
-    int pc = 0;
-    float worst = __int_as_float(0x7f800000);
     auto insert = [&](float d, unsigned j) {
         if (d < dl[KT - 1]) {  // strict: an equal distance with a larger index never displaces
             dl[KT - 1] = d;
@@ -342,30 +392,43 @@ knn_thread_kernel(const float *__restrict__ q, const float *__restrict__ p, int 
     };
     auto drain = [&]() {
         const int n = __reduce_max_sync(FULL_MASK, pc);
-        for (int s = 0; s < n; ++s)
-            if (s < pc) insert(pend_d[s][threadIdx.x], pend_i[s][threadIdx.x]);
+        for (int s = 0; s < n; ++s) {
+            if (s < pc) {
+                const unsigned j = pend_i[s][threadIdx.x];
+                const float4 c = tile[j];
+                insert(dist2_rn(qx, qy, qz, c.x, c.y, c.z), j);   // bit-identical to the value that passed the test
+            }
+        }
         pc = 0;
-        worst = dl[KT - 1];
+        pq = &pend_i[0][threadIdx.x];
+        worst = fminf(worst, dl[KT - 1]);   // the list may not be full yet: keep the a-priori bound
     };
 
-    for (int t0 = 0; t0 < P2; t0 += KNN_TILE) {
-        const int tn = min(KNN_TILE, P2 - t0);
-        __syncthreads();
-        for (int pt = threadIdx.x; pt < tn; pt += KT_THREADS) {
-            const float *s = pc_ + static_cast<size_t>(t0 + pt) * 3;
-            tile[pt] = make_float4(s[0], s[1], s[2], 0.f);
-        }
-        __syncthreads();
-        for (int j = 0; j < tn; ++j) {
-            const float4 c = tile[j];
+    // main pass: 8 candidates per queue-occupancy vote (a queue never gains more than 8 entries in between)
+    constexpr int UN = 8;
+    int j = 0;
+    for (; j + UN <= tn; j += UN) {
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            const float4 c = tile[j + u];
             const float d = dist2_rn(qx, qy, qz, c.x, c.y, c.z);
             if (d < worst) {
-                pend_d[pc][threadIdx.x] = d;
-                pend_i[pc][threadIdx.x] = static_cast<unsigned>(t0 + j);
+                *pq = static_cast<unsigned short>(j + u);
+                pq += KT_THREADS;
                 ++pc;
             }
-            if (__any_sync(FULL_MASK, pc == PB)) drain();
         }
+        if (__any_sync(FULL_MASK, pc > PB - UN)) drain();
+    }
+    for (; j < tn; ++j) {
+        const float4 c = tile[j];
+        const float d = dist2_rn(qx, qy, qz, c.x, c.y, c.z);
+        if (d < worst) {
+            *pq = static_cast<unsigned short>(j);
+            pq += KT_THREADS;
+            ++pc;
+        }
+        if (__any_sync(FULL_MASK, pc > PB - UN)) drain();
     }
     drain();
     __syncthreads();  // tile no longer needed: reuse as output staging
@@ -394,7 +457,16 @@ knn_thread_kernel(const float *__restrict__ q, const float *__restrict__ p, int 
             out_idx[obase + e] = static_cast<int64_t>(stage[ql * STAGE_LD + k]);
         }
     }
-    if (out_nn) {
+    if (out_nn && K == KT) {   // compile-time divisors
+        for (int e = threadIdx.x; e < nq * KT * 3; e += KT_THREADS) {
+            const int pk = e / 3, c = e - pk * 3;
+            const int ql = pk / KT, k = pk - ql * KT;
+            float v = pc_[static_cast<size_t>(stage[ql * STAGE_LD + k]) * 3 + c];
+            if (centre_sub) v = __fsub_rn(v, sq[ql * 3 + c]);
+            if (nn_scale != 1.0f) v = __fmul_rn(v, nn_scale);
+            out_nn[obase * 3 + e] = v;
+        }
+    } else if (out_nn) {
         for (int e = threadIdx.x; e < nq * K * 3; e += KT_THREADS) {
             const int pk = e / 3, c = e - pk * 3;
             const int ql = pk / K, k = pk - ql * K;
