@@ -201,6 +201,35 @@ int pcc_pn_tail_bf16(const void *x, int64_t rows, int64_t ldx, const void *w2_bf
  */
 int pcc_eval_metrics_f32(const float *dx, const float *per_cloud, const float *bbox, int B, int P1, double *out, void *stream);
 
+/*
+ * Octree coding of the patch centres, the stage between FPS and kNN patching.
+ * pcc_octree_encode_f32 replaces octree_np.encode (/root/reference/octree_np.py:10-45, with its getDecodeFromPc snap,
+ * :114-133) and the per-cloud depth search of pn_kit.encode_sampled_np (/root/reference/pn_kit.py:380-401; call sites
+ * train.py:176, compress.py:98) at scale = 1:  fixed_depth = 0 searches depth 1..16 for the first depth whose stream has
+ * nbits / n_points > min_bpp with all S centres in distinct cells (depth 16 if none does); fixed_depth in 1..16 encodes at
+ * that depth.  centres [B, S, 3] must lie in [0, 1) (octree_np.py:5-7); a cloud that does not gets out_depth = -1,
+ * out_nbits = 0.  S <= 8192.
+ *   out_bits  [B, max_bits] uint8, one byte per bit (the reference's np.uint8 array), zero beyond out_nbits[b];
+ *             max_bits >= pcc_octree_max_bits(S) (or 1 + 8 * fixed_depth * S);
+ *   out_nbits [B] int32, out_depth [B] int32 (depth of the returned code);
+ *   out_bytes (nullable) [B, (max_bits + 7) / 8]: pn_kit.binary_array_to_byte_array of the stream (pn_kit.py:463-467;
+ *             compress.py:144), (out_nbits + 7) / 8 bytes used;
+ *   out_quant (nullable) [B, S, 3]: octree_np.getDecodeFromPc of every centre at the chosen depth, input order;
+ *   out_rec_ref (nullable) [B, 64, 3]: what the reference's decoder returns for this stream (see below);
+ *   out_stream_xyz (nullable) [B, S, 3]: what pcc_octree_decode_f32 mode 1 returns for this stream (the distinct leaf
+ *             centres in stream order, the last one repeated up to S rows) -- the centres a decoder will see.
+ * pcc_octree_decode_f32: mode 0 = octree_np.decode exactly as written (/root/reference/octree_np.py:47-112;
+ * pn_kit.decode_sampled_np, pn_kit.py:424-431): it consumes the first 8 bits only, returns depth-1 octant centres and pads
+ * to 64 rows (cap must be 64); mode 1 = the inverse of the encoder (leaf centres in stream order, the last one
+ * repeated after out_count[b], at most cap).  bits [B, max_bits] uint8, nbits [B] int32, out_xyz [B, cap, 3].
+ */
+int pcc_octree_max_bits(int S);
+int pcc_octree_encode_f32(const float *centres, int B, int S, int n_points, double min_bpp, int fixed_depth,
+                          uint8_t *out_bits, int max_bits, int32_t *out_nbits, int32_t *out_depth, uint8_t *out_bytes,
+                          float *out_quant, float *out_rec_ref, float *out_stream_xyz, void *stream);
+int pcc_octree_decode_f32(const uint8_t *bits, const int32_t *nbits, int B, int max_bits, int mode, int cap, float *out_xyz,
+                          int32_t *out_count, int32_t *out_depth, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

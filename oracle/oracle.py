@@ -18,6 +18,7 @@ _f32p = ctypes.POINTER(ctypes.c_float)
 _i64p = ctypes.POINTER(ctypes.c_int64)
 _f64p = ctypes.POINTER(ctypes.c_double)
 _i64 = ctypes.c_int64
+_u8p = ctypes.POINTER(ctypes.c_uint8)
 
 
 def build(force=False):
@@ -45,6 +46,16 @@ def lib():
         L.orc_chamfer_bwd.argtypes = [_f32p, _f32p, _i64p, _i64p, _i64, _i64, _i64, ctypes.c_float, _f32p, _f32p]
         L.orc_d1_psnr.argtypes = [_f32p, _i64, _f32p, _i64, _f64p]
         L.orc_d1_psnr.restype = ctypes.c_double
+        L.orc_octree_quantise.argtypes = [_f32p, _i64, ctypes.c_double, ctypes.c_int, _f32p, _f32p]
+        L.orc_octree_quantise.restype = _i64
+        L.orc_octree_encode.argtypes = [_f32p, _i64, ctypes.c_double, ctypes.c_int, _u8p, _i64, _i64p]
+        L.orc_octree_encode.restype = _i64
+        L.orc_octree_encode_sampled.argtypes = [_f32p, _i64, ctypes.c_double, _i64, ctypes.c_double, _u8p, _i64,
+                                                ctypes.POINTER(ctypes.c_int)]
+        L.orc_octree_encode_sampled.restype = _i64
+        L.orc_octree_decode_ref.argtypes = [_u8p, _i64, ctypes.c_double, _f32p]
+        L.orc_bits_to_bytes.argtypes = [_u8p, _i64, _u8p]
+        L.orc_bits_to_bytes.restype = _i64
         _lib = L
     return _lib
 
@@ -165,3 +176,64 @@ def d1_psnr(orig, recon):
     mse = ctypes.c_double(0.0)
     psnr = lib().orc_d1_psnr(_pf(orig), orig.shape[0], _pf(recon), recon.shape[0], ctypes.byref(mse))
     return float(psnr), float(mse.value)
+
+
+# ---- octree centre coding (octree_np.py, pn_kit.py:380-475) -------------------------------------------------------
+def _pu8(a):
+    return a.ctypes.data_as(_u8p)
+
+
+def octree_quantise(pc, resolution, depth):
+    """octree_np.getDecodeFromPc for one [S,3] cloud: returns (snapped [S,3] in input order, unique rows [U,3])."""
+    pc = _f32(pc)
+    S = pc.shape[0]
+    snapped = np.empty((S, 3), np.float32)
+    uniq = np.empty((max(S, 1), 3), np.float32)
+    n = lib().orc_octree_quantise(_pf(pc), S, float(resolution), int(depth), _pf(snapped), _pf(uniq))
+    return snapped, uniq[:n].copy()
+
+
+def octree_encode(pc, resolution, depth):
+    """octree_np.encode(pc, resolution, depth) -> uint8 bit array."""
+    pc = _f32(pc)
+    S = pc.shape[0]
+    cap = 1 + 8 * (depth + 1) * max(S, 1) + 64
+    bits = np.zeros(cap, np.uint8)
+    n = lib().orc_octree_encode(_pf(pc), S, float(resolution), int(depth), _pu8(bits), cap, None)
+    assert n >= 0
+    return bits[:n].copy()
+
+
+def encode_sampled_np(sampled_xyz, scale, N, min_bpp):
+    """pn_kit.encode_sampled_np -> (codes list, total bits, depths)."""
+    sampled_xyz = _f32(sampled_xyz)
+    codes, depths, total = [], [], 0
+    S = sampled_xyz.shape[1]
+    cap = 1 + 8 * 17 * max(S, 1) + 64
+    for pc in sampled_xyz:
+        pc = np.ascontiguousarray(pc)
+        bits = np.zeros(cap, np.uint8)
+        d = ctypes.c_int(0)
+        n = lib().orc_octree_encode_sampled(_pf(pc), S, float(scale), int(N), float(min_bpp), _pu8(bits), cap,
+                                            ctypes.byref(d))
+        assert n >= 0
+        codes.append(bits[:n].copy())
+        depths.append(d.value)
+        total += int(n)
+    return codes, total, depths
+
+
+def octree_decode_ref(bits, resolution=1.0):
+    """octree_np.decode exactly as the reference wrote it (first 8 bits -> depth-1 octant centres, padded to 64)."""
+    bits = np.ascontiguousarray(bits, dtype=np.uint8)
+    out = np.empty((64, 3), np.float32)
+    lib().orc_octree_decode_ref(_pu8(bits), bits.shape[0], float(resolution), _pf(out))
+    return out
+
+
+def bits_to_bytes(bits):
+    """pn_kit.binary_array_to_byte_array."""
+    bits = np.ascontiguousarray(bits, dtype=np.uint8)
+    out = np.zeros((bits.shape[0] + 7) // 8, np.uint8)
+    n = lib().orc_bits_to_bytes(_pu8(bits), bits.shape[0], _pu8(out))
+    return out[:n]

@@ -330,3 +330,170 @@ ORC_API double orc_d1_psnr(const float *orig, int64_t No, const float *recon, in
     for (int c = 0; c < 3; ++c) diag2 += (mx[c] - mn[c]) * (mx[c] - mn[c]);
     return mse > 0 ? 10.0 * log10(diag2 / mse) : INFINITY;
 }
+
+/* ================================================================================================
+ * Octree centre coding.  Restates, literally, the reference's numpy coder:
+ *   octree_np.getDecodeFromPc   /root/reference/octree_np.py:114-133   (float32 floor-divide snap + np.unique)
+ *   octree_np.encode            /root/reference/octree_np.py:10-45     (stack DFS, children popped 7..0,
+ *                                                                        bits appended per level, inclusive masks)
+ *   octree_np.decode            /root/reference/octree_np.py:47-112    (as written: it consumes only the first
+ *                                                                        8 bits, emits depth-1 octant centres and
+ *                                                                        pads to 64 rows -- SURVEY.md appendix B-2)
+ *   pn_kit.encode_sampled_np    /root/reference/pn_kit.py:380-401      (depth search 1..16)
+ *   pn_kit.binary_array_to_byte_array / byte_array_to_binary_array   pn_kit.py:463-475
+ * PINNED: tests/golden/ref_octree.npz holds the outputs of these reference functions themselves.
+ * ============================================================================================== */
+
+/* numpy's float32 floor_divide (npy_divmodf, numpy/core/src/npymath/npy_math_internal.h.src) */
+static float np_floor_divide_f32(float a, float b) {
+    float mod = fmodf(a, b);
+    if (b == 0.0f) return a / b;
+    float div = (a - mod) / b;
+    if (mod != 0.0f) {
+        if ((b < 0) != (mod < 0)) div -= 1.0f;
+    }
+    float floordiv;
+    if (div != 0.0f) {
+        floordiv = floorf(div);
+        if (div - floordiv > 0.5f) floordiv += 1.0f;
+    } else {
+        floordiv = copysignf(0.0f, a / b);
+    }
+    return floordiv;
+}
+
+static int cmp_row3(const void *pa, const void *pb) {
+    const float *a = (const float *)pa, *b = (const float *)pb;
+    for (int c = 0; c < 3; ++c) {
+        if (a[c] < b[c]) return -1;
+        if (a[c] > b[c]) return 1;
+    }
+    return 0;
+}
+
+/* getDecodeFromPc for one [S,3] cloud: snapped points (row order kept) into `snapped` (nullable), the np.unique'd rows
+ * into `uniq` (lexicographically ascending); returns the number of unique rows. */
+ORC_API int64_t orc_octree_quantise(const float *pc, int64_t S, double resolution, int depth, float *snapped, float *uniq) {
+    int capped = depth < 30 ? depth : 30;
+    double divisor = pow(2.0, (double)capped);
+    if (divisor < 1.0) divisor = 1.0;
+    double cube = resolution / divisor;
+    if (cube < 1e-6) cube = 1e-6;
+    const float cr = (float)cube;          /* python float is a weak scalar against a float32 array (NEP 50) */
+    const float half = (float)(cube / 2);
+    for (int64_t i = 0; i < S * 3; ++i) {
+        float v = np_floor_divide_f32(pc[i], cr) * cr + half;
+        if (isnan(v)) v = 0.0f;            /* np.nan_to_num */
+        else if (isinf(v)) v = v > 0 ? FLT_MAX : -FLT_MAX;
+        uniq[i] = v;
+        if (snapped) snapped[i] = v;
+    }
+    qsort(uniq, (size_t)S, 3 * sizeof(float), cmp_row3);
+    int64_t n = 0;
+    for (int64_t i = 0; i < S; ++i)
+        if (i == 0 || cmp_row3(uniq + 3 * i, uniq + 3 * (n - 1)) != 0) {
+            memmove(uniq + 3 * n, uniq + 3 * i, 3 * sizeof(float));
+            ++n;
+        }
+    return n;
+}
+
+typedef struct { double x, y, z; int d; } OrcNode;
+
+/* octree_np.encode: returns the number of bits written to out_bits (one uint8 per bit), or -1 if cap is too small. */
+ORC_API int64_t orc_octree_encode(const float *pc, int64_t S, double resolution, int depth, uint8_t *out_bits, int64_t cap,
+                                  int64_t *out_unique) {
+    float *uniq = (float *)malloc((size_t)(S > 0 ? S : 1) * 3 * sizeof(float));
+    const int64_t U = orc_octree_quantise(pc, S, resolution, depth, NULL, uniq);
+    if (out_unique) *out_unique = U;
+    /* per-level bit lists */
+    int64_t *len = (int64_t *)calloc((size_t)depth + 1, sizeof(int64_t));
+    int64_t *capl = (int64_t *)calloc((size_t)depth + 1, sizeof(int64_t));
+    uint8_t **lev = (uint8_t **)calloc((size_t)depth + 1, sizeof(uint8_t *));
+    int64_t scap = 64, sp = 0;
+    OrcNode *stack = (OrcNode *)malloc((size_t)scap * sizeof(OrcNode));
+    stack[sp++] = (OrcNode){0.0, 0.0, 0.0, 0};
+    while (sp > 0) {
+        const OrcNode nd = stack[--sp];
+        const double reso = resolution / pow(2.0, (double)nd.d);
+        int any = 0;
+        for (int64_t i = 0; i < U && !any; ++i) {
+            /* float32 array against python floats: the scalars are cast to float32 (weak scalars) */
+            const float x = uniq[3 * i], y = uniq[3 * i + 1], z = uniq[3 * i + 2];
+            any = (float)nd.x <= x && x <= (float)(nd.x + reso) && (float)nd.y <= y && y <= (float)(nd.y + reso) &&
+                  (float)nd.z <= z && z <= (float)(nd.z + reso);
+        }
+        if (len[nd.d] == capl[nd.d]) {
+            capl[nd.d] = capl[nd.d] ? 2 * capl[nd.d] : 64;
+            lev[nd.d] = (uint8_t *)realloc(lev[nd.d], (size_t)capl[nd.d]);
+        }
+        lev[nd.d][len[nd.d]++] = (uint8_t)any;
+        if (any && nd.d < depth) {
+            const double h = reso / 2;
+            if (sp + 8 > scap) {
+                scap *= 2;
+                stack = (OrcNode *)realloc(stack, (size_t)scap * sizeof(OrcNode));
+            }
+            for (int c = 0; c < 8; ++c)  /* pushed 0..7 (x is the slowest bit), popped 7..0 */
+                stack[sp++] = (OrcNode){nd.x + ((c >> 2) & 1) * h, nd.y + ((c >> 1) & 1) * h, nd.z + (c & 1) * h, nd.d + 1};
+        }
+    }
+    int64_t n = 0, ok = 1;
+    for (int l = 0; l <= depth; ++l) {
+        if (n + len[l] > cap) ok = 0;
+        if (ok) memcpy(out_bits + n, lev[l], (size_t)len[l]);
+        n += len[l];
+        free(lev[l]);
+    }
+    free(lev); free(len); free(capl); free(stack); free(uniq);
+    return ok ? n : -1;
+}
+
+/* pn_kit.encode_sampled_np for one cloud: depth search 1..16 (pn_kit.py:386-396); returns nbits, *out_depth = the depth
+ * of the returned code (the reference's DEPTH counter overshoots to 17 when nothing converged; the code is depth 16). */
+ORC_API int64_t orc_octree_encode_sampled(const float *pc, int64_t S, double scale, int64_t N, double min_bpp, uint8_t *out_bits,
+                                          int64_t cap, int *out_depth) {
+    int64_t nb = -1;
+    int depth = 1;
+    for (int attempt = 0; attempt < 16; ++attempt) {
+        int64_t U = 0;
+        nb = orc_octree_encode(pc, S, scale, depth, out_bits, cap, &U);
+        if (nb < 0) return -1;
+        const double bpp = (double)nb / (double)N;
+        if (bpp > min_bpp && U == S) break;
+        if (attempt < 15) depth += 1;
+    }
+    if (out_depth) *out_depth = depth;
+    return nb;
+}
+
+/* octree_np.decode exactly as written (see the header note): out [64,3]. */
+ORC_API void orc_octree_decode_ref(const uint8_t *bits, int64_t nbits, double resolution, float *out) {
+    const int64_t g = nbits < 8 ? nbits : 8;
+    int64_t n = 0;
+    const double reso = resolution / 2.0;  /* curr_cube_reso at depth 1 */
+    for (int64_t j = 0; j < g; ++j) {      /* j-th popped child is octant 7 - j */
+        if (bits[j] != 1) continue;
+        const int c = 7 - (int)j;
+        out[3 * n + 0] = (float)(((c >> 2) & 1) * reso + reso / 2);
+        out[3 * n + 1] = (float)(((c >> 1) & 1) * reso + reso / 2);
+        out[3 * n + 2] = (float)((c & 1) * reso + reso / 2);
+        ++n;
+    }
+    if (n == 0) {
+        memset(out, 0, 64 * 3 * sizeof(float));
+        return;
+    }
+    for (int64_t i = n; i < 64; ++i) memcpy(out + 3 * i, out + 3 * (n - 1), 3 * sizeof(float));
+}
+
+/* pn_kit.binary_array_to_byte_array: chunks of 8 bits, MSB first; a short last chunk is read as a short binary number. */
+ORC_API int64_t orc_bits_to_bytes(const uint8_t *bits, int64_t nbits, uint8_t *out) {
+    int64_t nb = 0;
+    for (int64_t i = 0; i < nbits; i += 8) {
+        unsigned v = 0;
+        for (int64_t t = i; t < i + 8 && t < nbits; ++t) v = (v << 1) | (bits[t] & 1u);
+        out[nb++] = (uint8_t)v;
+    }
+    return nb;
+}

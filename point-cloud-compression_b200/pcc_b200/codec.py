@@ -1,11 +1,15 @@
 """Batched compress / decompress / eval drivers for the IPDAE patch codec: the hot path of the reference's
 compress.py:78-127, decompress.py:96-116 and eval.py:180,199-205 run for many clouds per launch.
 
-Only the data-parallel hot path is here.  Octree centre coding and the entropy coder stay on the reference path
-(north_star); where the reference round-trips the FPS centres through its octree coder on the host
-(compress.py:98-101) this driver applies the coder's quantisation rule (octree_np.getDecodeFromPc:
-floor(c / cube) * cube + cube / 2) on the device at a fixed depth, keeping the FPS order -- SURVEY.md 8d
-"intended" centres (ii).
+Only the data-parallel hot path is here; the entropy coder stays on the reference path (north_star).  Where the
+reference round-trips the FPS centres through its octree coder on the host (compress.py:98-101) this driver has three
+centre modes:
+  "fixed"      the coder's quantisation rule (octree_np.getDecodeFromPc: floor(c / cube) * cube + cube / 2) fused into
+               the FPS kernel at a fixed depth, FPS order kept -- SURVEY.md 8d "intended" centres (ii); no bit stream;
+  "coded"      the reference's coder on the device (ops.octree_encode: pn_kit.encode_sampled_np's depth search, bit-exact
+               stream and .s.bin bytes) and the centres a correct decoder recovers from that stream (stream order);
+  "reference"  the same stream, and the centres the reference's own decoder returns for it (octree_np.decode as written:
+               at most 8 distinct depth-1 octant centres padded to 64 -- SURVEY.md appendix B-2); needs S == 64.
 """
 import math
 
@@ -39,9 +43,14 @@ def quantise_centres(centres, depth, resolution=1.0):
     return torch.floor(centres / cube) * cube + cube / 2
 
 
+OCTREE_BPP_DICT = {1024: 0.07, 512: 0.125, 256: 0.25, 128: 0.5, 64: 1.0}  # pn_kit.py:17-23
+
+
 class PatchCodec:
-    def __init__(self, ae: AE, N0=1024, alpha=2, centre_depth=6):
-        self.ae, self.N0, self.alpha, self.centre_depth = ae, N0, alpha, centre_depth
+    def __init__(self, ae: AE, N0=1024, alpha=2, centre_depth=6, centre_mode="fixed"):
+        if centre_mode not in ("fixed", "coded", "reference"):
+            raise ValueError("PatchCodec: centre_mode must be 'fixed', 'coded' or 'reference'")
+        self.ae, self.N0, self.alpha, self.centre_depth, self.centre_mode = ae, N0, alpha, centre_depth, centre_mode
 
     def patch_scale(self, N):
         return (N / self.N0) ** (1 / 3)  # compress.py:108
@@ -55,13 +64,23 @@ class PatchCodec:
         pc, center, longest, bbox = ops.normalize(xyz)                            # compress.py:90 (one fused kernel)
         if start_idx is None:                                                     # compress.py:96 (CPU RNG draw, pn_kit.py:321)
             start_idx = torch.randint(0, N, (B,), dtype=torch.long).to(xyz.device)
-        cube = 1.0 / max(1.0, math.pow(2.0, min(self.centre_depth, 30)))
-        _, rec_centres = ops.fps(pc, S, start_idx, 1e10, return_xyz=True, quant_cube=cube)  # compress.py:96-101
+        octree = None
+        if self.centre_mode == "fixed":
+            cube = 1.0 / max(1.0, math.pow(2.0, min(self.centre_depth, 30)))
+            _, rec_centres = ops.fps(pc, S, start_idx, 1e10, return_xyz=True, quant_cube=cube)  # compress.py:96-101
+        else:
+            if self.centre_mode == "reference" and S != 64:
+                raise ValueError("centre_mode='reference': octree_np.decode returns 64 rows (octree_np.py:100), so S must be 64")
+            _, centres = ops.fps(pc, S, start_idx, 1e10, return_xyz=True)         # compress.py:96
+            ref = self.centre_mode == "reference"
+            octree = ops.octree_encode(centres, N, OCTREE_BPP_DICT[K], 0, want_bytes=True,  # compress.py:98,144
+                                       want_rec_ref=ref, want_stream_xyz=not ref)
+            rec_centres = octree["rec_ref"] if ref else octree["stream_xyz"]      # compress.py:100-101
         _, _, patches = ops.knn(rec_centres, pc, K, return_nn=True, centre_sub=True,
                                 nn_scale=self.patch_scale(N), nn_only=True)       # compress.py:105-108
         latent, latent_q = self.ae.encode_patches(patches.view(B * S, K, 3))      # compress.py:113-127
         return dict(latent_q=latent_q.view(B, S, -1), latent=latent.view(B, S, -1), centres=rec_centres, center=center,
-                    longest=longest, bbox=bbox, pc=pc)
+                    longest=longest, bbox=bbox, pc=pc, octree=octree)
 
     @torch.no_grad()
     def decompress(self, latent_q, centres, N, center=None, longest=None):

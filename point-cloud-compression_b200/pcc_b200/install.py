@@ -8,7 +8,7 @@ Use:  import pcc_b200; pcc_b200.install(); import pn_kit, AE, ...      (see INTE
 import sys
 import types
 
-from . import pn_kit_ops, pointnet_ops, pytorch3d_compat as p3d
+from . import octree_ops, pn_kit_ops, pointnet_ops, pytorch3d_compat as p3d
 
 
 def _module(name):
@@ -40,6 +40,11 @@ def patch_reference_modules():
         pn.farthest_point_sample_batch = pn_kit_ops.farthest_point_sample_batch
         pn.index_points = pn_kit_ops.index_points
         pn.knn_points, pn.knn_gather = p3d.knn_points, p3d.knn_gather
+        pn.encode_sampled_np = octree_ops.encode_sampled_np          # pn_kit.py:380-401
+        pn.decode_sampled_np = octree_ops.decode_sampled_np          # pn_kit.py:424-431
+    on = sys.modules.get("octree_np")
+    if on is not None:
+        on.encode, on.decode = octree_ops.encode, octree_ops.decode  # octree_np.py:10-45, 47-112
     pp = sys.modules.get("pppe_pcd_ae")
     if pp is not None:
         pp.farthest_point_sample_batch = pn_kit_ops.farthest_point_sample_batch

@@ -233,3 +233,48 @@ class _Chamfer(torch.autograd.Function):
 def chamfer(x, y):
     """Differentiable Chamfer distance (mean/mean), scalar tensor."""
     return _Chamfer.apply(_cuda_f32(x, "x"), _cuda_f32(y, "y"))
+
+
+def octree_encode(centres, n_points, min_bpp=0.0, fixed_depth=0, want_bytes=False, want_quant=False, want_rec_ref=False,
+                  want_stream_xyz=False):
+    """Octree coding of patch centres [B,S,3] in [0,1) (octree_np.encode + pn_kit.encode_sampled_np's depth search).
+    Returns dict(bits uint8 [B,max_bits], nbits int32 [B], depth int32 [B], and the requested by-products: bytes,
+    quant [B,S,3], rec_ref [B,64,3], stream_xyz [B,S,3]).  Everything stays on the device; nothing is synchronised."""
+    lib = _lib.load()
+    centres = _cuda_f32(centres, "centres")
+    if centres.dim() != 3 or centres.shape[2] != 3:
+        raise ValueError("pcc_b200.octree_encode: centres must be [B, S, 3]")
+    B, S, _ = centres.shape
+    dev = centres.device
+    max_bits = 1 + 8 * fixed_depth * S if fixed_depth > 0 else lib.pcc_octree_max_bits(S)
+    bits = torch.empty((B, max_bits), dtype=torch.uint8, device=dev)
+    nbits = torch.empty((B,), dtype=torch.int32, device=dev)
+    depth = torch.empty((B,), dtype=torch.int32, device=dev)
+    by = torch.empty((B, (max_bits + 7) // 8), dtype=torch.uint8, device=dev) if want_bytes else None
+    quant = torch.empty((B, S, 3), dtype=torch.float32, device=dev) if want_quant else None
+    rec = torch.empty((B, 64, 3), dtype=torch.float32, device=dev) if want_rec_ref else None
+    sx = torch.empty((B, S, 3), dtype=torch.float32, device=dev) if want_stream_xyz else None
+    with torch.cuda.device(dev):
+        _lib.check(lib.pcc_octree_encode_f32(_ptr(centres), B, S, int(n_points), float(min_bpp), int(fixed_depth), _ptr(bits),
+                                             max_bits, _ptr(nbits), _ptr(depth), _ptr(by), _ptr(quant), _ptr(rec), _ptr(sx),
+                                             _stream()), "pcc_octree_encode_f32")
+    return dict(bits=bits, nbits=nbits, depth=depth, bytes=by, quant=quant, rec_ref=rec, stream_xyz=sx)
+
+
+def octree_decode(bits, nbits, mode=1, cap=64):
+    """bits uint8 [B,max_bits] (one byte per bit), nbits int32 [B].  mode 0: the reference's octree_np.decode as written
+    (first 8 bits -> depth-1 octant centres padded to 64 rows); mode 1: the inverse of octree_encode.
+    Returns (xyz [B,cap,3], count int32 [B], depth int32 [B])."""
+    lib = _lib.load()
+    if not bits.is_cuda or bits.dtype != torch.uint8 or bits.dim() != 2:
+        raise RuntimeError("pcc_b200.octree_decode: bits must be a CUDA uint8 [B, max_bits] tensor (there is no CPU path)")
+    bits = bits.contiguous()
+    nbits = nbits.to(device=bits.device, dtype=torch.int32).contiguous()
+    B, max_bits = bits.shape
+    out = torch.empty((B, cap, 3), dtype=torch.float32, device=bits.device)
+    count = torch.empty((B,), dtype=torch.int32, device=bits.device)
+    depth = torch.empty((B,), dtype=torch.int32, device=bits.device)
+    with torch.cuda.device(bits.device):
+        _lib.check(lib.pcc_octree_decode_f32(_ptr(bits), _ptr(nbits), B, max_bits, int(mode), int(cap), _ptr(out), _ptr(count),
+                                             _ptr(depth), _stream()), "pcc_octree_decode_f32")
+    return out, count, depth

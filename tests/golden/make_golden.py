@@ -4,6 +4,8 @@
 
 * ref_fps_gather.npz  -- outputs of the REFERENCE's own pn_kit.farthest_point_sample_batch / index_points
                          (imported from /root/reference), including the CPU-RNG start indices it drew.
+* ref_octree.npz      -- outputs of the REFERENCE's own octree centre coder (pn_kit.encode_sampled_np, decode_sampled_np,
+                         binary_array_to_byte_array, octree_np.encode, getDecodeFromPc) on seeded FPS centres.
 * p3d_ops.npz         -- outputs of the oracle restatement of the PyTorch3D ops (knn_points, ball_query,
                          sample_farthest_points, chamfer_distance) on seeded inputs, cross-checked here against
                          an independent torch brute-force statement before being written.  PyTorch3D itself
@@ -151,8 +153,70 @@ def ae_modules():
     print("ae_modules.npz:", tuple(new_xyz.shape), tuple(latent.shape))
 
 
+def octree_cases():
+    """name -> (centres [B,S,3] in (0,1), N, min_bpp): the inputs of the octree goldens (regenerated by the tests)."""
+    def centres(n_clouds, n_points, S, seed):
+        p = synth.modelnet_like(n_clouds, n_points, seed=seed)
+        mn, mx = p.min(axis=1, keepdims=True), p.max(axis=1, keepdims=True)  # pn_kit.normalize's range [0.01, 0.99]
+        p = ((p - (mx + mn) / 2) * np.float32(0.99) / (mx - mn).max(axis=2, keepdims=True) + np.float32(0.5)).astype(np.float32)
+        return orc.gather(p, orc.fps(p, S, np.zeros(n_clouds, np.int64), 1e10))
+    c64 = centres(5, 8192, 64, 61)
+    dup = c64[:2].copy()
+    dup[:, 40:] = dup[:, :24]                      # two centres in one cell at every depth: the search runs to depth 16
+    grid = synth.grid_quantised(2, 64, depth=3, seed=62)
+    return {
+        "k256": (c64, 8192, 0.25),                 # the headline setting: K=256 -> OCTREE_BPP_DICT[256] (pn_kit.py:17-23)
+        "k128": (centres(2, 8192, 128, 63), 8192, 0.5),
+        "k1024": (centres(2, 8192, 16, 64), 8192, 0.07),
+        "s300": (centres(1, 4096, 300, 65), 4096, 1.0),   # more than one chunk of 256 sorted keys per CTA
+        "dup": (dup, 8192, 0.25),
+        "grid": (grid, 8192, 0.01),                # cell-centre inputs (ties at the snapping boundaries), tiny bpp target
+        "one": (c64[:3, :1].copy(), 8192, 0.0001),
+        "edge": (np.array([[[0.0, 0.0, 0.0], [0.99999994, 0.99999994, 0.99999994], [0.5, 0.5, 0.5], [0.49999997, 0.5, 0.25]]],
+                          dtype=np.float32), 16, 0.25),
+    }
+
+
+def ref_octree():
+    """Outputs of the REFERENCE's own octree centre coder (pn_kit.encode_sampled_np / decode_sampled_np /
+    binary_array_to_byte_array, octree_np.encode / getDecodeFromPc) imported from /root/reference."""
+    pn = ref_loader.load("pn_kit")
+    on = ref_loader.load("octree_np")
+    out = {}
+    for name, (c, N, min_bpp) in octree_cases().items():
+        codes, codebits = pn.encode_sampled_np(c, scale=1, N=N, min_bpp=min_bpp)
+        rec = pn.decode_sampled_np(codes, scale=1)
+        ocodes, obits, depths = orc.encode_sampled_np(c, 1, N, min_bpp)
+        assert codebits == obits, name
+        nb = np.array([len(x) for x in codes], np.int32)
+        bits = np.zeros((len(codes), nb.max()), np.uint8)
+        by = np.zeros((len(codes), (nb.max() + 7) // 8), np.uint8)
+        for b, code in enumerate(codes):
+            assert np.array_equal(code, ocodes[b]), name
+            assert np.array_equal(code, on.encode(c[b], 1, depths[b])), name   # the returned code is the depth-`depths[b]` code
+            assert np.array_equal(rec[b], orc.octree_decode_ref(code)), name
+            bs = bytes(pn.binary_array_to_byte_array(code))
+            assert bs == orc.bits_to_bytes(code).tobytes(), name
+            bits[b, :nb[b]] = code
+            by[b, :len(bs)] = np.frombuffer(bs, np.uint8)
+            u = on.getDecodeFromPc(c[b], 1, depths[b])
+            snapped, uu = orc.octree_quantise(c[b], 1, depths[b])
+            assert np.array_equal(u, uu), name
+            out[f"{name}_uniq{b}"] = u
+        out[f"{name}_c"], out[f"{name}_N"], out[f"{name}_min_bpp"] = c, np.int64(N), np.float64(min_bpp)
+        out[f"{name}_bits"], out[f"{name}_nbits"], out[f"{name}_depth"] = bits, nb, np.array(depths, np.int32)
+        out[f"{name}_bytes"], out[f"{name}_rec"] = by, rec.astype(np.float32)
+    # fixed-depth octree_np.encode
+    c = octree_cases()["k256"][0][0]
+    for d in (1, 2, 5, 9):
+        out[f"fixed_d{d}"] = on.encode(c, 1, d)
+    np.savez_compressed(os.path.join(HERE, "ref_octree.npz"), **out)
+    print("ref_octree.npz:", {k: (out[k].tolist()) for k in out if k.endswith("_depth")})
+
+
 if __name__ == "__main__":
     ref_fps_gather()
     p3d_ops()
     pppf_modules()
     ae_modules()
+    ref_octree()

@@ -65,3 +65,37 @@ def test_ae_forward_signature_and_shapes(setup):
     assert new_xyz.shape == (5, 128, 3) and latent.shape == (5, 16) and latent_q.shape == (5, 16)
     assert torch.equal(latent_q, latent.round())
     assert float(latent.abs().max()) <= 3.4 + 1e-6  # sigmoid spread (L - 0.2) / 2
+
+
+def test_centre_modes_coded_and_reference(setup):
+    """compress.py:96-101 with the octree coder on the device: the stream equals the oracle's (pinned to the reference's
+    pn_kit.encode_sampled_np), 'reference' centres equal the reference decoder's output, 'coded' centres are what the
+    inverse decoder recovers, and decompress works from the coded bytes alone."""
+    from oracle import oracle as orc
+    from pcc_b200.codec import PatchCodec
+    pcc, codec, sd = setup
+    clouds = synth.modelnet_like(3, 8192, seed=33)
+    x = torch.from_numpy(clouds).cuda()
+    start = torch.tensor([1, 2, 3], dtype=torch.int64).cuda()
+    pc, _, _, _ = pcc.ops.normalize(x)
+    _, fps_xyz = pcc.ops.fps(pc, 64, start, 1e10, return_xyz=True)
+    codes, total, depths = orc.encode_sampled_np(fps_xyz.cpu().numpy(), 1, 8192, 0.25)
+    for mode in ("coded", "reference"):
+        c = PatchCodec(codec.ae, centre_mode=mode).compress(x, start)
+        o = c["octree"]
+        assert o["depth"].cpu().tolist() == depths
+        for b, code in enumerate(codes):
+            assert np.array_equal(o["bits"][b, :len(code)].cpu().numpy(), code)
+            assert np.array_equal(o["bytes"][b, :(len(code) + 7) // 8].cpu().numpy(), orc.bits_to_bytes(code))
+        if mode == "reference":
+            ref = np.stack([orc.octree_decode_ref(code) for code in codes])
+            assert np.array_equal(c["centres"].cpu().numpy(), ref)
+            assert len(np.unique(ref[0], axis=0)) <= 8
+        else:
+            dec, count, _ = pcc.ops.octree_decode(o["bits"], o["nbits"], mode=1, cap=64)
+            assert torch.equal(dec, c["centres"]) and count.cpu().tolist() == [64, 64, 64]
+            snapped = np.stack([orc.octree_quantise(fps_xyz[b].cpu().numpy(), 1, depths[b])[0] for b in range(3)])
+            assert np.array_equal(np.sort(c["centres"].cpu().numpy(), axis=1), np.sort(snapped, axis=1))
+        rec = codec.decompress(c["latent_q"], c["centres"], 8192, c["center"], c["longest"])
+        met = codec.evaluate(rec, x).cpu().numpy()
+        assert rec.shape == (3, 8192, 3) and np.isfinite(met).all()

@@ -308,3 +308,75 @@ def test_assemble_matches_reference_ops(pcc):
     ref = (pc - 0.5) * longest[:, None, None] / (1 - 0.01) + center[:, None, :]  # pn_kit.denormalize
     assert torch.allclose(got, ref, rtol=0, atol=1e-6)
     assert torch.equal(pcc.ops.assemble(patches, centres, 2.0), pc)
+
+
+# ---- octree centre coding: bit-exact against the REFERENCE's own coder and against the oracle ----------
+@pytest.fixture(scope="module")
+def g_oct(golden_dir):
+    return np.load(os.path.join(golden_dir, "ref_octree.npz"))
+
+
+@pytest.mark.parametrize("name", ["k256", "k128", "k1024", "s300", "dup", "grid", "one", "edge"])
+def test_octree_encode_reference_golden(pcc, g_oct, name):
+    c, N, min_bpp = g_oct[f"{name}_c"], int(g_oct[f"{name}_N"]), float(g_oct[f"{name}_min_bpp"])
+    r = pcc.ops.octree_encode(cu(c), N, min_bpp, 0, want_bytes=True, want_quant=True, want_rec_ref=True, want_stream_xyz=True)
+    nbits, depth = r["nbits"].cpu().numpy(), r["depth"].cpu().numpy()
+    assert np.array_equal(nbits, g_oct[f"{name}_nbits"]) and np.array_equal(depth, g_oct[f"{name}_depth"])
+    bits, by = r["bits"].cpu().numpy(), r["bytes"].cpu().numpy()
+    B, S, _ = c.shape
+    for b in range(B):
+        n = int(nbits[b])
+        assert np.array_equal(bits[b, :n], g_oct[f"{name}_bits"][b, :n]) and not bits[b, n:].any()
+        assert np.array_equal(by[b, :(n + 7) // 8], g_oct[f"{name}_bytes"][b, :(n + 7) // 8])
+        # snapped centres: as a set they are the reference's getDecodeFromPc (np.unique rows); the stream-order list is
+        # the same set in descending (x, y, z) cell order with the last leaf repeated
+        u = g_oct[f"{name}_uniq{b}"]
+        q = r["quant"][b].cpu().numpy()
+        assert np.array_equal(np.unique(q, axis=0), u)
+        sx = r["stream_xyz"][b].cpu().numpy()
+        cells = np.floor(u * np.float32(2.0 ** depth[b])).astype(np.int64)
+        morton = np.zeros(len(u), np.int64)
+        for lvl in range(int(depth[b]) - 1, -1, -1):  # child index 4x + 2y + z per level, coarsest level most significant
+            morton = (morton << 3) | (((cells[:, 0] >> lvl) & 1) << 2) | (((cells[:, 1] >> lvl) & 1) << 1) | ((cells[:, 2] >> lvl) & 1)
+        assert np.array_equal(sx[:len(u)], u[np.argsort(-morton, kind="stable")]) and np.all(sx[len(u):] == sx[len(u) - 1])
+    assert np.array_equal(r["rec_ref"].cpu().numpy(), g_oct[f"{name}_rec"])
+    # decoders: mode 0 = the reference's decode_sampled_np, mode 1 = inverse of the encoder
+    rec0, _, _ = pcc.ops.octree_decode(r["bits"], r["nbits"], mode=0, cap=64)
+    assert np.array_equal(rec0.cpu().numpy(), g_oct[f"{name}_rec"])
+    rec1, count, d1 = pcc.ops.octree_decode(r["bits"], r["nbits"], mode=1, cap=S)
+    assert np.array_equal(rec1.cpu().numpy(), r["stream_xyz"].cpu().numpy())
+    assert np.array_equal(d1.cpu().numpy(), depth)
+    assert count.cpu().numpy().tolist() == [len(g_oct[f"{name}_uniq{b}"]) for b in range(B)]
+
+
+def test_octree_fixed_depth_and_drop_in_names(pcc, g_oct):
+    from pcc_b200 import octree_ops
+    c = g_oct["k256_c"]
+    for d in (1, 2, 5, 9):
+        assert np.array_equal(octree_ops.encode(c[0], 1, d), g_oct[f"fixed_d{d}"])
+    codes, total = octree_ops.encode_sampled_np(c, scale=1, N=8192, min_bpp=0.25)       # pn_kit.py:380 signature, numpy in
+    assert total == int(g_oct["k256_nbits"].sum())
+    assert all(np.array_equal(code, g_oct["k256_bits"][b, :len(code)]) for b, code in enumerate(codes))
+    assert np.array_equal(octree_ops.decode_sampled_np(codes, scale=1), g_oct["k256_rec"])
+    assert np.array_equal(octree_ops.decode(codes[0], 1), g_oct["k256_rec"][0])
+    with pytest.raises(NotImplementedError):
+        octree_ops.encode_sampled_np(c, scale=2, N=8192, min_bpp=0.25)
+    bad = c.copy()
+    bad[1, 3, 0] = 1.0
+    with pytest.raises(ValueError):
+        octree_ops.encode_sampled_np(bad, scale=1, N=8192, min_bpp=0.25)
+
+
+@pytest.mark.parametrize("B,S,N,min_bpp", [(4, 2, 64, 0.3), (3, 63, 2048, 0.25), (2, 257, 8192, 0.2), (1, 1000, 16384, 0.5),
+                                           (1, 2500, 100000, 0.3), (1, 7812, 1000000, 0.05)])
+def test_octree_encode_vs_oracle(pcc, orc, B, S, N, min_bpp):
+    c = synth.uniform_cube(B, S, seed=S)
+    if S == 257:
+        c[:, 200:] = c[:, :57]  # duplicated centres
+    r = pcc.ops.octree_encode(cu(c), N, min_bpp, 0, want_bytes=True)
+    codes, total, depths = orc.encode_sampled_np(c, 1, N, min_bpp)
+    assert r["depth"].cpu().numpy().tolist() == depths
+    bits = r["bits"].cpu().numpy()
+    for b, code in enumerate(codes):
+        assert int(r["nbits"][b]) == len(code) and np.array_equal(bits[b, :len(code)], code)
+        assert np.array_equal(r["bytes"][b, :(len(code) + 7) // 8].cpu().numpy(), orc.bits_to_bytes(code))

@@ -107,3 +107,40 @@ def test_fps_matches_live_reference():
         start = torch.randint(0, N, (B,), dtype=torch.long)
         assert np.array_equal(orc.fps(xyz.numpy(), S, start.numpy(), 1e10), ref.numpy())
         assert np.array_equal(orc.gather(xyz.numpy(), ref.numpy()), pn.index_points(xyz, ref).numpy())
+
+
+# ---- octree centre coding: the oracle against the REFERENCE's own coder (tests/golden/ref_octree.npz) -------------------
+OCTREE_CASES = ["k256", "k128", "k1024", "s300", "dup", "grid", "one", "edge"]
+
+
+@pytest.fixture(scope="module")
+def g_oct(golden_dir):
+    return np.load(os.path.join(golden_dir, "ref_octree.npz"))
+
+
+@pytest.mark.parametrize("name", OCTREE_CASES)
+def test_octree_oracle_matches_reference_golden(g_oct, name):
+    c, N, min_bpp = g_oct[f"{name}_c"], int(g_oct[f"{name}_N"]), float(g_oct[f"{name}_min_bpp"])
+    codes, total, depths = orc.encode_sampled_np(c, 1, N, min_bpp)
+    assert depths == g_oct[f"{name}_depth"].tolist()
+    assert total == int(g_oct[f"{name}_nbits"].sum())
+    for b, code in enumerate(codes):
+        n = int(g_oct[f"{name}_nbits"][b])
+        assert np.array_equal(code, g_oct[f"{name}_bits"][b, :n])
+        assert np.array_equal(orc.bits_to_bytes(code), g_oct[f"{name}_bytes"][b, :(n + 7) // 8])
+        assert np.array_equal(orc.octree_decode_ref(code), g_oct[f"{name}_rec"][b])
+        assert np.array_equal(orc.octree_quantise(c[b], 1, depths[b])[1], g_oct[f"{name}_uniq{b}"])
+
+
+def test_octree_oracle_fixed_depth_and_live_reference(g_oct):
+    c = g_oct["k256_c"][0]
+    for d in (1, 2, 5, 9):
+        assert np.array_equal(orc.octree_encode(c, 1, d), g_oct[f"fixed_d{d}"])
+    if not ref_loader.available():
+        pytest.skip("/root/reference not present")
+    pn = ref_loader.load("pn_kit")
+    x = synth.uniform_cube(3, 48, seed=77) * np.float32(0.98) + np.float32(0.01)
+    codes, bits = pn.encode_sampled_np(x, scale=1, N=2048, min_bpp=0.5)
+    ocodes, obits, _ = orc.encode_sampled_np(x, 1, 2048, 0.5)
+    assert bits == obits and all(np.array_equal(a, b) for a, b in zip(codes, ocodes))
+    assert np.array_equal(pn.decode_sampled_np(codes, scale=1), np.stack([orc.octree_decode_ref(k) for k in ocodes]))
