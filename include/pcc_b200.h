@@ -230,6 +230,30 @@ int pcc_octree_encode_f32(const float *centres, int B, int S, int n_points, doub
 int pcc_octree_decode_f32(const uint8_t *bits, const int32_t *nbits, int B, int max_bits, int mode, int cap, float *out_xyz,
                           int32_t *out_count, int32_t *out_depth, void *stream);
 
+/*
+ * One wide shared-MLP layer as a streamed tensor-core GEMM (csrc/gemm_ws.cu): out = act(a . w^T + bias).
+ * Replaces the Conv2d(1x1)+BatchNorm(folded)+ReLU layers of PointnetSAModule (/root/reference/pointnet_sa_module.py:39-56,87-91
+ * as configured by PPPF_AE.py:29-33) and the Linear layers of AE.inv_pool (/root/reference/AE.py:19-26) whose weights do not
+ * fit in shared memory beside the activations.
+ * a [M, K] bf16 (row pitch lda), w [N, K] bf16 (row pitch ldw), bias [N] fp32; K % 64 == 0, N % 128 == 0 (pad with zero
+ * columns / use pcc_gather_concat_bf16); pitches multiples of 8 elements, 16-byte aligned bases.
+ * group <= 1: out [M, N] bf16 (row pitch ld_out).  group > 1: the max over every run of `group` consecutive rows
+ * (pointnet_sa_module.py:91 torch.max over nsample): out [M / group, N] fp32, group % 32 == 0 and either a divisor or a
+ * multiple of 128, M % group == 0, relu required when group > 32.
+ * Numerics: operands bf16, products accumulated in fp32 (tolerance stated in tests/test_gpu_mlp.py).
+ */
+int pcc_linear_bf16(const void *a, int64_t M, int K, int64_t lda, const void *w, int64_t ldw, const float *bias, int N, int relu,
+                    int group, void *out, int64_t ld_out, void *stream);
+
+/*
+ * Grouping of one PointNet++ set-abstraction level (/root/reference/pointnet_sa_module.py:73-85: group_points of the features
+ * and of xyz, torch.cat): out[b * M + j, :] = [feat[b, idx[b, j], 0..C) | xyz[b, idx[b, j], 0..3) | 0 ...] as bf16 rows of
+ * kpad columns (kpad % 8 == 0) -- the A operand of pcc_linear_bf16.  feat [B, N, C] fp32 or NULL (C = 0), xyz [B, N, 3] fp32 or
+ * NULL, idx [B, M] int64; negative indices read point 0 (pointnet_sa_module.py:27).
+ */
+int pcc_gather_concat_bf16(const float *feat, int C, const float *xyz, const int64_t *idx, int B, int N, int64_t M, int kpad,
+                           void *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

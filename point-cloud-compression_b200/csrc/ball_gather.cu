@@ -8,6 +8,8 @@
 // gather kernels replace pn_kit.index_points (/root/reference/pn_kit.py:332-360), pytorch3d knn_gather
 //   (/root/reference/pointnet_sa_module.py:28) and torch.gather (pointnet_sa_module.py:68): pure data movement,
 //   HBM/L2 bound; 16-byte vector path when C % 4 == 0.
+#include <cuda_bf16.h>
+
 #include "pcc_common.cuh"
 
 namespace pcc {
@@ -103,6 +105,48 @@ static int grid_for(long long total) {
     return static_cast<int>(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
 }
 
+__device__ __forceinline__ unsigned pack2_bf16(float lo, float hi) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const unsigned *>(&h);
+}
+
+// Grouping of a PointNet++ set-abstraction level in one pass (/root/reference/pointnet_sa_module.py:73-85): row r of the output
+// is [features[b, idx[r], 0..C) | xyz[b, idx[r], 0..3) | zeros up to kpad] in bf16 -- the gathers, the torch.cat and the
+// operand conversion of the GEMM that follows.  Negative indices (ball-query padding) read point 0 (pointnet_sa_module.py:27).
+// One thread per 8 output columns (one 16-byte store).
+__global__ void __launch_bounds__(256)
+gather_concat_bf16_kernel(const float *__restrict__ feat, int C, const float *__restrict__ xyz, const int64_t *__restrict__ idx,
+                          long long rows, int N, long long M, int kpad, uint4 *__restrict__ out) {
+    const int chunks = kpad >> 3;
+    const long long total = rows * chunks;
+    for (long long t = blockIdx.x * 256ll + threadIdx.x; t < total; t += static_cast<long long>(gridDim.x) * 256) {
+        const long long r = t / chunks;
+        const int c0 = static_cast<int>(t % chunks) * 8;
+        const long long b = r / M;
+        long long j = idx[r];
+        j = j < 0 ? 0 : j;
+        const long long src = b * N + j;
+        float v[8];
+        if (feat && c0 + 8 <= C && (C & 3) == 0) {
+            const float4 a = __ldg(reinterpret_cast<const float4 *>(feat + src * C + c0));
+            const float4 d = __ldg(reinterpret_cast<const float4 *>(feat + src * C + c0 + 4));
+            v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = d.x, v[5] = d.y, v[6] = d.z, v[7] = d.w;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int c = c0 + e;
+                v[e] = (feat && c < C) ? __ldg(feat + src * C + c) : (xyz && c >= C && c < C + 3) ? __ldg(xyz + src * 3 + (c - C)) : 0.0f;
+            }
+        }
+        uint4 o;
+        o.x = pack2_bf16(v[0], v[1]);
+        o.y = pack2_bf16(v[2], v[3]);
+        o.z = pack2_bf16(v[4], v[5]);
+        o.w = pack2_bf16(v[6], v[7]);
+        out[t] = o;
+    }
+}
+
 }  // namespace pcc
 
 PCC_API int pcc_ball_query_f32(const float *q, const float *p, int B, int P1, int P2, int K, float radius,
@@ -149,4 +193,20 @@ PCC_API int pcc_gather_bwd_f32(const float *grad_out, const int64_t *idx, int B,
     gather_bwd_kernel<<<grid_for(rows * C), 256, 0, static_cast<cudaStream_t>(stream)>>>(grad_out, idx, rows, N, C, M,
                                                                                          grad_feat);
     return check_launch("gather_bwd_kernel");
+}
+
+PCC_API int pcc_gather_concat_bf16(const float *feat, int C, const float *xyz, const int64_t *idx, int B, int N, int64_t M, int kpad,
+                                   void *out, void *stream) {
+    using namespace pcc;
+    PCC_REQUIRE((feat || xyz) && idx && out, "pcc_gather_concat_bf16: null pointer");
+    PCC_REQUIRE(B >= 0 && N >= 1 && M >= 0 && C >= 0 && (feat || C == 0), "pcc_gather_concat_bf16: bad shape");
+    PCC_REQUIRE(kpad % 8 == 0 && kpad >= C + (xyz ? 3 : 0), "pcc_gather_concat_bf16: kpad=%d must be a multiple of 8 and >= %d", kpad,
+                C + (xyz ? 3 : 0));
+    PCC_REQUIRE(reinterpret_cast<uintptr_t>(out) % 16 == 0 && (!feat || reinterpret_cast<uintptr_t>(feat) % 16 == 0),
+                "pcc_gather_concat_bf16: feat / out must be 16-byte aligned");
+    const long long rows = static_cast<long long>(B) * M;
+    if (rows == 0) return 0;
+    gather_concat_bf16_kernel<<<grid_for(rows * (kpad / 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        feat, C, xyz, idx, rows, N, M, kpad, static_cast<uint4 *>(out));
+    return check_launch("gather_concat_bf16_kernel");
 }

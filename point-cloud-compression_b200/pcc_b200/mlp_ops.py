@@ -224,3 +224,87 @@ def mlp_chain_groupmax(x, layers, group):
     if x.shape[0] % group:
         raise ValueError("pcc_b200.mlp_chain_groupmax: rows must be a multiple of the group size")
     return run_chain(x, layers, group)
+
+
+# ---- streamed tensor-core GEMM layers (csrc/gemm_ws.cu): weights too large to sit beside the activations ---------------
+_wpad_cache = {}
+
+
+def _w_bf16_padded(w, kpad):
+    """[cout, cin] parameter -> cached bf16 [cout, kpad] with zero columns past cin."""
+    bw = _base(w)
+    key = (id(bw), w.data_ptr(), tuple(w.shape), tuple(w.stride()), kpad)
+    hit = _wpad_cache.get(key)
+    if hit is not None and hit[0]() is bw and hit[1] == bw._version:
+        return hit[2]
+    if len(_wpad_cache) > 256:
+        _wpad_cache.clear()
+    val = torch.zeros((w.shape[0], kpad), dtype=torch.bfloat16, device=w.device)
+    val[:, :w.shape[1]] = w.detach()
+    _wpad_cache[key] = (weakref.ref(bw), bw._version, val)
+    return val
+
+
+def linear_supported(rows, cout, group=0):
+    """Shapes pcc_linear_bf16 takes (the input is zero padded to a multiple of 64 columns by the caller)."""
+    if cout % 128 or rows < 1:
+        return False
+    if group > 1:
+        return group % 32 == 0 and (128 % group == 0 or group % 128 == 0) and rows % group == 0
+    return True
+
+
+def linear(x, w, b, relu, group=0):
+    """One layer on the streamed GEMM kernel.  x [M, Kp] bf16 with Kp % 64 == 0 and Kp >= cin (columns past cin must be
+    zero or finite: the weight is zero padded).  Returns bf16 [M, cout], or fp32 [M / group, cout] when group > 1."""
+    lib = _lib.load()
+    _check(x)
+    if x.dtype != torch.bfloat16 or x.dim() != 2 or x.stride(1) != 1 or x.shape[1] % 64 or x.stride(0) % 8 or x.data_ptr() % 16:
+        raise ValueError("pcc_b200.linear: x must be a 16-byte aligned bf16 [M, K] tensor with K % 64 == 0")
+    M, kp = x.shape
+    cout, cin = w.shape
+    if cin > kp:
+        raise ValueError("pcc_b200.linear: the input has fewer columns than the weight")
+    if group > 32 and not relu:
+        raise ValueError("pcc_b200.linear: pooling over more than 32 rows needs the ReLU")
+    wp = _w_bf16_padded(w, kp)
+    bf = b.detach().float().contiguous()
+    if group > 1:
+        out = torch.empty((M // group, cout), dtype=torch.float32, device=x.device)
+    else:
+        out = torch.empty((M, cout), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.pcc_linear_bf16(x.data_ptr(), M, kp, x.stride(0), wp.data_ptr(), kp, bf.data_ptr(), cout, int(bool(relu)),
+                                       int(group), out.data_ptr(), cout, torch.cuda.current_stream().cuda_stream),
+                   "pcc_linear_bf16")
+    return out
+
+
+def stream_chain(x, layers, group=0):
+    """A run of layers on the streamed GEMM kernel, bf16 in HBM between layers, the pooling fused into the last one."""
+    for i, (w, b, relu) in enumerate(layers):
+        x = linear(x, w, b, relu, group if i + 1 == len(layers) else 0)
+    return x
+
+
+def gather_concat_bf16(feat, xyz, idx, kpad):
+    """Rows [feat[b, idx] | xyz[b, idx] | 0...] in bf16, kpad columns (pointnet_sa_module.py:73-85 grouping + cat)."""
+    lib = _lib.load()
+    _check(idx)
+    B = idx.shape[0]
+    idx = idx.reshape(B, -1).contiguous()
+    M = idx.shape[1]
+    src = feat if feat is not None else xyz
+    N = src.shape[1]
+    C = 0
+    if feat is not None:
+        feat = feat.float().contiguous()
+        C = feat.shape[2]
+    if xyz is not None:
+        xyz = xyz.float().contiguous()
+    out = torch.empty((B * M, kpad), dtype=torch.bfloat16, device=idx.device)
+    with torch.cuda.device(idx.device):
+        _lib.check(lib.pcc_gather_concat_bf16(feat.data_ptr() if feat is not None else None, C,
+                                              xyz.data_ptr() if xyz is not None else None, idx.data_ptr(), B, N, M, kpad,
+                                              out.data_ptr(), torch.cuda.current_stream().cuda_stream), "pcc_gather_concat_bf16")
+    return out

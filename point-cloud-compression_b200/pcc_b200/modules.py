@@ -181,9 +181,14 @@ class AE(nn.Module):
             self._perm_w4 = w4.detach().view(128, self.k, -1).permute(1, 0, 2).reshape(128 * self.k, -1).contiguous()
             self._perm_b4 = b4.detach().view(128, self.k).t().reshape(-1).contiguous()
             self._perm_key = key
-        lin = mlp_ops.library_chain(latent_q.detach(), [(self.inv_pool[0].weight, self.inv_pool[0].bias, True),
-                                                        (self.inv_pool[2].weight, self.inv_pool[2].bias, True),
-                                                        (self._perm_w4, self._perm_b4, True)], out_dtype=torch.bfloat16)
+        inv_layers = [(self.inv_pool[0].weight, self.inv_pool[0].bias, True), (self.inv_pool[2].weight, self.inv_pool[2].bias, True),
+                      (self._perm_w4, self._perm_b4, True)]
+        if all(mlp_ops.linear_supported(BS, w.shape[0]) for w, _, _ in inv_layers):
+            # AE.py:19-26 on the streamed tensor-core GEMM (csrc/gemm_ws.cu); the latent is zero padded to the K granule
+            lat = torch.nn.functional.pad(latent_q.detach().to(torch.bfloat16), (0, (-self.d) % 64))
+            lin = mlp_ops.stream_chain(lat, inv_layers)
+        else:
+            lin = mlp_ops.library_chain(latent_q.detach(), inv_layers, out_dtype=torch.bfloat16)
         # AE.py:50-52: cat(features, tiled latent) -> inv_mlp, as two input segments of the fused chain
         out = mlp_ops.fused_chain([(lin.view(BS * self.k, 128), 1), (latent_q.detach().float().contiguous(), self.k)],
                                   self.inv_mlp.layers())

@@ -55,12 +55,23 @@ class PointnetSAModule(nn.Module):
             new_xyz = ops.gather(xyz, fps_idx.clamp(min=0))
         _, idx = ops.ball_query(new_xyz, xyz, self.nsample, self.radius, return_dists=False)  # :71
         idx = idx.clamp(min=0)                                                               # :27 (pads -> point 0)
+        layers = self.folded_layers()
+        rows = B * self.npoint * self.nsample
+        cin = (features.shape[1] if features is not None else 0) + (3 if self.use_xyz else 0)
+        if cin >= 64 and all(mlp_ops.linear_supported(rows, w.shape[0]) for w, _, _ in layers) and \
+                mlp_ops.linear_supported(rows, layers[-1][0].shape[0], self.nsample):
+            # wide stack: one grouping pass (gather + cat + bf16, zero padded to the GEMM's K granule), then every layer on
+            # the streamed tensor-core GEMM with the max over nsample fused into the last one       :73-91
+            a = mlp_ops.gather_concat_bf16(features.permute(0, 2, 1) if features is not None else None,
+                                           xyz if self.use_xyz else None, idx, (cin + 63) // 64 * 64)
+            out = mlp_ops.stream_chain(a, layers, group=self.nsample)
+            return new_xyz, out.view(B, self.npoint, -1).permute(0, 2, 1)
         segs = []
         if features is not None:
             segs.append((ops.gather(features.permute(0, 2, 1).contiguous(), idx).view(-1, features.shape[1]), 1))  # :74-77
         if self.use_xyz:
             segs.append((ops.gather(xyz, idx).view(-1, 3), 1))                                # :80-85 (not recentred)
-        out = mlp_ops.run_chain(segs, self.folded_layers(), group=self.nsample)             # :89-91
+        out = mlp_ops.run_chain(segs, layers, group=self.nsample)                           # :89-91
         return new_xyz, out.view(B, self.npoint, -1).permute(0, 2, 1)
 
 

@@ -168,3 +168,72 @@ def test_pn_tail_fused_kernel(mlp, patches, cout):
     assert y.shape == ym.shape
     assert (y - ym).abs().max().item() / scale < MODEL_RTOL
     assert (y - yf.float()).abs().max().item() / scale < BF16_RTOL
+
+
+# ---- streamed tensor-core GEMM layer (csrc/gemm_ws.cu) and the fused grouping pass ------------------------------------
+LINEAR_CASES = [
+    # rows, cin, cout, relu, group
+    (1000, 64, 128, True, 0),        # tail rows (M % 128 != 0), one K slab
+    (4096, 131, 128, True, 0),       # PointNet++ SA2 first layer: cin padded 131 -> 192
+    (5000, 256, 256, False, 0),      # no ReLU, BN = 256, tail rows
+    (2048, 1024, 512, True, 0),      # deep K: ring wraps many times
+    (2048, 128, 128, True, 32),      # pooled, one warp per output row
+    (4096, 128, 256, True, 64),      # pooled over two warps (atomicMax path)
+    (8192, 512, 1024, True, 128),    # PointNet++ SA3 last layer (PPPF_AE.py:33), pooled over the tile
+    (4096, 259, 256, True, 0),       # SA3 first layer
+    (1024, 64, 384, True, 256),      # N = 3 x 128 (BN = 128), group spanning two tiles
+    (300 * 128, 1024, 2048, True, 0),  # many tiles per CTA: accumulator double buffering, staging reuse
+]
+
+
+@pytest.mark.parametrize("rows,cin,cout,relu,group", LINEAR_CASES)
+def test_streamed_linear_numerics(mlp, rows, cin, cout, relu, group):
+    g = torch.Generator(device="cuda").manual_seed(rows + cin + cout)
+    kp = (cin + 63) // 64 * 64
+    x = torch.zeros(rows, kp, device="cuda", dtype=torch.bfloat16)
+    x[:, :cin] = (torch.rand(rows, cin, device="cuda", generator=g) - 0.5) * 2
+    w = (torch.rand(cout, cin, device="cuda", generator=g) - 0.5) * (2.0 / cin ** 0.5)
+    b = (torch.rand(cout, device="cuda", generator=g) - 0.5) * 0.2
+    y = mlp.linear(x, w, b, relu, group)
+    torch.cuda.synchronize()
+    ref = x[:, :cin].float() @ w.to(torch.bfloat16).float().t() + b          # bf16 operands, fp32 accumulation
+    if relu:
+        ref = torch.relu(ref)
+    if group > 1:
+        ref = ref.view(rows // group, group, cout).max(dim=1)[0]
+        assert y.dtype == torch.float32 and y.shape == ref.shape
+        tol = 2e-3   # fp32 out: only the accumulation order differs
+    else:
+        assert y.dtype == torch.bfloat16 and y.shape == ref.shape
+        tol = 6e-3   # + one bf16 rounding of the output (2^-8 relative)
+    scale = ref.abs().max().item() + 1e-12
+    assert (y.float() - ref).abs().max().item() / scale < tol
+
+
+def test_streamed_linear_rejects_unsupported_shapes(mlp):
+    x = torch.zeros(256, 64, device="cuda", dtype=torch.bfloat16)
+    w, b = torch.zeros(100, 64, device="cuda"), torch.zeros(100, device="cuda")
+    with pytest.raises(ValueError):
+        mlp.linear(x, w, b, True)                       # cout not a multiple of 128
+    w, b = torch.zeros(128, 64, device="cuda"), torch.zeros(128, device="cuda")
+    with pytest.raises(ValueError):
+        mlp.linear(x, w, b, False, group=64)            # pooling over > 32 rows without the ReLU
+    with pytest.raises(ValueError):
+        mlp.linear(x[:, :48], w[:, :48], b, True)       # K not padded to 64
+
+
+def test_gather_concat_bf16_matches_torch(mlp):
+    g = torch.Generator(device="cuda").manual_seed(5)
+    B, N, C, M = 3, 500, 128, 777
+    feat = torch.rand(B, N, C, device="cuda", generator=g)
+    xyz = torch.rand(B, N, 3, device="cuda", generator=g)
+    idx = torch.randint(0, N, (B, M), device="cuda", generator=g)
+    idx[0, :5] = -1                                     # ball-query padding reads point 0 (pointnet_sa_module.py:27)
+    out = mlp.gather_concat_bf16(feat, xyz, idx, 192)
+    ci = idx.clamp(min=0)
+    ref = torch.zeros(B, M, 192, device="cuda")
+    ref[:, :, :C] = torch.gather(feat, 1, ci[:, :, None].expand(-1, -1, C))
+    ref[:, :, C:C + 3] = torch.gather(xyz, 1, ci[:, :, None].expand(-1, -1, 3))
+    assert torch.equal(out.view(B, M, 192), ref.to(torch.bfloat16))
+    out2 = mlp.gather_concat_bf16(None, xyz, idx, 64)   # xyz only
+    assert torch.equal(out2.view(B, M, 64)[:, :, :3], ref[:, :, C:C + 3].to(torch.bfloat16)) and not out2.view(B, M, 64)[:, :, 3:].any()

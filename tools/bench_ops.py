@@ -66,6 +66,34 @@ def main():
     bi = bi.clamp(min=0)
     rec("gather 64x(512x32)x128ch", lambda: ops.gather(feat, bi))
     res["gather 64x(512x32)x128ch"]["GB_per_s"] = round(2 * 64 * 512 * 32 * 128 * 4 / res["gather 64x(512x32)x128ch"]["best_ms"] / 1e6, 1)
+    # octree centre coding (8f-1): 32 clouds x 64 FPS centres, depth search + bit stream + bytes + decoded centres
+    pcn, _, _, _ = ops.normalize(xyz)
+    _, cxyz = ops.fps(pcn, 64, start, 1e10, return_xyz=True)
+    rec(f"octree encode {B}x64 (search, bytes, stream centres)",
+        lambda: ops.octree_encode(cxyz, 8192, 0.25, 0, want_bytes=True, want_stream_xyz=True))
+    # whole-path rows: IPDAE compress / roundtrip per centre mode, train step (cfg2), PPPF_AE forward (cfg3)
+    from pcc_b200.codec import PatchCodec
+    from pcc_b200.modules import AE
+    ae = AE(256, 128, 16, 7)
+    ae.load_state_dict(synth.seeded_state_dict(synth.ae_shapes(128, 16, 7), 11))
+    ae = ae.cuda().eval()
+    for mode in ("fixed", "coded", "reference"):
+        codec = PatchCodec(ae, centre_mode=mode)
+        rec(f"roundtrip {B}x8192 centre_mode={mode}", lambda: codec.roundtrip(xyz, start))
+        res[f"roundtrip {B}x8192 centre_mode={mode}"]["clouds_per_s"] = round(B / res[f"roundtrip {B}x8192 centre_mode={mode}"]["best_ms"] * 1e3)
+    from pcc_b200.train import Trainer
+    tr = Trainer(state_dict=synth.seeded_state_dict(synth.ae_shapes(128, 16, 7), 11))
+    rec(f"train step {B}x8192 K256 (cfg2: fwd + Chamfer + bwd + Adam)", lambda: tr.step(xyz, start))
+    res[f"train step {B}x8192 K256 (cfg2: fwd + Chamfer + bwd + Adam)"]["clouds_per_s"] = round(
+        B / res[f"train step {B}x8192 K256 (cfg2: fwd + Chamfer + bwd + Adam)"]["best_ms"] * 1e3)
+    from pcc_b200 import pppf
+    model = pppf.PPPF_AE(K=512, k=0, d=16, L=7)
+    model.load_state_dict(synth.seeded_module_state(model, 17))
+    model = model.cuda().eval()
+    with torch.no_grad():
+        rec("PPPF_AE forward 64x2048 (cfg3: PointNet++ SA x3 + FoldingNet)", lambda: model(sh))
+    res["PPPF_AE forward 64x2048 (cfg3: PointNet++ SA x3 + FoldingNet)"]["clouds_per_s"] = round(
+        64 / res["PPPF_AE forward 64x2048 (cfg3: PointNet++ SA x3 + FoldingNet)"]["best_ms"] * 1e3)
     if os.environ.get("SCENE", "1") == "1":
         sc = torch.from_numpy(synth.scene_like(1_000_000, seed=3)).cuda()
         rec("fps 1x1M->7812", lambda: ops.fps(sc, 7812, start[:1], 1e10), 1e6 * 7812)
