@@ -3,8 +3,9 @@
 
 Metric (BASELINE.json): point clouds/s, 8192 points, K=256, compress + decompress + Chamfer / D1 eval.
 A "step" is one pass of the hot path over one batch of 32 synthetic ModelNet40-shaped clouds (cfg2's batch shape):
-normalise -> FPS (64 centres) -> centre quantisation -> kNN patching (K=256) -> in-patch kNN (K=16) + shared MLP +
-max (SetAbstraction) -> PointNet -> quantise -> decoder -> re-assemble -> Chamfer + D1 PSNR against the input.
+normalise -> FPS (64 centres) -> octree centre coding (depth search, bit stream, .s.bin bytes) -> kNN patching (K=256) ->
+in-patch kNN (K=16) + shared MLP + max (SetAbstraction) -> PointNet -> quantise -> decoder -> re-assemble -> Chamfer +
+D1 PSNR against the input.
 
   value : clouds/s with inputs resident in HBM (device-timed with CUDA events, max over ranks)
   e2e   : the same through the public API from pinned HOST buffers (H2D of the batch + D2H of latents, centres and
@@ -100,7 +101,8 @@ def cpu_reference_rate(n_clouds, threads, seed=100, repeats=1):
     for _ in range(repeats):
         t0 = time.perf_counter()
         for i in range(n_clouds):
-            tm.compress_decompress_eval(sd, clouds[i], 0, K_PATCH, K_OUT, D_LATENT, L_LEVELS, N0, ALPHA, threads=threads)
+            tm.compress_decompress_eval(sd, clouds[i], 0, K_PATCH, K_OUT, D_LATENT, L_LEVELS, N0, ALPHA, threads=threads,
+                                        centre_mode="coded")
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
     return n_clouds / best, best
@@ -154,7 +156,7 @@ def run_b200(args):
     ae = AE(K_PATCH, K_OUT, D_LATENT, L_LEVELS)
     ae.load_state_dict(synth.seeded_state_dict(synth.ae_shapes(K_OUT, D_LATENT, L_LEVELS), 11))
     ae = ae.to(dev).eval()
-    codec = PatchCodec(ae, N0=N0, alpha=ALPHA)
+    codec = PatchCodec(ae, N0=N0, alpha=ALPHA, centre_mode="coded")
 
     # distinct inputs per rank (whole clouds sharded by rank), a rotating pool larger than L2
     pool_host = torch.from_numpy(synth.modelnet_like(4 * BATCH, N_POINTS, seed=1000 + rank))
@@ -236,11 +238,16 @@ def run_b200(args):
     out_lat = torch.empty((BATCH, N_POINTS * ALPHA // K_PATCH, D_LATENT), dtype=torch.int8).pin_memory()
     out_cen = torch.empty((BATCH, N_POINTS * ALPHA // K_PATCH, 3), dtype=torch.float32).pin_memory()
     out_met = torch.empty((BATCH, 3), dtype=torch.float64).pin_memory()
+    n_cent = N_POINTS * ALPHA // K_PATCH
+    out_oct = torch.empty((BATCH, (1 + 8 * 16 * n_cent + 7) // 8), dtype=torch.uint8).pin_memory()   # .s.bin bytes (pn_kit.py:463)
+    out_nbits = torch.empty((BATCH,), dtype=torch.int32).pin_memory()
     stage = torch.empty((BATCH, N_POINTS, 3), dtype=torch.float32, device=dev)
 
     def e2e_step(s):
         stage.copy_(batch_of(pool_host, s), non_blocking=True)
-        lat, cen, met, _ = codec.roundtrip(stage, start_idx)
+        lat, cen, met, _, octree = codec.roundtrip(stage, start_idx, return_octree=True)
+        out_oct.copy_(octree["bytes"], non_blocking=True)
+        out_nbits.copy_(octree["nbits"], non_blocking=True)
         out_lat.copy_(lat, non_blocking=True)
         out_cen.copy_(cen, non_blocking=True)
         out_met.copy_(met, non_blocking=True)
@@ -256,16 +263,17 @@ def run_b200(args):
     barrier()
     e2e_value = world * BATCH * args.steps / e2e_s
     h2d = stage.numel() * 4
-    d2h = out_lat.numel() + out_cen.numel() * 4 + out_met.numel() * 8
+    d2h = out_lat.numel() + out_cen.numel() * 4 + out_met.numel() * 8 + out_oct.numel() + out_nbits.numel() * 4
 
     cpu_base = None
     if rank == 0 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        n = 16
+        n = 48  # ~10 s of host work
         rate, secs = cpu_reference_rate(n, threads)
         cpu_base = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                     "sample": f"{n} clouds of the same workload ({secs:.1f} s), oracle port (C restatement of the "
-                              f"PyTorch3D/pn_kit CPU algorithms + torch CPU fp32 network), {threads} threads"}
+                              f"PyTorch3D/pn_kit CPU algorithms and of the octree coder -- faster than the reference's numpy "
+                              f"coder -- + torch CPU fp32 network), {threads} threads"}
 
     if rank == 0:
         peaks = {}
@@ -319,9 +327,11 @@ def run_b200(args):
             "config": {"workload": WORKLOAD, "clouds_per_step_per_gpu": BATCH, "points": N_POINTS, "K": K_PATCH,
                        "parallelism": f"dp{world} (whole clouds sharded by rank, metrics all_gather only)",
                        "l2": f"rotating pool of {POOL_BATCHES} distinct input batches (138 MB > 126 MB L2), no flush",
-                       "mlp": "hand-written tcgen05 kernels: SetAbstraction 3-32-64-128+max16, PointNet 131-128-256 and its "
-                              "256-512-16+max tail (W2 streamed by TMA), decoder 144-128-64-32-3; only inv_pool's three "
-                              "Linear layers (16-256-1024-16384, 4 % of the step) are still library GEMMs"},
+                       "centres": "octree centre coder on the device (pn_kit.encode_sampled_np depth search, bit-exact stream and "
+                                  ".s.bin bytes); patches are built on the centres a decoder recovers from that stream",
+                       "mlp": "hand-written tcgen05 kernels only: SetAbstraction 3-32-64-128+max16, PointNet 131-128-256 and its "
+                              "256-512-16+max tail (W2 streamed by TMA), inv_pool 16-256-1024-16384 (streamed GEMM, TMA ring), "
+                              "decoder 144-128-64-32-3; no library GEMM in the timed region"},
             "clocks": clk, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "roofline": roofline, "cpu_baseline": cpu_base,

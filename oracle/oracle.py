@@ -237,3 +237,18 @@ def bits_to_bytes(bits):
     out = np.zeros((bits.shape[0] + 7) // 8, np.uint8)
     n = lib().orc_bits_to_bytes(_pu8(bits), bits.shape[0], _pu8(out))
     return out[:n]
+
+
+def octree_stream_centres(pc, depth, rows):
+    """The centres a correct decoder recovers from octree_encode(pc, 1, depth): the distinct snapped cells in the
+    stream's own order (the reference's DFS pops children 7..0 => descending (x, y, z)-interleaved cell code), the last
+    one repeated up to `rows` rows (the reference's padding rule, octree_np.py:101-105).  numpy, small inputs."""
+    _, u = octree_quantise(pc, 1.0, depth)
+    cells = np.floor(u * np.float32(2.0 ** depth)).astype(np.int64)
+    code = np.zeros(len(u), np.int64)
+    for lvl in range(depth - 1, -1, -1):
+        code = (code << 3) | (((cells[:, 0] >> lvl) & 1) << 2) | (((cells[:, 1] >> lvl) & 1) << 1) | ((cells[:, 2] >> lvl) & 1)
+    u = u[np.argsort(-code, kind="stable")]
+    if len(u) < rows:
+        u = np.concatenate([u, np.repeat(u[-1:], rows - len(u), axis=0)])
+    return u[:rows]

@@ -83,16 +83,28 @@ def quantise_centres(c, depth):
     return (c // cube * cube) + (cube / 2)
 
 
+OCTREE_BPP_DICT = {1024: 0.07, 512: 0.125, 256: 0.25, 128: 0.5, 64: 1.0}  # pn_kit.py:17-23
+
+
 def compress_decompress_eval(sd, cloud, start_idx, K=256, k=128, d=16, L=7, N0=1024, alpha=2, centre_depth=6,
-                             threads=1, per_patch_loop=False):
+                             threads=1, per_patch_loop=False, centre_mode="fixed"):
     """One cloud [N,3] through the hot path of compress.py:90-127 -> decompress.py:96-116 -> eval.py:180,199-205.
-    per_patch_loop=True feeds the encoder one patch at a time exactly as compress.py:113-122 does."""
+    per_patch_loop=True feeds the encoder one patch at a time exactly as compress.py:113-122 does.
+    centre_mode="coded" runs the octree centre coder of compress.py:98 (pn_kit.encode_sampled_np, C restatement pinned to
+    the reference) and continues with the centres a correct decoder recovers from that stream."""
     pc = _t(cloud)[None]
     N = pc.shape[1]
     S = int(N * alpha // K)
     pcn, center, longest = normalize(pc)
     idx = orc.fps(pcn.numpy(), S, np.asarray([start_idx], dtype=np.int64), 1e10)
-    centres = quantise_centres(orc.gather(pcn.numpy(), idx), centre_depth).astype(np.float32)
+    octree = None
+    if centre_mode == "coded":
+        fps_xyz = orc.gather(pcn.numpy(), idx)
+        codes, _, depths = orc.encode_sampled_np(fps_xyz, 1, N, OCTREE_BPP_DICT[K])
+        octree = dict(bits=codes[0], depth=depths[0], bytes=orc.bits_to_bytes(codes[0]))
+        centres = orc.octree_stream_centres(fps_xyz[0], depths[0], S)[None].astype(np.float32)
+    else:
+        centres = quantise_centres(orc.gather(pcn.numpy(), idx), centre_depth).astype(np.float32)
     _, _, nn = orc.knn_points(centres, pcn.numpy(), K, True, threads=threads)
     patches = (_t(nn) - _t(centres).view(1, S, 1, 3)).view(S, K, 3)
     scale = (N / N0) ** (1 / 3)
@@ -112,4 +124,4 @@ def compress_decompress_eval(sd, cloud, start_idx, K=256, k=128, d=16, L=7, N0=1
     cham = orc.chamfer(((rec_np - mn) / (mx - mn))[None], ((orig - mn) / (mx - mn))[None], threads=threads)[0]
     psnr, mse = orc.d1_psnr(orig, rec_np)                                        # eval.py:43-98 (float64)
     return dict(latent=latent.numpy(), latent_q=latent_q.numpy(), centres=centres[0], rec=rec_np, chamfer=cham,
-                d1_psnr=psnr, d1_mse=mse)
+                d1_psnr=psnr, d1_mse=mse, octree=octree)

@@ -113,37 +113,51 @@ __device__ __forceinline__ unsigned pack2_bf16(float lo, float hi) {
 // Grouping of a PointNet++ set-abstraction level in one pass (/root/reference/pointnet_sa_module.py:73-85): row r of the output
 // is [features[b, idx[r], 0..C) | xyz[b, idx[r], 0..3) | zeros up to kpad] in bf16 -- the gathers, the torch.cat and the
 // operand conversion of the GEMM that follows.  Negative indices (ball-query padding) read point 0 (pointnet_sa_module.py:27).
-// One thread per 8 output columns (one 16-byte store).
+// One warp per group of 4 output rows: the 4 indices are read first (independent loads), then lanes walk each row's 16-byte
+// chunks with the rows unrolled, so several rows' feature loads are in flight at once.
 __global__ void __launch_bounds__(256)
 gather_concat_bf16_kernel(const float *__restrict__ feat, int C, const float *__restrict__ xyz, const int64_t *__restrict__ idx,
                           long long rows, int N, long long M, int kpad, uint4 *__restrict__ out) {
-    const int chunks = kpad >> 3;
-    const long long total = rows * chunks;
-    for (long long t = blockIdx.x * 256ll + threadIdx.x; t < total; t += static_cast<long long>(gridDim.x) * 256) {
-        const long long r = t / chunks;
-        const int c0 = static_cast<int>(t % chunks) * 8;
-        const long long b = r / M;
-        long long j = idx[r];
-        j = j < 0 ? 0 : j;
-        const long long src = b * N + j;
-        float v[8];
-        if (feat && c0 + 8 <= C && (C & 3) == 0) {
-            const float4 a = __ldg(reinterpret_cast<const float4 *>(feat + src * C + c0));
-            const float4 d = __ldg(reinterpret_cast<const float4 *>(feat + src * C + c0 + 4));
-            v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = d.x, v[5] = d.y, v[6] = d.z, v[7] = d.w;
-        } else {
+    constexpr int R = 4;
+    const int chunks = kpad >> 3, lane = threadIdx.x & 31;
+    const bool vec = feat && (C & 7) == 0;
+    for (long long r0 = (blockIdx.x * 8ll + (threadIdx.x >> 5)) * R; r0 < rows; r0 += static_cast<long long>(gridDim.x) * 8 * R) {
+        long long src[R];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const int c = c0 + e;
-                v[e] = (feat && c < C) ? __ldg(feat + src * C + c) : (xyz && c >= C && c < C + 3) ? __ldg(xyz + src * 3 + (c - C)) : 0.0f;
-            }
+        for (int i = 0; i < R; ++i) {
+            const long long r = r0 + i < rows ? r0 + i : rows - 1;
+            long long j = __ldg(idx + r);
+            j = j < 0 ? 0 : j;
+            src[i] = (r / M) * N + j;
         }
-        uint4 o;
-        o.x = pack2_bf16(v[0], v[1]);
-        o.y = pack2_bf16(v[2], v[3]);
-        o.z = pack2_bf16(v[4], v[5]);
-        o.w = pack2_bf16(v[6], v[7]);
-        out[t] = o;
+        for (int ch = lane; ch < chunks; ch += 32) {
+            const int c0 = ch * 8;
+            uint4 q[R];
+#pragma unroll
+            for (int i = 0; i < R; ++i) {
+                const float *f = feat ? feat + src[i] * C : nullptr;
+                const float *p = xyz ? xyz + src[i] * 3 : nullptr;
+                float v[8];
+                if (vec && c0 + 8 <= C) {
+                    const float4 a = __ldg(reinterpret_cast<const float4 *>(f + c0));
+                    const float4 d = __ldg(reinterpret_cast<const float4 *>(f + c0 + 4));
+                    v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = d.x, v[5] = d.y, v[6] = d.z, v[7] = d.w;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int c = c0 + e;
+                        v[e] = (f && c < C) ? __ldg(f + c) : (p && c >= C && c < C + 3) ? __ldg(p + (c - C)) : 0.0f;
+                    }
+                }
+                q[i].x = pack2_bf16(v[0], v[1]);
+                q[i].y = pack2_bf16(v[2], v[3]);
+                q[i].z = pack2_bf16(v[4], v[5]);
+                q[i].w = pack2_bf16(v[6], v[7]);
+            }
+#pragma unroll
+            for (int i = 0; i < R; ++i)
+                if (r0 + i < rows) out[(r0 + i) * chunks + ch] = q[i];
+        }
     }
 }
 
@@ -206,7 +220,7 @@ PCC_API int pcc_gather_concat_bf16(const float *feat, int C, const float *xyz, c
                 "pcc_gather_concat_bf16: feat / out must be 16-byte aligned");
     const long long rows = static_cast<long long>(B) * M;
     if (rows == 0) return 0;
-    gather_concat_bf16_kernel<<<grid_for(rows * (kpad / 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    gather_concat_bf16_kernel<<<grid_for(rows * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         feat, C, xyz, idx, rows, N, M, kpad, static_cast<uint4 *>(out));
     return check_launch("gather_concat_bf16_kernel");
 }

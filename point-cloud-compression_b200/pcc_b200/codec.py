@@ -102,8 +102,10 @@ class PatchCodec:
         return ops.eval_metrics(r["dx"], r["per_cloud"], bbox)                    # eval.py:84,88-92,199-205 in one kernel
 
     @torch.no_grad()
-    def roundtrip(self, xyz, start_idx=None):
-        """compress -> decompress -> eval for a batch; returns (latent_q int8 [B,S,d], centres, metrics [B,3], rec)."""
+    def roundtrip(self, xyz, start_idx=None, return_octree=False):
+        """compress -> decompress -> eval for a batch; returns (latent_q int8 [B,S,d], centres, metrics [B,3], rec), plus
+        the octree coder's output dict (None in 'fixed' mode) when return_octree is set."""
         c = self.compress(xyz, start_idx)
         rec = self.decompress(c["latent_q"], c["centres"], xyz.shape[1], c["center"], c["longest"])
-        return c["latent_q"].to(torch.int8), c["centres"], self.evaluate(rec, xyz, c["bbox"]), rec
+        out = (c["latent_q"].to(torch.int8), c["centres"], self.evaluate(rec, xyz, c["bbox"]), rec)
+        return out + (c["octree"],) if return_octree else out

@@ -24,8 +24,13 @@ def estimate_bits_from_pmf(pmf, sym):
 
 class Trainer:
     def __init__(self, K=256, k=128, d=16, L=7, N0=1024, alpha=2, lr=0.0005, lamda=1e-6, rate_loss_enable_step=40000,
-                 centre_depth=6, device="cuda", ddp=False, state_dict=None):
+                 centre_depth=6, device="cuda", ddp=False, state_dict=None, tf32=True):
         self.K, self.k, self.d, self.L, self.N0, self.alpha = K, k, d, L, N0, alpha
+        # The reference's network bodies are 1x1 Conv2d layers, which PyTorch runs through cuDNN with TF32 enabled by
+        # default (torch.backends.cudnn.allow_tf32); the addmm form used here gets the same arithmetic only when the
+        # matmul flag is switched on as well.  fp32 storage and accumulation, 10-bit operand mantissas.
+        if tf32:
+            torch.backends.cuda.matmul.allow_tf32 = True
         self.lamda, self.rate_loss_enable_step, self.centre_depth = lamda, rate_loss_enable_step, centre_depth
         self.ae = AE(K, k, d, L).to(device)
         if state_dict is not None:

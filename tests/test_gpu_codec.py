@@ -94,8 +94,12 @@ def test_centre_modes_coded_and_reference(setup):
         else:
             dec, count, _ = pcc.ops.octree_decode(o["bits"], o["nbits"], mode=1, cap=64)
             assert torch.equal(dec, c["centres"]) and count.cpu().tolist() == [64, 64, 64]
-            snapped = np.stack([orc.octree_quantise(fps_xyz[b].cpu().numpy(), 1, depths[b])[0] for b in range(3)])
-            assert np.array_equal(np.sort(c["centres"].cpu().numpy(), axis=1), np.sort(snapped, axis=1))
+            want = np.stack([orc.octree_stream_centres(fps_xyz[b].cpu().numpy(), depths[b], 64) for b in range(3)])
+            assert np.array_equal(c["centres"].cpu().numpy(), want)
+            from oracle import torch_modules as tm   # the CPU flow in the same mode: same stream, same centres
+            ref = tm.compress_decompress_eval(sd, clouds[0], 1, threads=8, centre_mode="coded")
+            assert np.array_equal(ref["centres"], want[0]) and np.array_equal(ref["octree"]["bits"], codes[0])
+            assert np.abs(c["latent"][0].cpu().numpy() - ref["latent"]).max() < LATENT_ATOL
         rec = codec.decompress(c["latent_q"], c["centres"], 8192, c["center"], c["longest"])
         met = codec.evaluate(rec, x).cpu().numpy()
         assert rec.shape == (3, 8192, 3) and np.isfinite(met).all()
