@@ -109,3 +109,45 @@ class PatchCodec:
         rec = self.decompress(c["latent_q"], c["centres"], xyz.shape[1], c["center"], c["longest"])
         out = (c["latent_q"].to(torch.int8), c["centres"], self.evaluate(rec, xyz, c["bbox"]), rec)
         return out + (c["octree"],) if return_octree else out
+
+    @torch.no_grad()
+    def roundtrip_sweep(self, host_batches, start_idx=None, sink=None):
+        """compress -> decompress -> eval over a stream of HOST batches (the per-file loops of compress.py:78-155 and
+        eval.py:167-221 as one sweep).  `host_batches` yields pinned CPU tensors [B,N,3]; the upload of batch s + 1 runs
+        on a copy stream while batch s is being processed (two device staging buffers), and `sink(s, latent_q, centres,
+        metrics, octree)` -- called on the compute stream's timeline -- is where the caller issues its device -> host
+        copies.  Returns the number of batches processed; the caller synchronises."""
+        dev = next(self.ae.parameters()).device
+        main = torch.cuda.current_stream(dev)
+        copy = getattr(self, "_copy_stream", None)
+        if copy is None:
+            copy = self._copy_stream = torch.cuda.Stream(dev)
+        it = iter(host_batches)
+        bufs, ready, free = [None, None], [torch.cuda.Event(), torch.cuda.Event()], [None, None]
+
+        def upload(slot, host):
+            if bufs[slot] is None or bufs[slot].shape != host.shape:
+                bufs[slot] = torch.empty(host.shape, dtype=torch.float32, device=dev)
+            with torch.cuda.stream(copy):
+                if free[slot] is not None:
+                    copy.wait_event(free[slot])        # the step that read this buffer has finished
+                bufs[slot].copy_(host, non_blocking=True)
+                ready[slot].record(copy)
+
+        nxt = next(it, None)
+        if nxt is not None:
+            upload(0, nxt)
+        s = 0
+        while nxt is not None:
+            slot = s & 1
+            nxt = next(it, None)
+            if nxt is not None:
+                upload(slot ^ 1, nxt)
+            main.wait_event(ready[slot])
+            lat, cen, met, _, octree = self.roundtrip(bufs[slot], start_idx, return_octree=True)
+            free[slot] = torch.cuda.Event()
+            free[slot].record(main)
+            if sink is not None:
+                sink(s, lat, cen, met, octree)
+            s += 1
+        return s

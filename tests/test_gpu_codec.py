@@ -103,3 +103,24 @@ def test_centre_modes_coded_and_reference(setup):
         rec = codec.decompress(c["latent_q"], c["centres"], 8192, c["center"], c["longest"])
         met = codec.evaluate(rec, x).cpu().numpy()
         assert rec.shape == (3, 8192, 3) and np.isfinite(met).all()
+
+
+def test_roundtrip_sweep_matches_per_batch_calls(setup):
+    """The double-buffered host sweep (upload of batch s + 1 under batch s) returns what per-batch calls return."""
+    from pcc_b200.codec import PatchCodec
+    pcc, codec, sd = setup
+    codec = PatchCodec(codec.ae, centre_mode="coded")
+    host = [torch.from_numpy(synth.modelnet_like(2, 8192, seed=70 + i)).pin_memory() for i in range(5)]
+    start = torch.zeros(2, dtype=torch.int64, device="cuda")
+    got = {}
+
+    def sink(s, lat, cen, met, octree):
+        got[s] = (lat.cpu(), cen.cpu(), met.cpu(), octree["bytes"].cpu(), octree["nbits"].cpu())
+
+    assert codec.roundtrip_sweep(iter(host), start, sink) == 5
+    torch.cuda.synchronize()
+    for s, h in enumerate(host):
+        lat, cen, met, _, octree = codec.roundtrip(h.cuda(), start, return_octree=True)
+        assert torch.equal(got[s][0], lat.cpu()) and torch.equal(got[s][1], cen.cpu())
+        assert torch.equal(got[s][2], met.cpu())
+        assert torch.equal(got[s][3], octree["bytes"].cpu()) and torch.equal(got[s][4], octree["nbits"].cpu())
