@@ -17,6 +17,8 @@
 //                       which settles it when the best d2 is closer than the block's faces.  Step 2 (far neighbours),
 //                       warp-cooperative: an upper bound from a strided sample of the candidates if nothing was found,
 //                       then the warp walks the union of its unsettled queries' balls with uniform control flow
+#include <stdlib.h>
+
 #include "pcc_common.cuh"
 
 namespace pcc {
@@ -253,9 +255,19 @@ grid_nn_kernel(int P1, int P2, const float4 *__restrict__ sorted, const unsigned
             for (int yy = ya; yy <= yb; ++yy) {
                 const float gy = slab_gap(q.y, g.mny, g.h, yy, g.margin);
                 // a row is skipped only if it lies outside the ball of every unsettled query of the warp
-                if (__all_sync(FULL_MASK, !need || (gz * gz + gy * gy) * 0.9999f > key_d2(best))) continue;
+                const float rem = key_d2(best) - (gz * gz + gy * gy) * 0.9999f;
+                const bool hit = need && rem >= 0.0f;
+                if (!__any_sync(FULL_MASK, hit)) continue;
+                // x extent of the row that can still matter: the chord of each lane's ball at this (y, z) slab, in cells.
+                // cell_coord is monotone in the coordinate and is the function the build used, so a point with
+                // |p.x - q.x| <= rx lies in a cell of [cell(q.x - rx), cell(q.x + rx)]: no extra cell of slack is needed
+                const float rx = hit ? sqrtf(rem) * 1.0001f + g.margin : 0.0f;
+                const int lx = hit ? cell_coord(q.x - rx, g.mnx, g.inv_h, G) : G;
+                const int hx = hit ? cell_coord(q.x + rx, g.mnx, g.inv_h, G) : -1;
+                const int xa2 = max(xa, __reduce_min_sync(FULL_MASK, lx)), xb2 = min(xb, __reduce_max_sync(FULL_MASK, hx));
+                if (xa2 > xb2) continue;   // (visiting the rows centre-out was measured: no gain, the balls are already tight)
                 const unsigned row = static_cast<unsigned>((z * G + yy) * G);
-                const unsigned a = __ldg(st + row + xa), e = __ldg(st + row + xb + 1);
+                const unsigned a = __ldg(st + row + xa2), e = __ldg(st + row + xb2 + 1);
                 for (unsigned j = a; j < e; ++j) {
                     const float4 c = __ldg(cand + j);
                     const unsigned long long k = pack_key(dist2_rn(q.x, q.y, q.z, c.x, c.y, c.z), __float_as_uint(c.w));
@@ -277,6 +289,10 @@ int64_t chamfer_grid_extra_bytes(int B, int P1, int P2, int G) {
 int chamfer_grid_pick(int P1, int P2) {   // grid resolution, or 0: use the brute-force kernels
     const int lo = P1 < P2 ? P1 : P2, hi = P1 < P2 ? P2 : P1;
     if (lo < 1024 || hi > (1 << 24)) return 0;
+    if (const char *e = getenv("PCC_CHAMFER_GRID")) {   // tuning knob: cells per axis, 4..32
+        const int g = atoi(e);
+        if (g >= 4 && g <= 32) return g;
+    }
     return lo >= 4096 ? 32 : 16;
 }
 
