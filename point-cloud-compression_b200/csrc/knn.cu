@@ -162,6 +162,34 @@ __device__ __forceinline__ int block_sum(int v, int (*part)[KB_WARPS], int &buf)
     return __reduce_add_sync(FULL_MASK, r);
 }
 
+// Block-wide bitonic sort of one value per thread (512 threads), ascending in thread order.  Exchanges at distance < 32 are
+// warp shuffles; the 10 exchanges at distance >= 32 go through two alternating shared-memory buffers (one barrier each).
+template <typename T>
+__device__ __forceinline__ T block_sort_512(T v, T *buf0, T *buf1) {
+    const unsigned tid = threadIdx.x;
+    int flip = 0;
+#pragma unroll
+    for (unsigned k = 2; k <= KB_THREADS; k <<= 1) {
+#pragma unroll
+        for (unsigned j = k >> 1; j > 0; j >>= 1) {
+            T other;
+            if (j >= 32) {
+                T *b = flip ? buf1 : buf0;
+                flip ^= 1;
+                b[tid] = v;
+                __syncthreads();
+                other = b[tid ^ j];
+            } else {
+                other = __shfl_xor_sync(FULL_MASK, v, j);
+            }
+            const bool lower = (tid & j) == 0, up = (tid & k) == 0;
+            const T lo = v < other ? v : other, hi = v < other ? other : v;
+            v = (lower == up) ? lo : hi;
+        }
+    }
+    return v;
+}
+
 template <int CPT>
 __global__ void __launch_bounds__(KB_THREADS)
 knn_block_kernel(const float *__restrict__ q, const float *__restrict__ p, int P1, int P2, int K,
@@ -187,6 +215,50 @@ knn_block_kernel(const float *__restrict__ q, const float *__restrict__ p, int P
     }
     const int Keff = K < P2 ? K : P2;
     int buf = 0;
+    // ---- fast path (K <= 512): selection by two small sorts instead of ~32 bisection passes over all candidates ----
+    // The Keff-th smallest of the 512 per-thread minima is an upper bound tau of the Keff-th smallest distance (Keff
+    // distinct candidates are <= it), and only ~1.4 Keff candidates pass it (each minimum is the best of CPT values).
+    // Those are compacted and sorted as (d2, idx) keys; the first Keff are the answer -- the same set and order as any
+    // other exact selection.  Falls through to the bisection when fewer than Keff threads hold a candidate or when ties
+    // let more than 512 candidates through.
+    bool fast = false;
+    if (CPT >= 16 && Keff <= KB_THREADS) {   // with few candidates per thread the bisection passes are cheaper than two sorts (measured)
+        unsigned m = d[0];
+#pragma unroll
+        for (int s = 1; s < CPT; ++s) m = d[s] < m ? d[s] : m;
+        const unsigned ms = block_sort_512<unsigned>(m, reinterpret_cast<unsigned *>(sel), reinterpret_cast<unsigned *>(sorted));
+        __shared__ unsigned s_tau;
+        if (tid == Keff - 1) s_tau = ms;
+        __syncthreads();
+        const unsigned tau = s_tau;
+        int c = 0;
+#pragma unroll
+        for (int s = 0; s < CPT; ++s) c += d[s] <= tau ? 1 : 0;
+        const int n = block_sum(c, part, buf);   // (its barrier also orders the sort's last buffer reads before the writes below)
+        if (tau != 0xffffffffu && n <= KB_THREADS) {
+            fast = true;
+#pragma unroll
+            for (int s = 0; s < CPT; ++s) {
+                const unsigned j = static_cast<unsigned>(s * KB_THREADS + tid);
+                const bool take = d[s] <= tau;
+                const unsigned mk = __ballot_sync(FULL_MASK, take);
+                if (mk) {
+                    int base = 0;
+                    if (lane_id() == static_cast<unsigned>(__ffs(mk) - 1)) base = atomicAdd(&sel_count, __popc(mk));
+                    base = __shfl_sync(FULL_MASK, base, __ffs(mk) - 1);
+                    if (take) sel[base + __popc(mk & ((1u << lane_id()) - 1u))] = (static_cast<unsigned long long>(d[s]) << 32) | j;
+                }
+            }
+            __syncthreads();
+            unsigned long long key = tid < n ? sel[tid] : KEY_MAX;
+            __syncthreads();   // sel doubles as an exchange buffer of the sort
+            key = block_sort_512<unsigned long long>(key, sel, sorted);
+            __syncthreads();   // the last exchange may still be reading `sorted`
+            if (tid < Keff) sorted[tid] = key;
+            __syncthreads();
+        }
+    }
+    if (!fast) {
     // bisection on the distance pattern: smallest v with count(d <= v) >= Keff
     unsigned lo = 0u, hi = 0xfffffffeu;
     bool exact = false;
@@ -243,6 +315,7 @@ knn_block_kernel(const float *__restrict__ q, const float *__restrict__ p, int P
         sorted[rank] = key;
     }
     __syncthreads();
+    }  // !fast
     const size_t obase = (static_cast<size_t>(b) * P1 + qi) * K;
     for (int k = tid; k < K; k += KB_THREADS) {
         float dd = 0.0f;
