@@ -254,6 +254,23 @@ int pcc_linear_bf16(const void *a, int64_t M, int K, int64_t lda, const void *w,
 int pcc_gather_concat_bf16(const float *feat, int C, const float *xyz, const int64_t *idx, int B, int N, int64_t M, int kpad,
                            void *out, void *stream);
 
+/*
+ * The remaining eval.py metrics, computed from outputs of pcc_knn_f32 / pcc_chamfer_fwd_f32.
+ * pcc_normals_pca_f32: Open3D estimate_normals(KDTreeSearchParamKNN(knn = 30)) of /root/reference/eval.py:58-59 --
+ *   nn [rows, knn, 3] = the knn nearest points of every point of the original cloud, itself included (pcc_knn_f32's out_nn
+ *   without recentring); out_normals [rows, 3] = unit eigenvector of the smallest eigenvalue of their covariance (double
+ *   arithmetic; sign arbitrary, eval.py squares the projection).
+ * pcc_p2plane_f32: eval.py:68-92 -- ix [B, P1] = nearest original point of every reconstructed point (pcc_chamfer_fwd_f32's
+ *   out_ix for (recon, orig)); out [B, 2] float64 = (mean (diff . normal)^2, 10 log10(|bbox diag|^2 / mse)); bbox [B, 6].
+ * pcc_uc_f32: the variance ratio that ends calc_uc (eval.py:127-151) -- d2_in / d2_dec [B, n] = squared distance of every point
+ *   of the 1024-point region around point 0 to its nearest other region point (pcc_knn_f32 with K = 2, column 1), for the
+ *   input and the decompressed cloud; out [B] float64 = var(sqrt(d2_dec)) / var(sqrt(d2_in)), population variance (np.var).
+ */
+int pcc_normals_pca_f32(const float *nn, int64_t rows, int knn, float *out_normals, void *stream);
+int pcc_p2plane_f32(const float *recon, const float *orig, const int64_t *ix, const float *normals, const float *bbox, int B,
+                    int P1, int P2, double *out, void *stream);
+int pcc_uc_f32(const float *d2_in, const float *d2_dec, int B, int n, double *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

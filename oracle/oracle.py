@@ -252,3 +252,40 @@ def octree_stream_centres(pc, depth, rows):
     if len(u) < rows:
         u = np.concatenate([u, np.repeat(u[-1:], rows - len(u), axis=0)])
     return u[:rows]
+
+
+# ---- the remaining eval.py metrics ---------------------------------------------------------------------
+def calc_uc(input_pc, decomp_pc, region=1024):
+    """eval.py:127-151 calc_uc: 1024-NN region of point 0 (knn_points), distance of every region point to its nearest
+    other region point (the reference takes column 1 of a topk over torch.cdist), np.var ratio."""
+    def region_dist(pc):
+        pc = _f32(pc)
+        _, _, nn = knn_points(pc[None, :1], pc[None], region, True)
+        reg = nn[0, 0] - pc[0]                                   # eval.py:134 recentring
+        d, _, _ = knn_points(reg[None], reg[None], 2, False)
+        return np.sqrt(d[0, :, 1].astype(np.float64))
+    return float(np.var(region_dist(decomp_pc)) / np.var(region_dist(input_pc)))
+
+
+def estimate_normals(points, knn=30):
+    """Open3D estimate_normals(KDTreeSearchParamKNN(knn)), eval.py:58-59 (Open3D is not installed here: PARITY UNPINNED;
+    restated from its published algorithm -- covariance of the knn nearest points, eigenvector of the smallest eigenvalue)."""
+    points = _f32(points)
+    _, idx, _ = knn_points(points[None], points[None], knn, False)
+    nb = points[idx[0]].astype(np.float64)                        # [N, knn, 3]
+    mean = nb.mean(axis=1, keepdims=True)
+    cov = np.einsum("nki,nkj->nij", nb, nb) / knn - np.einsum("nki,nkj->nij", mean, mean)
+    _, v = np.linalg.eigh(cov)
+    return v[:, :, 0]
+
+
+def p2plane_psnr(orig, recon, knn=30):
+    """eval.py:43-98 compute_p2point_p2plane_psnr, p2plane half (float64): returns (psnr_db, mse)."""
+    orig, recon = _f32(orig), _f32(recon)
+    normals = estimate_normals(orig, knn)
+    _, ix = nn1(recon[None], orig[None])
+    diff = recon.astype(np.float64) - orig[ix[0]].astype(np.float64)
+    e = np.einsum("ni,ni->n", diff, normals[ix[0]]) ** 2
+    mse = float(e.mean())
+    diag = np.linalg.norm(orig.max(axis=0).astype(np.float64) - orig.min(axis=0).astype(np.float64))
+    return (float(10 * np.log10(diag ** 2 / mse)) if mse > 0 else float("inf")), mse

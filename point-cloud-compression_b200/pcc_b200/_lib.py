@@ -57,6 +57,9 @@ SIGNATURES.update({
     "pcc_pn_tail_bf16": (_i, [_vp, _i64, _i64, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "pcc_linear_bf16": (_i, [_vp, _i64, _i, _i64, _vp, _i64, _vp, _i, _i, _i, _vp, _i64, _vp]),
     "pcc_gather_concat_bf16": (_i, [_vp, _i, _vp, _vp, _i, _i, _i64, _i, _vp, _vp]),
+    "pcc_normals_pca_f32": (_i, [_vp, _i64, _i, _vp, _vp]),
+    "pcc_p2plane_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "pcc_uc_f32": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "pcc_octree_max_bits": (_i, [_i]),
     "pcc_octree_encode_f32": (_i, [_vp, _i, _i, _i, ctypes.c_double, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pcc_octree_decode_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),

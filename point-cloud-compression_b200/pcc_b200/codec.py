@@ -102,6 +102,18 @@ class PatchCodec:
         return ops.eval_metrics(r["dx"], r["per_cloud"], bbox)                    # eval.py:84,88-92,199-205 in one kernel
 
     @torch.no_grad()
+    def evaluate_all(self, decomp, original):
+        """Every per-file metric of eval.py:167-221 except the bitrate: dict of float64 tensors [B] -- chamfer (eval.py:199-205),
+        d1_psnr and d2_psnr (eval.py:43-98: point-to-point and point-to-plane, normals by 30-NN PCA of the original),
+        uc (eval.py:127-151).  One Chamfer launch serves chamfer, D1 and the nearest-neighbour indices of D2."""
+        bbox = torch.cat((original.amin(dim=1), original.amax(dim=1)), dim=1)
+        r = ops.chamfer_forward(decomp, original, want_idx=True)
+        m = ops.eval_metrics(r["dx"], r["per_cloud"], bbox)
+        d2 = ops.p2plane_psnr(decomp, original, ix=r["ix"], bbox=bbox)
+        return dict(chamfer=m[:, 0], d1_psnr=m[:, 1], d1_mse=m[:, 2], d2_psnr=d2[:, 1], d2_mse=d2[:, 0],
+                    uc=ops.uniformity_coefficient(original, decomp))
+
+    @torch.no_grad()
     def roundtrip(self, xyz, start_idx=None, return_octree=False):
         """compress -> decompress -> eval for a batch; returns (latent_q int8 [B,S,d], centres, metrics [B,3], rec), plus
         the octree coder's output dict (None in 'fixed' mode) when return_octree is set."""

@@ -278,3 +278,59 @@ def octree_decode(bits, nbits, mode=1, cap=64):
         _lib.check(lib.pcc_octree_decode_f32(_ptr(bits), _ptr(nbits), B, max_bits, int(mode), int(cap), _ptr(out), _ptr(count),
                                              _ptr(depth), _stream()), "pcc_octree_decode_f32")
     return out, count, depth
+
+
+def estimate_normals(points, knn_k=30):
+    """Open3D estimate_normals(KDTreeSearchParamKNN(knn)) as eval.py:58-59 uses it: [B,N,3] -> unit normals [B,N,3]
+    (PCA of the knn nearest points, the point itself included; sign arbitrary)."""
+    lib = _lib.load()
+    points = _cuda_f32(points, "points")
+    B, N, _ = points.shape
+    _, _, nn = knn(points, points, knn_k, return_nn=True, nn_only=True)
+    out = torch.empty((B, N, 3), dtype=torch.float32, device=points.device)
+    with torch.cuda.device(points.device):
+        _lib.check(lib.pcc_normals_pca_f32(_ptr(nn), B * N, knn_k, _ptr(out), _stream()), "pcc_normals_pca_f32")
+    return out
+
+
+def p2plane_psnr(recon, orig, normals=None, ix=None, bbox=None, knn_k=30):
+    """eval.py:43-98 compute_p2point_p2plane_psnr, the p2plane half: returns float64 [B,2] = (mse, psnr dB).
+    normals / ix / bbox are computed here when not supplied (normals of `orig`, 1-NN of recon in orig, bbox of orig)."""
+    lib = _lib.load()
+    recon, orig = _cuda_f32(recon, "recon"), _cuda_f32(orig, "orig")
+    _check_pair(recon, orig)
+    B, P1, _ = recon.shape
+    P2 = orig.shape[1]
+    if normals is None:
+        normals = estimate_normals(orig, knn_k)
+    if ix is None:
+        _, ix = nn1(recon, orig)
+    if bbox is None:
+        bbox = torch.cat((orig.amin(dim=1), orig.amax(dim=1)), dim=1)
+    bbox = bbox.float().contiguous()
+    ix = ix.to(torch.int64).contiguous()
+    out = torch.empty((B, 2), dtype=torch.float64, device=recon.device)
+    with torch.cuda.device(recon.device):
+        _lib.check(lib.pcc_p2plane_f32(_ptr(recon), _ptr(orig), _ptr(ix), _ptr(normals.contiguous()), _ptr(bbox), B, P1, P2,
+                                       _ptr(out), _stream()), "pcc_p2plane_f32")
+    return out
+
+
+def uniformity_coefficient(input_pc, decomp_pc, region=1024):
+    """eval.py:127-151 calc_uc for a batch: the 1024 nearest points of point 0 of each cloud, every region point's distance
+    to its nearest other region point, var(decompressed) / var(input).  Returns float64 [B]."""
+    lib = _lib.load()
+    input_pc, decomp_pc = _cuda_f32(input_pc, "input_pc"), _cuda_f32(decomp_pc, "decomp_pc")
+    B = input_pc.shape[0]
+    if input_pc.shape[1] < region or decomp_pc.shape[1] < region:
+        raise ValueError("pcc_b200.uniformity_coefficient: clouds need at least `region` points")
+    d2 = []
+    for pc in (input_pc, decomp_pc):
+        _, _, reg = knn(pc[:, :1].contiguous(), pc, region, return_nn=True, centre_sub=True, nn_only=True)  # KNN_Region incl.
+        reg = reg.view(B, region, 3)                                                        # the recentring of eval.py:134
+        dd, _, _ = knn(reg, reg, 2)
+        d2.append(dd[:, :, 1].contiguous())
+    out = torch.empty((B,), dtype=torch.float64, device=input_pc.device)
+    with torch.cuda.device(input_pc.device):
+        _lib.check(lib.pcc_uc_f32(_ptr(d2[0]), _ptr(d2[1]), B, region, _ptr(out), _stream()), "pcc_uc_f32")
+    return out

@@ -6,6 +6,8 @@
                          (imported from /root/reference), including the CPU-RNG start indices it drew.
 * ref_octree.npz      -- outputs of the REFERENCE's own octree centre coder (pn_kit.encode_sampled_np, decode_sampled_np,
                          binary_array_to_byte_array, octree_np.encode, getDecodeFromPc) on seeded FPS centres.
+* ref_eval.npz        -- eval.py's calc_uc run from the reference's own source (extracted with ast), and the oracle's
+                         p2plane PSNR (Open3D absent: unpinned).
 * p3d_ops.npz         -- outputs of the oracle restatement of the PyTorch3D ops (knn_points, ball_query,
                          sample_farthest_points, chamfer_distance) on seeded inputs, cross-checked here against
                          an independent torch brute-force statement before being written.  PyTorch3D itself
@@ -214,9 +216,29 @@ def ref_octree():
     print("ref_octree.npz:", {k: (out[k].tolist()) for k in out if k.endswith("_depth")})
 
 
+def ref_eval():
+    """eval.py metrics.  calc_uc is the REFERENCE's own function: eval.py cannot be imported (it parses argv and globs files at
+    import), so the function definition is extracted from its source with `ast` and executed with the stubbed knn_points.
+    The p2plane numbers are the oracle's (Open3D is not installed: parity unpinned)."""
+    import ast
+    ref_loader.install_stubs()
+    tree = ast.parse(open(os.path.join(ref_loader.REFERENCE_ROOT, "eval.py")).read())
+    fn = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "calc_uc"][0]
+    ns = {"np": np, "torch": torch, "knn_points": sys.modules["pytorch3d.ops.knn"].knn_points}
+    exec(compile(ast.Module([fn], []), "eval.py", "exec"), ns)
+    x = synth.modelnet_like(3, 8192, seed=81)
+    y = synth.decompressed_like(x, seed=82)
+    uc = np.array([ns["calc_uc"](x[b], y[b]) for b in range(3)], np.float64)
+    assert np.allclose(uc, [orc.calc_uc(x[b], y[b]) for b in range(3)], rtol=1e-4)   # cdist's matmul path: 6th digit
+    pp = np.array([orc.p2plane_psnr(x[b], y[b]) for b in range(3)], np.float64)
+    np.savez_compressed(os.path.join(HERE, "ref_eval.npz"), uc=uc, p2plane=pp)
+    print("ref_eval.npz: uc", uc, "p2plane", pp[:, 0])
+
+
 if __name__ == "__main__":
     ref_fps_gather()
     p3d_ops()
     pppf_modules()
     ae_modules()
     ref_octree()
+    ref_eval()

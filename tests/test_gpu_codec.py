@@ -124,3 +124,19 @@ def test_roundtrip_sweep_matches_per_batch_calls(setup):
         assert torch.equal(got[s][0], lat.cpu()) and torch.equal(got[s][1], cen.cpu())
         assert torch.equal(got[s][2], met.cpu())
         assert torch.equal(got[s][3], octree["bytes"].cpu()) and torch.equal(got[s][4], octree["nbits"].cpu())
+
+
+def test_evaluate_all_matches_oracle_metrics(setup):
+    from oracle import oracle as orc
+    pcc, codec, sd = setup
+    x = synth.modelnet_like(2, 8192, seed=91)
+    y = synth.decompressed_like(x, seed=92)
+    m = {k: v.cpu().numpy() for k, v in codec.evaluate_all(torch.from_numpy(y).cuda(), torch.from_numpy(x).cuda()).items()}
+    for b in range(2):
+        psnr1, mse1 = orc.d1_psnr(x[b], y[b])
+        psnr2, mse2 = orc.p2plane_psnr(x[b], y[b])
+        assert abs(m["d1_psnr"][b] - psnr1) < 1e-3 and abs(m["d2_psnr"][b] - psnr2) < 1e-3     # dB
+        assert abs(m["uc"][b] - orc.calc_uc(x[b], y[b])) <= 1e-9 * m["uc"][b]
+        mn, mx = x[b].min(), x[b].max()
+        cham = orc.chamfer(((y[b] - mn) / (mx - mn))[None], ((x[b] - mn) / (mx - mn))[None])[0]
+        assert abs(m["chamfer"][b] - cham) <= 1e-5 * cham

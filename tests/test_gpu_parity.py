@@ -380,3 +380,26 @@ def test_octree_encode_vs_oracle(pcc, orc, B, S, N, min_bpp):
     for b, code in enumerate(codes):
         assert int(r["nbits"][b]) == len(code) and np.array_equal(bits[b, :len(code)], code)
         assert np.array_equal(r["bytes"][b, :(len(code) + 7) // 8].cpu().numpy(), orc.bits_to_bytes(code))
+
+
+# ---- eval.py's remaining metrics: uniformity coefficient and point-to-plane PSNR -------------------------
+def test_uniformity_coefficient_and_p2plane(pcc, orc, golden_dir):
+    g = np.load(os.path.join(golden_dir, "ref_eval.npz"))
+    x = synth.modelnet_like(3, 8192, seed=81)
+    y = synth.decompressed_like(x, seed=82)
+    uc = pcc.ops.uniformity_coefficient(cu(x), cu(y)).cpu().numpy()
+    for b in range(3):
+        assert abs(uc[b] - orc.calc_uc(x[b], y[b])) <= 1e-9 * uc[b]       # same d2 bit patterns, double reductions
+        assert abs(uc[b] - g["uc"][b]) <= 1e-4 * g["uc"][b]              # the reference's own calc_uc (cdist matmul path)
+    pp = pcc.ops.p2plane_psnr(cu(y), cu(x)).cpu().numpy()                 # (recon, orig)
+    for b in range(3):
+        assert abs(pp[b, 1] - g["p2plane"][b, 0]) < 1e-3                  # dB; analytic eigenvectors vs numpy eigh
+        assert abs(pp[b, 0] - g["p2plane"][b, 1]) <= 1e-4 * g["p2plane"][b, 1]
+    # normals: unit length, orthogonal to the local surface of a plane
+    plane = np.random.default_rng(3).random((1, 2000, 3)).astype(np.float32)
+    plane[..., 2] = 0.25
+    n = pcc.ops.estimate_normals(cu(plane)).cpu().numpy()
+    assert np.allclose(np.abs(n[..., 2]), 1.0, atol=1e-5)
+    nx = pcc.ops.estimate_normals(cu(x[:1])).cpu().numpy()[0]
+    ref = orc.estimate_normals(x[0])
+    assert np.median(np.abs(np.abs((nx * ref).sum(-1)) - 1.0)) < 1e-6     # same direction up to sign

@@ -144,3 +144,15 @@ def test_octree_oracle_fixed_depth_and_live_reference(g_oct):
     ocodes, obits, _ = orc.encode_sampled_np(x, 1, 2048, 0.5)
     assert bits == obits and all(np.array_equal(a, b) for a, b in zip(codes, ocodes))
     assert np.array_equal(pn.decode_sampled_np(codes, scale=1), np.stack([orc.octree_decode_ref(k) for k in ocodes]))
+
+
+def test_eval_metrics_oracle_vs_reference_golden(golden_dir):
+    """calc_uc (eval.py:127-151): the golden holds the output of the reference's own function; it takes distances from
+    torch.cdist's matmul formulation (fp32), so the restatement (direct d2) agrees to the 5th digit -- 1e-4 relative."""
+    g = np.load(os.path.join(golden_dir, "ref_eval.npz"))
+    x = synth.modelnet_like(3, 8192, seed=81)
+    y = synth.decompressed_like(x, seed=82)
+    for b in range(2):
+        assert abs(orc.calc_uc(x[b], y[b]) - g["uc"][b]) <= 1e-4 * g["uc"][b]
+    psnr, mse = orc.p2plane_psnr(x[0], y[0])
+    assert abs(psnr - g["p2plane"][0, 0]) < 1e-9 and psnr > orc.d1_psnr(x[0], y[0])[0]   # |diff . n| <= |diff|
