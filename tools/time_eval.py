@@ -11,7 +11,7 @@ from tools import synth
 ae = AE(256, 128, 16, 7)
 ae.load_state_dict(synth.seeded_state_dict(synth.ae_shapes(128, 16, 7), 11))
 ae = ae.cuda().eval()
-codec = PatchCodec(ae)
+codec = PatchCodec(ae, centre_mode="coded")
 xyz = torch.from_numpy(synth.modelnet_like(32, 8192, seed=1000)).cuda()
 start = torch.zeros(32, dtype=torch.int64, device="cuda")
 c = codec.compress(xyz, start)
