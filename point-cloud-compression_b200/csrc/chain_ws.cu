@@ -23,6 +23,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "chain_ws.h"
 #include "pcc_common.cuh"
@@ -306,6 +307,202 @@ __global__ void __launch_bounds__(sa::THREADS, 2) sa_chain_kernel(const __grid_c
     }
     tmem_free(tmem_base, TMEM_COLS, warp, 8);
 #undef SA_TICK
+}
+
+// ======================================================================================================================
+// SA, second form: same slots (2 CTAs / SM x 2 tiles in flight), but the fp32 3 -> 32 layer of the NEXT tile is computed by
+// the slot's MMA warp in the shadow of the current tile's epilogues.  In the first form the four epilogue warps of a slot run
+// layer 0, epilogue 1 and epilogue 2 back to back, one warp per scheduler, and their per-warp instruction latency IS the tile
+// time (adding 80 instructions to epilogue 1 cost 12 %; a fully decoupled one-CTA pipeline with dedicated producer /
+// epilogue-1 / epilogue-2 warp groups was measured slower, 382 us vs 330 us: it has a single MMA issuer per SM).
+// Moving layer 0 (46 % of the group's instructions) onto the otherwise idle MMA warp shortens the slot's critical path to
+// MMA1 -> epilogue 1 -> MMA2 -> epilogue 2.
+//   MMA warp of slot s, per tile:  wait "accumulator free" -> MMA1 (X1 -> acc) -> wait MMA1 done (X1 consumed) -> layer 0 of
+//       the next tile -> X1, polling "X2 ready" between position pairs to issue MMA2 (X2 -> acc) as soon as it can
+//   epilogue group of slot s, per tile:  wait MMA1 -> epilogue 1 (acc -> X2) -> signal -> wait MMA2 -> epilogue 2 (max over 16
+//       neighbours -> out) -> signal "accumulator free"
+// ======================================================================================================================
+template <int DUMMY>
+__global__ void __launch_bounds__(sa::THREADS, 2) sa_chain2_kernel(const __grid_constant__ SaParams prm) {
+    using namespace sa;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    const uint32_t sb = smem_u32(smem);
+    const int tid = threadIdx.x, warp = __shfl_sync(FULL_MASK, tid >> 5, 0), lane = tid & 31;
+    const uint32_t bar_acc = sb + OFF_BAR, bar_act = sb + OFF_BAR + 16, bar_x1 = sb + OFF_BAR + 32;  // [2] each
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BAR + 48);
+
+    copy_to_smem(smem + OFF_W1, prm.w1p, 64 * KP1 * 2, tid, THREADS);
+    copy_to_smem(smem + OFF_W2, prm.w2p, 128 * KP2 * 2, tid, THREADS);
+    fill_ones_block(smem + OFF_ONES, tid, THREADS);
+    for (int e = tid; e < 32 * 4; e += THREADS)
+        reinterpret_cast<float *>(smem + OFF_W0)[e] = (e & 3) < 3 ? prm.w0[(e >> 2) * 3 + (e & 3)] : prm.b0[e >> 2];
+    if (tid == 0) {
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(bar_acc + 8 * s, 1);
+            mbar_init(bar_act + 8 * s, 4);
+            mbar_init(bar_x1 + 8 * s, 1);
+        }
+    }
+    const uint32_t tmem_base = tmem_alloc_and_sync(tmem_slot, TMEM_COLS, warp, 8);
+    const int n_tiles = prm.n_tiles;
+    const int tstride = 2 * gridDim.x;
+
+    if (warp >= 8) {
+        // ---- MMA warp of slot s: issues both layers' MMAs and computes layer 0 of the next tile ----
+        const int s = warp - 8;
+        const uint32_t acc = __shfl_sync(FULL_MASK, tmem_base, 0) + s * 128;
+        const uint32_t id64 = umma_idesc(128, 64), id128 = umma_idesc(128, 128);
+        const uint64_t d_ones = desc_k16(sb + OFF_ONES);
+        const uint64_t d_w1 = desc_w(sb + OFF_W1, KP1, 0), d_w2 = desc_w(sb + OFF_W2, KP2, 0);
+        const uint32_t x1 = sb + OFF_SLOT + s * SLOT_BYTES + SL_X1;
+        const uint64_t d_x1 = umma_desc_sw128(x1);
+        const uint64_t d_x2 = umma_desc_sw128(sb + OFF_SLOT + s * SLOT_BYTES + SL_X2);
+        const float4 *w0s = reinterpret_cast<const float4 *>(smem + OFF_W0);
+        float px[4], py[4], pz[4];   // lane owns positions lane + 32 i of the tile
+        auto load_xyz = [&](long long tile) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float *src = prm.xyz + (tile * P + lane + 32 * i) * prm.ld;
+                px[i] = __ldg(src);
+                py[i] = __ldg(src + 1);
+                pz[i] = __ldg(src + 2);
+            }
+        };
+        // layer 0 of positions lane + 32 i0 and lane + 32 (i0 + 1): 2 x 32 channels -> X1 (4 16-byte chunks per position)
+        auto layer0_pair = [&](int i0) {
+            uint32_t pk[2][16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                const float4 wa = w0s[2 * c], wb = w0s[2 * c + 1];
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const float a = fmaf(wa.z, pz[i0 + i], fmaf(wa.y, py[i0 + i], fmaf(wa.x, px[i0 + i], wa.w)));
+                    const float b = fmaf(wb.z, pz[i0 + i], fmaf(wb.y, py[i0 + i], fmaf(wb.x, px[i0 + i], wb.w)));
+                    pk[i][c] = pack_relu_bf16x2(a, b);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int p = lane + 32 * (i0 + i);
+#pragma unroll
+                for (int c8 = 0; c8 < 4; ++c8)
+                    st_shared_v4(x1 + p * 128 + ((c8 ^ (p & 7)) << 4), pk[i][4 * c8], pk[i][4 * c8 + 1], pk[i][4 * c8 + 2], pk[i][4 * c8 + 3]);
+            }
+        };
+        auto issue_mma2 = [&]() {
+            tc_fence_after();
+            if (elect_one()) {  // T-form: D^T[128 channels, 128 positions]
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) umma_bf16(acc, d_w2 + 16 * ks, d_x2 + 2 * ks, id128, ks > 0);
+                umma_bf16(acc, d_w2 + 64, d_ones, id128, 1u);
+                umma_commit(bar_acc + 8 * s);
+            }
+            __syncwarp();
+        };
+        long long tile = 2ll * blockIdx.x + s;
+        if (tile < n_tiles) {
+            load_xyz(tile);
+            layer0_pair(0);
+            layer0_pair(2);
+            fence_async_smem();
+            if (tile + tstride < n_tiles) load_xyz(tile + tstride);
+        }
+        uint32_t ph_act = 0, ph_x1 = 0;
+        for (; tile < n_tiles; tile += tstride) {
+            mbar_wait(bar_act + 8 * s, ph_act);   // the accumulator is free (epilogue 2 of the previous tile has read it)
+            ph_act ^= 1u;
+            tc_fence_after();
+            if (elect_one()) {
+                umma_bf16(acc, d_x1, d_w1, id64, 0u);
+                umma_bf16(acc, d_x1 + 2, d_w1 + 16, id64, 1u);
+                umma_bf16(acc, d_ones, d_w1 + 32, id64, 1u);
+                umma_commit(bar_x1 + 8 * s);
+                umma_commit(bar_acc + 8 * s);
+            }
+            __syncwarp();
+            const bool more = tile + tstride < n_tiles;
+            bool mma2_done = false;
+            if (more) {
+                mbar_wait(bar_x1 + 8 * s, ph_x1);   // layer 1 has consumed X1: the next tile's layer 0 may overwrite it
+                ph_x1 ^= 1u;
+                tc_fence_after();
+                layer0_pair(0);
+                if (mbar_test(bar_act + 8 * s, ph_act)) {   // X2 ready already?
+                    ph_act ^= 1u;
+                    issue_mma2();
+                    mma2_done = true;
+                }
+                layer0_pair(2);
+                fence_async_smem();
+                if (tile + 2 * tstride < n_tiles) load_xyz(tile + 2 * tstride);
+            } else {
+                mbar_wait(bar_x1 + 8 * s, ph_x1);   // keep the phases in step
+                ph_x1 ^= 1u;
+            }
+            if (!mma2_done) {
+                mbar_wait(bar_act + 8 * s, ph_act);
+                ph_act ^= 1u;
+                issue_mma2();
+            }
+        }
+    } else {
+        // ---- epilogue group g = warp / 4 serves slot g; warp q = warp % 4 owns TMEM lanes 32q.. ----
+        const int s = warp >> 2, q = warp & 3;
+        const int row = q * 32 + lane;
+        const uint32_t acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + s * 128;
+        const uint32_t slot = sb + OFF_SLOT + s * SLOT_BYTES;
+        uint32_t ph_acc = 0;
+        float *out_f = prm.out_bf16 ? nullptr : static_cast<float *>(prm.out);
+        __nv_bfloat16 *out_h = prm.out_bf16 ? static_cast<__nv_bfloat16 *>(prm.out) : nullptr;
+        if (lane == 0) mbar_arrive1(bar_act + 8 * s);   // the accumulator starts out free
+        for (long long tile = 2ll * blockIdx.x + s; tile < n_tiles; tile += tstride) {
+            // ---- layer 1 epilogue: 64 channels of my position -> X2 (one 128-byte row of the slab) ----
+            mbar_wait(bar_acc + 8 * s, ph_acc);
+            ph_acc ^= 1u;
+            tc_fence_after();
+            {
+                uint32_t v0[32], v1[32];
+                tmem_ld32_issue(acc, v0);
+                tmem_ld32_issue(acc + 32, v1);
+                tmem_ld32_wait(v0);
+                store_row_chunks<32, true>(slot + SL_X2, row, 0, v0);
+                tmem_ld32_wait(v1);
+                store_row_chunks<32, true>(slot + SL_X2, row, 32, v1);
+            }
+            fence_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive1(bar_act + 8 * s);
+            // ---- layer 2 epilogue (T-form): lane = channel `row`, columns = positions; max over each run of 16 ----
+            mbar_wait(bar_acc + 8 * s, ph_acc);
+            ph_acc ^= 1u;
+            tc_fence_after();
+            const long long o = tile * 8 * 128 + row;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                uint32_t v0[32], v1[32];
+                tmem_ld32_issue(acc + j * 64, v0);
+                tmem_ld32_issue(acc + j * 64 + 32, v1);
+                tmem_ld32_wait(v0);
+                tmem_ld32_wait(v1);
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const uint32_t(&v)[32] = g < 2 ? v0 : v1;
+                    const int b = (g & 1) * 16;
+                    float mm = fmax3(__uint_as_float(v[b]), __uint_as_float(v[b + 1]), __uint_as_float(v[b + 2]));
+#pragma unroll
+                    for (int i = 3; i < 15; i += 2) mm = fmax3(mm, __uint_as_float(v[b + i]), __uint_as_float(v[b + i + 1]));
+                    mm = fmax3(mm, __uint_as_float(v[b + 15]), 0.0f);  // the ReLU commutes with the max
+                    if (out_h) out_h[o + (j * 4 + g) * 128] = __float2bfloat16_rn(mm); else out_f[o + (j * 4 + g) * 128] = mm;
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive1(bar_act + 8 * s);   // accumulator free
+        }
+    }
+    tmem_free(tmem_base, TMEM_COLS, warp, 8);
 }
 
 // ======================================================================================================================
@@ -749,11 +946,17 @@ int ws_dispatch(const PccMlpInput *in, int n_inputs, int64_t rows, const PccMlpL
         p.out_bf16 = out_dtype;
         p.n_tiles = n_tiles;
         p.dbg = g_ws_dbg;
+        static const bool form1 = getenv("PCC_SA_KERNEL") && !strcmp(getenv("PCC_SA_KERNEL"), "1");
         const int pairs = (n_tiles + 1) / 2;
         const int grid = pairs < 2 * sms ? pairs : 2 * sms;  // 2 CTAs per SM, 2 tiles in flight each
         if (g_ws_dbg) {
             if (int r = set_smem(sa_chain_kernel<true>, sa::SMEM)) return r;
             sa_chain_kernel<true><<<grid, sa::THREADS, sa::SMEM, st>>>(p);
+        } else if (!form1) {
+            if (int r = set_smem(sa_chain2_kernel<0>, sa::SMEM)) return r;
+            sa_chain2_kernel<0><<<grid, sa::THREADS, sa::SMEM, st>>>(p);
+            *handled = true;
+            return check_launch("sa_chain2_kernel");
         } else {
             if (int r = set_smem(sa_chain_kernel<false>, sa::SMEM)) return r;
             sa_chain_kernel<false><<<grid, sa::THREADS, sa::SMEM, st>>>(p);
