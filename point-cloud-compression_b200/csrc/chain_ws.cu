@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(sa::THREADS, 2) sa_chain_kernel(const __grid_c
 // Moving layer 0 (46 % of the group's instructions) onto the otherwise idle MMA warp shortens the slot's critical path to
 // MMA1 -> epilogue 1 -> MMA2 -> epilogue 2.
 //   MMA warp of slot s, per tile:  wait "accumulator free" -> MMA1 (X1 -> acc) -> wait MMA1 done (X1 consumed) -> layer 0 of
-//       the next tile -> X1, polling "X2 ready" between position pairs to issue MMA2 (X2 -> acc) as soon as it can
+//       the next tile -> X1, polling "X2 ready" every 4 channel pairs to issue MMA2 (X2 -> acc) as soon as it can
 //   epilogue group of slot s, per tile:  wait MMA1 -> epilogue 1 (acc -> X2) -> signal -> wait MMA2 -> epilogue 2 (max over 16
 //       neighbours -> out) -> signal "accumulator free"
 // ======================================================================================================================
@@ -370,10 +370,27 @@ __global__ void __launch_bounds__(sa::THREADS, 2) sa_chain2_kernel(const __grid_
             }
         };
         // layer 0 of positions lane + 32 i0 and lane + 32 (i0 + 1): 2 x 32 channels -> X1 (4 16-byte chunks per position)
+        auto issue_mma2 = [&]() {
+            tc_fence_after();
+            if (elect_one()) {  // T-form: D^T[128 channels, 128 positions]
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) umma_bf16(acc, d_w2 + 16 * ks, d_x2 + 2 * ks, id128, ks > 0);
+                umma_bf16(acc, d_w2 + 64, d_ones, id128, 1u);
+                umma_commit(bar_acc + 8 * s);
+            }
+            __syncwarp();
+        };
+        uint32_t ph_act = 0, ph_x1 = 0;
+        bool mma2_pending = false;   // layer 2 of the current tile still has to be issued: polled inside layer 0
         auto layer0_pair = [&](int i0) {
             uint32_t pk[2][16];
 #pragma unroll
             for (int c = 0; c < 16; ++c) {
+                if ((c & 3) == 0 && mma2_pending && __any_sync(FULL_MASK, mbar_test(bar_act + 8 * s, ph_act))) {   // X2 ready
+                    ph_act ^= 1u;
+                    issue_mma2();
+                    mma2_pending = false;
+                }
                 const float4 wa = w0s[2 * c], wb = w0s[2 * c + 1];
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
@@ -390,16 +407,6 @@ __global__ void __launch_bounds__(sa::THREADS, 2) sa_chain2_kernel(const __grid_
                     st_shared_v4(x1 + p * 128 + ((c8 ^ (p & 7)) << 4), pk[i][4 * c8], pk[i][4 * c8 + 1], pk[i][4 * c8 + 2], pk[i][4 * c8 + 3]);
             }
         };
-        auto issue_mma2 = [&]() {
-            tc_fence_after();
-            if (elect_one()) {  // T-form: D^T[128 channels, 128 positions]
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks) umma_bf16(acc, d_w2 + 16 * ks, d_x2 + 2 * ks, id128, ks > 0);
-                umma_bf16(acc, d_w2 + 64, d_ones, id128, 1u);
-                umma_commit(bar_acc + 8 * s);
-            }
-            __syncwarp();
-        };
         long long tile = 2ll * blockIdx.x + s;
         if (tile < n_tiles) {
             load_xyz(tile);
@@ -408,7 +415,6 @@ __global__ void __launch_bounds__(sa::THREADS, 2) sa_chain2_kernel(const __grid_
             fence_async_smem();
             if (tile + tstride < n_tiles) load_xyz(tile + tstride);
         }
-        uint32_t ph_act = 0, ph_x1 = 0;
         for (; tile < n_tiles; tile += tstride) {
             mbar_wait(bar_act + 8 * s, ph_act);   // the accumulator is free (epilogue 2 of the previous tile has read it)
             ph_act ^= 1u;
@@ -422,28 +428,21 @@ __global__ void __launch_bounds__(sa::THREADS, 2) sa_chain2_kernel(const __grid_
             }
             __syncwarp();
             const bool more = tile + tstride < n_tiles;
-            bool mma2_done = false;
+            mbar_wait(bar_x1 + 8 * s, ph_x1);       // layer 1 has consumed X1: the next tile's layer 0 may overwrite it
+            ph_x1 ^= 1u;
+            mma2_pending = true;
             if (more) {
-                mbar_wait(bar_x1 + 8 * s, ph_x1);   // layer 1 has consumed X1: the next tile's layer 0 may overwrite it
-                ph_x1 ^= 1u;
                 tc_fence_after();
-                layer0_pair(0);
-                if (mbar_test(bar_act + 8 * s, ph_act)) {   // X2 ready already?
-                    ph_act ^= 1u;
-                    issue_mma2();
-                    mma2_done = true;
-                }
+                layer0_pair(0);                     // (issues layer 2 from inside as soon as X2 is ready)
                 layer0_pair(2);
                 fence_async_smem();
                 if (tile + 2 * tstride < n_tiles) load_xyz(tile + 2 * tstride);
-            } else {
-                mbar_wait(bar_x1 + 8 * s, ph_x1);   // keep the phases in step
-                ph_x1 ^= 1u;
             }
-            if (!mma2_done) {
+            if (mma2_pending) {
                 mbar_wait(bar_act + 8 * s, ph_act);
                 ph_act ^= 1u;
                 issue_mma2();
+                mma2_pending = false;
             }
         }
     } else {
