@@ -286,7 +286,7 @@ def run_b200(args):
         peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
         roofline = None
         if "sa_chain" in kernel_ms:
-            # Dominant kernel of the step = ws::sa_chain_kernel (pn_kit.SetAbstraction's 3-32-64-128 shared MLP + max over the
+            # Dominant kernel of the step = ws::sa_chain2_kernel (pn_kit.SetAbstraction's 3-32-64-128 shared MLP + max over the
             # 16 neighbours): tensor-pipe work.  Algorithmic FLOP per launch: 2 * MACs =
             # 2 * (3*32 + 32*64 + 64*128) = 20,672 FLOP per (patch point, neighbour) position, B*S*K*16 positions per launch.
             # (The 3 -> 32 layer runs in fp32 on the CUDA cores; it is 0.9 % of the FLOP and is counted.)
@@ -313,13 +313,13 @@ def run_b200(args):
                 others["pn_tail_kernel"] = {"ms_per_launch": kernel_ms["pn_tail"], "bound": "tensor",
                                             "achieved_tflops": fl / (kernel_ms["pn_tail"] / 1e3) / 1e12,
                                             "frac": fl / (kernel_ms["pn_tail"] / 1e3) / 1e12 / tf_peak}
-            roofline = {"kernel": "ws::sa_chain_kernel -- SetAbstraction shared MLP 3-32-64-128 + max over 16 neighbours (tcgen05)",
+            roofline = {"kernel": "ws::sa_chain2_kernel -- SetAbstraction shared MLP 3-32-64-128 + max over 16 neighbours (tcgen05)",
                         "bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
                         "traffic": SA_DRAM_BYTES, "peak_source": peak_src + " bf16_tflops_sustained (kernel timed inside a long step)",
                         "ms_per_launch": ms, "flop_per_launch": flop,
                         "note": "K is 32..64 per layer, so the kernel is paced by the MMA -> epilogue -> MMA hand-offs of its four "
-                                "tiles in flight per SM (TMEM: 128 accumulator columns per tile), not by the tensor pipe; see "
-                                "DESIGN.md 4 and profiles/",
+                                "tiles in flight per SM (TMEM: 128 accumulator columns per tile) and by the per-warp latency of the "
+                                "epilogue / fp32 layer-0 code, not by the tensor pipe; see DESIGN.md 4 and profiles/",
                         "other_kernels": others}
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
