@@ -109,6 +109,30 @@ def test_knn_warp_kernel_vs_oracle(pcc, orc, B, P1, P2, K):
         assert np.array_equal(nn.cpu().numpy(), want)
 
 
+@pytest.mark.parametrize("kind,P2,K", [("identical", 8192, 256), ("two_values", 8192, 300), ("grid", 8192, 512),
+                                       ("grid", 5000, 64), ("uniform", 4097, 512), ("half_dup", 6000, 256)])
+def test_knn_block_kernel_selection_paths_vs_oracle(pcc, orc, kind, P2, K):
+    """CTA-per-query kernel (4096 < P2 <= 8192): the sort-based selection (per-thread minima bound + admitted keys) and its
+    fall-back to the bisection when ties let more than 512 candidates through -- identical results either way."""
+    rng = np.random.default_rng(P2 + K)
+    if kind == "identical":
+        p = np.full((2, P2, 3), 0.25, np.float32)                      # every distance ties: admitted = P2 -> bisection path
+    elif kind == "two_values":
+        p = np.where(rng.random((2, P2, 1)) < 0.5, 0.25, 0.75).astype(np.float32).repeat(3, axis=2)
+    elif kind == "grid":
+        p = synth.grid_quantised(2, P2, depth=3, seed=P2)              # heavy ties at the K-th distance
+    elif kind == "half_dup":
+        p = synth.uniform_cube(2, P2, seed=P2)
+        p[:, P2 // 2:] = p[:, :P2 - P2 // 2]                            # every point twice: tie pairs ordered by index
+    else:
+        p = synth.uniform_cube(2, P2, seed=P2)
+    q = synth.uniform_cube(2, 5, seed=K)
+    q[:, 0] = p[:, 17]                                                  # a query that coincides with a candidate
+    d, i, _ = pcc.ops.knn(cu(q), cu(p), K)
+    od, oi, _ = orc.knn_points(q, p, K, False, threads=8)
+    assert np.array_equal(i.cpu().numpy(), oi) and np.array_equal(d.cpu().numpy(), od)
+
+
 @pytest.mark.parametrize("BS,P,K", [(200, 256, 16), (300, 128, 8), (150, 256, 32), (140, 250, 20), (600, 64, 3)])
 def test_knn_thread_kernel_in_patch_vs_oracle(pcc, orc, BS, P, K):
     """Many small self-searches (the pn_kit.SetAbstraction K=16 case) -> thread-per-query kernel."""
