@@ -103,6 +103,8 @@ def knn(p1, p2, K, return_nn=False, centre_sub=False, nn_scale=1.0, nn_only=Fals
     d = None if nn_only else torch.empty((B, P1, K), dtype=torch.float32, device=p1.device)
     i = None if nn_only else torch.empty((B, P1, K), dtype=torch.int64, device=p1.device)
     nn = torch.empty((B, P1, K, 3), dtype=torch.float32, device=p1.device) if return_nn else None
+    if B == 0 or P1 == 0:   # nothing to search for: empty results, no launch (empty tensors have no storage to point at)
+        return d, i, nn
     with torch.cuda.device(p1.device):
         _lib.check(lib.pcc_knn_f32(_ptr(p1), _ptr(p2), B, P1, P2, K, _ptr(d), _ptr(i), _ptr(nn), int(centre_sub),
                                    float(nn_scale), _stream()), "pcc_knn_f32")
@@ -117,6 +119,8 @@ def ball_query(p1, p2, K, radius, return_dists=True):
     P2 = p2.shape[1]
     i = torch.empty((B, P1, K), dtype=torch.int64, device=p1.device)
     d = torch.empty((B, P1, K), dtype=torch.float32, device=p1.device) if return_dists else None
+    if B == 0 or P1 == 0:
+        return d, i
     with torch.cuda.device(p1.device):
         _lib.check(lib.pcc_ball_query_f32(_ptr(p1), _ptr(p2), B, P1, P2, K, float(radius), _ptr(i), _ptr(d), _stream()),
                    "pcc_ball_query_f32")
@@ -130,8 +134,9 @@ class _Gather(torch.autograd.Function):
         B, N, C = feat.shape
         M = idx.numel() // max(B, 1)
         out = torch.empty(tuple(idx.shape) + (C,), dtype=torch.float32, device=feat.device)
-        with torch.cuda.device(feat.device):
-            _lib.check(lib.pcc_gather_f32(_ptr(feat), _ptr(idx), B, N, C, M, _ptr(out), _stream()), "pcc_gather_f32")
+        if out.numel() > 0:
+            with torch.cuda.device(feat.device):
+                _lib.check(lib.pcc_gather_f32(_ptr(feat), _ptr(idx), B, N, C, M, _ptr(out), _stream()), "pcc_gather_f32")
         ctx.save_for_backward(idx)
         ctx.shape = (B, N, C, M)
         return out
@@ -143,9 +148,10 @@ class _Gather(torch.autograd.Function):
         B, N, C, M = ctx.shape
         grad_out = grad_out.contiguous().float()
         grad_feat = torch.zeros((B, N, C), dtype=torch.float32, device=grad_out.device)
-        with torch.cuda.device(grad_out.device):
-            _lib.check(lib.pcc_gather_bwd_f32(_ptr(grad_out), _ptr(idx), B, N, C, M, _ptr(grad_feat), _stream()),
-                       "pcc_gather_bwd_f32")
+        if grad_out.numel() > 0:
+            with torch.cuda.device(grad_out.device):
+                _lib.check(lib.pcc_gather_bwd_f32(_ptr(grad_out), _ptr(idx), B, N, C, M, _ptr(grad_feat), _stream()),
+                           "pcc_gather_bwd_f32")
         return grad_feat, None
 
 
@@ -167,6 +173,8 @@ def nn1(p1, p2, return_idx=True):
     P2 = p2.shape[1]
     d = torch.empty((B, P1), dtype=torch.float32, device=p1.device)
     i = torch.empty((B, P1), dtype=torch.int64, device=p1.device) if return_idx else None
+    if B == 0 or P1 == 0:
+        return d, i
     with torch.cuda.device(p1.device):
         ws = torch.empty((max(lib.pcc_nn1_workspace_bytes(B, P1, P2), 8),), dtype=torch.uint8, device=p1.device)
         _lib.check(lib.pcc_nn1_f32(_ptr(p1), _ptr(p2), B, P1, P2, _ptr(d), _ptr(i), _ptr(ws), _stream()), "pcc_nn1_f32")

@@ -427,3 +427,28 @@ def test_uniformity_coefficient_and_p2plane(pcc, orc, golden_dir):
     nx = pcc.ops.estimate_normals(cu(x[:1])).cpu().numpy()[0]
     ref = orc.estimate_normals(x[0])
     assert np.median(np.abs(np.abs((nx * ref).sum(-1)) - 1.0)) < 1e-6     # same direction up to sign
+
+
+def test_empty_and_degenerate_inputs(pcc):
+    """Zero-sized batches / query sets return empty tensors (no launch), single points work, bad shapes raise."""
+    dev = "cuda"
+    p = torch.rand(2, 50, 3, device=dev)
+    d, i, nn = pcc.ops.knn(torch.empty(2, 0, 3, device=dev), p, 4, return_nn=True)
+    assert d.shape == (2, 0, 4) and i.shape == (2, 0, 4) and nn.shape == (2, 0, 4, 3)
+    d, i, _ = pcc.ops.knn(torch.empty(0, 5, 3, device=dev), torch.empty(0, 50, 3, device=dev), 4)
+    assert d.shape == (0, 5, 4)
+    assert pcc.ops.gather(torch.rand(2, 50, 7, device=dev), torch.empty(2, 0, dtype=torch.int64, device=dev)).shape == (2, 0, 7)
+    _, bi = pcc.ops.ball_query(torch.empty(2, 0, 3, device=dev), p, 8, 0.2)
+    assert bi.shape == (2, 0, 8)
+    one = torch.rand(1, 1, 3, device=dev)
+    d, i, _ = pcc.ops.knn(one, one, 1)
+    assert float(d) == 0.0 and int(i) == 0
+    r = pcc.ops.chamfer_forward(one, one)
+    assert float(r["loss"]) == 0.0
+    assert pcc.ops.fps(one, 1, None, pcc.ops.FLT_MAX).tolist() == [[0]]
+    with pytest.raises(ValueError):
+        pcc.ops.knn(torch.rand(2, 5, 3, device=dev), torch.rand(3, 50, 3, device=dev), 4)      # batch mismatch
+    with pytest.raises(ValueError):
+        pcc.ops.knn(torch.rand(2, 5, 2, device=dev), torch.rand(2, 50, 2, device=dev), 4)      # D != 3
+    with pytest.raises(RuntimeError):
+        pcc.ops.knn(torch.rand(2, 5, 3), torch.rand(2, 50, 3), 4)                              # CPU tensors: no fallback
