@@ -250,9 +250,14 @@ grid_nn_kernel(int P1, int P2, const float4 *__restrict__ sorted, const unsigned
         const int ya = max(cell_coord(lo[1], g.mny, g.inv_h, G) - 1, 0), yb = min(cell_coord(hi[1], g.mny, g.inv_h, G) + 1, G - 1);
         const int za = max(cell_coord(lo[2], g.mnz, g.inv_h, G) - 1, 0), zb = min(cell_coord(hi[2], g.mnz, g.inv_h, G) + 1, G - 1);
         for (int z = za; z <= zb; ++z) {
+            // empty slabs and rows cost two uniform table loads instead of the whole pruning test (a clumpy candidate
+            // cloud -- e.g. the reconstruction of an untrained decoder -- leaves most of the walked box empty)
+            if (__ldg(st + (z * G + ya) * G) == __ldg(st + (z * G + yb + 1) * G)) continue;
             const float gz = slab_gap(q.z, g.mnz, g.h, z, g.margin);
             if (__all_sync(FULL_MASK, !need || gz * gz * 0.9999f > key_d2(best))) continue;
             for (int yy = ya; yy <= yb; ++yy) {
+                const unsigned row0 = static_cast<unsigned>((z * G + yy) * G);
+                if (__ldg(st + row0 + xa) == __ldg(st + row0 + xb + 1)) continue;
                 const float gy = slab_gap(q.y, g.mny, g.h, yy, g.margin);
                 // a row is skipped only if it lies outside the ball of every unsettled query of the warp
                 const float rem = key_d2(best) - (gz * gz + gy * gy) * 0.9999f;
