@@ -271,6 +271,23 @@ int pcc_p2plane_f32(const float *recon, const float *orig, const int64_t *ix, co
                     int P1, int P2, double *out, void *stream);
 int pcc_uc_f32(const float *d2_in, const float *d2_dec, int B, int n, double *out, void *stream);
 
+/*
+ * Entropy stage: the host code between the probability model and the .p.bin file.
+ * pcc_pmf_to_cdf_u16: pn_kit.pmf_to_cdf (/root/reference/pn_kit.py:452-461; compress.py:134, decompress.py:92) fused with
+ *   torchac's float -> 16-bit CDF conversion (encode_float_cdf(..., needs_normalization = True)): pmf [rows, L] fp32 ->
+ *   cdf [rows, L + 1] uint16.  pcc_cdf_to_u16 converts a float CDF [rows, Lp] the caller already holds.
+ * pcc_range_encode_u16 / pcc_range_decode_u16: torchac.encode_float_cdf / decode_float_cdf's coder (compress.py:136,
+ *   decompress.py:93), one byte stream per cloud: cdf [B, n_sym, Lp] uint16, sym [B, n_sym] int16 in [0, Lp - 2],
+ *   bytes [B, cap] with cap >= 2 * n_sym + 8, nbytes [B] int32.
+ * torchac is a third-party package absent from /root/reference: its published algorithm is restated (parity unpinned).
+ */
+int pcc_pmf_to_cdf_u16(const float *pmf, int64_t rows, int L, uint16_t *out_cdf, void *stream);
+int pcc_cdf_to_u16(const float *cdf_float, int64_t rows, int Lp, uint16_t *out_cdf, void *stream);
+int pcc_range_encode_u16(const uint16_t *cdf, const int16_t *sym, int B, int n_sym, int Lp, uint8_t *out_bytes, int cap,
+                         int32_t *out_nbytes, void *stream);
+int pcc_range_decode_u16(const uint16_t *cdf, const uint8_t *bytes, const int32_t *nbytes, int B, int n_sym, int Lp, int cap,
+                         int16_t *out_sym, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -56,6 +56,11 @@ def lib():
         L.orc_octree_decode_ref.argtypes = [_u8p, _i64, ctypes.c_double, _f32p]
         L.orc_bits_to_bytes.argtypes = [_u8p, _i64, _u8p]
         L.orc_bits_to_bytes.restype = _i64
+        _u16p, _i16p = ctypes.POINTER(ctypes.c_uint16), ctypes.POINTER(ctypes.c_int16)
+        L.orc_pmf_to_cdf_u16.argtypes = [_f32p, _i64, ctypes.c_int, _u16p]
+        L.orc_range_encode.argtypes = [_u16p, _i16p, _i64, ctypes.c_int, _u8p, _i64]
+        L.orc_range_encode.restype = _i64
+        L.orc_range_decode.argtypes = [_u16p, _i64, ctypes.c_int, _u8p, _i64, _i16p]
         _lib = L
     return _lib
 
@@ -289,3 +294,34 @@ def p2plane_psnr(orig, recon, knn=30):
     mse = float(e.mean())
     diag = np.linalg.norm(orig.max(axis=0).astype(np.float64) - orig.min(axis=0).astype(np.float64))
     return (float(10 * np.log10(diag ** 2 / mse)) if mse > 0 else float("inf")), mse
+
+
+# ---- entropy stage (pn_kit.pmf_to_cdf + torchac's coder; torchac is absent: PARITY UNPINNED) ----------------------------
+def pmf_to_cdf_u16(pmf):
+    """pn_kit.pmf_to_cdf followed by torchac's _convert_to_int_and_normalize(needs_normalization=True): [..., L] -> uint16 [..., L+1]."""
+    pmf = _f32(pmf)
+    L = pmf.shape[-1]
+    out = np.empty(pmf.shape[:-1] + (L + 1,), np.uint16)
+    lib().orc_pmf_to_cdf_u16(_pf(pmf), pmf.size // L, L, out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint16)))
+    return out
+
+
+def range_encode(cdf_u16, sym):
+    """torchac.encode_float_cdf's coder on an integer CDF: cdf uint16 [n, Lp], sym int16 [n] -> bytes."""
+    cdf = np.ascontiguousarray(cdf_u16, np.uint16).reshape(-1, cdf_u16.shape[-1])
+    sym = np.ascontiguousarray(sym, np.int16).reshape(-1)
+    cap = 4 * sym.size + 64
+    out = np.zeros(cap, np.uint8)
+    n = lib().orc_range_encode(cdf.ctypes.data_as(ctypes.POINTER(ctypes.c_uint16)), sym.ctypes.data_as(ctypes.POINTER(ctypes.c_int16)),
+                               sym.size, cdf.shape[1], _pu8(out), cap)
+    assert n <= cap
+    return out[:n].tobytes()
+
+
+def range_decode(cdf_u16, data):
+    cdf = np.ascontiguousarray(cdf_u16, np.uint16).reshape(-1, cdf_u16.shape[-1])
+    buf = np.frombuffer(data, np.uint8).copy()
+    sym = np.empty(cdf.shape[0], np.int16)
+    lib().orc_range_decode(cdf.ctypes.data_as(ctypes.POINTER(ctypes.c_uint16)), cdf.shape[0], cdf.shape[1], _pu8(buf), buf.size,
+                           sym.ctypes.data_as(ctypes.POINTER(ctypes.c_int16)))
+    return sym

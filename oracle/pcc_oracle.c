@@ -497,3 +497,134 @@ ORC_API int64_t orc_bits_to_bytes(const uint8_t *bits, int64_t nbits, uint8_t *o
     }
     return nb;
 }
+
+/* ================================================================================================
+ * Entropy stage: pn_kit.pmf_to_cdf (/root/reference/pn_kit.py:452-461) and the arithmetic coder the
+ * reference calls through torchac.encode_float_cdf / decode_float_cdf (compress.py:134-136, decompress.py:92-93).
+ * torchac (torchac==0.9.3, requirements_gpu.txt:30) is a third-party package that is absent from /root/reference and from
+ * this image: PARITY UNPINNED.  This restates its published algorithm (torchac/torchac.py::_convert_to_int_and_normalize
+ * and torchac/backend/torchac_backend.cpp: 32-bit low / high range coder, 16-bit CDFs, pending-bit carry handling,
+ * MSB-first bit packing); it is anchored by round trips and by the reference's call sites.
+ * ============================================================================================== */
+
+/* pmf [rows, L] float32 -> cdf uint16 [rows, L + 1]:  cdf_float = clamp(cat(0, cumsum(pmf)), max = 1)  (pn_kit.pmf_to_cdf),
+ * then torchac's needs_normalization path: round(cdf_float * (2^16 - L)) as int16 bit pattern, + arange(L + 1). */
+ORC_API void orc_pmf_to_cdf_u16(const float *pmf, int64_t rows, int L, uint16_t *cdf) {
+    const int Lp = L + 1;
+    const float new_max = (float)(65536 - (Lp - 1));
+    for (int64_t r = 0; r < rows; ++r) {
+        double run = 0.0;
+        for (int k = 0; k < Lp; ++k) {
+            float c = 0.0f;
+            if (k > 0) {
+                run = run + (double)pmf[r * L + k - 1];   /* torch CPU cumsum accumulates float inputs in double (acc_type) */
+                c = (float)run;
+                c = c > 1.0f ? 1.0f : c;
+            }
+            const float scaled = nearbyintf(c * new_max);   /* torch.round: half to even */
+            cdf[r * Lp + k] = (uint16_t)((int32_t)scaled + k);
+        }
+    }
+}
+
+typedef struct { uint8_t *out; int64_t cap, n; uint8_t cache; int count; } OrcBitOut;
+static void bo_append(OrcBitOut *o, int bit) {
+    o->cache = (uint8_t)((o->cache << 1) | (bit & 1));
+    if (++o->count == 8) {
+        if (o->n < o->cap) o->out[o->n] = o->cache;
+        o->n++;
+        o->count = 0;
+        o->cache = 0;
+    }
+}
+static void bo_append_and_pending(OrcBitOut *o, int bit, uint64_t *pending) {
+    bo_append(o, bit);
+    while (*pending > 0) {
+        bo_append(o, !bit);
+        *pending -= 1;
+    }
+}
+
+/* torchac encode_cdf: cdf uint16 [n_sym, Lp], sym int16 [n_sym] in [0, Lp - 2]; returns the number of bytes (written up to cap). */
+ORC_API int64_t orc_range_encode(const uint16_t *cdf, const int16_t *sym, int64_t n_sym, int Lp, uint8_t *out, int64_t cap) {
+    OrcBitOut bo = {out, cap, 0, 0, 0};
+    uint32_t low = 0, high = 0xFFFFFFFFu;
+    uint64_t pending = 0;
+    const int max_symbol = Lp - 2;
+    for (int64_t i = 0; i < n_sym; ++i) {
+        const int s = sym[i];
+        const uint64_t span = (uint64_t)high - (uint64_t)low + 1;
+        const uint32_t c_low = cdf[i * Lp + s];
+        const uint32_t c_high = s == max_symbol ? 0x10000u : cdf[i * Lp + s + 1];
+        high = (low - 1) + (uint32_t)((span * (uint64_t)c_high) >> 16);
+        low = low + (uint32_t)((span * (uint64_t)c_low) >> 16);
+        for (;;) {
+            if (high < 0x80000000u) {
+                bo_append_and_pending(&bo, 0, &pending);
+                low <<= 1; high <<= 1; high |= 1;
+            } else if (low >= 0x80000000u) {
+                bo_append_and_pending(&bo, 1, &pending);
+                low <<= 1; high <<= 1; high |= 1;
+            } else if (low >= 0x40000000u && high < 0xC0000000u) {
+                pending++;
+                low <<= 1; low &= 0x7FFFFFFFu; high <<= 1; high |= 0x80000001u;
+            } else {
+                break;
+            }
+        }
+    }
+    pending += 1;
+    bo_append_and_pending(&bo, low < 0x40000000u ? 0 : 1, &pending);
+    while (bo.count != 0) bo_append(&bo, 0);   /* flush the partial byte */
+    return bo.n;
+}
+
+typedef struct { const uint8_t *in; int64_t n, pos; uint8_t cache; int cached; } OrcBitIn;
+static void bi_get(OrcBitIn *b, uint32_t *value) {
+    if (b->cached == 0) {
+        if (b->pos == b->n) { *value <<= 1; return; }
+        b->cache = b->in[b->pos++];
+        b->cached = 8;
+    }
+    *value <<= 1;
+    *value |= (uint32_t)((b->cache >> (b->cached - 1)) & 1);
+    b->cached--;
+}
+
+/* torchac decode_cdf */
+ORC_API void orc_range_decode(const uint16_t *cdf, int64_t n_sym, int Lp, const uint8_t *in, int64_t n_bytes, int16_t *sym) {
+    OrcBitIn bi = {in, n_bytes, 0, 0, 0};
+    uint32_t low = 0, high = 0xFFFFFFFFu, value = 0;
+    const int max_symbol = Lp - 2;
+    for (int i = 0; i < 32; ++i) bi_get(&bi, &value);
+    for (int64_t i = 0; i < n_sym; ++i) {
+        const uint64_t span = (uint64_t)high - (uint64_t)low + 1;
+        const uint16_t count = (uint16_t)(((((uint64_t)value - (uint64_t)low + 1) << 16) - 1) / span);
+        int left = 0, right = max_symbol + 1;
+        while (left + 1 < right) {   /* largest s with cdf[s] <= count */
+            const int m = (left + right) / 2;
+            const uint16_t v = cdf[i * Lp + m];
+            if (v < count) left = m;
+            else if (v > count) right = m;
+            else { left = m; break; }
+        }
+        const int s = left;
+        sym[i] = (int16_t)s;
+        const uint32_t c_low = cdf[i * Lp + s];
+        const uint32_t c_high = s == max_symbol ? 0x10000u : cdf[i * Lp + s + 1];
+        high = (low - 1) + (uint32_t)((span * (uint64_t)c_high) >> 16);
+        low = low + (uint32_t)((span * (uint64_t)c_low) >> 16);
+        for (;;) {
+            if (low >= 0x80000000u || high < 0x80000000u) {
+                low <<= 1; high <<= 1; high |= 1;
+                bi_get(&bi, &value);
+            } else if (low >= 0x40000000u && high < 0xC0000000u) {
+                low <<= 1; low &= 0x7FFFFFFFu; high <<= 1; high |= 0x80000001u;
+                value -= 0x40000000u;
+                bi_get(&bi, &value);
+            } else {
+                break;
+            }
+        }
+    }
+}

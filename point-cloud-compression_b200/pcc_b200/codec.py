@@ -102,6 +102,28 @@ class PatchCodec:
         return ops.eval_metrics(r["dx"], r["per_cloud"], bbox)                    # eval.py:84,88-92,199-205 in one kernel
 
     @torch.no_grad()
+    def encode_latents(self, prob, latent_q, centres):
+        """compress.py:131-136 for a batch: conditional PMF of every latent symbol given the decoded centres, 16-bit CDFs,
+        arithmetic coding -- one .p.bin byte stream per cloud.  Returns (bytes uint8 [B, cap], nbytes int32 [B])."""
+        B, S, d = latent_q.shape
+        pmf = prob(centres)                                                        # [B, S, d, L]          compress.py:131
+        L = pmf.shape[-1]
+        cdf = ops.pmf_to_cdf_u16(pmf).view(B, S * d, L + 1)                        # pn_kit.pmf_to_cdf + torchac's normalisation
+        sym = (latent_q.round().to(torch.int16) + L // 2).view(B, S * d)           # compress.py:135
+        return ops.range_encode(cdf, sym)                                          # compress.py:136
+
+    @torch.no_grad()
+    def decode_latents(self, prob, centres, data, nbytes, d=None):
+        """decompress.py:88-93: the inverse; returns latent_q float [B, S, d]."""
+        B, S, _ = centres.shape
+        pmf = prob(centres)
+        L = pmf.shape[-1]
+        d = pmf.shape[2] if d is None else d
+        cdf = ops.pmf_to_cdf_u16(pmf).view(B, S * d, L + 1)
+        sym = ops.range_decode(cdf, data, nbytes)
+        return (sym.view(B, S, d) - L // 2).float()
+
+    @torch.no_grad()
     def evaluate_all(self, decomp, original):
         """Every per-file metric of eval.py:167-221 except the bitrate: dict of float64 tensors [B] -- chamfer (eval.py:199-205),
         d1_psnr and d2_psnr (eval.py:43-98: point-to-point and point-to-plane, normals by 30-NN PCA of the original),

@@ -8,7 +8,7 @@ Use:  import pcc_b200; pcc_b200.install(); import pn_kit, AE, ...      (see INTE
 import sys
 import types
 
-from . import octree_ops, pn_kit_ops, pointnet_ops, pytorch3d_compat as p3d
+from . import octree_ops, pn_kit_ops, pointnet_ops, pytorch3d_compat as p3d, torchac_compat
 
 
 def _module(name):
@@ -29,6 +29,8 @@ def install(patch_loaded=True):
     ops_m.ball_query = p3d.ball_query
     ops_m.sample_farthest_points = p3d.sample_farthest_points
     loss_m.chamfer_distance = p3d.chamfer_distance
+    tac = _module("torchac")                                      # compress.py / decompress.py: `import torchac`
+    tac.encode_float_cdf, tac.decode_float_cdf = torchac_compat.encode_float_cdf, torchac_compat.decode_float_cdf
     if patch_loaded:
         patch_reference_modules()
 

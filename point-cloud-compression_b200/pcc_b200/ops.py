@@ -342,3 +342,61 @@ def uniformity_coefficient(input_pc, decomp_pc, region=1024):
     with torch.cuda.device(input_pc.device):
         _lib.check(lib.pcc_uc_f32(_ptr(d2[0]), _ptr(d2[1]), B, region, _ptr(out), _stream()), "pcc_uc_f32")
     return out
+
+
+# ---- entropy stage (pn_kit.pmf_to_cdf + torchac's coder) ----------------------------------------------------------------
+def pmf_to_cdf_u16(pmf):
+    """pmf [..., L] (CUDA fp32) -> uint16 CDF [..., L + 1]: pn_kit.pmf_to_cdf + torchac's 16-bit normalisation."""
+    lib = _lib.load()
+    pmf = _cuda_f32(pmf, "pmf")
+    L = pmf.shape[-1]
+    out = torch.empty(pmf.shape[:-1] + (L + 1,), dtype=torch.uint16, device=pmf.device)
+    if pmf.numel():
+        with torch.cuda.device(pmf.device):
+            _lib.check(lib.pcc_pmf_to_cdf_u16(_ptr(pmf), pmf.numel() // L, L, _ptr(out), _stream()), "pcc_pmf_to_cdf_u16")
+    return out
+
+
+def cdf_to_u16(cdf_float):
+    """float CDF [..., Lp] (what pn_kit.pmf_to_cdf returns) -> uint16 CDF, torchac's needs_normalization=True conversion."""
+    lib = _lib.load()
+    cdf_float = _cuda_f32(cdf_float, "cdf_float")
+    Lp = cdf_float.shape[-1]
+    out = torch.empty(cdf_float.shape, dtype=torch.uint16, device=cdf_float.device)
+    if cdf_float.numel():
+        with torch.cuda.device(cdf_float.device):
+            _lib.check(lib.pcc_cdf_to_u16(_ptr(cdf_float), cdf_float.numel() // Lp, Lp, _ptr(out), _stream()), "pcc_cdf_to_u16")
+    return out
+
+
+def range_encode(cdf_u16, sym):
+    """cdf uint16 [B, n, Lp], sym int16 [B, n] (CUDA) -> (bytes uint8 [B, cap], nbytes int32 [B]); one stream per cloud."""
+    lib = _lib.load()
+    if not cdf_u16.is_cuda or cdf_u16.dtype != torch.uint16 or cdf_u16.dim() != 3:
+        raise RuntimeError("pcc_b200.range_encode: cdf must be a CUDA uint16 [B, n, Lp] tensor (there is no CPU path)")
+    cdf_u16 = cdf_u16.contiguous()
+    B, n, Lp = cdf_u16.shape
+    sym = sym.to(device=cdf_u16.device, dtype=torch.int16).reshape(B, n).contiguous()
+    cap = 2 * n + 8
+    out = torch.empty((B, cap), dtype=torch.uint8, device=cdf_u16.device)
+    nbytes = torch.empty((B,), dtype=torch.int32, device=cdf_u16.device)
+    with torch.cuda.device(cdf_u16.device):
+        _lib.check(lib.pcc_range_encode_u16(_ptr(cdf_u16), _ptr(sym), B, n, Lp, _ptr(out), cap, _ptr(nbytes), _stream()),
+                   "pcc_range_encode_u16")
+    return out, nbytes
+
+
+def range_decode(cdf_u16, data, nbytes):
+    """Inverse of range_encode: returns sym int16 [B, n]."""
+    lib = _lib.load()
+    if not cdf_u16.is_cuda or cdf_u16.dtype != torch.uint16 or cdf_u16.dim() != 3:
+        raise RuntimeError("pcc_b200.range_decode: cdf must be a CUDA uint16 [B, n, Lp] tensor (there is no CPU path)")
+    cdf_u16 = cdf_u16.contiguous()
+    B, n, Lp = cdf_u16.shape
+    data = data.to(device=cdf_u16.device, dtype=torch.uint8).reshape(B, -1).contiguous()
+    nbytes = nbytes.to(device=cdf_u16.device, dtype=torch.int32).contiguous()
+    sym = torch.empty((B, n), dtype=torch.int16, device=cdf_u16.device)
+    with torch.cuda.device(cdf_u16.device):
+        _lib.check(lib.pcc_range_decode_u16(_ptr(cdf_u16), _ptr(data), _ptr(nbytes), B, n, Lp, data.shape[1], _ptr(sym), _stream()),
+                   "pcc_range_decode_u16")
+    return sym

@@ -140,3 +140,35 @@ def test_evaluate_all_matches_oracle_metrics(setup):
         mn, mx = x[b].min(), x[b].max()
         cham = orc.chamfer(((y[b] - mn) / (mx - mn))[None], ((x[b] - mn) / (mx - mn))[None])[0]
         assert abs(m["chamfer"][b] - cham) <= 1e-5 * cham
+
+
+def test_entropy_stage_matches_oracle_and_round_trips(setup):
+    """compress.py:131-136 / decompress.py:88-93 on the device: the CDFs equal pn_kit.pmf_to_cdf + torchac's normalisation (CPU
+    statement), the byte streams equal the CPU restatement of the coder on the same CDFs, and decoding returns the latents."""
+    from oracle import oracle as orc
+    from pcc_b200.modules import ConditionalProbabilityModel
+    from pcc_b200 import torchac_compat
+    pcc, codec, sd = setup
+    torch.manual_seed(5)
+    prob = ConditionalProbabilityModel(7, 16).cuda().eval()
+    x = torch.from_numpy(synth.modelnet_like(3, 8192, seed=95)).cuda()
+    c = codec.compress(x, torch.zeros(3, dtype=torch.int64, device="cuda"))
+    data, nbytes = codec.encode_latents(prob, c["latent_q"], c["centres"])
+    with torch.no_grad():
+        pmf = prob(c["centres"])
+    cdf_dev = pcc.ops.pmf_to_cdf_u16(pmf).cpu().numpy()
+    cdf_cpu = orc.pmf_to_cdf_u16(pmf.cpu().numpy())
+    assert np.array_equal(cdf_dev, cdf_cpu)
+    sym = (c["latent_q"].cpu().numpy().astype(np.int16) + 3).reshape(3, -1)
+    for b in range(3):
+        want = orc.range_encode(cdf_cpu[b].reshape(-1, 8), sym[b])
+        got = data[b, :int(nbytes[b])].cpu().numpy().tobytes()
+        assert got == want
+        assert np.array_equal(orc.range_decode(cdf_cpu[b].reshape(-1, 8), got), sym[b])
+    back = codec.decode_latents(prob, c["centres"], data, nbytes)
+    assert torch.equal(back, c["latent_q"])
+    # the torchac-named entry points (one stream for the whole tensor, CPU tensors in, as compress.py:134-136 calls them)
+    cdf_float = torch.cat([torch.zeros_like(pmf[..., :1]), pmf.cumsum(-1)], -1).clamp(max=1.0)[:1].cpu()
+    s16 = torch.from_numpy(sym[:1].reshape(1, 64, 16))
+    stream = torchac_compat.encode_float_cdf(cdf_float, s16, check_input_bounds=True)
+    assert isinstance(stream, bytes) and torch.equal(torchac_compat.decode_float_cdf(cdf_float, stream), s16)

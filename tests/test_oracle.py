@@ -156,3 +156,32 @@ def test_eval_metrics_oracle_vs_reference_golden(golden_dir):
         assert abs(orc.calc_uc(x[b], y[b]) - g["uc"][b]) <= 1e-4 * g["uc"][b]
     psnr, mse = orc.p2plane_psnr(x[0], y[0])
     assert abs(psnr - g["p2plane"][0, 0]) < 1e-9 and psnr > orc.d1_psnr(x[0], y[0])[0]   # |diff . n| <= |diff|
+
+
+# ---- entropy stage: pn_kit.pmf_to_cdf (run from the reference when present) + the restated torchac coder ----------------
+@pytest.mark.parametrize("L,n,peaky", [(7, 1024, 1.0), (7, 20000, 6.0), (3, 100, 0.1), (16, 3000, 3.0), (7, 2000, 30.0)])
+def test_range_coder_roundtrip_and_size(L, n, peaky):
+    rng = np.random.default_rng(L * n)
+    pmf = torch.softmax(torch.from_numpy(rng.normal(size=(n, L)).astype(np.float32) * peaky), -1)
+    cdf = orc.pmf_to_cdf_u16(pmf.numpy())
+    # pn_kit.pmf_to_cdf + torchac's _convert_to_int_and_normalize, stated with torch CPU ops
+    c = torch.cat([torch.zeros(n, 1), pmf.cumsum(-1)], -1).clamp(max=1.0)
+    if ref_loader.available():
+        c = ref_loader.load("pn_kit").pmf_to_cdf(pmf)                       # the reference's own function
+    ci = c.mul(2 ** 16 - L).round().to(torch.int16) + torch.arange(L + 1, dtype=torch.int16)
+    assert np.array_equal(ci.numpy().view(np.uint16), cdf)
+    assert (np.diff(cdf[:, :-1].astype(np.int64), axis=1) > 0).all()        # every symbol keeps a non-zero interval
+    sym = np.array([rng.choice(L, p=p / p.sum()) for p in pmf.numpy()], np.int16)
+    data = orc.range_encode(cdf, sym)
+    assert np.array_equal(orc.range_decode(cdf, data), sym)
+    ideal = -np.log2(np.maximum(pmf.numpy()[np.arange(n), sym], 2.0 ** -16)).sum() / 8
+    assert len(data) <= ideal * 1.02 + 8                                    # an arithmetic coder sits within bits of the entropy
+
+
+def test_range_coder_known_streams():
+    """Hand-checkable streams of the 32-bit coder: a certain symbol costs nothing, a 1/2-probability symbol one bit."""
+    cdf = np.array([[0, 32768, 0]], np.uint16).repeat(16, axis=0)            # two symbols, p = 1/2 each (last entry unused)
+    bits = np.array([1, 0, 1, 1, 0, 0, 1, 0, 1, 1, 1, 0, 0, 1, 0, 1], np.int16)
+    data = orc.range_encode(cdf, bits)
+    assert len(data) == 3 and np.array_equal(np.unpackbits(np.frombuffer(data, np.uint8))[:16], bits)
+    assert np.array_equal(orc.range_decode(cdf, data), bits)
