@@ -123,6 +123,66 @@ class PatchCodec:
         sym = ops.range_decode(cdf, data, nbytes)
         return (sym.view(B, S, d) - L // 2).float()
 
+    # ---- the reference's file formats (compress.py:138-151, decompress.py:72-116) -----------------------------------------
+    @torch.no_grad()
+    def compress_to_files(self, xyz, names, out_dir, prob, start_idx=None):
+        """compress.py:78-155 for a batch of clouds: writes <name>.p.bin (arithmetic-coded latents), <name>.s.bin (octree
+        code of the centres, pn_kit.binary_array_to_byte_array packing) and <name>.c.bin (centre xyz + longest side, 4 float32)
+        for every cloud.  Everything is computed on the device; one device -> host copy per array.  Returns bits per cloud."""
+        import os
+        import numpy as np
+        if self.centre_mode == "fixed":
+            raise ValueError("compress_to_files needs the octree stream: use centre_mode='coded' or 'reference'")
+        c = self.compress(xyz, start_idx)
+        data, nbytes = self.encode_latents(prob, c["latent_q"], c["centres"])
+        o = c["octree"]
+        data, nbytes = data.cpu().numpy(), nbytes.cpu().numpy()
+        obytes, onbits = o["bytes"].cpu().numpy(), o["nbits"].cpu().numpy()
+        cs = torch.cat((c["center"], c["longest"][:, None]), dim=1).cpu().numpy().astype(np.float32)
+        os.makedirs(out_dir, exist_ok=True)
+        bits = []
+        for b, name in enumerate(names):
+            with open(os.path.join(out_dir, name + ".p.bin"), "wb") as f:
+                f.write(data[b, :nbytes[b]].tobytes())
+            with open(os.path.join(out_dir, name + ".s.bin"), "wb") as f:
+                f.write(obytes[b, :(onbits[b] + 7) // 8].tobytes())
+            cs[b].tofile(os.path.join(out_dir, name + ".c.bin"))
+            bits.append(8 * (int(nbytes[b]) + (int(onbits[b]) + 7) // 8 + 16))
+        return bits
+
+    @torch.no_grad()
+    def decompress_from_files(self, names, in_dir, prob, S, centre_decoder=None):
+        """decompress.py:72-116 for a batch: reads the three files of every cloud and returns the reconstructions [B, S*k, 3].
+        centre_decoder: 'inverse' (the centres the coded stream holds) or 'reference' (octree_np.decode as written, S == 64);
+        default follows centre_mode."""
+        import os
+        import numpy as np
+        dev = next(self.ae.parameters()).device
+        mode = centre_decoder or ("reference" if self.centre_mode == "reference" else "inverse")
+        streams, codes, cs = [], [], []
+        for name in names:
+            streams.append(np.fromfile(os.path.join(in_dir, name + ".p.bin"), dtype=np.uint8))
+            sb = np.fromfile(os.path.join(in_dir, name + ".s.bin"), dtype=np.uint8)
+            if mode == "reference":      # pn_kit.byte_array_to_binary_array: every byte expands to 8 bits (pn_kit.py:469-475)
+                codes.append(np.unpackbits(sb))
+            else:                        # the stream holds 1 + 8 m bits: the last byte is the last bit (pn_kit.py:463-467)
+                codes.append(np.concatenate((np.unpackbits(sb[:-1]), sb[-1:] & 1)))
+            cs.append(np.fromfile(os.path.join(in_dir, name + ".c.bin"), dtype=np.float32))
+        B = len(names)
+        nb = np.array([len(c_) for c_ in codes], np.int32)
+        bits = np.zeros((B, int(nb.max())), np.uint8)
+        for b, c_ in enumerate(codes):
+            bits[b, :nb[b]] = c_
+        centres, _, _ = ops.octree_decode(torch.from_numpy(bits).to(dev), torch.from_numpy(nb).to(dev),
+                                          mode=0 if mode == "reference" else 1, cap=S)          # decompress.py:80-85
+        ns = np.array([len(s_) for s_ in streams], np.int32)
+        data = np.zeros((B, max(int(ns.max()), 1)), np.uint8)
+        for b, s_ in enumerate(streams):
+            data[b, :ns[b]] = s_
+        latent_q = self.decode_latents(prob, centres, torch.from_numpy(data).to(dev), torch.from_numpy(ns).to(dev))  # :88-93
+        cs = torch.from_numpy(np.stack(cs)).to(dev)
+        return self.decompress(latent_q, centres, S * self.ae.k, cs[:, :3].contiguous(), cs[:, 3].contiguous())   # :96-116
+
     @torch.no_grad()
     def evaluate_all(self, decomp, original):
         """Every per-file metric of eval.py:167-221 except the bitrate: dict of float64 tensors [B] -- chamfer (eval.py:199-205),

@@ -172,3 +172,33 @@ def test_entropy_stage_matches_oracle_and_round_trips(setup):
     s16 = torch.from_numpy(sym[:1].reshape(1, 64, 16))
     stream = torchac_compat.encode_float_cdf(cdf_float, s16, check_input_bounds=True)
     assert isinstance(stream, bytes) and torch.equal(torchac_compat.decode_float_cdf(cdf_float, stream), s16)
+
+
+@pytest.mark.parametrize("mode", ["coded", "reference"])
+def test_file_formats_round_trip(setup, tmp_path, mode):
+    """compress.py:138-151 / decompress.py:72-116 file formats: .p.bin / .s.bin / .c.bin written for a batch decode back to the
+    reconstruction the in-memory path produces; the .s.bin bytes are pn_kit.binary_array_to_byte_array of the reference coder's
+    stream and the .c.bin is (center, longest) as 4 float32."""
+    from oracle import oracle as orc
+    from pcc_b200.codec import PatchCodec
+    from pcc_b200.modules import ConditionalProbabilityModel
+    pcc, codec, sd = setup
+    torch.manual_seed(7)
+    prob = ConditionalProbabilityModel(7, 16).cuda().eval()
+    codec = PatchCodec(codec.ae, centre_mode=mode)
+    x = torch.from_numpy(synth.modelnet_like(3, 8192, seed=97)).cuda()
+    start = torch.tensor([4, 5, 6], dtype=torch.int64, device="cuda")
+    names = ["a", "b", "c"]
+    bits = codec.compress_to_files(x, names, str(tmp_path), prob, start)
+    c = codec.compress(x, start)
+    want = codec.decompress(c["latent_q"], c["centres"], 8192, c["center"], c["longest"])
+    got = codec.decompress_from_files(names, str(tmp_path), prob, S=64)
+    assert torch.equal(got, want)
+    pc, _, _, _ = pcc.ops.normalize(x)
+    _, fps_xyz = pcc.ops.fps(pc, 64, start, 1e10, return_xyz=True)
+    codes, _, _ = orc.encode_sampled_np(fps_xyz.cpu().numpy(), 1, 8192, 0.25)
+    for b, n in enumerate(names):
+        assert (tmp_path / (n + ".s.bin")).read_bytes() == orc.bits_to_bytes(codes[b]).tobytes()
+        cs = np.fromfile(tmp_path / (n + ".c.bin"), dtype=np.float32)
+        assert cs.shape == (4,) and np.array_equal(cs[:3], c["center"][b].cpu().numpy()) and cs[3] == float(c["longest"][b])
+        assert bits[b] == 8 * sum((tmp_path / (n + e)).stat().st_size for e in (".p.bin", ".s.bin", ".c.bin"))
