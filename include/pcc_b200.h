@@ -288,6 +288,14 @@ int pcc_range_encode_u16(const uint16_t *cdf, const int16_t *sym, int B, int n_s
 int pcc_range_decode_u16(const uint16_t *cdf, const uint8_t *bytes, const int32_t *nbytes, int B, int n_sym, int Lp, int cap,
                          int16_t *out_sym, void *stream);
 
+/*
+ * The quantiser between encoder and decoder (/root/reference/AE.py:42-45, compress.py:125-127):
+ * latent = sigmoid(raw) * spread - spread / 2 with spread = L - 0.2, latent_q = round(latent); raw [rows, d] fp32.
+ * out_q_bf16 (nullable) [rows, kpad]: the rounded latent as bf16 rows zero padded to kpad columns (operand of pcc_linear_bf16).
+ */
+int pcc_quantise_latent_f32(const float *raw, int64_t rows, int d, int kpad, float spread, float *out_latent, float *out_q,
+                            void *out_q_bf16, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

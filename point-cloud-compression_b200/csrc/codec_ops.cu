@@ -3,6 +3,8 @@
 //   normalize_kernel  pn_kit.normalize   (/root/reference/pn_kit.py:47-60), one CTA per cloud: bbox reduction then
 //                     out = (p - center) * (1 - margin) / longest + 0.5, same fp32 op order as the reference.
 //   assemble_kernel   decompress.py:104-116: patches / scale + patch centre, then pn_kit.denormalize (pn_kit.py:62-66).
+#include <cuda_bf16.h>
+
 #include "pcc_common.cuh"
 
 namespace pcc {
@@ -129,6 +131,30 @@ eval_metrics_kernel(const float *__restrict__ dx, const float *__restrict__ per_
     }
 }
 
+// AE.py:42-45 / compress.py:125-127 in one pass: latent = sigmoid(raw) * spread - spread / 2 (same fp32 operation order as the
+// reference), latent_q = round(latent) (half to even, torch.round), and the rounded latent again as bf16 rows zero padded to
+// kpad columns -- the A operand of inv_pool's first GEMM (AE.py:48).
+__global__ void __launch_bounds__(256)
+quantise_latent_kernel(const float *__restrict__ raw, long long rows, int d, int kpad, float spread, float *__restrict__ latent,
+                       float *__restrict__ latent_q, __nv_bfloat16 *__restrict__ q_bf16) {
+    const long long total = rows * kpad;
+    const float half = spread / 2;
+    for (long long e = blockIdx.x * 256ll + threadIdx.x; e < total; e += static_cast<long long>(gridDim.x) * 256ll) {
+        const long long r = e / kpad;
+        const int c = static_cast<int>(e - r * kpad);
+        float q = 0.0f;
+        if (c < d) {
+            const float x = raw[r * d + c];
+            const float sg = 1.0f / (1.0f + expf(-x));                    // torch.sigmoid (fp32)
+            const float l = __fsub_rn(__fmul_rn(sg, spread), half);
+            q = rintf(l);
+            latent[r * d + c] = l;
+            latent_q[r * d + c] = q;
+        }
+        if (q_bf16) q_bf16[e] = __float2bfloat16_rn(q);
+    }
+}
+
 }  // namespace pcc
 
 PCC_API int pcc_normalize_f32(const float *xyz, int B, int N, float margin, float *out, float *center, float *longest,
@@ -164,4 +190,19 @@ PCC_API int pcc_eval_metrics_f32(const float *dx, const float *per_cloud, const 
     PCC_REQUIRE(B >= 1 && P1 >= 1, "pcc_eval_metrics_f32: bad shape B=%d P1=%d", B, P1);
     eval_metrics_kernel<<<B, 256, 0, static_cast<cudaStream_t>(stream)>>>(dx, per_cloud, bbox, P1, out);
     return check_launch("eval_metrics_kernel");
+}
+
+PCC_API int pcc_quantise_latent_f32(const float *raw, int64_t rows, int d, int kpad, float spread, float *out_latent, float *out_q,
+                                    void *out_q_bf16, void *stream) {
+    using namespace pcc;
+    PCC_REQUIRE(raw && out_latent && out_q, "pcc_quantise_latent_f32: null pointer");
+    PCC_REQUIRE(rows >= 0 && d >= 1 && kpad >= d, "pcc_quantise_latent_f32: bad shape rows=%lld d=%d kpad=%d", static_cast<long long>(rows), d, kpad);
+    if (rows == 0) return 0;
+    const long long total = rows * kpad;
+    long long blocks = (total + 255) / 256;
+    const long long cap = static_cast<long long>(num_sms()) * 16;
+    if (blocks > cap) blocks = cap;
+    quantise_latent_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        raw, rows, d, kpad, spread, out_latent, out_q, static_cast<__nv_bfloat16 *>(out_q_bf16));
+    return check_launch("quantise_latent_kernel");
 }

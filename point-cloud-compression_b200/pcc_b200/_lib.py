@@ -64,6 +64,7 @@ SIGNATURES.update({
     "pcc_cdf_to_u16": (_i, [_vp, _i64, _i, _vp, _vp]),
     "pcc_range_encode_u16": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp]),
     "pcc_range_decode_u16": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "pcc_quantise_latent_f32": (_i, [_vp, _i64, _i, _i, _f, _vp, _vp, _vp, _vp]),
     "pcc_octree_max_bits": (_i, [_i]),
     "pcc_octree_encode_f32": (_i, [_vp, _i, _i, _i, ctypes.c_double, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pcc_octree_decode_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),

@@ -166,9 +166,8 @@ class AE(nn.Module):
         """patches [BS, K, 3] (recentred, scaled) -> (latent [BS, d] after the sigmoid spread, rounded latent)."""
         feat = self.sa.forward_points(patches, out_dtype=torch.bfloat16)          # AE.py:38
         latent = self.pn.forward_xyz_feat(patches, feat)                          # AE.py:39
-        spread = self.L - 0.2                                                     # AE.py:42-45
-        latent = torch.sigmoid(latent) * spread - spread / 2
-        return latent, STEQuantize.apply(latent)
+        latent, latent_q, _ = ops.quantise_latent(latent, self.L - 0.2)           # AE.py:42-45, one kernel
+        return latent, latent_q
 
     def decode_patches(self, latent_q):
         """latent_q [BS, d] -> patches [BS, k, 3]   (AE.py:48-53)."""

@@ -400,3 +400,18 @@ def range_decode(cdf_u16, data, nbytes):
         _lib.check(lib.pcc_range_decode_u16(_ptr(cdf_u16), _ptr(data), _ptr(nbytes), B, n, Lp, data.shape[1], _ptr(sym), _stream()),
                    "pcc_range_decode_u16")
     return sym
+
+
+def quantise_latent(raw, spread, kpad=0):
+    """AE.py:42-45: (latent, latent_q[, latent_q as bf16 rows zero padded to kpad columns]) from the encoder output [rows, d]."""
+    lib = _lib.load()
+    raw = _cuda_f32(raw, "raw")
+    rows, d = raw.shape
+    latent = torch.empty_like(raw)
+    q = torch.empty_like(raw)
+    qb = torch.empty((rows, kpad), dtype=torch.bfloat16, device=raw.device) if kpad else None
+    if rows:
+        with torch.cuda.device(raw.device):
+            _lib.check(lib.pcc_quantise_latent_f32(_ptr(raw), rows, d, kpad if kpad else d, float(spread), _ptr(latent), _ptr(q),
+                                                   _ptr(qb), _stream()), "pcc_quantise_latent_f32")
+    return latent, q, qb
