@@ -133,6 +133,35 @@ def test_knn_block_kernel_selection_paths_vs_oracle(pcc, orc, kind, P2, K):
     assert np.array_equal(i.cpu().numpy(), oi) and np.array_equal(d.cpu().numpy(), od)
 
 
+@pytest.mark.parametrize("kind", ["uniform", "grid", "identical", "offset", "tiny", "line", "two_clusters", "qp_differ"])
+def test_knn_in_patch_adversarial_vs_oracle(pcc, orc, kind):
+    """256 x 256, K = 16 (pn_kit.py:190 as AE.py:16 calls it) on inputs that stress the a-priori threshold and the tie rules:
+    exact ties, all-identical points, large offsets, tiny scales, collinear points, two far clusters, queries != candidates."""
+    BS = 160   # 160 * 256 queries >= the dispatch threshold of the batched kernels
+    rng = np.random.default_rng(len(kind))
+    x = synth.uniform_cube(BS, 256, seed=7).astype(np.float32) - np.float32(0.5)
+    if kind == "grid":
+        x = synth.grid_quantised(BS, 256, depth=3, seed=8) - np.float32(0.5)           # exact ties everywhere
+    elif kind == "identical":
+        x[:] = x[:, :1]                                                               # all distances 0: order by index
+    elif kind == "offset":
+        x = x + np.float32(100.0)                                                     # |x|^2 ~ 3e4: the margin admits almost everything
+    elif kind == "tiny":
+        x = x * np.float32(1e-4)
+    elif kind == "line":
+        x[:, :, 1:] = 0                                                               # collinear points
+    elif kind == "two_clusters":
+        x[:, ::2] *= np.float32(1e-3)
+        x[:, 1::2] = x[:, 1::2] * np.float32(1e-3) + np.float32(1.0)
+    q = x
+    if kind == "qp_differ":
+        q = np.ascontiguousarray(x[:, ::-1]) * np.float32(0.9)
+    d, i, nn = pcc.ops.knn(cu(q), cu(x), 16, return_nn=True, centre_sub=True)
+    od, oi, onn = orc.knn_points(q, x, 16, True, threads=8)
+    assert np.array_equal(i.cpu().numpy(), oi) and np.array_equal(d.cpu().numpy(), od)
+    assert np.array_equal(nn.cpu().numpy(), onn - q[:, :, None, :])
+
+
 @pytest.mark.parametrize("BS,P,K", [(200, 256, 16), (300, 128, 8), (150, 256, 32), (140, 250, 20), (600, 64, 3)])
 def test_knn_thread_kernel_in_patch_vs_oracle(pcc, orc, BS, P, K):
     """Many small self-searches (the pn_kit.SetAbstraction K=16 case) -> thread-per-query kernel."""
