@@ -166,7 +166,10 @@ class AE(nn.Module):
         """patches [BS, K, 3] (recentred, scaled) -> (latent [BS, d] after the sigmoid spread, rounded latent)."""
         feat = self.sa.forward_points(patches, out_dtype=torch.bfloat16)          # AE.py:38
         latent = self.pn.forward_xyz_feat(patches, feat)                          # AE.py:39
-        latent, latent_q, _ = ops.quantise_latent(latent, self.L - 0.2)           # AE.py:42-45, one kernel
+        # AE.py:42-45 in one kernel; it also emits the rounded latent as zero-padded bf16 rows, the operand of inv_pool's first
+        # GEMM, which decode_patches picks up when it is handed this very tensor (compress -> decompress in one process)
+        latent, latent_q, qb = ops.quantise_latent(latent, self.L - 0.2, kpad=(self.d + 63) // 64 * 64)
+        self._q_pad = (latent_q, latent_q._version, qb)   # holds the tensor itself: its storage cannot be recycled under the key
         return latent, latent_q
 
     def decode_patches(self, latent_q):
@@ -184,7 +187,13 @@ class AE(nn.Module):
                       (self._perm_w4, self._perm_b4, True)]
         if all(mlp_ops.linear_supported(BS, w.shape[0]) for w, _, _ in inv_layers):
             # AE.py:19-26 on the streamed tensor-core GEMM (csrc/gemm_ws.cu); the latent is zero padded to the K granule
-            lat = torch.nn.functional.pad(latent_q.detach().to(torch.bfloat16), (0, (-self.d) % 64))
+            cached = getattr(self, "_q_pad", None)
+            base = latent_q._base if latent_q._base is not None else latent_q
+            if (cached is not None and base is cached[0] and latent_q._version == cached[1] and latent_q.is_contiguous() and
+                    latent_q.numel() == cached[0].numel() and latent_q.data_ptr() == cached[0].data_ptr()):
+                lat = cached[2]
+            else:
+                lat = torch.nn.functional.pad(latent_q.detach().to(torch.bfloat16), (0, (-self.d) % 64))
             lin = mlp_ops.stream_chain(lat, inv_layers)
         else:
             lin = mlp_ops.library_chain(latent_q.detach(), inv_layers, out_dtype=torch.bfloat16)
