@@ -6,8 +6,15 @@ checkpoints load unchanged; the forward bodies are batched device code:
     Conv2d+BatchNorm(eval, folded)+ReLU stack on the tensor cores -> max over nsample   (one fused chain per run of
     layers whose weights fit in shared memory; wider layers are library GEMMs, see mlp_ops.run_chain).
 
-Inference only: train-mode BatchNorm (batch statistics) is not part of the fused path and raises.
+With autograd enabled and trainable parameters (training), every module runs a differentiable body instead: FPS, ball query
+and the row gathers stay on the pcc kernels (no gradient flows into the indices; the gather has a hand-written backward), the
+Conv2d + BatchNorm (batch statistics) + ReLU stacks and FoldingNet's Conv1d layers run as torch layers under autograd.
 """
+
+
+def _training_pass(module):
+    return torch.is_grad_enabled() and any(p.requires_grad for p in module.parameters())
+
 import torch
 import torch.nn as nn
 
@@ -44,11 +51,36 @@ class PointnetSAModule(nn.Module):
             self._folded = (key, [_fold_bn(mods[i], mods[i + 1]) + (True,) for i in range(0, len(mods), 3)])
         return self._folded[1]
 
-    @torch.no_grad()
+    def forward_train(self, xyz, features=None):
+        """pointnet_sa_module.py:58-93 under autograd: sampling / ball query / grouping on the pcc kernels, the shared MLP
+        (Conv2d + BatchNorm with batch statistics when self.training + ReLU) as torch layers, max over nsample."""
+        B, N, _ = xyz.shape
+        with torch.no_grad():
+            fps_idx, _ = ops.fps(xyz, self.npoint, None, ops.FLT_MAX, return_xyz=True)       # :66
+            fps_idx = fps_idx.clamp(min=0)                                                  # :67
+        new_xyz = ops.gather(xyz, fps_idx)                                                  # :68
+        with torch.no_grad():
+            _, idx = ops.ball_query(new_xyz, xyz, self.nsample, self.radius, return_dists=False)  # :71
+            idx = idx.clamp(min=0)                                                          # :27
+        parts = []
+        if features is not None:
+            parts.append(ops.gather(features.permute(0, 2, 1).contiguous(), idx))          # :74-77  [B, npoint, nsample, C]
+        if self.use_xyz:
+            parts.append(ops.gather(xyz, idx))                                              # :80-85
+        grouped = torch.cat(parts, dim=-1).permute(0, 3, 1, 2)                              # :88  [B, C, npoint, nsample]
+        return new_xyz, torch.max(self.mlp(grouped), 3)[0]                                  # :89-91
+
     def forward(self, xyz, features=None):
         """xyz [B,N,3], features [B,C,N] or None -> (new_xyz [B,npoint,3], new_features [B,C_out,npoint])."""
+        if _training_pass(self):
+            return self.forward_train(xyz, features)
         if self.training:
-            raise NotImplementedError("pcc_b200.PointnetSAModule: train-mode BatchNorm is not built (call .eval())")
+            raise NotImplementedError("pcc_b200.PointnetSAModule: train-mode BatchNorm without autograd is not built "
+                                      "(call .eval() for inference)")
+        with torch.no_grad():
+            return self._forward_fused(xyz, features)
+
+    def _forward_fused(self, xyz, features=None):
         B, N, _ = xyz.shape
         fps_idx, new_xyz = ops.fps(xyz, self.npoint, None, ops.FLT_MAX, return_xyz=True)   # :66-68 (start index 0)
         if self.npoint > N:                                                                  # :67 clamp: pads read point 0
@@ -124,12 +156,23 @@ class FoldingNet(nn.Module):
         h = mlp_ops.run_chain(h, [(mlp[2].weight.squeeze(-1), mlp[2].bias, True), (mlp[4].weight.squeeze(-1), mlp[4].bias, False)])
         return h.view(B, N, 3)
 
-    @torch.no_grad()
-    def forward(self, latent_quantized):
+    def forward_train(self, latent_quantized):
+        """PPPF_AE.py:91-109 under autograd (torch Conv1d layers)."""
         B = latent_quantized.size(0)
-        grid = self.build_grid(B, latent_quantized.device)                           # [B, N, 2]
-        coarse = self._stage(self.mlp1, grid, latent_quantized, 2, False)            # PPPF_AE.py:100-104
-        return self._stage(self.mlp2, coarse, latent_quantized, 3, True)             # PPPF_AE.py:106-109
+        grid = self.build_grid(B, latent_quantized.device)
+        latent_expanded = latent_quantized.unsqueeze(1).repeat(1, self.num_points, 1)
+        coarse = self.mlp1(torch.cat([grid, latent_expanded], dim=-1).transpose(2, 1))
+        fine = self.mlp2(torch.cat([coarse, latent_expanded.transpose(2, 1)], dim=1))
+        return fine.transpose(2, 1)
+
+    def forward(self, latent_quantized):
+        if _training_pass(self):
+            return self.forward_train(latent_quantized)
+        with torch.no_grad():
+            B = latent_quantized.size(0)
+            grid = self.build_grid(B, latent_quantized.device)                           # [B, N, 2]
+            coarse = self._stage(self.mlp1, grid, latent_quantized, 2, False)            # PPPF_AE.py:100-104
+            return self._stage(self.mlp2, coarse, latent_quantized, 3, True)             # PPPF_AE.py:106-109
 
 
 class PPPF_AE(nn.Module):
@@ -144,8 +187,12 @@ class PPPF_AE(nn.Module):
         self.dec_proj = nn.Linear(d, dim)
         self.quantize = STEQuantize.apply
 
-    @torch.no_grad()
     def forward(self, xyz):
+        """PPPF_AE.py:131-150; differentiable when autograd is on and the parameters are trainable, fused otherwise."""
+        with torch.set_grad_enabled(_training_pass(self)):
+            return self._forward(xyz)
+
+    def _forward(self, xyz):
         _, latent = self.encoder(xyz)
         spread = self.L - 0.2
         latent = torch.sigmoid(latent) * spread - spread / 2

@@ -50,22 +50,26 @@ def test_pppf_encoder_decoder_vs_reference_module_golden(pcc, golden_dir):
     model = pppf.PPPF_AE(K=512, k=0, d=16, L=7)
     model.load_state_dict(synth.seeded_module_state(model, 17))
     model = model.cuda().eval()
-    x = torch.from_numpy(g["x"]).cuda()
-    xyz1, f1 = model.encoder.sa1(x, None)
-    assert np.array_equal(xyz1.cpu().numpy(), g["xyz1"])             # FPS (start 0) centres: exact
-    assert rel(f1.cpu().numpy(), g["f1"]) < FEATURE_RTOL
-    # feed the reference's own intermediate features forward so each stage is judged on its own
-    xyz2, f2 = model.encoder.sa2(torch.from_numpy(g["xyz1"]).cuda(), torch.from_numpy(g["f1"]).cuda())
-    assert np.array_equal(xyz2.cpu().numpy(), g["xyz2"])
-    assert rel(f2.cpu().numpy(), g["f2"]) < FEATURE_RTOL
-    xyz3, f3 = model.encoder.sa3(torch.from_numpy(g["xyz2"]).cuda(), torch.from_numpy(g["f2"]).cuda())
-    assert np.array_equal(xyz3.cpu().numpy(), g["xyz3"])
-    assert rel(f3.cpu().numpy(), g["f3"]) < FEATURE_RTOL
-    recon, latent, lq = model(x)                                     # end to end
-    assert recon.shape == (2, 256, 3) and latent.shape == (2, 1024) and lq.shape == (2, 16)
-    assert np.abs(latent.cpu().numpy() - g["latent"]).max() < 0.1     # sigmoid-spread latent in [-3.4, 3.4]
-    dec = model.decoder(model.dec_proj(torch.from_numpy(g["lq"]).cuda()))
-    assert np.abs(dec.cpu().numpy() - g["recon"]).max() < COORD_ATOL * max(1.0, float(np.abs(g["recon"]).max()))
+    torch.set_grad_enabled(False)   # the fused inference bodies (with autograd on, the modules run their differentiable form)
+    try:
+        x = torch.from_numpy(g["x"]).cuda()
+        xyz1, f1 = model.encoder.sa1(x, None)
+        assert np.array_equal(xyz1.cpu().numpy(), g["xyz1"])             # FPS (start 0) centres: exact
+        assert rel(f1.cpu().numpy(), g["f1"]) < FEATURE_RTOL
+        # feed the reference's own intermediate features forward so each stage is judged on its own
+        xyz2, f2 = model.encoder.sa2(torch.from_numpy(g["xyz1"]).cuda(), torch.from_numpy(g["f1"]).cuda())
+        assert np.array_equal(xyz2.cpu().numpy(), g["xyz2"])
+        assert rel(f2.cpu().numpy(), g["f2"]) < FEATURE_RTOL
+        xyz3, f3 = model.encoder.sa3(torch.from_numpy(g["xyz2"]).cuda(), torch.from_numpy(g["f2"]).cuda())
+        assert np.array_equal(xyz3.cpu().numpy(), g["xyz3"])
+        assert rel(f3.cpu().numpy(), g["f3"]) < FEATURE_RTOL
+        recon, latent, lq = model(x)                                     # end to end
+        assert recon.shape == (2, 256, 3) and latent.shape == (2, 1024) and lq.shape == (2, 16)
+        assert np.abs(latent.cpu().numpy() - g["latent"]).max() < 0.1     # sigmoid-spread latent in [-3.4, 3.4]
+        dec = model.decoder(model.dec_proj(torch.from_numpy(g["lq"]).cuda()))
+        assert np.abs(dec.cpu().numpy() - g["recon"]).max() < COORD_ATOL * max(1.0, float(np.abs(g["recon"]).max()))
+    finally:
+        torch.set_grad_enabled(True)
 
 
 def test_pointnet_ops_wrapper_matches_reference_names(pcc):

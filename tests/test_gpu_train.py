@@ -42,3 +42,35 @@ def test_training_forward_matches_fused_inference_forward():
     assert float((lat_t - lat_i).abs().max()) < 5e-3
     if torch.equal(lq_t, lq_i):
         assert float((rec_t - rec_i).abs().max()) < 1e-2
+
+
+def test_pppf_training_pass_and_fused_inference_agree():
+    """PPPF_AE (PointNet++ SA x3 + FoldingNet, cfg3): with autograd on, the differentiable body runs (pcc kernels for sampling /
+    ball query / grouping / Chamfer, torch layers for the MLPs); in eval mode it computes what the fused inference path computes,
+    and a few optimisation steps reduce the Chamfer loss."""
+    import __graft_entry__  # noqa: F401
+    from pcc_b200 import pppf
+    from pcc_b200.pytorch3d_compat import chamfer_distance
+    torch.manual_seed(3)
+    model = pppf.PPPF_AE(K=512, k=0, d=16, L=7)
+    model.load_state_dict(synth.seeded_module_state(model, 17))
+    model = model.cuda()
+    x = torch.from_numpy(synth.shapenet_like(4, 2048, seed=71)).cuda()
+    model.eval()
+    rec_t, lat_t, lq_t = model(x)                          # autograd on -> differentiable body (BatchNorm in eval mode)
+    with torch.no_grad():
+        rec_i, lat_i, lq_i = model(x)                      # fused inference body
+    assert rec_t.requires_grad and not rec_i.requires_grad
+    assert float((lat_t - lat_i).abs().max()) < 2e-2      # bf16 tensor-core chain vs fp32 torch layers on a 1024-wide latent
+    model.train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    losses = []
+    for _ in range(6):
+        opt.zero_grad(set_to_none=True)
+        rec, _, _ = model(x)
+        loss, _ = chamfer_distance(rec, x)                 # PPPF_AE.get_loss, PPPF_AE.py:168
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    assert all(np.isfinite(losses)) and min(losses[-2:]) < losses[0]
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.parameters())
