@@ -24,13 +24,16 @@ def estimate_bits_from_pmf(pmf, sym):
 
 class Trainer:
     def __init__(self, K=256, k=128, d=16, L=7, N0=1024, alpha=2, lr=0.0005, lamda=1e-6, rate_loss_enable_step=40000,
-                 centre_depth=6, device="cuda", ddp=False, state_dict=None, tf32=True):
+                 centre_depth=6, device="cuda", ddp=False, state_dict=None, tf32=True, amp=False):
         self.K, self.k, self.d, self.L, self.N0, self.alpha = K, k, d, L, N0, alpha
         # The reference's network bodies are 1x1 Conv2d layers, which PyTorch runs through cuDNN with TF32 enabled by
         # default (torch.backends.cudnn.allow_tf32); the addmm form used here gets the same arithmetic only when the
         # matmul flag is switched on as well.  fp32 storage and accumulation, 10-bit operand mantissas.
         if tf32:
             torch.backends.cuda.matmul.allow_tf32 = True
+        # amp=True: the network bodies run under bf16 autocast -- the counterpart of the reference's fp16 autocast + GradScaler
+        # path (train.py:114,154-160, taken when --device is the string 'cuda'); bf16 needs no loss scaling.
+        self.amp = amp
         self.lamda, self.rate_loss_enable_step, self.centre_depth = lamda, rate_loss_enable_step, centre_depth
         self.ae = AE(K, k, d, L).to(device)
         if state_dict is not None:
@@ -70,9 +73,11 @@ class Trainer:
         scale = (N / self.N0) ** (1 / 3)
         _, _, patches = ops.knn(rec_centres, x, self.K, return_nn=True, centre_sub=True, nn_scale=scale,
                                 nn_only=True)                                     # train.py:185-192
-        patches_pred, _, latent_q = self.ae_fwd(patches.view(B * S, self.K, 3))   # train.py:193
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.amp):
+            patches_pred, _, latent_q = self.ae_fwd(patches.view(B * S, self.K, 3))   # train.py:193
+            pmf = self.prob_fwd(rec_centres)                                      # train.py:197
+        patches_pred, latent_q, pmf = patches_pred.float(), latent_q.float(), pmf.float()
         patches_pred = patches_pred / scale                                       # train.py:194
-        pmf = self.prob_fwd(rec_centres)                                          # train.py:197
         sym = (latent_q.view(B, S, self.d) + self.L // 2).long().clamp(0, self.L - 1)
         feature_bits = estimate_bits_from_pmf(pmf, sym) / (B * N)                 # train.py:201
         fbpp = feature_bits / (B * N)                                             # train.py:205 (divided twice, appendix B-7)

@@ -86,6 +86,9 @@ def main():
     rec(f"train step {B}x8192 K256 (cfg2: fwd + Chamfer + bwd + Adam)", lambda: tr.step(xyz, start))
     res[f"train step {B}x8192 K256 (cfg2: fwd + Chamfer + bwd + Adam)"]["clouds_per_s"] = round(
         B / res[f"train step {B}x8192 K256 (cfg2: fwd + Chamfer + bwd + Adam)"]["best_ms"] * 1e3)
+    tr = Trainer(state_dict=synth.seeded_state_dict(synth.ae_shapes(128, 16, 7), 11), amp=True)
+    rec(f"train step {B}x8192 K256, bf16 autocast", lambda: tr.step(xyz, start))
+    del tr
     from pcc_b200 import pppf
     model = pppf.PPPF_AE(K=512, k=0, d=16, L=7)
     model.load_state_dict(synth.seeded_module_state(model, 17))
