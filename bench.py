@@ -33,7 +33,7 @@ METRIC = "point clouds/sec (8192 pts, K=256) compress+Chamfer eval"
 UNIT = "clouds/s"
 N_POINTS, K_PATCH, K_OUT, D_LATENT, L_LEVELS, N0, ALPHA = 8192, 256, 128, 16, 7, 1024, 2
 BATCH = 32
-SA_DRAM_BYTES = 189.16e6  # dram read+write of one sa_chain_kernel launch (profiles/r01_step_kernels_ncu_full.txt: 100.72 + 88.44 MB)
+SA_DRAM_BYTES = 190.0e6  # dram read+write of one sa_chain2_kernel launch (profiles/r01_step_kernels_ncu_full.txt: 100.82 + 89.19 MB)
 POOL_BATCHES = 44  # 44 x 3.1 MB = 138 MB of distinct inputs > 126 MB L2 (no L2 flush needed between steps)
 WORKLOAD = ("cfg2-shape batch: 32 synthetic ModelNet40-shaped clouds x 8192 pts, K=256, S=64, d=16; "
             "compress -> decompress -> Chamfer + D1-PSNR eval (forward)")
