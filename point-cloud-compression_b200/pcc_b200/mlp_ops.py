@@ -10,7 +10,6 @@ Chains whose packed bf16 weights fit in shared memory run in ONE launch of the f
 fit (PointNet's 256->512->16 tail, the 1024->16384 decoder Linear) are still issued as plain library GEMMs
 (torch.addmm in bf16 -> cuBLAS) in round 1; the split point is chosen here.  There is no CPU path.
 """
-import ctypes
 import weakref
 
 import torch

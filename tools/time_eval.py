@@ -1,5 +1,5 @@
 """Device time of the eval stage (Chamfer + D1) on real reconstructions of the headline workload, per stage of roundtrip."""
-import os, sys, time
+import os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "point-cloud-compression_b200")]
