@@ -8,6 +8,7 @@
                          binary_array_to_byte_array, octree_np.encode, getDecodeFromPc) on seeded FPS centres.
 * ref_eval.npz        -- eval.py's calc_uc run from the reference's own source (extracted with ast), and the oracle's
                          p2plane PSNR (Open3D absent: unpinned).
+* ref_entropy.npz     -- outputs of the REFERENCE's own pn_kit.pmf_to_cdf / estimate_bits_from_pmf on seeded PMFs.
 * p3d_ops.npz         -- outputs of the oracle restatement of the PyTorch3D ops (knn_points, ball_query,
                          sample_farthest_points, chamfer_distance) on seeded inputs, cross-checked here against
                          an independent torch brute-force statement before being written.  PyTorch3D itself
@@ -235,6 +236,25 @@ def ref_eval():
     print("ref_eval.npz: uc", uc, "p2plane", pp[:, 0])
 
 
+def ref_entropy():
+    """pn_kit.pmf_to_cdf (the REFERENCE's own function, pn_kit.py:452-461) on seeded PMFs, and pn_kit.estimate_bits_from_pmf
+    (pn_kit.py:439-450); the 16-bit conversion and the coder are torchac's (absent: unpinned) and are not stored."""
+    pn = ref_loader.load("pn_kit")
+    out = {}
+    rng = np.random.default_rng(71)
+    for name, (n, L, peaky) in {"flat": (512, 7, 0.5), "peaky": (2048, 7, 8.0), "wide": (300, 16, 3.0)}.items():
+        pmf = torch.softmax(torch.from_numpy(rng.normal(size=(n, L)).astype(np.float32) * peaky), -1)
+        cdf = pn.pmf_to_cdf(pmf)
+        sym = torch.from_numpy(rng.integers(0, L, size=(n,)))
+        out[f"{name}_pmf"], out[f"{name}_cdf"] = pmf.numpy(), cdf.numpy()
+        out[f"{name}_sym"], out[f"{name}_bits"] = sym.numpy(), np.float64(pn.estimate_bits_from_pmf(pmf, sym).item())
+        L_ = pmf.shape[-1]
+        want = (cdf.mul(2 ** 16 - L_).round().to(torch.int16) + torch.arange(L_ + 1, dtype=torch.int16)).numpy().view(np.uint16)
+        assert np.array_equal(orc.pmf_to_cdf_u16(pmf.numpy()), want), name
+    np.savez_compressed(os.path.join(HERE, "ref_entropy.npz"), **out)
+    print("ref_entropy.npz:", {k: v.shape for k, v in out.items() if k.endswith("_cdf")})
+
+
 if __name__ == "__main__":
     ref_fps_gather()
     p3d_ops()
@@ -242,3 +262,4 @@ if __name__ == "__main__":
     ae_modules()
     ref_octree()
     ref_eval()
+    ref_entropy()

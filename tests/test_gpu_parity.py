@@ -481,3 +481,18 @@ def test_empty_and_degenerate_inputs(pcc):
         pcc.ops.knn(torch.rand(2, 5, 2, device=dev), torch.rand(2, 50, 2, device=dev), 4)      # D != 3
     with pytest.raises(RuntimeError):
         pcc.ops.knn(torch.rand(2, 5, 3), torch.rand(2, 50, 3), 4)                              # CPU tensors: no fallback
+
+
+@pytest.mark.parametrize("name", ["flat", "peaky", "wide"])
+def test_pmf_to_cdf_reference_golden(pcc, golden_dir, name):
+    """pcc_pmf_to_cdf_u16 against the reference's own pn_kit.pmf_to_cdf (tests/golden/ref_entropy.npz) + torchac's 16-bit
+    conversion; pcc_cdf_to_u16 on the reference's float CDF; the rate estimate of pn_kit.estimate_bits_from_pmf."""
+    g = np.load(os.path.join(golden_dir, "ref_entropy.npz"))
+    cdf = torch.from_numpy(g[f"{name}_cdf"])
+    L = cdf.shape[-1] - 1
+    want = (cdf.mul(2 ** 16 - L).round().to(torch.int16) + torch.arange(L + 1, dtype=torch.int16)).numpy().view(np.uint16)
+    assert np.array_equal(pcc.ops.pmf_to_cdf_u16(cu(g[f"{name}_pmf"])).cpu().numpy(), want)
+    assert np.array_equal(pcc.ops.cdf_to_u16(cu(g[f"{name}_cdf"])).cpu().numpy(), want)
+    from pcc_b200.train import estimate_bits_from_pmf
+    bits = float(estimate_bits_from_pmf(cu(g[f"{name}_pmf"]), torch.from_numpy(g[f"{name}_sym"]).cuda()))
+    assert abs(bits - float(g[f"{name}_bits"])) <= 1e-5 * float(g[f"{name}_bits"])

@@ -185,3 +185,13 @@ def test_range_coder_known_streams():
     data = orc.range_encode(cdf, bits)
     assert len(data) == 3 and np.array_equal(np.unpackbits(np.frombuffer(data, np.uint8))[:16], bits)
     assert np.array_equal(orc.range_decode(cdf, data), bits)
+
+
+@pytest.mark.parametrize("name", ["flat", "peaky", "wide"])
+def test_pmf_to_cdf_matches_reference_golden(golden_dir, name):
+    """The 16-bit CDF of the oracle equals torchac's conversion applied to the output of the reference's own pn_kit.pmf_to_cdf."""
+    g = np.load(os.path.join(golden_dir, "ref_entropy.npz"))
+    cdf = torch.from_numpy(g[f"{name}_cdf"])
+    L = cdf.shape[-1] - 1
+    want = (cdf.mul(2 ** 16 - L).round().to(torch.int16) + torch.arange(L + 1, dtype=torch.int16)).numpy().view(np.uint16)
+    assert np.array_equal(orc.pmf_to_cdf_u16(g[f"{name}_pmf"]), want)
