@@ -196,6 +196,27 @@ class PatchCodec:
                     uc=ops.uniformity_coefficient(original, decomp))
 
     @torch.no_grad()
+    def evaluate_to_csv(self, names, decomp, original, bits, output_file=None):
+        """The table eval.py:189-219 writes, for a batch: columns filename, p2pointPSNR, p2planePSNR, chamfer_distance,
+        n_points_input, n_points_output, bpp, 'uniformity coefficient', with the reference's rounding (3 decimals for the
+        PSNRs and the uniformity coefficient).  `bits` = compressed size of every cloud in bits (compress_to_files returns it)."""
+        import numpy as np
+        import pandas as pd
+        m = {k: v.cpu().numpy() for k, v in self.evaluate_all(decomp, original).items()}
+        df = pd.DataFrame()
+        df["filename"] = list(names)
+        df["p2pointPSNR"] = [round(float(v), 3) for v in m["d1_psnr"]]
+        df["p2planePSNR"] = [round(float(v), 3) for v in m["d2_psnr"]]
+        df["chamfer_distance"] = [float(v) for v in m["chamfer"]]
+        df["n_points_input"] = [int(original.shape[1])] * len(df)
+        df["n_points_output"] = [int(decomp.shape[1])] * len(df)
+        df["bpp"] = [float(b) / original.shape[1] for b in bits]
+        df["uniformity coefficient"] = [float(np.round(v, 3)) for v in m["uc"]]
+        if output_file is not None:
+            df.to_csv(output_file)
+        return df
+
+    @torch.no_grad()
     def roundtrip(self, xyz, start_idx=None, return_octree=False):
         """compress -> decompress -> eval for a batch; returns (latent_q int8 [B,S,d], centres, metrics [B,3], rec), plus
         the octree coder's output dict (None in 'fixed' mode) when return_octree is set."""

@@ -202,3 +202,10 @@ def test_file_formats_round_trip(setup, tmp_path, mode):
         cs = np.fromfile(tmp_path / (n + ".c.bin"), dtype=np.float32)
         assert cs.shape == (4,) and np.array_equal(cs[:3], c["center"][b].cpu().numpy()) and cs[3] == float(c["longest"][b])
         assert bits[b] == 8 * sum((tmp_path / (n + e)).stat().st_size for e in (".p.bin", ".s.bin", ".c.bin"))
+    # the evaluation table of eval.py:189-219 (same columns, same rounding)
+    df = codec.evaluate_to_csv(names, got, x, bits, str(tmp_path / "eval.csv"))
+    assert list(df.columns) == ["filename", "p2pointPSNR", "p2planePSNR", "chamfer_distance", "n_points_input",
+                                "n_points_output", "bpp", "uniformity coefficient"]
+    assert (tmp_path / "eval.csv").exists() and len(df) == 3 and df["n_points_output"][0] == 8192
+    psnr1, _ = orc.d1_psnr(x[0].cpu().numpy(), got[0].cpu().numpy())
+    assert abs(df["p2pointPSNR"][0] - round(psnr1, 3)) <= 2e-3 and df["bpp"][0] == bits[0] / 8192
