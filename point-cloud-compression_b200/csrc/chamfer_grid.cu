@@ -310,14 +310,16 @@ int chamfer_grid_run(const float *x, const float *y, int B, int P1, int P2, int 
     unsigned *starts = reinterpret_cast<unsigned *>(static_cast<char *>(extra) + pts);
     GridInfo *info = reinterpret_cast<GridInfo *>(static_cast<char *>(extra) + pts + ((tab + 15) / 16) * 16);
     const size_t smem = static_cast<size_t>(G) * G * G * 4 + 4;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static bool attr_done_dev[64] = {false};   // per device: the attribute belongs to the device's copy of the kernel
+    int attr_done_d = 0;
+    if (cudaGetDevice(&attr_done_d) != cudaSuccess || attr_done_d < 0 || attr_done_d >= 64) attr_done_d = 0;
+    if (!attr_done_dev[attr_done_d]) {
         const cudaError_t e = cudaFuncSetAttribute(grid_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 32 * 32 * 4 + 4);
         if (e != cudaSuccess) {
             set_error("chamfer grid: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
             return static_cast<int>(e);
         }
-        attr_done = true;
+        attr_done_dev[attr_done_d] = true;
     }
     grid_build_kernel<<<dim3(B, 2), GRID_BUILD_THREADS, smem, st>>>(x, y, P1, P2, G, sorted, starts, info);
     int rc = check_launch("grid_build_kernel");

@@ -592,15 +592,17 @@ PCC_API int pcc_knn_f32(const float *q, const float *p, int B, int P1, int P2, i
     // 8 warps per CTA; fewer when the key buffers would not fit (K = 1024 -> 16 KB per warp).
     constexpr int W = 8;
     const size_t smem = 3 * KNN_TILE * sizeof(float) + static_cast<size_t>(W) * cap * sizeof(unsigned long long);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set_dev[64] = {false};   // per device: the attribute belongs to the device's copy of the kernel
+    int attr_set_d = 0;
+    if (cudaGetDevice(&attr_set_d) != cudaSuccess || attr_set_d < 0 || attr_set_d >= 64) attr_set_d = 0;
+    if (!attr_set_dev[attr_set_d]) {
         cudaError_t e = cudaFuncSetAttribute(knn_warp_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              3 * KNN_TILE * 4 + W * 2 * PCC_MAX_KNN_K * 8);
         if (e != cudaSuccess) {
             set_error("pcc_knn_f32: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
             return static_cast<int>(e);
         }
-        attr_set = true;
+        attr_set_dev[attr_set_d] = true;
     }
     dim3 grid((P1 + W - 1) / W, B);
     knn_warp_kernel<W><<<grid, W * 32, smem, st>>>(q, p, P1, P2, K, cap, out_d2, out_idx, out_nn, centre_sub, nn_scale);
