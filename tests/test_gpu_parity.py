@@ -496,3 +496,26 @@ def test_pmf_to_cdf_reference_golden(pcc, golden_dir, name):
     from pcc_b200.train import estimate_bits_from_pmf
     bits = float(estimate_bits_from_pmf(cu(g[f"{name}_pmf"]), torch.from_numpy(g[f"{name}_sym"]).cuda()))
     assert abs(bits - float(g[f"{name}_bits"])) <= 1e-5 * float(g[f"{name}_bits"])
+
+
+def test_scene_scale_cfg5(pcc, orc):
+    """BASELINE cfg5 at full size: one 1,000,000-point S3DIS-shaped scene.  FPS and kNN patching are checked bit-exactly against
+    the oracle on a prefix the oracle finishes in seconds (the first 300 of the 7812 centres; 48 queries of the K = 256 search),
+    and on the whole problem through properties: distinct in-range indices, ascending distances, the query's own point first."""
+    scene = synth.scene_like(1_000_000, seed=3)
+    xyz = cu(scene)
+    start = np.array([12345], np.int64)
+    S = 1_000_000 * 2 // 256                                         # compress.py:93 with ALPHA = 2, K = 256 -> 7812
+    idx = pcc.ops.fps(xyz, S, cu(start), 1e10)
+    got = idx.cpu().numpy()
+    assert got.shape == (1, S) and len(np.unique(got)) == S and got.min() >= 0 and got.max() < 1_000_000
+    assert np.array_equal(got[:, :300], orc.fps(scene, 300, start, 1e10, threads=8))   # FPS is a prefix-stable sequence
+    centres = pcc.index_points(xyz, idx)
+    d, i, nn = pcc.ops.knn(centres, xyz, 256, return_nn=True)
+    dn, inn = d.cpu().numpy(), i.cpu().numpy()
+    assert (np.diff(dn, axis=2) >= 0).all() and (dn[:, :, 0] == 0).all()             # sorted; a centre is a cloud point
+    cen = centres.cpu().numpy()
+    assert np.array_equal(scene[0][inn[0, :, 0]], cen[0])                              # nearest = the centre itself (or a duplicate)
+    assert np.array_equal(nn.cpu().numpy()[0, ::500], scene[0][inn[0, ::500]])         # gathered neighbours = indexed points
+    od, oi, _ = orc.knn_points(cen[:, :48], scene, 256, False, threads=8)
+    assert np.array_equal(inn[:, :48], oi) and np.array_equal(dn[:, :48], od)
