@@ -226,12 +226,15 @@ class PatchCodec:
         return out + (c["octree"],) if return_octree else out
 
     @torch.no_grad()
-    def roundtrip_sweep(self, host_batches, start_idx=None, sink=None):
+    def roundtrip_sweep(self, host_batches, start_idx=None, sink=None, graphed=False):
         """compress -> decompress -> eval over a stream of HOST batches (the per-file loops of compress.py:78-155 and
         eval.py:167-221 as one sweep).  `host_batches` yields pinned CPU tensors [B,N,3]; the upload of batch s + 1 runs
         on a copy stream while batch s is being processed (two device staging buffers), and `sink(s, latent_q, centres,
         metrics, octree)` -- called on the compute stream's timeline -- is where the caller issues its device -> host
-        copies.  Returns the number of batches processed; the caller synchronises."""
+        copies; it may return a CUDA event that marks the end of those copies.
+        graphed=True replays one captured CUDA graph per staging buffer instead of launching the step's kernels one by one
+        (needs a fixed batch shape and an explicit start_idx; the tensors handed to `sink` are then the graph's static outputs,
+        reused two batches later -- after the event `sink` returned).  Returns the number of batches; the caller synchronises."""
         dev = next(self.ae.parameters()).device
         main = torch.cuda.current_stream(dev)
         copy = getattr(self, "_copy_stream", None)
@@ -239,6 +242,7 @@ class PatchCodec:
             copy = self._copy_stream = torch.cuda.Stream(dev)
         it = iter(host_batches)
         bufs, ready, free = [None, None], [torch.cuda.Event(), torch.cuda.Event()], [None, None]
+        drained = [None, None]
 
         def upload(slot, host):
             if bufs[slot] is None or bufs[slot].shape != host.shape:
@@ -250,6 +254,28 @@ class PatchCodec:
                 ready[slot].record(copy)
 
         nxt = next(it, None)
+        graphs = None
+        if graphed and nxt is not None:
+            if start_idx is None:
+                raise ValueError("roundtrip_sweep(graphed=True) needs an explicit start_idx (the CPU RNG draw cannot be captured)")
+            key = (tuple(nxt.shape), start_idx.data_ptr(), self.centre_mode)
+            cache = getattr(self, "_sweep_graphs", None)
+            if cache is None or cache[0] != key:
+                sb = [nxt.to(dev), nxt.to(dev)]         # static staging buffers, filled with real data for the capture
+                side = torch.cuda.Stream(dev)
+                side.wait_stream(main)
+                with torch.cuda.stream(side):           # warm-up outside the capture: weight packing, attribute set-up
+                    self.roundtrip(sb[0], start_idx, return_octree=True)
+                main.wait_stream(side)
+                torch.cuda.synchronize(dev)
+                gs = []
+                for slot in range(2):
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        outs = self.roundtrip(sb[slot], start_idx, return_octree=True)
+                    gs.append((g, outs))
+                cache = self._sweep_graphs = (key, sb, gs)
+            bufs, graphs = list(cache[1]), cache[2]
         if nxt is not None:
             upload(0, nxt)
         s = 0
@@ -259,10 +285,47 @@ class PatchCodec:
             if nxt is not None:
                 upload(slot ^ 1, nxt)
             main.wait_event(ready[slot])
-            lat, cen, met, _, octree = self.roundtrip(bufs[slot], start_idx, return_octree=True)
+            if graphs is not None:
+                if drained[slot] is not None:
+                    main.wait_event(drained[slot])     # the caller's copies of this graph's previous outputs are done
+                graphs[slot][0].replay()
+                lat, cen, met, _, octree = graphs[slot][1]
+            else:
+                lat, cen, met, _, octree = self.roundtrip(bufs[slot], start_idx, return_octree=True)
             free[slot] = torch.cuda.Event()
             free[slot].record(main)
             if sink is not None:
-                sink(s, lat, cen, met, octree)
+                drained[slot] = sink(s, lat, cen, met, octree)
             s += 1
         return s
+
+    def graphed_roundtrip(self, B, N):
+        """Capture roundtrip() for [B, N, 3] inputs into a CUDA graph and return `run(xyz, start_idx)`, which copies the inputs
+        into the graph's static buffers and replays it: for small batches (cfg1: one cloud) the ~25 launches of the step are
+        latency bound on the host side, a replay issues them as one.  The returned tensors are the graph's static outputs
+        (overwritten by the next call)."""
+        dev = next(self.ae.parameters()).device
+        xs = torch.rand((B, N, 3), dtype=torch.float32, device=dev)   # a generic cloud for the warm-up / capture launches
+        ss = torch.zeros((B,), dtype=torch.int64, device=dev)        # (all-equal points would be the search's worst case)
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):                      # warm-up outside the capture: weight packing, attribute set-up
+            for _ in range(2):
+                self.roundtrip(xs, ss)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        from . import _lib
+        lib = _lib.load()
+        graph = torch.cuda.CUDAGraph()
+        n0 = lib.pcc_launch_count()
+        with torch.cuda.graph(graph):
+            outs = self.roundtrip(xs, ss)
+        launches = int(lib.pcc_launch_count() - n0)    # kernels of this library inside one replay
+
+        def run(xyz, start_idx):
+            xs.copy_(xyz, non_blocking=True)
+            ss.copy_(start_idx, non_blocking=True)
+            graph.replay()
+            return outs
+
+        run.launches = launches
+        return run

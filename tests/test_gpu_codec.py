@@ -119,6 +119,12 @@ def test_roundtrip_sweep_matches_per_batch_calls(setup):
 
     assert codec.roundtrip_sweep(iter(host), start, sink) == 5
     torch.cuda.synchronize()
+    eager = dict(got)
+    got.clear()
+    assert codec.roundtrip_sweep(iter(host), start, sink, graphed=True) == 5      # CUDA-graph replay: same results
+    torch.cuda.synchronize()
+    for s in range(5):
+        assert all(torch.equal(a, b) for a, b in zip(got[s], eager[s]))
     for s, h in enumerate(host):
         lat, cen, met, _, octree = codec.roundtrip(h.cuda(), start, return_octree=True)
         assert torch.equal(got[s][0], lat.cpu()) and torch.equal(got[s][1], cen.cpu())

@@ -81,6 +81,8 @@ def main():
         codec = PatchCodec(ae, centre_mode=mode)
         rec(f"roundtrip {B}x8192 centre_mode={mode}", lambda: codec.roundtrip(xyz, start))
         res[f"roundtrip {B}x8192 centre_mode={mode}"]["clouds_per_s"] = round(B / res[f"roundtrip {B}x8192 centre_mode={mode}"]["best_ms"] * 1e3)
+    codec1 = PatchCodec(ae, centre_mode="coded")
+    rec("roundtrip 1x8192 (cfg1: one cloud, compress + decompress + eval latency)", lambda: codec1.roundtrip(x1, start[:1]))
     from pcc_b200.train import Trainer
     tr = Trainer(state_dict=synth.seeded_state_dict(synth.ae_shapes(128, 16, 7), 11))
     rec(f"train step {B}x8192 K256 (cfg2: fwd + Chamfer + bwd + Adam)", lambda: tr.step(xyz, start))
