@@ -138,9 +138,15 @@ class FoldingNet(nn.Module):
                                   nn.Conv1d(128, 3, 1))
 
     def build_grid(self, batch_points, device):
-        x = torch.linspace(-1, 1, self.grid_size)
-        gx, gy = torch.meshgrid(x, x, indexing="ij")
-        return torch.stack([gx, gy], dim=-1).reshape(-1, 2).unsqueeze(0).repeat(batch_points, 1, 1).to(device)
+        """PPPF_AE.py:80-89; the grid is a constant: built once per (batch, device) and kept on the device."""
+        key = (batch_points, str(device))
+        cached = getattr(self, "_grid_cache", None)
+        if cached is None or cached[0] != key:
+            x = torch.linspace(-1, 1, self.grid_size)
+            gx, gy = torch.meshgrid(x, x, indexing="ij")
+            grid = torch.stack([gx, gy], dim=-1).reshape(-1, 2).unsqueeze(0).repeat(batch_points, 1, 1).to(device)
+            cached = self._grid_cache = (key, grid)
+        return cached[1]
 
     @staticmethod
     def _stage(mlp, local, latent, n_local, latent_first):

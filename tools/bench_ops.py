@@ -97,6 +97,10 @@ def main():
     model = model.cuda().eval()
     with torch.no_grad():
         rec("PPPF_AE forward 64x2048 (cfg3: PointNet++ SA x3 + FoldingNet)", lambda: model(sh))
+        from pcc_b200 import graph as pgraph
+        replay = pgraph.capture(model, sh)
+        assert torch.equal(replay(sh)[0], model(sh)[0])
+        rec("PPPF_AE forward 64x2048, CUDA-graph replay", lambda: replay(sh))
     res["PPPF_AE forward 64x2048 (cfg3: PointNet++ SA x3 + FoldingNet)"]["clouds_per_s"] = round(
         64 / res["PPPF_AE forward 64x2048 (cfg3: PointNet++ SA x3 + FoldingNet)"]["best_ms"] * 1e3)
     if os.environ.get("SCENE", "1") == "1":
