@@ -242,9 +242,10 @@ def run_b200(args):
     launches = run.launches * args.steps
     value = world * BATCH * args.steps / (dev_ms / 1e3)
 
-    # ---- the same K steps launched kernel by kernel, with CUDA events around the dominant kernels (a graph replay has no
-    # per-kernel boundaries to record on): per-kernel averages for the roofline, and the eager step time for comparison ----
-    record["on"] = True
+    # ---- the same steps launched kernel by kernel: (i) plain, for the eager step time; (ii) with CUDA events around the
+    # dominant kernels for the roofline (a graph replay has no per-kernel boundaries to record on).  In (ii) every step starts
+    # with a short device-side sleep so that the host has the step's launches queued before the GPU reaches them: otherwise an
+    # event pair also measures the Python time between `e0.record()` and the launch whenever the host falls behind. ----
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     g0.record()
@@ -252,8 +253,13 @@ def run_b200(args):
         codec.roundtrip(batch_of(pool_dev, args.warmup + s), start_idx)
     g1.record()
     barrier()
-    record["on"] = False
     eager_ms = max_over_ranks(g0.elapsed_time(g1)) / args.steps
+    record["on"] = True
+    for s in range(min(args.steps, 100)):
+        torch.cuda._sleep(4_000_000)                # ~2 ms at 1.965 GHz
+        codec.roundtrip(batch_of(pool_dev, args.warmup + s), start_idx)
+    barrier()
+    record["on"] = False
     clk = clocks.stop() if rank == 0 else None
     kernel_ms = {k: float(np.mean([a.elapsed_time(b) for a, b in v])) for k, v in events.items() if v}
 

@@ -17,7 +17,7 @@ def _worker(rank, world, port, n_total, q):
     b, e = shard_range(n_total, rank, world)
     local = torch.arange(b, e, dtype=torch.float64)[:, None] * torch.tensor([1.0, 10.0, 100.0], dtype=torch.float64)
     full = gather_rows(local, n_total)
-    q.put((rank, full))
+    q.put((rank, full.tolist()))   # plain lists: a shared-memory tensor would need this process alive until it is received
     dist.destroy_process_group()
 
 
@@ -36,7 +36,11 @@ def test_shard_range_partitions():
 def test_gather_rows_world2_gloo():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    n_total, world, port = 7, 2, 29573
+    import socket
+    with socket.socket() as sk:          # a free port: the suite may run beside other rendezvous on this host
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    n_total, world = 7, 2
     procs = [ctx.Process(target=_worker, args=(r, world, port, n_total, q)) for r in range(world)]
     for p in procs:
         p.start()
@@ -46,4 +50,4 @@ def test_gather_rows_world2_gloo():
         assert p.exitcode == 0
     want = torch.arange(n_total, dtype=torch.float64)[:, None] * torch.tensor([1.0, 10.0, 100.0], dtype=torch.float64)
     for r in range(world):
-        assert torch.equal(got[r], want)
+        assert torch.equal(torch.tensor(got[r], dtype=torch.float64), want)
