@@ -13,6 +13,8 @@ def main(path):
         if r["Metric Name"] != "gpu__time_duration.sum":
             continue
         name = re.sub(r"\(.*", "", r["Kernel Name"])[:72]
+        if "spin_kernel" in name:   # bench.py's device-side sleep in front of each instrumented step: not part of the step
+            continue
         v = float(r["Metric Value"].replace(",", ""))
         u = r["Metric Unit"]
         ms = v / 1e6 if u.startswith("n") else v / 1e3 if u.startswith("u") else v
