@@ -77,7 +77,8 @@ range_encode_kernel(const uint16_t *__restrict__ cdf, const int16_t *__restrict_
     unsigned long long pending = 0;
     const int max_symbol = Lp - 2;
     for (int i = 0; i < n_sym; ++i) {
-        const int v = s[i];
+        int v = s[i];
+        v = v < 0 ? 0 : (v > max_symbol ? max_symbol : v);   // out-of-range symbols are the caller's error; never index past the row
         const unsigned long long span = static_cast<unsigned long long>(high) - static_cast<unsigned long long>(low) + 1ull;
         const unsigned c_low = c[static_cast<size_t>(i) * Lp + v];
         const unsigned c_high = v == max_symbol ? 0x10000u : c[static_cast<size_t>(i) * Lp + v + 1];

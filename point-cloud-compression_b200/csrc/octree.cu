@@ -242,7 +242,7 @@ octree_decode_kernel(const uint8_t *__restrict__ bits, const int *__restrict__ n
     __shared__ int warp_tot[OCT_THREADS / 32];
     const int b = blockIdx.x, tid = threadIdx.x;
     const uint8_t *in = bits + static_cast<size_t>(b) * max_bits;
-    const int nbits = nbits_in[b];
+    const int nbits = nbits_in[b] < max_bits ? (nbits_in[b] > 0 ? nbits_in[b] : 0) : max_bits;   // never read past the row
     float *o = out + static_cast<size_t>(b) * cap * 3;
     if (mode == 0) {
         if (tid < cap) {
