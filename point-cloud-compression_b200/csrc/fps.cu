@@ -14,7 +14,8 @@
 //
 // fps_grid_kernel: clouds with N > 8192 (the 1M-point scene).  The cloud is spread
 //   over C = ceil(N/8192) co-resident CTAs (cooperative launch), still register resident; per iteration each
-//   CTA publishes its best key with one atomicMax and the C CTAs meet at a monotonic-counter barrier.
+//   CTA publishes its best candidate as tagged 64-bit words in its own slot and polls the other CTAs' slots
+//   (no atomics, no fences: see the comment above the kernel).
 #include "pcc_common.cuh"
 
 namespace pcc {
@@ -162,30 +163,60 @@ fps_block_kernel(const float *__restrict__ xyz, int N, int npoint, const int64_t
 }
 
 // ---- multi-CTA variant ----------------------------------------------------------------------------------
-struct FpsGridWs {             // one per cloud, zero-filled by the host before the launch
-    unsigned long long key[3]; // rotating arg-max slots: (d2 bits << 32) | ~idx
-    unsigned counter;          // monotonic barrier counter
-    unsigned pad;
+// Grid-wide arg-max without atomics or fences.  Every CTA publishes its candidate per iteration into its own 32-byte slot of a
+// double-buffered table as self-describing 64-bit words,
+//     w0 = d2 bits << 32 | tag << 21 | (2^21 - 1 - index)      tag = (iteration + 1) mod 2^11
+//     w1 = x bits  << 32 | tag << 21 | z bits [31:11]          (WIDE slots only)
+//     w2 = y bits  << 32 | tag << 21 | z bits [10:0] << 10     (WIDE slots only)
+// and warp 0 of every CTA polls all the slots of its cloud until their tags are this iteration's, taking the maximum w0
+// (largest d2, then lowest index: all fresh words carry the same tag).  Each word is written and read as one relaxed 8-byte
+// access, so a value and its tag can never be seen apart, and nothing else needs ordering (the coordinates are read-only
+// input).  A slot of parity (i & 1) is rewritten at iteration i + 2, which a CTA reaches only after every CTA has published
+// iteration i + 1, i.e. has finished reading iteration i.
+// WIDE slots carry the winner's coordinates, saving the dependent load of xyz[winner] (one L2 round trip) at three times the
+// polling traffic; that traffic (C^2 slot reads per iteration on a few L2 lines) is what costs at large C, so WIDE is used up
+// to 128 CTAs per cloud.  Measured per iteration on B200 (C = 2 / 13 / 123 CTAs per cloud; C = 147 is 4.0-4.9 us for every
+// variant, with more spread between boxes than between variants):
+//     atomicMax + arrival counter + two fences + load of the winner (previous version)      -    / -         / 4.60 us
+//     one word per slot + load of the winner                                                  1.93 / 2.06-2.72 / 3.76-3.89 us
+//     WIDE slots                                                                              1.84 / 1.88-1.96 / 3.87-4.00 us
+// and, not kept: one polling thread per slot instead of one warp (4.16 at C = 123: more pollers, more contention), eight
+// replicas of the table (no better), a reducer CTA that republishes the winner to an outbox (two store -> poll hops: 3.8 us
+// already at C = 2).
+struct FpsGridWs {             // workspace unit per SM: 2 buffers x 32-byte slot per CTA, zero-filled by the host
+    unsigned long long word[8];
 };
 
 constexpr int GRID_THREADS = 1024;
 constexpr int GRID_PPT = 8;
 constexpr int GRID_PTS_PER_CTA = GRID_THREADS * GRID_PPT;
+constexpr unsigned GRID_IDX_MASK = (1u << 21) - 1u;   // 148 CTAs x 8192 points < 2^21
+constexpr int GRID_WIDE_MAX_CTAS = 128;
 
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <bool WIDE>
 __global__ void __launch_bounds__(GRID_THREADS, 1)
 fps_grid_kernel(const float *__restrict__ xyz, int N, int npoint, const int64_t *__restrict__ start_idx,
-                float init_dist, int64_t *__restrict__ out_idx, FpsGridWs *ws, int ctas_per_cloud, int cloud0,
+                float init_dist, int64_t *__restrict__ out_idx, unsigned long long *ws, int ctas_per_cloud, int cloud0,
                 float *__restrict__ out_xyz, float quant_cube) {
     constexpr int NWARPS = GRID_THREADS / 32;
     __shared__ FpsSlots slots;
-    __shared__ unsigned long long s_win;
+    __shared__ unsigned long long s_w0, s_w1, s_w2;
     const int cloud_local = blockIdx.x / ctas_per_cloud;
     const int part = blockIdx.x % ctas_per_cloud;
     const int b = cloud0 + cloud_local;
     const int tid = threadIdx.x;
     const float *pc = xyz + static_cast<size_t>(b) * N * 3;
     int64_t *out = out_idx + static_cast<size_t>(b) * npoint;
-    FpsGridWs *w = ws + cloud_local;
+    unsigned long long *table = ws + static_cast<size_t>(cloud_local) * 8 * ctas_per_cloud;   // [2][ctas_per_cloud][4]
     const int base = part * GRID_PTS_PER_CTA;
 
     float px[GRID_PPT], py[GRID_PPT], pz[GRID_PPT], md[GRID_PPT];
@@ -231,25 +262,79 @@ fps_grid_kernel(const float *__restrict__ xyz, int N, int npoint, const int64_t 
         unsigned gidx = static_cast<unsigned>(base + slot * GRID_THREADS + tid);
         if (gidx >= static_cast<unsigned>(N)) gidx = 0x7fffffffu;  // padding lanes: above every real index
         block_argmax<NWARPS>(slots, i & 1, bits, gidx, x, y, z, w_bits, w_idx, bx, by, bz);
-        if (tid == 0) {
-            const unsigned long long key = (static_cast<unsigned long long>(w_bits) << 32) | (0xffffffffu - w_idx);
-            if (part == 0) w->key[(i + 1) % 3] = 0ull;  // slot of iteration i+1: last read before barrier i-1
-            atomicMax(&w->key[i % 3], key);
-            __threadfence();
-            atomicAdd(&w->counter, 1u);
-            const unsigned target = static_cast<unsigned>(ctas_per_cloud) * static_cast<unsigned>(i + 1);
-            while (*reinterpret_cast<volatile unsigned *>(&w->counter) < target) {
+        // every CTA holds at least one real point and padding lanes lose ties, so w_idx < N < 2^21
+        const unsigned long long tag = static_cast<unsigned long long>((i + 1) & 2047) << 21;
+        constexpr unsigned long long TAG_MASK = 2047ull << 21;
+        unsigned long long *row = table + static_cast<size_t>(i & 1) * ctas_per_cloud * 4;
+        const unsigned long long my0 = (static_cast<unsigned long long>(w_bits) << 32) | tag | static_cast<unsigned long long>(GRID_IDX_MASK - w_idx);
+        if constexpr (!WIDE) {
+            if (tid < 32) {
+                if (tid == 0) st_relaxed_u64(row + part * 4, my0);
+                unsigned long long best = 0ull;
+                for (int p = tid; p < ctas_per_cloud; p += 32) {
+                    unsigned long long v;
+                    do {
+                        v = ld_relaxed_u64(row + p * 4);
+                    } while ((v & TAG_MASK) != tag);
+                    best = v > best ? v : best;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+                    best = other > best ? other : best;
+                }
+                if (tid == 0) s_w0 = best;
             }
-            __threadfence();
-            s_win = *reinterpret_cast<volatile unsigned long long *>(&w->key[i % 3]);
+            __syncthreads();
+            far = static_cast<int>(GRID_IDX_MASK - (static_cast<unsigned>(s_w0) & GRID_IDX_MASK));
+            cx = __ldg(pc + static_cast<size_t>(far) * 3 + 0);
+            cy = __ldg(pc + static_cast<size_t>(far) * 3 + 1);
+            cz = __ldg(pc + static_cast<size_t>(far) * 3 + 2);
+        } else {
+            if (tid < 32) {
+                if (tid == 0) {
+                    const unsigned zb = __float_as_uint(bz);
+                    st_relaxed_u64(row + part * 4 + 0, my0);
+                    st_relaxed_u64(row + part * 4 + 1, (static_cast<unsigned long long>(__float_as_uint(bx)) << 32) | tag | (zb >> 11));
+                    st_relaxed_u64(row + part * 4 + 2, (static_cast<unsigned long long>(__float_as_uint(by)) << 32) | tag |
+                                                           static_cast<unsigned long long>((zb & 2047u) << 10));
+                }
+                unsigned long long best = 0ull, b1 = 0ull, b2 = 0ull;
+                for (int p = tid; p < ctas_per_cloud; p += 32) {
+                    unsigned long long v0, v1, v2;
+                    do {
+                        v0 = ld_relaxed_u64(row + p * 4 + 0);
+                        v1 = ld_relaxed_u64(row + p * 4 + 1);
+                        v2 = ld_relaxed_u64(row + p * 4 + 2);
+                    } while ((v0 & TAG_MASK) != tag || (v1 & TAG_MASK) != tag || (v2 & TAG_MASK) != tag);
+                    if (v0 > best || p == tid) {
+                        best = v0;
+                        b1 = v1;
+                        b2 = v2;
+                    }
+                }
+                unsigned long long top = best;   // lanes past the last slot hold 0, below every fresh word unless tag == 0 ...
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const unsigned long long other = __shfl_xor_sync(0xffffffffu, top, o);
+                    top = other > top ? other : top;
+                }
+                // ... where an empty lane's 0 can at most tie with a real word (d2 = 0, index 2^21 - 1): first REAL owner
+                const unsigned owner = __ffs(__ballot_sync(0xffffffffu, tid < ctas_per_cloud && best == top)) - 1;
+                if (tid == owner) {
+                    s_w0 = best;
+                    s_w1 = b1;
+                    s_w2 = b2;
+                }
+            }
+            __syncthreads();
+            const unsigned long long t1 = s_w1, t2 = s_w2;
+            far = static_cast<int>(GRID_IDX_MASK - (static_cast<unsigned>(s_w0) & GRID_IDX_MASK));
+            cx = __uint_as_float(static_cast<unsigned>(t1 >> 32));
+            cy = __uint_as_float(static_cast<unsigned>(t2 >> 32));
+            cz = __uint_as_float(((static_cast<unsigned>(t1) & GRID_IDX_MASK) << 11) | ((static_cast<unsigned>(t2) >> 10) & 2047u));
         }
-        __syncthreads();
-        const unsigned long long win = s_win;
-        far = static_cast<int>(0xffffffffu - static_cast<unsigned>(win & 0xffffffffu));
-        cx = __ldcg(pc + static_cast<size_t>(far) * 3 + 0);
-        cy = __ldcg(pc + static_cast<size_t>(far) * 3 + 1);
-        cz = __ldcg(pc + static_cast<size_t>(far) * 3 + 2);
-        // s_win is rewritten only after the next block_argmax's __syncthreads, which every thread reaches
+        // s_w0..2 are rewritten only after the next block_argmax's __syncthreads, which every thread reaches
         // after reading it here.
     }
 }
@@ -288,22 +373,23 @@ PCC_API int pcc_fps_f32(const float *xyz, int B, int N, int npoint, const int64_
     PCC_REQUIRE(workspace, "pcc_fps_f32: N=%d needs a workspace of pcc_fps_workspace_bytes()", N);
     const int sms = num_sms();
     const int C = (N + GRID_PTS_PER_CTA - 1) / GRID_PTS_PER_CTA;
-    if (C > sms) {
+    if (C > sms || static_cast<long long>(C) * GRID_PTS_PER_CTA > GRID_IDX_MASK) {
         set_error("pcc_fps_f32: N=%d exceeds the co-resident capacity %d", N, sms * GRID_PTS_PER_CTA);
         return PCC_ERR_UNSUPPORTED;
     }
     const int clouds_per_launch = sms / C;
-    FpsGridWs *ws = static_cast<FpsGridWs *>(workspace);
+    unsigned long long *ws = static_cast<unsigned long long *>(workspace);   // 2 x 32 bytes per CTA of a launch
     for (int c0 = 0; c0 < B; c0 += clouds_per_launch) {
         int nc = B - c0 < clouds_per_launch ? B - c0 : clouds_per_launch;
-        cudaError_t e = cudaMemsetAsync(ws, 0, sizeof(FpsGridWs) * nc, st);
+        cudaError_t e = cudaMemsetAsync(ws, 0, sizeof(unsigned long long) * 8 * nc * C, st);
         if (e != cudaSuccess) {
             set_error("pcc_fps_f32: memset failed: %s", cudaGetErrorString(e));
             return static_cast<int>(e);
         }
         int ctas = C, cloud0 = c0;
         void *args[] = {&xyz, &N, &npoint, &start_idx, &init_dist, &out_idx, &ws, &ctas, &cloud0, &out_xyz, &quant_cube};
-        e = cudaLaunchCooperativeKernel(reinterpret_cast<void *>(fps_grid_kernel), dim3(nc * C), dim3(GRID_THREADS),
+        void *fn = C <= GRID_WIDE_MAX_CTAS ? reinterpret_cast<void *>(fps_grid_kernel<true>) : reinterpret_cast<void *>(fps_grid_kernel<false>);
+        e = cudaLaunchCooperativeKernel(fn, dim3(nc * C), dim3(GRID_THREADS),
                                         args, 0, st);
         if (e != cudaSuccess) {
             set_error("pcc_fps_f32: cooperative launch failed: %s", cudaGetErrorString(e));

@@ -71,7 +71,8 @@ def test_fps_sizes_vs_oracle(pcc, orc, B, N, S):
 
 def test_fps_multi_cta_cloud(pcc, orc):
     """N > 8192: the cooperative multi-CTA kernel (the 1M-point scene path at a size the oracle finishes fast)."""
-    for B, N, S in [(1, 20000, 200), (2, 9000, 64), (1, 100_000, 64)]:
+    # 3, 2 and 13 CTAs per cloud (slots that carry the winner's coordinates) and 135 (> 128: index-only slots)
+    for B, N, S in [(1, 20000, 200), (2, 9000, 64), (1, 100_000, 64), (1, 1_100_000, 24)]:
         xyz = synth.scene_like(N, seed=N)[0][None].repeat(B, 0) if N > 50000 else synth.uniform_cube(B, N, seed=N)
         start = np.arange(B) * 17
         got = pcc.ops.fps(cu(xyz), S, cu(start), 1e10).cpu().numpy()
