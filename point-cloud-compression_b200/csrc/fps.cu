@@ -181,8 +181,9 @@ fps_block_kernel(const float *__restrict__ xyz, int N, int npoint, const int64_t
 //     one word per slot + load of the winner                                                  1.93 / 2.06-2.72 / 3.76-3.89 us
 //     WIDE slots                                                                              1.84 / 1.88-1.96 / 3.87-4.00 us
 // and, not kept: one polling thread per slot instead of one warp (4.16 at C = 123: more pollers, more contention), eight
-// replicas of the table (no better), a reducer CTA that republishes the winner to an outbox (two store -> poll hops: 3.8 us
-// already at C = 2).
+// replicas of the table (no better), a reducer CTA that republishes the winner to an outbox (3.8 us already at C = 2) and
+// two-level groups of 8..32 CTAs (5.4-5.7 us at C = 123): a second, dependent store -> poll hop costs 1.3 us or more, far more
+// than the polling traffic it saves.
 struct FpsGridWs {             // workspace unit per SM: 2 buffers x 32-byte slot per CTA, zero-filled by the host
     unsigned long long word[8];
 };
