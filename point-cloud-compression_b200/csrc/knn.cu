@@ -9,8 +9,10 @@
 //   by the CTA's warps.  Each lane evaluates one candidate per step and packs (d2 bits, idx) into a u64 key
 //   whose unsigned order is the lexicographic order.  Keys below the current K-th best are appended (ballot +
 //   popc compaction) to a per-warp shared buffer of 2*Kp keys; when it fills, a warp-level bitonic sort keeps
-//   the best K and tightens the threshold.  After warm-up almost every 32-candidate step is rejected by one
-//   ballot, so the cost is ~12 instructions per pair.
+//   the best K and tightens the threshold.  After warm-up almost every step is rejected: the loop takes 128
+//   candidates per step (one LDS.128 per candidate from an (x, y, z, -) tile), compares the smallest of a
+//   lane's four d2 bit patterns with the threshold's and leaves on one vote -- 12 instructions per 32 pairs
+//   (ncu, 7812 x 1M, K = 256: the earlier one-ballot-per-32 loop with an SoA tile executed 47).
 //
 // knn_thread_kernel (K <= 32, small candidate sets, many queries -- the in-patch 256x256 K=16 search of
 //   pn_kit.SetAbstraction): one THREAD per query, sorted top-K in registers, candidates read as float4
@@ -57,10 +59,8 @@ knn_warp_kernel(const float *__restrict__ q, const float *__restrict__ p, int P1
                 float *__restrict__ out_d2, int64_t *__restrict__ out_idx, float *__restrict__ out_nn,
                 int centre_sub, float nn_scale) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float *tx = reinterpret_cast<float *>(smem_raw);
-    float *ty = tx + KNN_TILE;
-    float *tz = ty + KNN_TILE;
-    unsigned long long *all_keys = reinterpret_cast<unsigned long long *>(tz + KNN_TILE);
+    float4 *tile = reinterpret_cast<float4 *>(smem_raw);                                  // (x, y, z, -) per candidate
+    unsigned long long *all_keys = reinterpret_cast<unsigned long long *>(tile + KNN_TILE);
 
     const int b = blockIdx.y;
     const unsigned lane = lane_id();
@@ -79,31 +79,54 @@ knn_warp_kernel(const float *__restrict__ q, const float *__restrict__ p, int P1
     }
     int count = 0;
     unsigned long long thresh = KEY_MAX;
+    unsigned thresh_hi = 0xffffffffu;   // d2 bit pattern of the threshold: d2 >= +0, so unsigned order = value order
+
+    // exact step for 32 candidates: append the keys below the threshold, reselect when the buffer is full
+    auto consider = [&](unsigned d2_bits, unsigned idx, bool valid) {
+        const unsigned long long key = valid ? ((static_cast<unsigned long long>(d2_bits) << 32) | idx) : KEY_MAX;
+        const bool pass = key < thresh;
+        const unsigned m = __ballot_sync(FULL_MASK, pass);
+        if (m == 0u) return;
+        if (pass) keys[count + __popc(m & ((1u << lane) - 1u))] = key;
+        count += __popc(m);
+        if (count + 32 > cap) {
+            __syncwarp();
+            count = warp_select(keys, count, cap, K);
+            thresh = count >= K ? keys[K - 1] : KEY_MAX;
+            thresh_hi = static_cast<unsigned>(thresh >> 32);
+        }
+    };
 
     for (int t0 = 0; t0 < P2; t0 += KNN_TILE) {
         const int tn = min(KNN_TILE, P2 - t0);
         __syncthreads();  // previous tile fully consumed
-        for (int e = threadIdx.x; e < tn * 3; e += WARPS * 32) {
-            const float v = pc[static_cast<size_t>(t0) * 3 + e];
-            const int pt = e / 3, c = e - pt * 3;
-            (c == 0 ? tx : (c == 1 ? ty : tz))[pt] = v;
+        for (int pt = threadIdx.x; pt < tn; pt += WARPS * 32) {
+            const float *src = pc + static_cast<size_t>(t0 + pt) * 3;
+            tile[pt] = make_float4(src[0], src[1], src[2], 0.0f);
         }
         __syncthreads();
         if (!active) continue;
-        for (int c0 = 0; c0 < tn; c0 += 32) {
+        // 128 candidates per step, one LDS.128 each; a step whose four d2 are all above the threshold's d2 costs one vote
+        const int full = tn & ~127;
+        for (int c0 = 0; c0 < full; c0 += 128) {
+            const float4 a0 = tile[c0 + lane], a1 = tile[c0 + 32 + lane], a2 = tile[c0 + 64 + lane], a3 = tile[c0 + 96 + lane];
+            const unsigned d0 = __float_as_uint(dist2_rn(qx, qy, qz, a0.x, a0.y, a0.z));
+            const unsigned d1 = __float_as_uint(dist2_rn(qx, qy, qz, a1.x, a1.y, a1.z));
+            const unsigned d2 = __float_as_uint(dist2_rn(qx, qy, qz, a2.x, a2.y, a2.z));
+            const unsigned d3 = __float_as_uint(dist2_rn(qx, qy, qz, a3.x, a3.y, a3.z));
+            const unsigned dmin = min(min(d0, d1), min(d2, d3));
+            if (!__any_sync(FULL_MASK, dmin <= thresh_hi)) continue;
+            const unsigned base = static_cast<unsigned>(t0 + c0) + lane;
+            consider(d0, base, true);
+            consider(d1, base + 32u, true);
+            consider(d2, base + 64u, true);
+            consider(d3, base + 96u, true);
+        }
+        for (int c0 = full; c0 < tn; c0 += 32) {
             const int j = c0 + lane;
-            unsigned long long key = KEY_MAX;
-            if (j < tn) key = pack_key(dist2_rn(qx, qy, qz, tx[j], ty[j], tz[j]), static_cast<unsigned>(t0 + j));
-            const bool pass = key < thresh;
-            const unsigned m = __ballot_sync(FULL_MASK, pass);
-            if (m == 0u) continue;
-            if (pass) keys[count + __popc(m & ((1u << lane) - 1u))] = key;
-            count += __popc(m);
-            if (count + 32 > cap) {
-                __syncwarp();
-                count = warp_select(keys, count, cap, K);
-                thresh = count >= K ? keys[K - 1] : KEY_MAX;
-            }
+            const bool valid = j < tn;
+            const float4 a = tile[valid ? j : 0];
+            consider(__float_as_uint(dist2_rn(qx, qy, qz, a.x, a.y, a.z)), static_cast<unsigned>(t0 + j), valid);
         }
     }
     if (!active) return;
@@ -591,13 +614,13 @@ PCC_API int pcc_knn_f32(const float *q, const float *p, int B, int P1, int P2, i
     const int cap = 2 * kp;
     // 8 warps per CTA; fewer when the key buffers would not fit (K = 1024 -> 16 KB per warp).
     constexpr int W = 8;
-    const size_t smem = 3 * KNN_TILE * sizeof(float) + static_cast<size_t>(W) * cap * sizeof(unsigned long long);
+    const size_t smem = KNN_TILE * sizeof(float4) + static_cast<size_t>(W) * cap * sizeof(unsigned long long);
     static bool attr_set_dev[64] = {false};   // per device: the attribute belongs to the device's copy of the kernel
     int attr_set_d = 0;
     if (cudaGetDevice(&attr_set_d) != cudaSuccess || attr_set_d < 0 || attr_set_d >= 64) attr_set_d = 0;
     if (!attr_set_dev[attr_set_d]) {
         cudaError_t e = cudaFuncSetAttribute(knn_warp_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             3 * KNN_TILE * 4 + W * 2 * PCC_MAX_KNN_K * 8);
+                                             KNN_TILE * 16 + W * 2 * PCC_MAX_KNN_K * 8);
         if (e != cudaSuccess) {
             set_error("pcc_knn_f32: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
             return static_cast<int>(e);
