@@ -53,6 +53,58 @@ __device__ __forceinline__ int warp_select(unsigned long long *keys, int count, 
     return count < K ? count : K;
 }
 
+// Cheaper than sorting when the buffer fills (cap <= 512): find T = the K-th smallest d2 BIT PATTERN of keys[0..count) by
+// bisection over the lane's register copy of the high words, then compact the keys with d2 <= T in place (order is irrelevant
+// until the final sort).  Ties at T are all kept, so the new threshold (T, 0xffffffff) stays conservative; returns -1 when ties
+// leave no room (the caller then falls back to the exact sort).  ~1 k instructions against ~8 k for the 512-key bitonic sort,
+// which matters twice: the warps of a CTA meet at a barrier every tile, so one warp's selection stalls the other seven.
+constexpr int PRUNE_NPL = 16;
+__device__ __forceinline__ int warp_prune(unsigned long long *keys, int count, int cap, int K, unsigned &T_out) {
+    const unsigned lane = lane_id();
+    unsigned hi[PRUNE_NPL];
+    unsigned vmin = 0xffffffffu, vmax = 0u;
+#pragma unroll
+    for (int i = 0; i < PRUNE_NPL; ++i) {
+        const int t = i * 32 + static_cast<int>(lane);
+        hi[i] = 0xffffffffu;
+        if (t < count) {
+            hi[i] = static_cast<unsigned>(keys[t] >> 32);
+            vmin = min(vmin, hi[i]);
+            vmax = max(vmax, hi[i]);
+        }
+    }
+    unsigned lo = __reduce_min_sync(FULL_MASK, vmin), up = __reduce_max_sync(FULL_MASK, vmax);
+    while (lo < up) {   // smallest T with #(hi <= T) >= K; count >= K valid entries, so T <= up
+        const unsigned mid = lo + ((up - lo) >> 1);
+        int c = 0;
+#pragma unroll
+        for (int i = 0; i < PRUNE_NPL; ++i) c += hi[i] <= mid ? 1 : 0;
+        c = __reduce_add_sync(FULL_MASK, c);
+        if (c >= K) up = mid;
+        else lo = mid + 1u;
+    }
+    const unsigned T = lo;
+    int kept = 0;
+#pragma unroll
+    for (int i = 0; i < PRUNE_NPL; ++i) kept += hi[i] <= T ? 1 : 0;
+    kept = __reduce_add_sync(FULL_MASK, kept);
+    if (kept > cap - 64) return -1;
+    int out = 0;
+    for (int c0 = 0; c0 < count; c0 += 32) {
+        const int t = c0 + static_cast<int>(lane);
+        unsigned long long key = KEY_MAX;
+        if (t < count) key = keys[t];
+        const bool keep = t < count && static_cast<unsigned>(key >> 32) <= T;
+        const unsigned m = __ballot_sync(FULL_MASK, keep);
+        __syncwarp();
+        if (keep) keys[out + __popc(m & ((1u << lane) - 1u))] = key;   // out + rank <= t: never ahead of the reads
+        out += __popc(m);
+        __syncwarp();
+    }
+    T_out = T;
+    return out;
+}
+
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
 knn_warp_kernel(const float *__restrict__ q, const float *__restrict__ p, int P1, int P2, int K, int cap,
@@ -91,8 +143,16 @@ knn_warp_kernel(const float *__restrict__ q, const float *__restrict__ p, int P1
         count += __popc(m);
         if (count + 32 > cap) {
             __syncwarp();
-            count = warp_select(keys, count, cap, K);
-            thresh = count >= K ? keys[K - 1] : KEY_MAX;
+            int kept = -1;
+            unsigned T = 0u;
+            if (cap <= 32 * PRUNE_NPL) kept = warp_prune(keys, count, cap, K, T);   // count > cap - 32 >= K here
+            if (kept >= 0) {
+                count = kept;
+                thresh = (static_cast<unsigned long long>(T) << 32) | 0xffffffffull;
+            } else {
+                count = warp_select(keys, count, cap, K);
+                thresh = count >= K ? keys[K - 1] : KEY_MAX;
+            }
             thresh_hi = static_cast<unsigned>(thresh >> 32);
         }
     };

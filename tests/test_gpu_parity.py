@@ -110,6 +110,30 @@ def test_knn_warp_kernel_vs_oracle(pcc, orc, B, P1, P2, K):
         assert np.array_equal(nn.cpu().numpy(), want)
 
 
+@pytest.mark.parametrize("kind,P1,P2,K", [("uniform", 40, 20000, 256), ("grid", 17, 9001, 64), ("grid", 9, 30000, 256),
+                                          ("identical", 3, 10000, 100), ("uniform", 5, 12000, 1024), ("two_values", 6, 8300, 200),
+                                          ("uniform", 33, 8193, 16)])
+def test_knn_scene_kernel_vs_oracle(pcc, orc, kind, P1, P2, K):
+    """P2 > 8192: the warp-per-query kernel of the scene path -- 128-candidate steps with the one-vote reject, the ragged last
+    tile, the bisection prune of a full candidate buffer, its fall-back to the exact sort when ties leave no room (grid /
+    identical / two_values) and the sort-only path of K > 256."""
+    rng = np.random.default_rng(P2 + K)
+    if kind == "identical":
+        p = np.full((1, P2, 3), 0.25, np.float32)
+    elif kind == "two_values":
+        p = np.where(rng.random((1, P2, 1)) < 0.5, 0.25, 0.75).astype(np.float32).repeat(3, axis=2)
+    elif kind == "grid":
+        p = synth.grid_quantised(1, P2, depth=3, seed=P2)
+    else:
+        p = synth.uniform_cube(1, P2, seed=P2)
+    q = synth.uniform_cube(1, P1, seed=P1 + 1)
+    q[0, 0] = p[0, 7]                                                   # a query sitting on a candidate
+    d, i, nn = pcc.ops.knn(cu(q), cu(p), K, return_nn=True)
+    od, oi, onn = orc.knn_points(q, p, K, True, threads=8)
+    assert np.array_equal(i.cpu().numpy(), oi) and np.array_equal(d.cpu().numpy(), od)
+    assert np.array_equal(nn.cpu().numpy(), onn)
+
+
 @pytest.mark.parametrize("kind,P2,K", [("identical", 8192, 256), ("two_values", 8192, 300), ("grid", 8192, 512),
                                        ("grid", 5000, 64), ("uniform", 4097, 512), ("half_dup", 6000, 256)])
 def test_knn_block_kernel_selection_paths_vs_oracle(pcc, orc, kind, P2, K):
