@@ -42,7 +42,7 @@ int64_t pcc_launch_count(void);
 /*
  * Farthest point sampling of `npoint` indices from each of B clouds of N points.
  * Replaces pn_kit.farthest_point_sample_batch (/root/reference/pn_kit.py:309-330): pass the reference's
- * torch.randint draw in start_idx[B] (device int64) and init_dist = 1e10;
+ * torch.randint draw in start_idx[B] (device int64; values outside [0, N) are clamped into the cloud) and init_dist = 1e10;
  * and pytorch3d.ops.sample_farthest_points (/root/reference/pointnet_sa_module.py:10-13): start_idx = NULL
  * (start at index 0), init_dist = FLT_MAX.
  * out_idx[B, npoint] int64; entries k >= N are -1 (PyTorch3D padding when npoint > N).
@@ -237,13 +237,34 @@ int pcc_octree_decode_f32(const uint8_t *bits, const int32_t *nbits, int B, int 
  * fit in shared memory beside the activations.
  * a [M, K] bf16 (row pitch lda), w [N, K] bf16 (row pitch ldw), bias [N] fp32; K % 64 == 0, N % 128 == 0 (pad with zero
  * columns / use pcc_gather_concat_bf16); pitches multiples of 8 elements, 16-byte aligned bases.
- * group <= 1: out [M, N] bf16 (row pitch ld_out).  group > 1: the max over every run of `group` consecutive rows
+ * group <= 0: out [M, N] bf16 (row pitch ld_out).  group == 1: out [M, N] fp32, dense (logits / per-cloud vectors that must
+ * not be rounded to bf16).  group > 1: the max over every run of `group` consecutive rows
  * (pointnet_sa_module.py:91 torch.max over nsample): out [M / group, N] fp32, group % 32 == 0 and either a divisor or a
  * multiple of 128, M % group == 0, relu required when group > 32.
  * Numerics: operands bf16, products accumulated in fp32 (tolerance stated in tests/test_gpu_mlp.py).
  */
 int pcc_linear_bf16(const void *a, int64_t M, int K, int64_t lda, const void *w, int64_t ldw, const float *bias, int N, int relu,
                     int group, void *out, int64_t ld_out, void *stream);
+
+/*
+ * Skinny fp32 Linear for per-cloud vectors (csrc/small_ops.cu): out[M, N] = act(x[M, K] . w[N, K]^T + bias) with M = clouds.
+ * Replaces nn.Linear enc_proj / dec_proj of PPPF_AE (/root/reference/PPPF_AE.py:122-123,139,145), the latent columns of
+ * FoldingNet's first Conv1d of each stage (PPPF_AE.py:58-59,68-69,100-109: the latent is identical for every grid point) and
+ * the pooled-feature columns of AE.ConditionalProbabilityModel.model_mlp[0] (/root/reference/AE.py:99,115-116).
+ * Weight-bandwidth bound, fp32 FMA chains in k order: a row's result is independent of M (batch invariant).  bias nullable.
+ */
+int pcc_linear_small_f32(const float *x, int M, int K, int64_t ldx, const float *w, int64_t ldw, const float *bias, int N, int relu,
+                         float *out, int64_t ld_out, void *stream);
+
+/*
+ * First layer of a stage whose input is cat([n_local per-point values, a per-cloud vector tiled over the n_pts points of the
+ * cloud]) (PPPF_AE.py:100-101,106-107 torch.cat + Conv1d; AE.py:115-116): out[r, c] = act(per_cloud[r / n_pts, c] +
+ * sum_j local[r, j] * w[c, j]) in fp32, written as bf16 rows (pitch ld_out, columns C..ld_out zero) -- the A operand of
+ * pcc_linear_bf16 / pcc_mlp_chain.  local [M, n_local] fp32 (pitch ld_local, n_local <= 4), w [C, n_local] fp32 (pitch ldw: a
+ * column slice of the layer's weight), per_cloud [M / n_pts, C] fp32 (bias included, from pcc_linear_small_f32).
+ */
+int pcc_fold_first_bf16(const float *local, int n_local, int64_t ld_local, const float *w, int64_t ldw, const float *per_cloud,
+                        int64_t M, int n_pts, int C, int relu, void *out, int64_t ld_out, void *stream);
 
 /*
  * Grouping of one PointNet++ set-abstraction level (/root/reference/pointnet_sa_module.py:73-85: group_points of the features

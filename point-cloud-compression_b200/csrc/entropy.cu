@@ -4,7 +4,11 @@
 //   pmf_to_cdf_kernel     pn_kit.pmf_to_cdf (/root/reference/pn_kit.py:452-461: cat(0, cumsum(pmf)), clamp(max = 1)) fused with
 //                         torchac's _convert_to_int_and_normalize(needs_normalization = True): round(cdf * (2^16 - L)) as a
 //                         16-bit pattern, + arange(L + 1).  The running sum is kept in double and rounded to float at every
-//                         step, which is what torch's CPU cumsum does for float inputs (the reference's CPU path).
+//                         step, which is what torch's CPU cumsum does for float inputs (bit-exact to pn_kit.pmf_to_cdf run on
+//                         CPU tensors: tests/golden/ref_entropy.npz).  compress.py:134 calls pmf_to_cdf on the DEVICE tensor,
+//                         i.e. torch's CUDA cumsum, whose summation order is unspecified; together with torchac being
+//                         unpinned this means .p.bin streams are self-consistent (encode <-> decode of this library, any
+//                         batch size), not guaranteed interchangeable with streams the reference wrote on a GPU.
 //   cdf_to_u16_kernel     the same conversion for a float CDF that the caller already holds (torchac.encode_float_cdf's input)
 //   range_encode_kernel   torchac's arithmetic coder (32-bit low / high, 16-bit CDFs, pending-bit carry handling, MSB-first
 //   range_decode_kernel   bits), one stream per cloud.  The recurrence is serial per stream: one thread per stream, streams in

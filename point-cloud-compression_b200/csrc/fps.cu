@@ -142,7 +142,11 @@ fps_block_kernel(const float *__restrict__ xyz, int N, int npoint, const int64_t
         }
     }
 
-    int far = start_idx ? static_cast<int>(start_idx[b]) : 0;
+    int far = 0;
+    if (start_idx) {  // an out-of-range start (the reference would raise an IndexError on the host) must not read outside the cloud
+        const long long s0 = start_idx[b];
+        far = s0 < 0 ? 0 : (s0 >= N ? N - 1 : static_cast<int>(s0));
+    }
     float cx = pc[far * 3 + 0], cy = pc[far * 3 + 1], cz = pc[far * 3 + 2];
     for (int i = 0; i < k_n; ++i) {
         if (tid == 0) {
@@ -247,7 +251,11 @@ fps_grid_kernel(const float *__restrict__ xyz, int N, int npoint, const int64_t 
             }
         }
 
-    int far = start_idx ? static_cast<int>(start_idx[b]) : 0;
+    int far = 0;
+    if (start_idx) {  // an out-of-range start (the reference would raise an IndexError on the host) must not read outside the cloud
+        const long long s0 = start_idx[b];
+        far = s0 < 0 ? 0 : (s0 >= N ? N - 1 : static_cast<int>(s0));
+    }
     float cx = pc[static_cast<size_t>(far) * 3 + 0], cy = pc[static_cast<size_t>(far) * 3 + 1],
           cz = pc[static_cast<size_t>(far) * 3 + 2];
     for (int i = 0; i < k_n; ++i) {

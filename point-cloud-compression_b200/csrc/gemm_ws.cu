@@ -178,7 +178,20 @@ linear_kernel(const __grid_constant__ Params prm, const __grid_constant__ CUtens
                     v[4 * i + 2] = __float_as_uint(__uint_as_float(v[4 * i + 2]) + b4.z);
                     v[4 * i + 3] = __float_as_uint(__uint_as_float(v[4 * i + 3]) + b4.w);
                 }
-                if (POOL) {
+                if (POOL && prm.group == 1) {
+                    // fp32 rows, no pooling: lane = row, 32 consecutive columns (one 128-byte line per lane)
+                    const long long r = m0 + row;
+                    if (r < prm.M) {
+                        float4 *o = reinterpret_cast<float4 *>(prm.out_pool + r * prm.N + n0 + col);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            float4 f = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
+                                                   __uint_as_float(v[4 * i + 3]));
+                            if (prm.relu) f = make_float4(fmaxf(f.x, 0.0f), fmaxf(f.y, 0.0f), fmaxf(f.z, 0.0f), fmaxf(f.w, 0.0f));
+                            o[i] = f;
+                        }
+                    }
+                } else if (POOL) {
                     float mine = 0.0f;
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
@@ -245,8 +258,10 @@ PCC_API int pcc_linear_bf16(const void *a, int64_t M, int K, int64_t lda, const 
     PCC_REQUIRE(lda >= K && lda % 8 == 0 && ldw >= K && ldw % 8 == 0 && reinterpret_cast<uintptr_t>(a) % 16 == 0 &&
                     reinterpret_cast<uintptr_t>(w) % 16 == 0,
                 "pcc_linear_bf16: operands must be 16-byte aligned with row pitches that are multiples of 8 elements");
-    const bool pool = group > 1;
-    if (pool) {
+    const bool pool = group >= 1;  // group == 1: dense fp32 rows through the pooled kernel's plain-store epilogue
+    if (group == 1) {
+        PCC_REQUIRE(ld_out == N && reinterpret_cast<uintptr_t>(out) % 16 == 0, "pcc_linear_bf16: the fp32 output is dense [M, N], 16-byte aligned");
+    } else if (pool) {
         PCC_REQUIRE(group % 32 == 0 && (128 % group == 0 || group % 128 == 0) && M % group == 0,
                     "pcc_linear_bf16: group=%d must be a multiple of 32 that divides or is a multiple of 128, and divide M", group);
         PCC_REQUIRE(group == 32 || relu, "pcc_linear_bf16: pooling over more than 32 rows needs the ReLU (atomicMax on non-negative values)");

@@ -1,0 +1,131 @@
+// Small fp32 pieces around the tensor-core layers: per-cloud vectors and the "folded" first layer of a stage whose input is
+// cat([per-point coordinates, one per-cloud vector tiled over the points]).
+//
+//   pcc_linear_small_f32   out[M, N] = act(x[M, K] . w[N, K]^T + b)      for SKINNY problems (M = clouds, not points):
+//       PPPF_AE.enc_proj / dec_proj (/root/reference/PPPF_AE.py:122-123,139,145: Linear 1024 -> d and d -> 1024 on ONE row per
+//       cloud), the latent part of FoldingNet's first Conv1d of each stage (PPPF_AE.py:100-109: the 1024-wide latent is the same
+//       for every grid point, so W[:, n_local:] . latent is a per-cloud vector), the pooled-feature part of
+//       AE.ConditionalProbabilityModel's first Conv2d (AE.py:115-116).  These are weight-bandwidth bound (every weight is used
+//       M <= a few hundred times), so they run on the CUDA cores in fp32 -- which also keeps the value that is about to be
+//       ROUNDED to a symbol (enc_proj) in the reference's precision.  Every output is one serial k-ascending FMA chain, so a
+//       row's result does not depend on how many rows are in the call (batch invariance: the entropy coder needs the decoder to
+//       reproduce the encoder's PMFs bit for bit whatever the batch size).
+//
+//   pcc_fold_first_bf16    out[r, c] = relu(per_cloud[r / n_pts, c] + sum_j local[r, j] * w[c, j])   (bf16 rows)
+//       the per-point part of those first layers (2 grid coordinates, 3 coarse coordinates, 3 centre coordinates) in fp32,
+//       emitted as the bf16 A operand of the next layer's tensor-core GEMM (pcc_linear_bf16 / pcc_mlp_chain).  HBM bound
+//       (2 * C bytes written per row).
+#include <cuda_bf16.h>
+
+#include "pcc_common.cuh"
+
+namespace pcc {
+namespace {
+
+constexpr int LS_TM = 8, LS_TN = 64, LS_KC = 64, LS_THREADS = 128;
+
+__global__ void __launch_bounds__(LS_THREADS)
+linear_small_kernel(const float *__restrict__ x, long long ldx, const float *__restrict__ w, long long ldw,
+                    const float *__restrict__ bias, int M, int K, int N, int relu, float *__restrict__ out, long long ldo) {
+    __shared__ float xs[LS_TM][LS_KC];
+    __shared__ float ws[LS_TN][LS_KC + 1];
+    const int m0 = blockIdx.y * LS_TM, n0 = blockIdx.x * LS_TN;
+    const int col = threadIdx.x & (LS_TN - 1), rg = threadIdx.x / LS_TN;  // 2 row groups of 4 rows
+    float acc[4];
+    const float b = (bias && n0 + col < N) ? __ldg(bias + n0 + col) : 0.0f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[i] = b;
+    for (int k0 = 0; k0 < K; k0 += LS_KC) {
+        for (int e = threadIdx.x; e < LS_TM * LS_KC; e += LS_THREADS) {
+            const int r = e / LS_KC, k = e % LS_KC;
+            xs[r][k] = (m0 + r < M && k0 + k < K) ? __ldg(x + static_cast<long long>(m0 + r) * ldx + k0 + k) : 0.0f;
+        }
+        for (int e = threadIdx.x; e < LS_TN * LS_KC; e += LS_THREADS) {
+            const int c = e / LS_KC, k = e % LS_KC;
+            ws[c][k] = (n0 + c < N && k0 + k < K) ? __ldg(w + static_cast<long long>(n0 + c) * ldw + k0 + k) : 0.0f;
+        }
+        __syncthreads();
+        const int kn = K - k0 < LS_KC ? K - k0 : LS_KC;  // the zero tail is not accumulated: the chain is exactly k = 0..K-1
+        for (int k = 0; k < kn; ++k) {
+            const float wv = ws[col][k];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i] = fmaf(xs[rg * 4 + i][k], wv, acc[i]);
+        }
+        __syncthreads();
+    }
+    if (n0 + col < N) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = m0 + rg * 4 + i;
+            if (r < M) out[static_cast<long long>(r) * ldo + n0 + col] = relu ? fmaxf(acc[i], 0.0f) : acc[i];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+fold_first_kernel(const float *__restrict__ local, int n_local, long long ld_local, const float *__restrict__ w, long long ldw,
+                  const float *__restrict__ per_cloud, long long M, int n_pts, int C, int relu, __nv_bfloat16 *__restrict__ out,
+                  long long ldo) {
+    const int chunks = static_cast<int>(ldo >> 3);  // 8 channels (16 bytes) per thread
+    const long long total = M * chunks;
+    for (long long e = blockIdx.x * 256ll + threadIdx.x; e < total; e += gridDim.x * 256ll) {
+        const long long r = e / chunks;
+        const int c0 = static_cast<int>(e % chunks) * 8;
+        float l[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) l[j] = j < n_local ? __ldg(local + r * ld_local + j) : 0.0f;
+        const float *pc = per_cloud + (r / n_pts) * C;
+        uint32_t pk[4];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            float v[2];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int c = c0 + 2 * h + q;
+                float a = 0.0f;
+                if (c < C) {
+                    a = __ldg(pc + c);
+                    for (int j = 0; j < n_local; ++j) a = fmaf(l[j], __ldg(w + static_cast<long long>(c) * ldw + j), a);
+                    if (relu) a = fmaxf(a, 0.0f);
+                }
+                v[q] = a;
+            }
+            const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[0], v[1]);
+            pk[h] = *reinterpret_cast<const uint32_t *>(&b2);
+        }
+        *reinterpret_cast<uint4 *>(out + r * ldo + c0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+}
+
+}  // namespace
+}  // namespace pcc
+
+PCC_API int pcc_linear_small_f32(const float *x, int M, int K, int64_t ldx, const float *w, int64_t ldw, const float *bias, int N,
+                                 int relu, float *out, int64_t ld_out, void *stream) {
+    using namespace pcc;
+    PCC_REQUIRE(x && w && out, "pcc_linear_small_f32: null pointer");
+    PCC_REQUIRE(M >= 1 && M <= 65535 * LS_TM && K >= 1 && N >= 1, "pcc_linear_small_f32: M=%d K=%d N=%d out of range", M, K, N);
+    PCC_REQUIRE(ldx >= K && ldw >= K && ld_out >= N, "pcc_linear_small_f32: row pitch smaller than the row");
+    const dim3 grid((N + LS_TN - 1) / LS_TN, (M + LS_TM - 1) / LS_TM);
+    linear_small_kernel<<<grid, LS_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(x, ldx, w, ldw, bias, M, K, N, relu, out, ld_out);
+    return check_launch("linear_small_kernel");
+}
+
+PCC_API int pcc_fold_first_bf16(const float *local, int n_local, int64_t ld_local, const float *w, int64_t ldw, const float *per_cloud,
+                                int64_t M, int n_pts, int C, int relu, void *out, int64_t ld_out, void *stream) {
+    using namespace pcc;
+    PCC_REQUIRE(local && w && per_cloud && out, "pcc_fold_first_bf16: null pointer");
+    PCC_REQUIRE(n_local >= 1 && n_local <= 4 && ld_local >= n_local && ldw >= n_local, "pcc_fold_first_bf16: n_local=%d outside [1,4]", n_local);
+    PCC_REQUIRE(M >= 0 && n_pts >= 1 && M % n_pts == 0 && C >= 1, "pcc_fold_first_bf16: M=%lld must be a multiple of n_pts=%d",
+                static_cast<long long>(M), n_pts);
+    PCC_REQUIRE(ld_out >= C && ld_out % 8 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0,
+                "pcc_fold_first_bf16: out must be 16-byte aligned with a row pitch that is a multiple of 8 elements");
+    if (M == 0) return 0;
+    const long long total = M * (ld_out >> 3);
+    long long blocks = (total + 255) / 256;
+    const long long cap = static_cast<long long>(num_sms()) * 16;
+    if (blocks > cap) blocks = cap;
+    fold_first_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        local, n_local, ld_local, w, ldw, per_cloud, M, n_pts, C, relu, static_cast<__nv_bfloat16 *>(out), ld_out);
+    return check_launch("fold_first_kernel");
+}

@@ -137,6 +137,7 @@ class PatchCodec:
         data, nbytes = self.encode_latents(prob, c["latent_q"], c["centres"])
         o = c["octree"]
         data, nbytes = data.cpu().numpy(), nbytes.cpu().numpy()
+        ops.check_stream_sizes(nbytes, data.shape[1])
         obytes, onbits = o["bytes"].cpu().numpy(), o["nbits"].cpu().numpy()
         cs = torch.cat((c["center"], c["longest"][:, None]), dim=1).cpu().numpy().astype(np.float32)
         os.makedirs(out_dir, exist_ok=True)
@@ -245,6 +246,9 @@ class PatchCodec:
         drained = [None, None]
 
         def upload(slot, host):
+            if graphed and bufs[slot] is not None and tuple(bufs[slot].shape) != tuple(host.shape):
+                raise ValueError(f"roundtrip_sweep(graphed=True): batch of shape {tuple(host.shape)} in a sweep captured for "
+                                 f"{tuple(bufs[slot].shape)} (pad or drop the ragged last batch, or use graphed=False)")
             if bufs[slot] is None or bufs[slot].shape != host.shape:
                 bufs[slot] = torch.empty(host.shape, dtype=torch.float32, device=dev)
             with torch.cuda.stream(copy):
@@ -258,24 +262,12 @@ class PatchCodec:
         if graphed and nxt is not None:
             if start_idx is None:
                 raise ValueError("roundtrip_sweep(graphed=True) needs an explicit start_idx (the CPU RNG draw cannot be captured)")
-            key = (tuple(nxt.shape), start_idx.data_ptr(), self.centre_mode)
-            cache = getattr(self, "_sweep_graphs", None)
-            if cache is None or cache[0] != key:
-                sb = [nxt.to(dev), nxt.to(dev)]         # static staging buffers, filled with real data for the capture
-                side = torch.cuda.Stream(dev)
-                side.wait_stream(main)
-                with torch.cuda.stream(side):           # warm-up outside the capture: weight packing, attribute set-up
-                    self.roundtrip(sb[0], start_idx, return_octree=True)
-                main.wait_stream(side)
-                torch.cuda.synchronize(dev)
-                gs = []
-                for slot in range(2):
-                    g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g):
-                        outs = self.roundtrip(sb[slot], start_idx, return_octree=True)
-                    gs.append((g, outs))
-                cache = self._sweep_graphs = (key, sb, gs)
-            bufs, graphs = list(cache[1]), cache[2]
+            cache = self._captured_sweep(nxt, start_idx, dev, main)
+            bufs, graphs = list(cache["bufs"]), cache["graphs"]
+            cache["start"].copy_(start_idx.to(dev), non_blocking=True)   # the graphs read the cache's own copy, never the caller's tensor
+        # the first upload runs on the copy stream: it must not overtake main-stream work that may still be reading / about to
+        # recycle the staging memory (a previous sweep's last replay, or the allocator block the buffers come from)
+        copy.wait_stream(main)
         if nxt is not None:
             upload(0, nxt)
         s = 0
@@ -299,6 +291,42 @@ class PatchCodec:
             s += 1
         return s
 
+    def _weights_key(self):
+        from . import bodies
+        return bodies._state_key(self.ae)
+
+    @staticmethod
+    def _derived_tensors():
+        """Strong references to every packed / padded / converted weight the kernels were handed during the warm-up: a captured
+        graph holds raw pointers to them, so they must outlive the host-side caches (which drop entries when they grow)."""
+        from . import mlp_ops
+        return (dict(mlp_ops._pack_cache), dict(mlp_ops._wpad_cache), dict(mlp_ops._bf16_cache))
+
+    def _captured_sweep(self, first, start_idx, dev, main):
+        """Two captured graphs of roundtrip() (one per staging buffer), re-captured whenever the batch shape, the centre mode or
+        any weight (version counter / storage) changes.  The cache owns everything the graphs point at: the staging buffers, its
+        own copy of start_idx, and the derived weight tensors."""
+        key = (tuple(first.shape), self.centre_mode, self._weights_key())
+        cache = getattr(self, "_sweep_graphs", None)
+        if cache is None or cache["key"] != key:
+            sb = [first.to(dev), first.to(dev)]     # static staging buffers, filled with real data for the capture
+            st = start_idx.to(dev).clone()
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):           # warm-up outside the capture: weight packing, attribute set-up
+                self.roundtrip(sb[0], st, return_octree=True)
+            main.wait_stream(side)
+            torch.cuda.synchronize(dev)
+            gs = []
+            for slot in range(2):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    outs = self.roundtrip(sb[slot], st, return_octree=True)
+                gs.append((g, outs))
+            cache = self._sweep_graphs = dict(key=key, bufs=sb, graphs=gs, start=st, keep=self._derived_tensors(),
+                                              ae_cache=[dict(m.__dict__.get("_pcc_cache", {})) for m in self.ae.modules()])
+        return cache
+
     def graphed_roundtrip(self, B, N):
         """Capture roundtrip() for [B, N, 3] inputs into a CUDA graph and return `run(xyz, start_idx)`, which copies the inputs
         into the graph's static buffers and replays it: for small batches (cfg1: one cloud) the ~25 launches of the step are
@@ -320,12 +348,18 @@ class PatchCodec:
         with torch.cuda.graph(graph):
             outs = self.roundtrip(xs, ss)
         launches = int(lib.pcc_launch_count() - n0)    # kernels of this library inside one replay
+        wkey, keep = self._weights_key(), self._derived_tensors()   # the graph points at these packed weights
 
         def run(xyz, start_idx):
+            if self._weights_key() != wkey:
+                raise RuntimeError("graphed_roundtrip: the model's weights changed since the capture; capture again")
+            if tuple(xyz.shape) != tuple(xs.shape):
+                raise ValueError(f"graphed_roundtrip: captured for {tuple(xs.shape)}, got {tuple(xyz.shape)}")
             xs.copy_(xyz, non_blocking=True)
             ss.copy_(start_idx, non_blocking=True)
             graph.replay()
             return outs
 
         run.launches = launches
+        run.keep = keep
         return run

@@ -1,14 +1,19 @@
 """Shared-MLP chains (1x1-conv stacks) on the device: the dense contractions of the hot path.
 
-    mlp_chain(x [M, C0], layers)                  -> [M, CL]
-    mlp_chain_groupmax(x [M, C0], layers, group)  -> [M/group, CL]   (max over each run of `group` consecutive rows)
+    run_chain(inputs, layers, group)              -> [M, CL] or [M / group, CL]  (max over runs of `group` consecutive rows)
+    mlp_chain / mlp_chain_groupmax                   the same for one [M, C0] input tensor
 
-`layers` is a list of (weight [Cout, Cin], bias [Cout], relu: bool) -- the reference's Conv2d / Linear parameters.
+`layers` is a list of (weight [Cout, Cin], bias [Cout], relu: bool) -- the reference's Conv2d / Conv1d / Linear parameters.
 
-Chains whose packed bf16 weights fit in shared memory run in ONE launch of the fused tcgen05 kernel
-(csrc/mlp_chain.cu: bf16 operands, fp32 accumulation in TMEM, activations never leave the SM).  Layers that do not
-fit (PointNet's 256->512->16 tail, the 1024->16384 decoder Linear) are still issued as plain library GEMMs
-(torch.addmm in bf16 -> cuBLAS) in round 1; the split point is chosen here.  There is no CPU path.
+Three tcgen05 kernels cover every layer, all hand-written (bf16 operands, fp32 accumulation in TMEM):
+  * fused_chain  -- runs of layers whose packed weights fit in shared memory, ONE launch, activations never leave the SM
+                    (csrc/mlp_chain.cu; the AE's three chains dispatch to the warp-specialised kernels of csrc/chain_ws.cu);
+  * pn_tail      -- PointNet's 256 -> 512 -> d + max over the patch (csrc/pn_tail.cu), W2 streamed through a TMA ring;
+  * linear       -- one wide layer as a streamed GEMM (csrc/gemm_ws.cu): weights too large to sit beside the activations
+                    (AE.inv_pool's 1024 -> 16384, PointNet++'s 128..1024-wide layers, FoldingNet's 512 -> 512).
+Skinny per-cloud vectors (one row per cloud) and the per-point part of a "cat(point, tiled cloud vector)" first layer run in
+fp32 on the CUDA cores (linear_small, fold_first: csrc/small_ops.cu).
+There is no library GEMM and no CPU path: a layer none of the kernels takes raises ValueError (PCC_ERR_UNSUPPORTED).
 """
 import weakref
 
@@ -134,21 +139,6 @@ def _bf16(t):
     return val
 
 
-def library_chain(x, layers, out_dtype=torch.float32):
-    """Plain library GEMMs (cuBLAS through torch) in bf16 with fp32 accumulation, for layers too large for the fused
-    kernel's resident-weight design."""
-    x = x.to(torch.bfloat16)
-    for w, b, relu in layers:
-        if relu:  # bias + ReLU in the GEMM epilogue (cuBLASLt), no separate element-wise pass
-            x = torch._addmm_activation(_bf16(b), x, _bf16(w).t(), use_gelu=False)
-        else:
-            x = torch.addmm(_bf16(b), x, _bf16(w).t())
-    return x.to(out_dtype)
-
-
-_library_chain = library_chain
-
-
 def pn_tail_supported(x, layers, group):
     """The fused PointNet tail kernel: [M, 256] bf16 -> 512 (ReLU) -> cout <= 16, max over runs of 256 rows."""
     return (len(layers) == 2 and group == 256 and x.dtype == torch.bfloat16 and x.dim() == 2 and x.shape[1] == 256 and
@@ -181,35 +171,59 @@ def _split(layers, pooled=False):
     return n
 
 
-def _materialise(inputs):
-    """Concatenate input segments into one [M, C] tensor (only needed in front of a library GEMM)."""
+def _linear_operand(inputs):
+    """The A operand of the streamed GEMM for `inputs` (a tensor or a list of channel segments): 16-byte aligned bf16 [M, Kp]
+    with Kp % 64 == 0, zero columns past the data.  A bf16 activation a previous kernel wrote in that form is used as is."""
     if isinstance(inputs, torch.Tensor):
-        return inputs
+        inputs = [(inputs, 1)]
+    if len(inputs) == 1 and inputs[0][1] == 1:
+        t = inputs[0][0]
+        if (t.dtype == torch.bfloat16 and t.dim() == 2 and t.stride(1) == 1 and t.shape[1] % 64 == 0 and t.stride(0) % 8 == 0 and
+                t.data_ptr() % 16 == 0):
+            return t
     parts = []
     for t, div in inputs:
-        t = t.reshape(-1, t.shape[-1])
+        t = t.reshape(-1, t.shape[-1]).to(torch.bfloat16)
         parts.append(t.repeat_interleave(div, dim=0) if div > 1 else t)
-    return parts[0] if len(parts) == 1 else torch.cat([p.float() for p in parts], dim=1)
+    c = sum(p.shape[1] for p in parts)
+    out = torch.zeros((parts[0].shape[0], _ru(c, 64)), dtype=torch.bfloat16, device=parts[0].device)
+    at = 0
+    for p in parts:
+        out[:, at:at + p.shape[1]] = p
+        at += p.shape[1]
+    return out
+
+
+def _rows(inputs):
+    if isinstance(inputs, torch.Tensor):
+        return inputs.shape[0]
+    t, div = inputs[0]
+    return t.reshape(-1, t.shape[-1]).shape[0] * div
 
 
 def run_chain(inputs, layers, group=0, out_dtype=torch.float32):
-    """Shared-MLP chain of any size: greedy runs of layers that fit the fused tcgen05 kernel (activations stay on the
-    SM inside a run, bf16 in HBM between runs); a layer whose weights alone exceed shared memory is a library GEMM."""
+    """Shared-MLP chain of any size: greedy runs of layers that fit the fused tcgen05 kernel (activations stay on the SM
+    inside a run, bf16 in HBM between runs); a layer whose weights do not fit beside the activations runs on the streamed
+    GEMM; PointNet's 256 -> 512 -> d + max tail on its own kernel.  The pooling is always fused into the last launch."""
     L = len(layers)
     cur, i = inputs, 0
-    pooled_done = False
     while i < L:
-        n = _split(layers[i:], pooled=group > 1)
+        rest = layers[i:]
+        if i > 0 and group > 1 and isinstance(cur, torch.Tensor) and out_dtype == torch.float32 and pn_tail_supported(cur, rest, group):
+            return pn_tail(cur, rest)
+        n = _split(rest, pooled=group > 1)
         if n > 0:
             last = i + n == L
-            cur = fused_chain(cur, layers[i:i + n], group if last else 0, out_dtype if last else torch.bfloat16)
-            pooled_done = last and group > 1
+            cur = fused_chain(cur, rest[:n], group if last else 0, out_dtype if last else torch.bfloat16)
             i += n
         else:
-            cur = library_chain(_materialise(cur), layers[i:i + 1], out_dtype if i + 1 == L else torch.bfloat16)
+            last = i + 1 == L
+            w, b, relu = rest[0]
+            cur = linear(_linear_operand(cur), w, b, relu, group if (last and group > 1) else 0,
+                         out_f32=last and group <= 1 and out_dtype == torch.float32)
+            if last and cur.dtype != out_dtype:
+                cur = cur.to(out_dtype)
             i += 1
-    if group > 1 and not pooled_done:
-        cur = cur.view(-1, group, cur.shape[1]).max(dim=1)[0]
     return cur
 
 
@@ -229,33 +243,37 @@ def mlp_chain_groupmax(x, layers, group):
 _wpad_cache = {}
 
 
-def _w_bf16_padded(w, kpad):
-    """[cout, cin] parameter -> cached bf16 [cout, kpad] with zero columns past cin."""
-    bw = _base(w)
-    key = (id(bw), w.data_ptr(), tuple(w.shape), tuple(w.stride()), kpad)
+def _w_bf16_padded(w, b, kpad, npad):
+    """[cout, cin] parameter (+ bias) -> cached (bf16 [npad, kpad] with zero rows / columns past the data, fp32 bias [npad])."""
+    bw, bb = _base(w), _base(b)
+    key = (id(bw), id(bb), w.data_ptr(), b.data_ptr(), tuple(w.shape), tuple(w.stride()), kpad, npad)
     hit = _wpad_cache.get(key)
-    if hit is not None and hit[0]() is bw and hit[1] == bw._version:
-        return hit[2]
+    if hit is not None and hit[0]() is bw and hit[1]() is bb and hit[2] == (bw._version, bb._version):
+        return hit[3]
     if len(_wpad_cache) > 256:
         _wpad_cache.clear()
-    val = torch.zeros((w.shape[0], kpad), dtype=torch.bfloat16, device=w.device)
-    val[:, :w.shape[1]] = w.detach()
-    _wpad_cache[key] = (weakref.ref(bw), bw._version, val)
-    return val
+    wp = torch.zeros((npad, kpad), dtype=torch.bfloat16, device=w.device)
+    wp[:w.shape[0], :w.shape[1]] = w.detach()
+    bp = torch.zeros((npad,), dtype=torch.float32, device=w.device)
+    bp[:w.shape[0]] = b.detach().float()
+    _wpad_cache[key] = (weakref.ref(bw), weakref.ref(bb), (bw._version, bb._version), (wp, bp))
+    return wp, bp
 
 
 def linear_supported(rows, cout, group=0):
-    """Shapes pcc_linear_bf16 takes (the input is zero padded to a multiple of 64 columns by the caller)."""
-    if cout % 128 or rows < 1:
+    """Shapes pcc_linear_bf16 takes (operands are zero padded to its K / N granules by `linear`)."""
+    if rows < 1 or cout < 1:
         return False
     if group > 1:
         return group % 32 == 0 and (128 % group == 0 or group % 128 == 0) and rows % group == 0
     return True
 
 
-def linear(x, w, b, relu, group=0):
+def linear(x, w, b, relu, group=0, out_f32=False):
     """One layer on the streamed GEMM kernel.  x [M, Kp] bf16 with Kp % 64 == 0 and Kp >= cin (columns past cin must be
-    zero or finite: the weight is zero padded).  Returns bf16 [M, cout], or fp32 [M / group, cout] when group > 1."""
+    zero or finite: the weight is zero padded).  Returns bf16 [M, cout]; fp32 [M, cout] with out_f32 (logits, values that must
+    not be rounded); fp32 [M / group, cout] when group > 1 (max over runs of `group` rows).  cout is padded to the kernel's
+    128-column granule with zero weight rows and the padding is sliced off the result."""
     lib = _lib.load()
     _check(x)
     if x.dtype != torch.bfloat16 or x.dim() != 2 or x.stride(1) != 1 or x.shape[1] % 64 or x.stride(0) % 8 or x.data_ptr() % 16:
@@ -266,16 +284,71 @@ def linear(x, w, b, relu, group=0):
         raise ValueError("pcc_b200.linear: the input has fewer columns than the weight")
     if group > 32 and not relu:
         raise ValueError("pcc_b200.linear: pooling over more than 32 rows needs the ReLU")
-    wp = _w_bf16_padded(w, kp)
-    bf = b.detach().float().contiguous()
+    if not linear_supported(M, cout, group):
+        raise ValueError(f"pcc_b200.linear: rows={M} cout={cout} group={group} is not a shape the streamed GEMM takes")
+    npad = _ru(cout, 128)
+    wp, bp = _w_bf16_padded(w, b, kp, npad)
     if group > 1:
-        out = torch.empty((M // group, cout), dtype=torch.float32, device=x.device)
+        out = torch.empty((M // group, npad), dtype=torch.float32, device=x.device)
+    elif out_f32:
+        out = torch.empty((M, npad), dtype=torch.float32, device=x.device)
+        group = 1
     else:
-        out = torch.empty((M, cout), dtype=torch.bfloat16, device=x.device)
+        out = torch.empty((M, npad), dtype=torch.bfloat16, device=x.device)
+        group = 0
     with torch.cuda.device(x.device):
-        _lib.check(lib.pcc_linear_bf16(x.data_ptr(), M, kp, x.stride(0), wp.data_ptr(), kp, bf.data_ptr(), cout, int(bool(relu)),
-                                       int(group), out.data_ptr(), cout, torch.cuda.current_stream().cuda_stream),
+        _lib.check(lib.pcc_linear_bf16(x.data_ptr(), M, kp, x.stride(0), wp.data_ptr(), kp, bp.data_ptr(), npad, int(bool(relu)),
+                                       int(group), out.data_ptr(), npad, torch.cuda.current_stream().cuda_stream),
                    "pcc_linear_bf16")
+    return out if npad == cout else out[:, :cout]
+
+
+def linear_small(x, w, b, relu=False):
+    """Skinny fp32 Linear for per-cloud vectors (csrc/small_ops.cu): act(x [M, K] . w [N, K]^T + b) -> fp32 [M, N].
+    `w` may be a column slice of a wider weight (its row pitch is passed through)."""
+    lib = _lib.load()
+    _check(x)
+    x = x.detach().float()
+    if x.dim() != 2 or x.stride(1) != 1:
+        x = x.reshape(-1, x.shape[-1]).contiguous()
+    w = w.detach()
+    if w.dtype != torch.float32 or w.stride(1) != 1:
+        w = w.float().contiguous()
+    bf = b.detach().float().contiguous() if b is not None else None
+    M, K = x.shape
+    N = w.shape[0]
+    if w.shape[1] != K:
+        raise ValueError("pcc_b200.linear_small: x and w disagree on K")
+    out = torch.empty((M, N), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.pcc_linear_small_f32(x.data_ptr(), M, K, x.stride(0), w.data_ptr(), w.stride(0),
+                                            bf.data_ptr() if bf is not None else None, N, int(bool(relu)), out.data_ptr(), N,
+                                            torch.cuda.current_stream().cuda_stream), "pcc_linear_small_f32")
+    return out
+
+
+def fold_first(local, w_local, per_cloud, n_pts, relu=True):
+    """bf16 [M, roundup(C, 64)] = act(per_cloud[r // n_pts] + local[r] . w_local^T): the first layer of a stage fed
+    cat([per-point values, tiled per-cloud vector]) (csrc/small_ops.cu).  local [M, n_local <= 4] fp32, w_local [C, n_local]
+    (a column slice of the layer's weight), per_cloud [M / n_pts, C] fp32 including the bias."""
+    lib = _lib.load()
+    _check(local)
+    local = local.detach().float()
+    if local.dim() != 2 or local.stride(1) != 1:
+        local = local.reshape(-1, local.shape[-1]).contiguous()
+    w_local = w_local.detach()
+    if w_local.dtype != torch.float32 or w_local.stride(1) != 1:
+        w_local = w_local.float().contiguous()
+    per_cloud = per_cloud.float().contiguous()
+    M, n_local = local.shape
+    C = w_local.shape[0]
+    if per_cloud.shape != (M // n_pts, C) or w_local.shape[1] != n_local:
+        raise ValueError("pcc_b200.fold_first: shapes disagree")
+    out = torch.empty((M, _ru(C, 64)), dtype=torch.bfloat16, device=local.device)
+    with torch.cuda.device(local.device):
+        _lib.check(lib.pcc_fold_first_bf16(local.data_ptr(), n_local, local.stride(0), w_local.data_ptr(), w_local.stride(0),
+                                           per_cloud.data_ptr(), M, n_pts, C, int(bool(relu)), out.data_ptr(), out.stride(0),
+                                           torch.cuda.current_stream().cuda_stream), "pcc_fold_first_bf16")
     return out
 
 

@@ -8,12 +8,14 @@ shapes go, so `ae.pkl` checkpoints written by the reference's train.py load unch
     inv_pool.{0,2,4}.{weight,bias}               AE.inv_pool             (AE.py:19-26)
     inv_mlp.mlp_Modules.{0..3}.0.{weight,bias}   pn_kit.MLP              (pn_kit.py:263-287)
 The forward bodies are NOT the reference's: they run channel-last on flattened [rows, C] activations and call the
-fused kernels (in-patch kNN -> shared MLP -> max over neighbours, ...).
+fused kernels (in-patch kNN -> shared MLP -> max over neighbours, ...).  The bodies themselves live in bodies.py, written
+against the reference's attribute names, so the same code serves these containers and -- through install() -- instances of
+the reference's own classes.
 """
 import torch
 import torch.nn as nn
 
-from . import mlp_ops, ops
+from . import bodies, ops
 
 
 class STEQuantize(torch.autograd.Function):
@@ -28,10 +30,11 @@ class STEQuantize(torch.autograd.Function):
         return grad_outputs
 
 
-def _conv_stack(channels):
+def _conv_stack(channels, relu):
+    """pn_kit.py:104-121: one nn.Sequential(Conv2d[, ReLU]) per layer -- keys "<i>.0.weight" / "<i>.0.bias"."""
     mods = nn.ModuleList()
-    for cin, cout in zip(channels[:-1], channels[1:]):
-        mods.append(nn.Sequential(nn.Conv2d(cin, cout, 1)))  # key "<i>.0.weight", ReLU has no parameters
+    for cin, cout, r in zip(channels[:-1], channels[1:], relu):
+        mods.append(nn.Sequential(nn.Conv2d(cin, cout, 1), nn.ReLU()) if r else nn.Sequential(nn.Conv2d(cin, cout, 1)))
     return mods
 
 
@@ -42,7 +45,7 @@ class SetAbstraction(nn.Module):
         super().__init__()
         if bn:
             raise NotImplementedError("pcc_b200.SetAbstraction: bn=True is not used by the reference AE")
-        self.npoint, self.K, self.finalRelu = npoint, K, finalRelu
+        self.npoint, self.K, self.finalRelu, self.bn = npoint, K, finalRelu, False
         self.conv0 = nn.Conv2d(in_channel + 3, mlp[0], 1)
         self.conv1 = nn.Conv2d(mlp[0], mlp[1], 1)
         self.conv2 = nn.Conv2d(mlp[1], mlp[2], 1)
@@ -52,14 +55,9 @@ class SetAbstraction(nn.Module):
                 (self.conv2.weight.flatten(1), self.conv2.bias, self.finalRelu)]
 
     def forward_points(self, xyz, out_dtype=torch.float32):
-        """xyz [BS, P, 3] (channel-last) -> per-point features [BS, P, C_out] (channel-last).
+        """xyz [BS, P, 3] (channel-last) -> per-point features [BS, S, C_out] (channel-last).
         pn_kit.py:164-211: kNN(K) in the patch, recentre on the query, shared MLP, max over the K neighbours."""
-        BS, P, _ = xyz.shape
-        if self.npoint != P:
-            raise NotImplementedError("pcc_b200.SetAbstraction: only the S == N configuration of AE.py:16 is built")
-        _, _, grouped = ops.knn(xyz, xyz, self.K, return_nn=True, centre_sub=True, nn_only=True)  # [BS,P,K,3]
-        return mlp_ops.fused_chain(grouped.reshape(BS * P * self.K, 3), self.layers(), group=self.K,
-                                   out_dtype=out_dtype).reshape(BS, P, -1)
+        return bodies.sa_points(self, xyz, out_dtype)[1]
 
     def forward_points_train(self, xyz):
         """Differentiable body (training): the kNN grouping runs on the pcc kernel (no gradient flows into it, SURVEY.md
@@ -75,8 +73,8 @@ class SetAbstraction(nn.Module):
 
     def forward(self, xyz):
         """Reference signature: xyz [B, 3, N] -> (new_xyz [B, 3, S], new_points [B, D', S])."""
-        feat = self.forward_points(xyz.permute(0, 2, 1).contiguous())
-        return xyz, feat.permute(0, 2, 1)
+        new_xyz, feat = bodies.sa_points(self, xyz.permute(0, 2, 1).contiguous())
+        return new_xyz.permute(0, 2, 1), feat.permute(0, 2, 1)
 
 
 class PointNet(nn.Module):
@@ -87,40 +85,18 @@ class PointNet(nn.Module):
         if bn:
             raise NotImplementedError("pcc_b200.PointNet: bn=True is not used by the reference AE")
         self.relu = list(relu)
-        self.mlp_Modules = _conv_stack([in_channel] + list(mlps))
+        self.mlp_Modules = _conv_stack([in_channel] + list(mlps), self.relu)
 
     def layers(self):
         return [(m[0].weight.flatten(1), m[0].bias, r) for m, r in zip(self.mlp_Modules, self.relu)]
 
     def forward_points(self, x):
         """x [BS, P, C] channel-last -> [BS, D]."""
-        BS, P, C = x.shape
-        return mlp_ops.mlp_chain_groupmax(x.reshape(BS * P, C), self.layers(), group=P)
+        return bodies.pointnet_points(self, x)
 
     def forward_xyz_feat(self, xyz, feat):
-        """The AE.py:39 call `pn(cat((xyz, feat)))` without materialising the concatenation: xyz [BS,P,3] fp32 and
-        feat [BS,P,F] (bf16 from the SetAbstraction kernel) are two input segments of the fused chain; the first
-        layer's weight columns are rotated once so the 16-byte aligned feature block comes first."""
-        BS, P, F = feat.shape
-        layers = self.layers()
-        w0 = layers[0][0]
-        key = (w0.data_ptr(), w0._version)
-        if getattr(self, "_rot_key", None) != key:
-            self._rot_w0 = torch.cat((w0[:, 3:], w0[:, :3]), dim=1).detach().contiguous()
-            self._rot_key = key
-        layers[0] = (self._rot_w0, layers[0][1], layers[0][2])
-        n = mlp_ops._split(layers)
-        if n == 0:
-            raise RuntimeError("pcc_b200.PointNet: first layer does not fit the fused kernel")
-        h = mlp_ops.fused_chain([(feat.reshape(BS * P, F), 1), (xyz.reshape(BS * P, 3), 1)], layers[:n],
-                                group=P if n == len(layers) else 0,
-                                out_dtype=torch.float32 if n == len(layers) else torch.bfloat16)
-        if n == len(layers):
-            return h
-        if mlp_ops.pn_tail_supported(h, layers[n:], P):   # 256 -> 512 -> d + max over the patch, one launch
-            return mlp_ops.pn_tail(h, layers[n:])
-        h = mlp_ops.library_chain(h, layers[n:])
-        return h.view(BS, P, -1).max(dim=1)[0]
+        """The AE.py:39 call `pn(cat((xyz, feat)))` without materialising the concatenation (bodies.pointnet_xyz_feat)."""
+        return bodies.pointnet_xyz_feat(self, xyz, feat)
 
     def forward(self, points):
         """Reference signature: points [B, C, N] -> [B, D]."""
@@ -135,14 +111,13 @@ class MLP(nn.Module):
         if bn:
             raise NotImplementedError("pcc_b200.MLP: bn=True is not used by the reference AE")
         self.relu = list(relu)
-        self.mlp_Modules = _conv_stack([in_channel] + list(mlps))
+        self.mlp_Modules = _conv_stack([in_channel] + list(mlps), self.relu)
 
     def layers(self):
         return [(m[0].weight.flatten(1), m[0].bias, r) for m, r in zip(self.mlp_Modules, self.relu)]
 
     def forward_points(self, x):
-        BS, P, C = x.shape
-        return mlp_ops.mlp_chain(x.reshape(BS * P, C), self.layers()).reshape(BS, P, -1)
+        return bodies.mlp_points(self, x)
 
     def forward(self, points):
         return self.forward_points(points.permute(0, 2, 1).contiguous()).permute(0, 2, 1)
@@ -164,43 +139,11 @@ class AE(nn.Module):
     # -- the two halves the scripts use separately (compress.py:113-127, decompress.py:96-102) --
     def encode_patches(self, patches):
         """patches [BS, K, 3] (recentred, scaled) -> (latent [BS, d] after the sigmoid spread, rounded latent)."""
-        feat = self.sa.forward_points(patches, out_dtype=torch.bfloat16)          # AE.py:38
-        latent = self.pn.forward_xyz_feat(patches, feat)                          # AE.py:39
-        # AE.py:42-45 in one kernel; it also emits the rounded latent as zero-padded bf16 rows, the operand of inv_pool's first
-        # GEMM, which decode_patches picks up when it is handed this very tensor (compress -> decompress in one process)
-        latent, latent_q, qb = ops.quantise_latent(latent, self.L - 0.2, kpad=(self.d + 63) // 64 * 64)
-        self._q_pad = (latent_q, latent_q._version, qb)   # holds the tensor itself: its storage cannot be recycled under the key
-        return latent, latent_q
+        return bodies.ae_encode(self, patches)
 
     def decode_patches(self, latent_q):
         """latent_q [BS, d] -> patches [BS, k, 3]   (AE.py:48-53)."""
-        BS = latent_q.shape[0]
-        # inv_pool's last Linear emits [128 channels, k points] per patch (AE.py:49 `view(BS, -1, k)`); permuting its
-        # rows once makes the GEMM write [k points, 128 channels] (channel-last) directly.
-        w4, b4 = self.inv_pool[4].weight, self.inv_pool[4].bias
-        key = (w4.data_ptr(), w4._version, b4._version)
-        if getattr(self, "_perm_key", None) != key:
-            self._perm_w4 = w4.detach().view(128, self.k, -1).permute(1, 0, 2).reshape(128 * self.k, -1).contiguous()
-            self._perm_b4 = b4.detach().view(128, self.k).t().reshape(-1).contiguous()
-            self._perm_key = key
-        inv_layers = [(self.inv_pool[0].weight, self.inv_pool[0].bias, True), (self.inv_pool[2].weight, self.inv_pool[2].bias, True),
-                      (self._perm_w4, self._perm_b4, True)]
-        if all(mlp_ops.linear_supported(BS, w.shape[0]) for w, _, _ in inv_layers):
-            # AE.py:19-26 on the streamed tensor-core GEMM (csrc/gemm_ws.cu); the latent is zero padded to the K granule
-            cached = getattr(self, "_q_pad", None)
-            base = latent_q._base if latent_q._base is not None else latent_q
-            if (cached is not None and base is cached[0] and latent_q._version == cached[1] and latent_q.is_contiguous() and
-                    latent_q.numel() == cached[0].numel() and latent_q.data_ptr() == cached[0].data_ptr()):
-                lat = cached[2]
-            else:
-                lat = torch.nn.functional.pad(latent_q.detach().to(torch.bfloat16), (0, (-self.d) % 64))
-            lin = mlp_ops.stream_chain(lat, inv_layers)
-        else:
-            lin = mlp_ops.library_chain(latent_q.detach(), inv_layers, out_dtype=torch.bfloat16)
-        # AE.py:50-52: cat(features, tiled latent) -> inv_mlp, as two input segments of the fused chain
-        out = mlp_ops.fused_chain([(lin.view(BS * self.k, 128), 1), (latent_q.detach().float().contiguous(), self.k)],
-                                  self.inv_mlp.layers())
-        return out.view(BS, self.k, 3)
+        return bodies.ae_decode(self, latent_q)
 
     def forward_train(self, xyz):
         """AE.forward (AE.py:34-55) under autograd: fp32 library GEMMs for the network bodies, pcc kernels for the
@@ -228,15 +171,15 @@ class AE(nn.Module):
     def forward(self, xyz):
         """Reference signature (AE.py:34-55): xyz [BS, K, 3] -> (new_xyz [BS, k, 3], latent, latent_quantized).
         With autograd enabled and trainable parameters the differentiable body runs; otherwise the fused inference path."""
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+        if bodies.training_pass(self):
             return self.forward_train(xyz.contiguous())
-        latent, latent_q = self.encode_patches(xyz.contiguous())
-        return self.decode_patches(latent_q), latent, latent_q
+        return bodies.ae_forward(self, xyz)
 
 
 class ConditionalProbabilityModel(nn.Module):
     """AE.ConditionalProbabilityModel(L, d) (/root/reference/AE.py:87-123): PMF of every latent symbol given the patch
-    centres.  Tiny (0.5 M parameters, 63 MFLOP per cloud): plain library GEMMs, same parameter keys."""
+    centres, same parameter keys.  Inference runs on the pcc kernels (bodies.prob_forward: batch-invariant, so a stream coded
+    in a batch of 32 decodes in a batch of 1); under autograd the differentiable body below runs."""
 
     def __init__(self, L, d):
         super().__init__()
@@ -245,7 +188,7 @@ class ConditionalProbabilityModel(nn.Module):
         self.model_mlp = nn.Sequential(nn.Conv2d(3 + 256, 512, 1), nn.ReLU(), nn.Conv2d(512, 512, 1), nn.ReLU(),
                                        nn.Conv2d(512, d * L, 1))
 
-    def forward(self, sampled_xyz):
+    def forward_train(self, sampled_xyz):
         B, S, _ = sampled_xyz.shape
         h = sampled_xyz.reshape(B * S, 3)
         for w, b, relu in self.model_pn.layers():
@@ -258,3 +201,8 @@ class ConditionalProbabilityModel(nn.Module):
             if i < 4:
                 x = torch.relu(x)
         return torch.softmax(x.view(B, S, self.d, self.L), dim=3)                 # AE.py:118-121
+
+    def forward(self, sampled_xyz):
+        if bodies.training_pass(self):
+            return self.forward_train(sampled_xyz)
+        return bodies.prob_forward(self, sampled_xyz)

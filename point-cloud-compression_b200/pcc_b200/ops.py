@@ -370,7 +370,10 @@ def cdf_to_u16(cdf_float):
 
 
 def range_encode(cdf_u16, sym):
-    """cdf uint16 [B, n, Lp], sym int16 [B, n] (CUDA) -> (bytes uint8 [B, cap], nbytes int32 [B]); one stream per cloud."""
+    """cdf uint16 [B, n, Lp], sym int16 [B, n] (CUDA) -> (bytes uint8 [B, cap], nbytes int32 [B]); one stream per cloud.
+    cap = 2 n + 8 bytes bounds any stream over valid 16-bit CDFs (>= 1 count per symbol => <= 16 bits per symbol); a stream
+    that would exceed it (a zero-width CDF interval) reports nbytes > cap and is truncated: callers that bring nbytes to the
+    host check it with `check_stream_sizes`."""
     lib = _lib.load()
     if not cdf_u16.is_cuda or cdf_u16.dtype != torch.uint16 or cdf_u16.dim() != 3:
         raise RuntimeError("pcc_b200.range_encode: cdf must be a CUDA uint16 [B, n, Lp] tensor (there is no CPU path)")
@@ -384,6 +387,15 @@ def range_encode(cdf_u16, sym):
         _lib.check(lib.pcc_range_encode_u16(_ptr(cdf_u16), _ptr(sym), B, n, Lp, _ptr(out), cap, _ptr(nbytes), _stream()),
                    "pcc_range_encode_u16")
     return out, nbytes
+
+
+def check_stream_sizes(nbytes_host, cap):
+    """Raise when a coded stream did not fit its buffer (nbytes counts the bytes the coder produced, stored or not)."""
+    import numpy as np
+    nb = np.asarray(nbytes_host)
+    if nb.size and int(nb.max()) > int(cap):
+        raise RuntimeError(f"pcc_b200.range_encode: a stream needs {int(nb.max())} bytes but the buffer holds {int(cap)} "
+                           "(invalid CDF: a symbol with an empty interval?)")
 
 
 def range_decode(cdf_u16, data, nbytes):

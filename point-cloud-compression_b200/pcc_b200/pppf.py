@@ -1,33 +1,22 @@
 """PointNet++ set abstraction and the PPPF auto-encoder on the B200 ops: same class names, constructor arguments and
 state_dict keys as the reference (/root/reference/pointnet_sa_module.py:37-93, /root/reference/PPPF_AE.py:9-150), so its
-checkpoints load unchanged; the forward bodies are batched device code:
+checkpoints load unchanged; the forward bodies are batched device code (bodies.py):
 
     FPS (start 0, fused centre gather) -> ball query (first nsample in radius, -1 -> point 0) -> row gather ->
     Conv2d+BatchNorm(eval, folded)+ReLU stack on the tensor cores -> max over nsample   (one fused chain per run of
-    layers whose weights fit in shared memory; wider layers are library GEMMs, see mlp_ops.run_chain).
+    layers whose weights fit in shared memory; wider layers on the streamed tcgen05 GEMM, see mlp_ops.run_chain);
+    FoldingNet: per-cloud latent term (fp32) + per-point term -> streamed GEMM -> fused tail.  No library GEMM.
 
 With autograd enabled and trainable parameters (training), every module runs a differentiable body instead: FPS, ball query
 and the row gathers stay on the pcc kernels (no gradient flows into the indices; the gather has a hand-written backward), the
 Conv2d + BatchNorm (batch statistics) + ReLU stacks and FoldingNet's Conv1d layers run as torch layers under autograd.
 """
-
-
-def _training_pass(module):
-    return torch.is_grad_enabled() and any(p.requires_grad for p in module.parameters())
-
 import torch
 import torch.nn as nn
 
-from . import mlp_ops, ops
+from . import bodies, ops
+from .bodies import training_pass as _training_pass
 from .modules import STEQuantize
-
-
-def _fold_bn(conv, bn):
-    """Eval-mode BatchNorm folded into the preceding 1x1 convolution: y = (Wx + b - mean) * gamma / sqrt(var + eps) + beta."""
-    w = conv.weight.flatten(1)
-    b = conv.bias if conv.bias is not None else torch.zeros(w.shape[0], device=w.device)
-    scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
-    return (w * scale[:, None]).contiguous(), ((b - bn.running_mean) * scale + bn.bias).contiguous()
 
 
 class PointnetSAModule(nn.Module):
@@ -42,14 +31,6 @@ class PointnetSAModule(nn.Module):
             layers += [nn.Conv2d(last, out_channel, 1), nn.BatchNorm2d(out_channel), nn.ReLU(inplace=True)]
             last = out_channel
         self.mlp = nn.Sequential(*layers)
-        self._folded = None
-
-    def folded_layers(self):
-        key = tuple(p._version for p in self.parameters()) + tuple(b._version for b in self.buffers())
-        if self._folded is None or self._folded[0] != key:
-            mods = list(self.mlp)
-            self._folded = (key, [_fold_bn(mods[i], mods[i + 1]) + (True,) for i in range(0, len(mods), 3)])
-        return self._folded[1]
 
     def forward_train(self, xyz, features=None):
         """pointnet_sa_module.py:58-93 under autograd: sampling / ball query / grouping on the pcc kernels, the shared MLP
@@ -78,33 +59,7 @@ class PointnetSAModule(nn.Module):
             raise NotImplementedError("pcc_b200.PointnetSAModule: train-mode BatchNorm without autograd is not built "
                                       "(call .eval() for inference)")
         with torch.no_grad():
-            return self._forward_fused(xyz, features)
-
-    def _forward_fused(self, xyz, features=None):
-        B, N, _ = xyz.shape
-        fps_idx, new_xyz = ops.fps(xyz, self.npoint, None, ops.FLT_MAX, return_xyz=True)   # :66-68 (start index 0)
-        if self.npoint > N:                                                                  # :67 clamp: pads read point 0
-            new_xyz = ops.gather(xyz, fps_idx.clamp(min=0))
-        _, idx = ops.ball_query(new_xyz, xyz, self.nsample, self.radius, return_dists=False)  # :71
-        idx = idx.clamp(min=0)                                                               # :27 (pads -> point 0)
-        layers = self.folded_layers()
-        rows = B * self.npoint * self.nsample
-        cin = (features.shape[1] if features is not None else 0) + (3 if self.use_xyz else 0)
-        if cin >= 64 and all(mlp_ops.linear_supported(rows, w.shape[0]) for w, _, _ in layers) and \
-                mlp_ops.linear_supported(rows, layers[-1][0].shape[0], self.nsample):
-            # wide stack: one grouping pass (gather + cat + bf16, zero padded to the GEMM's K granule), then every layer on
-            # the streamed tensor-core GEMM with the max over nsample fused into the last one       :73-91
-            a = mlp_ops.gather_concat_bf16(features.permute(0, 2, 1) if features is not None else None,
-                                           xyz if self.use_xyz else None, idx, (cin + 63) // 64 * 64)
-            out = mlp_ops.stream_chain(a, layers, group=self.nsample)
-            return new_xyz, out.view(B, self.npoint, -1).permute(0, 2, 1)
-        segs = []
-        if features is not None:
-            segs.append((ops.gather(features.permute(0, 2, 1).contiguous(), idx).view(-1, features.shape[1]), 1))  # :74-77
-        if self.use_xyz:
-            segs.append((ops.gather(xyz, idx).view(-1, 3), 1))                                # :80-85 (not recentred)
-        out = mlp_ops.run_chain(segs, layers, group=self.nsample)                           # :89-91
-        return new_xyz, out.view(B, self.npoint, -1).permute(0, 2, 1)
+            return bodies.sa_module_forward(self, xyz, features)
 
 
 class PointNetPP(nn.Module):
@@ -125,9 +80,9 @@ class PointNetPP(nn.Module):
 
 
 class FoldingNet(nn.Module):
-    """PPPF_AE.FoldingNet (/root/reference/PPPF_AE.py:50-109).  The latent is the same for every grid point, so the
-    first layer of each folding stage is a per-cloud vector (latent part, a small library GEMM) plus a 2- or 3-wide
-    per-point term; the remaining Conv1d layers are plain [B*N, K] x [K, K] library GEMMs in bf16."""
+    """PPPF_AE.FoldingNet (/root/reference/PPPF_AE.py:50-109).  The latent is the same for every grid point, so the first
+    layer of each folding stage is a per-cloud vector (pcc_linear_small_f32) plus a 2- or 3-wide per-point term
+    (pcc_fold_first_bf16); the 512 -> 512 layer runs on the streamed tcgen05 GEMM and the narrow tail on the fused chain."""
 
     def __init__(self, points=512, grid_size=45, feature_dim=1024):
         super().__init__()
@@ -139,28 +94,7 @@ class FoldingNet(nn.Module):
 
     def build_grid(self, batch_points, device):
         """PPPF_AE.py:80-89; the grid is a constant: built once per (batch, device) and kept on the device."""
-        key = (batch_points, str(device))
-        cached = getattr(self, "_grid_cache", None)
-        if cached is None or cached[0] != key:
-            x = torch.linspace(-1, 1, self.grid_size)
-            gx, gy = torch.meshgrid(x, x, indexing="ij")
-            grid = torch.stack([gx, gy], dim=-1).reshape(-1, 2).unsqueeze(0).repeat(batch_points, 1, 1).to(device)
-            cached = self._grid_cache = (key, grid)
-        return cached[1]
-
-    @staticmethod
-    def _stage(mlp, local, latent, n_local, latent_first):
-        """One folding stage on [B, N, n_local] per-point inputs and a [B, F] latent."""
-        w0 = mlp[0].weight.squeeze(-1)
-        if latent_first:   # mlp2: cat([coarse(3), latent]) -> columns [0:n_local] local, rest latent
-            w_loc, w_lat = w0[:, :n_local], w0[:, n_local:]
-        else:              # mlp1: cat([grid(2), latent])
-            w_loc, w_lat = w0[:, :n_local], w0[:, n_local:]
-        B, N, _ = local.shape
-        per_cloud = torch.addmm(mlp[0].bias, latent, w_lat.t())                      # [B, K]
-        h = torch.relu(local @ w_loc.t() + per_cloud[:, None, :]).reshape(B * N, -1)
-        h = mlp_ops.run_chain(h, [(mlp[2].weight.squeeze(-1), mlp[2].bias, True), (mlp[4].weight.squeeze(-1), mlp[4].bias, False)])
-        return h.view(B, N, 3)
+        return bodies._folding_grid(self, batch_points, device)
 
     def forward_train(self, latent_quantized):
         """PPPF_AE.py:91-109 under autograd (torch Conv1d layers)."""
@@ -175,10 +109,7 @@ class FoldingNet(nn.Module):
         if _training_pass(self):
             return self.forward_train(latent_quantized)
         with torch.no_grad():
-            B = latent_quantized.size(0)
-            grid = self.build_grid(B, latent_quantized.device)                           # [B, N, 2]
-            coarse = self._stage(self.mlp1, grid, latent_quantized, 2, False)            # PPPF_AE.py:100-104
-            return self._stage(self.mlp2, coarse, latent_quantized, 3, True)             # PPPF_AE.py:106-109
+            return bodies.folding_forward(self, latent_quantized)
 
 
 class PPPF_AE(nn.Module):
@@ -195,16 +126,47 @@ class PPPF_AE(nn.Module):
 
     def forward(self, xyz):
         """PPPF_AE.py:131-150; differentiable when autograd is on and the parameters are trainable, fused otherwise."""
-        with torch.set_grad_enabled(_training_pass(self)):
-            return self._forward(xyz)
+        if _training_pass(self):
+            return self._forward_train(xyz)
+        if bodies.has_train_mode_bn(self):
+            raise NotImplementedError("pcc_b200.PPPF_AE: train-mode BatchNorm without autograd is not built (call .eval())")
+        with torch.no_grad():
+            return bodies.pppf_forward(self, xyz)
 
-    def _forward(self, xyz):
+    def _forward_train(self, xyz):
         _, latent = self.encoder(xyz)
         spread = self.L - 0.2
         latent = torch.sigmoid(latent) * spread - spread / 2
         latent_quantized = self.quantize(self.enc_proj(latent))
         recon = self.decoder(self.dec_proj(latent_quantized))
         return recon, latent, latent_quantized
+
+
+class ConditionalProbabilityModel(nn.Module):
+    """PPPF_AE.ConditionalProbabilityModel(L, d) (/root/reference/PPPF_AE.py:181-228): PointNet++ backbone over the sampled
+    points, then Conv2d 3+1024 -> 512 -> 512 -> d*L and a softmax over L."""
+
+    def __init__(self, L, d):
+        super().__init__()
+        self.L, self.d = L, d
+        self.model_pnpp = PointNetPP(sa1_mlp=[64, 64, 128], sa2_mlp=[128, 128, 256], sa3_mlp=[256, 512, 1024], bn=False)
+        self.model_mlp = nn.Sequential(nn.Conv2d(3 + 1024, 512, 1), nn.ReLU(), nn.Conv2d(512, 512, 1), nn.ReLU(),
+                                       nn.Conv2d(512, d * L, 1))
+
+    def forward_train(self, sampled_xyz):
+        B, S, _ = sampled_xyz.shape
+        _, feature = self.model_pnpp(sampled_xyz)                                       # :207
+        x = torch.cat((sampled_xyz, feature.unsqueeze(1).repeat(1, S, 1)), dim=2)       # :210-213
+        out = self.model_mlp(x.unsqueeze(-1).transpose(1, 2))                           # :216-219
+        return torch.softmax(out.transpose(1, 2).reshape(B, S, self.d, self.L), dim=3)  # :222-223
+
+    def forward(self, sampled_xyz):
+        if _training_pass(self):
+            return self.forward_train(sampled_xyz)
+        if bodies.has_train_mode_bn(self):
+            raise NotImplementedError("pcc_b200.pppf.ConditionalProbabilityModel: call .eval() for inference")
+        with torch.no_grad():
+            return bodies.pppf_prob_forward(self, sampled_xyz)
 
 
 AE = PPPF_AE  # PPPF_AE.py:230-232

@@ -35,7 +35,9 @@ def encode_float_cdf(cdf_float, sym, needs_normalization=True, check_input_bound
     if tuple(sym.shape) != tuple(cdf_float.shape[:-1]):
         raise ValueError("sym and cdf_float disagree on the leading dimensions")
     data, nbytes = ops.range_encode(cdf, sym.reshape(1, -1))
-    return bytes(data[0, :int(nbytes[0])].cpu().numpy().tobytes())
+    n = int(nbytes[0])
+    ops.check_stream_sizes([n], data.shape[1])
+    return bytes(data[0, :n].cpu().numpy().tobytes())
 
 
 def decode_float_cdf(cdf_float, byte_stream, needs_normalization=True):

@@ -6,6 +6,7 @@ appendix B-6).  Multi-GPU: one process per GPU, whole clouds per rank, gradients
 over NCCL -- the only collective of the path.  The octree centre coder stays on the reference path; the step applies its
 quantisation rule on the device (see codec.py).
 """
+import contextlib
 import math
 
 import torch
@@ -22,6 +23,16 @@ def estimate_bits_from_pmf(pmf, sym):
     return torch.sum(-torch.log2(p.clamp(min=1e-3)))
 
 
+@contextlib.contextmanager
+def _matmul_tf32(enabled):
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = bool(enabled) or old
+    try:
+        yield
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+
 class Trainer:
     def __init__(self, K=256, k=128, d=16, L=7, N0=1024, alpha=2, lr=0.0005, lamda=1e-6, rate_loss_enable_step=40000,
                  centre_depth=6, device="cuda", ddp=False, state_dict=None, tf32=True, amp=False):
@@ -29,8 +40,9 @@ class Trainer:
         # The reference's network bodies are 1x1 Conv2d layers, which PyTorch runs through cuDNN with TF32 enabled by
         # default (torch.backends.cudnn.allow_tf32); the addmm form used here gets the same arithmetic only when the
         # matmul flag is switched on as well.  fp32 storage and accumulation, 10-bit operand mantissas.
-        if tf32:
-            torch.backends.cuda.matmul.allow_tf32 = True
+        # The flag is set only around this trainer's own forward / backward (a context in step()), never process-wide: other
+        # code in the process -- e.g. a probability model whose PMFs must be reproduced bit for bit -- keeps its setting.
+        self.tf32 = bool(tf32)
         # amp=True: the network bodies run under bf16 autocast -- the counterpart of the reference's fp16 autocast + GradScaler
         # path (train.py:114,154-160, taken when --device is the string 'cuda'); bf16 needs no loss scaling.
         self.amp = amp
@@ -73,6 +85,10 @@ class Trainer:
         scale = (N / self.N0) ** (1 / 3)
         _, _, patches = ops.knn(rec_centres, x, self.K, return_nn=True, centre_sub=True, nn_scale=scale,
                                 nn_only=True)                                     # train.py:185-192
+        with _matmul_tf32(self.tf32):
+            return self._network_step(batch_x, x, rec_centres, patches, scale, B, N, S)
+
+    def _network_step(self, batch_x, x, rec_centres, patches, scale, B, N, S):
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.amp):
             patches_pred, _, latent_q = self.ae_fwd(patches.view(B * S, self.K, 3))   # train.py:193
             pmf = self.prob_fwd(rec_centres)                                      # train.py:197

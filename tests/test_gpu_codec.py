@@ -215,3 +215,73 @@ def test_file_formats_round_trip(setup, tmp_path, mode):
     assert (tmp_path / "eval.csv").exists() and len(df) == 3 and df["n_points_output"][0] == 8192
     psnr1, _ = orc.d1_psnr(x[0].cpu().numpy(), got[0].cpu().numpy())
     assert abs(df["p2pointPSNR"][0] - round(psnr1, 3)) <= 2e-3 and df["bpp"][0] == bits[0] / 8192
+
+
+def test_streams_coded_in_a_batch_decode_one_cloud_at_a_time(setup, tmp_path):
+    """the probability model runs on kernels whose per-row results do not depend on the batch size, so .p.bin
+    streams written by compress_to_files with B = 3 decode with B = 1 (the reference's own batch size), in any order, to
+    exactly the batched reconstruction -- also while a Trainer elsewhere in the process had switched TF32 matmuls on."""
+    from pcc_b200.codec import PatchCodec
+    from pcc_b200.modules import ConditionalProbabilityModel
+    pcc, codec, sd = setup
+    torch.manual_seed(9)
+    prob = ConditionalProbabilityModel(7, 16).cuda().eval()
+    codec = PatchCodec(codec.ae, centre_mode="coded")
+    x = torch.from_numpy(synth.modelnet_like(3, 8192, seed=131)).cuda()
+    start = torch.tensor([40, 50, 60], dtype=torch.int64, device="cuda")
+    names = ["p", "q", "r"]
+    codec.compress_to_files(x, names, str(tmp_path), prob, start)
+    want = codec.decompress_from_files(names, str(tmp_path), prob, S=64)
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        for b in (2, 0, 1):
+            got = codec.decompress_from_files([names[b]], str(tmp_path), prob, S=64)
+            assert torch.equal(got[0], want[b])
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    c = codec.compress(x, start)
+    assert torch.equal(want, codec.decompress(c["latent_q"], c["centres"], 8192, c["center"], c["longest"]))
+
+
+def test_graphed_sweep_guards(setup):
+    """ADVICE r1 hazards of the captured sweep: the graphs read the cache's own copy of start_idx (the caller may free or
+    change its tensor), a batch of another shape is refused, and a weight update re-captures instead of replaying stale
+    packed weights."""
+    import copy
+    from pcc_b200.codec import PatchCodec
+    pcc, codec, sd = setup
+    ae = copy.deepcopy(codec.ae)
+    codec = PatchCodec(ae, centre_mode="coded")
+    host = [torch.from_numpy(synth.modelnet_like(2, 8192, seed=170 + i)).pin_memory() for i in range(3)]
+    got = {}
+
+    def sink(s, lat, cen, met, octree):
+        got[s] = (lat.cpu(), cen.cpu(), met.cpu())
+
+    def eager(start):
+        return [tuple(t.cpu() for t in codec.roundtrip(h.cuda(), start)[:3]) for h in host]
+
+    start = torch.tensor([3, 4], dtype=torch.int64, device="cuda")
+    codec.roundtrip_sweep(iter(host), start, sink, graphed=True)
+    torch.cuda.synchronize()
+    assert all(all(torch.equal(a, b) for a, b in zip(got[s], e)) for s, e in enumerate(eager(start)))
+    # a different start tensor (the first one is gone): same captured graphs, new values
+    del start
+    start2 = torch.tensor([100, 2000], dtype=torch.int64, device="cuda")
+    graphs_before = codec._sweep_graphs["graphs"]
+    codec.roundtrip_sweep(iter(host), start2, sink, graphed=True)
+    torch.cuda.synchronize()
+    assert codec._sweep_graphs["graphs"] is graphs_before
+    assert all(all(torch.equal(a, b) for a, b in zip(got[s], e)) for s, e in enumerate(eager(start2)))
+    # ragged batch: refused, not silently computed on the stale staging buffer
+    with pytest.raises(ValueError):
+        codec.roundtrip_sweep(iter(host + [host[0][:1]]), start2, sink, graphed=True)
+    torch.cuda.synchronize()
+    # weight update: re-capture
+    with torch.no_grad():
+        ae.pn.mlp_Modules[3][0].bias.add_(0.25)
+    codec.roundtrip_sweep(iter(host), start2, sink, graphed=True)
+    torch.cuda.synchronize()
+    assert codec._sweep_graphs["graphs"] is not graphs_before
+    assert all(all(torch.equal(a, b) for a, b in zip(got[s], e)) for s, e in enumerate(eager(start2)))

@@ -126,7 +126,7 @@ def test_input_segments_bf16_and_broadcast(mlp):
 
 def test_wide_fp32_segment_single_layer_and_run_chain_planner(mlp):
     """PointnetSAModule SA3-like: [gathered features fp32 256ch | xyz 3ch] -> 256 -> 256 -> 512 -> 1024, max over 128.
-    The planner runs the layers that fit as fused launches and the rest as library GEMMs."""
+    The planner runs the layers that fit as fused launches and the rest on the streamed tcgen05 GEMM."""
     torch.manual_seed(5)
     rows = 128 * 16
     feat = torch.rand(rows, 256, device="cuda") - 0.5
@@ -213,8 +213,9 @@ def test_streamed_linear_numerics(mlp, rows, cin, cout, relu, group):
 def test_streamed_linear_rejects_unsupported_shapes(mlp):
     x = torch.zeros(256, 64, device="cuda", dtype=torch.bfloat16)
     w, b = torch.zeros(100, 64, device="cuda"), torch.zeros(100, device="cuda")
+    assert mlp.linear(x, w, b, True).shape == (256, 100)   # cout is padded to the 128-column granule and sliced
     with pytest.raises(ValueError):
-        mlp.linear(x, w, b, True)                       # cout not a multiple of 128
+        mlp.linear(x, w, b, True, group=48)             # a pooling group the kernel does not take
     w, b = torch.zeros(128, 64, device="cuda"), torch.zeros(128, device="cuda")
     with pytest.raises(ValueError):
         mlp.linear(x, w, b, False, group=64)            # pooling over > 32 rows without the ReLU

@@ -40,6 +40,11 @@ def test_ae_forward_vs_reference_module_golden(pcc, golden_dir):
     assert np.abs(latent.cpu().numpy() - g["latent"]).max() < 5e-3
     same = lq.cpu().numpy() == g["lq"]
     assert same.mean() > 0.97
+    # the decoder is judged on the reference's own symbols, whatever the encoder's symbols were (one flipped symbol of a
+    # near-.5 latent must not switch the check off)
+    with torch.no_grad():
+        dec = ae.decode_patches(torch.from_numpy(g["lq"]).cuda())
+    assert np.abs(dec.cpu().numpy() - g["new_xyz"]).max() < COORD_ATOL
     if same.all():
         assert np.abs(new_xyz.cpu().numpy() - g["new_xyz"]).max() < COORD_ATOL
 

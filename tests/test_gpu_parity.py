@@ -79,6 +79,16 @@ def test_fps_multi_cta_cloud(pcc, orc):
         assert np.array_equal(got, orc.fps(xyz, S, start, 1e10, threads=8))
 
 
+def test_fps_multi_cta_iteration_tag_wrap(pcc, orc):
+    """The multi-CTA exchange tags its slots with (iteration + 1) & 2047 (fps.cu fps_grid_kernel): more than 2048 iterations
+    wrap the tag twice.  N = 20,000 (3 CTAs per cloud), npoint = 4,200, every index against the oracle; a second cloud in the
+    batch and grid-quantised points (exact ties) for the tie rule under the wrap."""
+    for xyz in (synth.uniform_cube(2, 20000, seed=77), synth.grid_quantised(1, 20000, depth=5, seed=78)):
+        start = np.arange(xyz.shape[0]) * 4001 + 7
+        got = pcc.ops.fps(cu(xyz), 4200, cu(start), 1e10).cpu().numpy()
+        assert np.array_equal(got, orc.fps(xyz, 4200, start, 1e10, threads=8))
+
+
 @pytest.mark.parametrize("name", ["sfp", "sfp_pad", "sfp_ties"])
 def test_sample_farthest_points_golden(pcc, g_p3d, name):
     pts, idx = pcc.sample_farthest_points(cu(g_p3d[f"{name}_x"]), K=int(g_p3d[f"{name}_K"]))
@@ -525,7 +535,7 @@ def test_pmf_to_cdf_reference_golden(pcc, golden_dir, name):
 
 def test_scene_scale_cfg5(pcc, orc):
     """BASELINE cfg5 at full size: one 1,000,000-point S3DIS-shaped scene.  FPS and kNN patching are checked bit-exactly against
-    the oracle on a prefix the oracle finishes in seconds (the first 300 of the 7812 centres; 48 queries of the K = 256 search),
+    the oracle on a prefix the oracle finishes in seconds (the first 2200 of the 7812 centres; 48 queries of the K = 256 search),
     and on the whole problem through properties: distinct in-range indices, ascending distances, the query's own point first."""
     scene = synth.scene_like(1_000_000, seed=3)
     xyz = cu(scene)
@@ -534,7 +544,7 @@ def test_scene_scale_cfg5(pcc, orc):
     idx = pcc.ops.fps(xyz, S, cu(start), 1e10)
     got = idx.cpu().numpy()
     assert got.shape == (1, S) and len(np.unique(got)) == S and got.min() >= 0 and got.max() < 1_000_000
-    assert np.array_equal(got[:, :300], orc.fps(scene, 300, start, 1e10, threads=8))   # FPS is a prefix-stable sequence
+    assert np.array_equal(got[:, :2200], orc.fps(scene, 2200, start, 1e10, threads=8))   # FPS is a prefix-stable sequence; 2200 > one tag wrap
     centres = pcc.index_points(xyz, idx)
     d, i, nn = pcc.ops.knn(centres, xyz, 256, return_nn=True)
     dn, inn = d.cpu().numpy(), i.cpu().numpy()

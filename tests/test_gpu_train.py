@@ -40,8 +40,15 @@ def test_training_forward_matches_fused_inference_forward():
         rec_i, lat_i, lq_i = ae(x)             # fused inference body
     assert rec_t.requires_grad and not rec_i.requires_grad
     assert float((lat_t - lat_i).abs().max()) < 5e-3
-    if torch.equal(lq_t, lq_i):
-        assert float((rec_t - rec_i).abs().max()) < 1e-2
+    assert float((lq_t == lq_i).float().mean()) > 0.97
+    # decoders compared on identical symbols, unconditionally: the training body's decoder half re-run on the fused body's lq
+    with torch.no_grad():
+        lin = ae.inv_pool(lq_i).view(4, -1, ae.k)
+        h = torch.cat((lin, lq_i.unsqueeze(-1).repeat((1, 1, ae.k))), dim=1).permute(0, 2, 1).reshape(4 * ae.k, -1)
+        for w, b, relu in ae.inv_mlp.layers():
+            h = torch.addmm(b, h, w.t())
+            h = torch.relu(h) if relu else h
+    assert float((h.view(4, ae.k, 3) - rec_i).abs().max()) < 1e-2
 
 
 def test_pppf_training_pass_and_fused_inference_agree():
@@ -74,3 +81,35 @@ def test_pppf_training_pass_and_fused_inference_agree():
         losses.append(float(loss))
     assert all(np.isfinite(losses)) and min(losses[-2:]) < losses[0]
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.parameters())
+
+
+def test_trainer_ddp_world_size_one_nccl():
+    """Trainer(ddp=True) (train.py:148-247 as a DistributedDataParallel step): a 1-rank NCCL group exercises the wrappers, the
+    bucketed gradient all-reduce and the optimiser over both models; the step must give the same losses as ddp=False from the
+    same seed (a 1-rank all-reduce is the identity).  bench.py runs the same class at world sizes 2 / 4 / 8 (configs.cfg2)."""
+    import os
+    import torch.distributed as dist
+    import __graft_entry__  # noqa: F401
+    from pcc_b200.train import Trainer
+    sd = synth.seeded_state_dict(synth.ae_shapes(128, 16, 7), 11)
+    x = torch.from_numpy(synth.modelnet_like(2, 2048, seed=63)).cuda()
+    start = torch.zeros(2, dtype=torch.int64, device="cuda")
+
+    def run(ddp):
+        torch.manual_seed(5)
+        tr = Trainer(K=256, k=128, d=16, L=7, lr=1e-3, state_dict=sd, ddp=ddp)
+        return [float(tr.step(x, start)["loss"]) for _ in range(4)], tr
+
+    plain, _ = run(False)
+    created = not dist.is_initialized()
+    if created:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29611")
+        dist.init_process_group("nccl", rank=0, world_size=1)
+    try:
+        ddp_losses, tr = run(True)
+        assert all(p.grad is not None for p in tr.ae.parameters()) and all(p.grad is not None for p in tr.prob.parameters())
+    finally:
+        if created:
+            dist.destroy_process_group()
+    assert all(np.isfinite(ddp_losses)) and np.allclose(ddp_losses, plain, rtol=1e-4)

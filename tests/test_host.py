@@ -26,6 +26,7 @@ def test_install_registers_the_names_the_reference_imports(pcc):
         assert chamfer_distance is pcc.chamfer_distance and ball_query is pcc.ball_query
         assert sample_farthest_points is pcc.sample_farthest_points
     finally:
+        pcc.uninstall()
         for k, v in saved.items():
             if v is None:
                 sys.modules.pop(k, None)
@@ -75,3 +76,36 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("CPU oracle", "").replace("the oracle", ""), f
+
+
+def test_install_swaps_forwards_and_hands_cpu_calls_back(pcc):
+    """install(): reference-named modules imported afterwards get their network forwards swapped (import hook); a call that
+    cannot run fused (CPU tensor here; training / train-mode BatchNorm on the GPU box) runs the class's own forward."""
+    import importlib
+    import os
+    names = ("pn_kit", "AE", "pointnet_sa_module", "PPPF_AE")
+    shims = ("pytorch3d", "pytorch3d.ops", "pytorch3d.ops.knn", "pytorch3d.loss", "torchac")
+    saved = {k: sys.modules.pop(k, None) for k in names + shims}
+    standins = os.path.join(os.path.dirname(os.path.abspath(__file__)), "standins")
+    sys.path.insert(0, standins)
+    try:
+        pcc.install()
+        ae_mod = importlib.import_module("AE")                       # pulls pn_kit in; both are patched when their import ends
+        pn = sys.modules["pn_kit"]
+        assert pn.MLP.forward.__pcc_b200__ and pn.SetAbstraction.forward.__pcc_b200__ and ae_mod.AE.forward.__pcc_b200__
+        assert pn.farthest_point_sample_batch is pcc.farthest_point_sample_batch
+        mlp = pn.MLP(in_channel=8, mlps=[16, 4], relu=[True, False], bn=False).eval()
+        x = torch.rand(2, 8, 10)
+        with torch.no_grad():
+            y = mlp(x)                                               # CPU tensor: the class's own forward
+            want = pn.MLP.forward.__pcc_original__(mlp, x)
+        assert y.shape == (2, 4, 10) and torch.equal(y, want)
+        pcc.uninstall()
+        assert not hasattr(pn.MLP.forward, "__pcc_b200__")
+    finally:
+        pcc.uninstall()
+        sys.path.remove(standins)
+        for k, v in saved.items():
+            sys.modules.pop(k, None)
+            if v is not None:
+                sys.modules[k] = v

@@ -195,3 +195,87 @@ def test_pmf_to_cdf_matches_reference_golden(golden_dir, name):
     L = cdf.shape[-1] - 1
     want = (cdf.mul(2 ** 16 - L).round().to(torch.int16) + torch.arange(L + 1, dtype=torch.int16)).numpy().view(np.uint16)
     assert np.array_equal(orc.pmf_to_cdf_u16(g[f"{name}_pmf"]), want)
+
+
+def test_torch_modules_match_reference_ae_golden(golden_dir):
+    """oracle/torch_modules.py (the CPU baseline's network bodies) against the outputs of the reference's own AE.AE
+    (tests/golden/ae_modules.npz, minted by make_golden.py::ae_modules from /root/reference): bit for bit."""
+    from oracle import torch_modules as tm
+    g = np.load(os.path.join(golden_dir, "ae_modules.npz"))
+    sd = synth.seeded_state_dict(synth.ae_shapes(128, 16, 7), 11)
+    x = torch.from_numpy(g["x"])
+    with torch.no_grad():
+        feat = tm.set_abstraction(sd, x.transpose(2, 1))
+        latent, lq = tm.ae_encode(sd, x, L=7)
+        rec = tm.ae_decode(sd, lq, k=128)
+    assert np.array_equal(feat.numpy(), g["sa_feat"])
+    assert np.array_equal(latent.numpy(), g["latent"]) and np.array_equal(lq.numpy(), g["lq"])
+    assert np.array_equal(rec.numpy(), g["new_xyz"])
+
+
+def _state_keys(path_first, stub_with_oracle):
+    """state_dict keys / shapes of the network classes found under `path_first`, collected in a fresh interpreter."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = f"""
+import json, sys
+sys.path.insert(0, {root!r})
+from oracle import ref_loader
+ref_loader.install_stubs()
+sys.path.insert(0, {path_first!r})
+import AE, PPPF_AE
+out = {{}}
+for name, m in (("AE.AE", AE.AE(256, 128, 16, 7)), ("AE.prob", AE.ConditionalProbabilityModel(7, 16)),
+                ("PPPF_AE.PPPF_AE", PPPF_AE.PPPF_AE(K=512, k=0, d=16, L=7)), ("PPPF_AE.prob", PPPF_AE.ConditionalProbabilityModel(7, 16)),
+                ("PPPF_AE.AE", PPPF_AE.AE(K=256, k=0, d=16, L=7))):
+    out[name] = {{k: list(v.shape) for k, v in m.state_dict().items()}}
+    out[name + ":attrs"] = sorted(k for k in vars(m) if not k.startswith("_"))
+print(json.dumps(out))
+"""
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-3000:]
+    return json.loads(r.stdout.strip().splitlines()[-1])
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference is not present")
+def test_standins_match_reference_state_dict_keys():
+    """tests/standins/ (what the GPU box tests install() against) mirror the real reference's classes: same state_dict keys
+    and shapes, same public instance attributes."""
+    here = os.path.dirname(os.path.abspath(__file__))
+    assert _state_keys(os.path.join(here, "standins"), True) == _state_keys(ref_loader.REFERENCE_ROOT, True)
+
+
+def test_standin_forwards_reproduce_reference_goldens(golden_dir):
+    """The stand-ins' eager forward bodies, run on CPU with the oracle ops, reproduce the outputs of the real reference's
+    AE.AE and PPPF_AE.PPPF_AE (the committed goldens) -- so "stand-in under install() == reference under install()"."""
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    root = os.path.dirname(here)
+    code = f"""
+import sys
+import numpy as np, torch
+sys.path.insert(0, {root!r})
+from oracle import ref_loader
+from tools import synth
+ref_loader.install_stubs()
+sys.path.insert(0, {os.path.join(here, "standins")!r})
+import AE, PPPF_AE
+g = np.load({os.path.join(golden_dir, "ae_modules.npz")!r})
+m = AE.AE(256, 128, 16, 7); m.load_state_dict(synth.seeded_state_dict(synth.ae_shapes(128, 16, 7), 11)); m.eval()
+with torch.no_grad():
+    new_xyz, latent, lq = m(torch.from_numpy(g["x"]))
+assert np.array_equal(lq.numpy(), g["lq"]) and np.abs(latent.numpy() - g["latent"]).max() < 1e-5
+assert np.abs(new_xyz.numpy() - g["new_xyz"]).max() < 1e-5
+g = np.load({os.path.join(golden_dir, "pppf_modules.npz")!r})
+m = PPPF_AE.PPPF_AE(K=512, k=0, d=16, L=7); m.load_state_dict(synth.seeded_module_state(m, 17)); m.eval()
+with torch.no_grad():
+    recon, latent, lq = m(torch.from_numpy(g["x"]))
+assert np.array_equal(lq.numpy(), g["lq"]) and np.abs(latent.numpy() - g["latent"]).max() < 1e-4
+assert np.abs(recon.numpy() - g["recon"]).max() < 1e-4
+print("ok")
+"""
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-3000:]

@@ -23,7 +23,15 @@ cases = {
 tail = make_layers([256, 512, 16], [True, False], 4)
 h256 = mlp_ops.fused_chain([(feat, 1), (xyz, 1)], pna, out_dtype=torch.bfloat16)
 cases["pn tail 256-512-16 max256"] = (lambda: mlp_ops.pn_tail(h256, tail), BS * 256 * 2 * (256 * 512 + 512 * 16))
-cases["pn tail (library GEMMs)"] = (lambda: mlp_ops.library_chain(h256, tail).view(BS, 256, -1).max(dim=1)[0], BS * 256 * 2 * (256 * 512 + 512 * 16))
+
+
+
+def _library_tail():   # comparison arm only (tools/): the same two layers as plain torch bf16 GEMMs + a separate max
+    h = torch.relu(torch.addmm(tail[0][1].bfloat16(), h256, tail[0][0].bfloat16().t()))
+    return torch.addmm(tail[1][1].bfloat16(), h, tail[1][0].bfloat16().t()).view(BS, 256, -1).max(dim=1)[0]
+
+
+cases["pn tail (library GEMMs)"] = (_library_tail, BS * 256 * 2 * (256 * 512 + 512 * 16))
 for name, (fn, flop) in cases.items():
     for _ in range(3):
         fn()
