@@ -33,10 +33,26 @@ METRIC = "point clouds/sec (8192 pts, K=256) compress+Chamfer eval"
 UNIT = "clouds/s"
 N_POINTS, K_PATCH, K_OUT, D_LATENT, L_LEVELS, N0, ALPHA = 8192, 256, 128, 16, 7, 1024, 2
 BATCH = 32
-SA_DRAM_BYTES = 190.0e6  # dram read+write of one sa_chain2_kernel launch (profiles/r01_step_kernels_ncu_full.txt: 100.82 + 89.19 MB)
+DTYPE = "f32 geometry (FPS / kNN / Chamfer, exact-rounded); bf16 operands with fp32 accumulation in the MLP kernels"
 POOL_BATCHES = 44  # 44 x 3.1 MB = 138 MB of distinct inputs > 126 MB L2 (no L2 flush needed between steps)
 WORKLOAD = ("cfg2-shape batch: 32 synthetic ModelNet40-shaped clouds x 8192 pts, K=256, S=64, d=16; "
             "compress -> decompress -> Chamfer + D1-PSNR eval (forward)")
+
+
+def base_config(world):
+    """The workload description both arms print (the reference arm runs the same per-step batch on the host cores)."""
+    return {"workload": WORKLOAD, "clouds_per_step_per_gpu": BATCH, "points": N_POINTS, "K": K_PATCH,
+            "parallelism": f"dp{world} (whole clouds sharded by rank, metrics all_gather only)",
+            "l2": f"rotating pool of {POOL_BATCHES} distinct input batches (138 MB > 126 MB L2), no flush"}
+
+
+def sa_traffic():
+    """dram__bytes_read + dram__bytes_write of one launch of the dominant kernel, from the committed ncu summary."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")))
+        return float(t["dram_bytes_per_launch"]), t.get("source", "")
+    except (OSError, KeyError, ValueError):
+        return None, "profiles/dominant_kernel_traffic.json missing"
 
 
 def parse():
@@ -46,6 +62,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the cfg1..cfg5 sub-records (development runs)")
     return ap.parse_args()
 
 
@@ -115,7 +132,9 @@ def run_reference(args):
     from oracle import oracle as orc
     orc.lib()
     threads = os.cpu_count() or 1
-    per_step = 2  # clouds per step: ~1 s of CPU work, so K+W steps finish within minutes
+    # one step = the same batch of 32 clouds the GPU arm processes per step (~7 s of host work); when the requested K + W steps
+    # would not finish within a few minutes the per-step sample is cut down (and says so)
+    per_step = max(1, min(BATCH, int(280.0 / (args.steps + args.warmup) / 0.22)))
     for _ in range(args.warmup):
         cpu_reference_rate(per_step, threads)
     t0 = time.perf_counter()
@@ -128,7 +147,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "clouds_per_step": per_step},
+        "config": base_config(args.gpus), "clouds_per_step_sampled": per_step,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -309,6 +328,12 @@ def run_b200(args):
                               f"PyTorch3D/pn_kit CPU algorithms and of the octree coder -- faster than the reference's numpy "
                               f"coder -- + torch CPU fp32 network), {threads} threads"}
 
+    configs = None
+    if not args.no_configs:
+        from tools import bench_configs
+        sd = synth.seeded_state_dict(synth.ae_shapes(K_OUT, D_LATENT, L_LEVELS), 11)
+        configs = bench_configs.run_all(dev, rank, world, barrier, max_over_ranks, codec, sd)
+
     if rank == 0:
         peaks = {}
         try:
@@ -346,9 +371,10 @@ def run_b200(args):
                 others["pn_tail_kernel"] = {"ms_per_launch": kernel_ms["pn_tail"], "bound": "tensor",
                                             "achieved_tflops": fl / (kernel_ms["pn_tail"] / 1e3) / 1e12,
                                             "frac": fl / (kernel_ms["pn_tail"] / 1e3) / 1e12 / tf_peak}
+            traffic, traffic_src = sa_traffic()
             roofline = {"kernel": "ws::sa_chain2_kernel -- SetAbstraction shared MLP 3-32-64-128 + max over 16 neighbours (tcgen05)",
                         "bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
-                        "traffic": SA_DRAM_BYTES, "peak_source": peak_src + " bf16_tflops_sustained (kernel timed inside a long step)",
+                        "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src + " bf16_tflops_sustained (kernel timed inside a long step)",
                         "ms_per_launch": ms, "flop_per_launch": flop,
                         "note": "K is 32..64 per layer, so the kernel is paced by the MMA -> epilogue -> MMA hand-offs of its four "
                                 "tiles in flight per SM (TMEM: 128 accumulator columns per tile) and by the per-warp latency of the "
@@ -357,21 +383,18 @@ def run_b200(args):
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "clouds_per_step_per_gpu": BATCH, "points": N_POINTS, "K": K_PATCH,
-                       "parallelism": f"dp{world} (whole clouds sharded by rank, metrics all_gather only)",
-                       "l2": f"rotating pool of {POOL_BATCHES} distinct input batches (138 MB > 126 MB L2), no flush",
-                       "launch": "value and e2e replay a captured CUDA graph of the step (19 kernels of this library + 6 small torch "
-                                 "kernels); the per-kernel CUDA-event timings of `roofline` come from the same steps launched kernel "
-                                 f"by kernel right after ({eager_ms:.4f} ms per step that way)",
-                       "centres": "octree centre coder on the device (pn_kit.encode_sampled_np depth search, bit-exact stream and "
-                                  ".s.bin bytes); patches are built on the centres a decoder recovers from that stream",
-                       "mlp": "hand-written tcgen05 kernels only: SetAbstraction 3-32-64-128+max16, PointNet 131-128-256 and its "
-                              "256-512-16+max tail (W2 streamed by TMA), inv_pool 16-256-1024-16384 (streamed GEMM, TMA ring), "
-                              "decoder 144-128-64-32-3; no library GEMM in the timed region"},
+            "dtype": DTYPE, "data": "synthetic", "config": base_config(world),
+            "notes": {"launch": "value and e2e replay a captured CUDA graph of the step; the per-kernel CUDA-event timings of "
+                                "`roofline` come from the same steps launched kernel by kernel right after",
+                      "eager_ms_per_step": eager_ms,
+                      "centres": "octree centre coder on the device (pn_kit.encode_sampled_np depth search, bit-exact stream and "
+                                 ".s.bin bytes); patches are built on the centres a decoder recovers from that stream",
+                      "mlp": "hand-written tcgen05 kernels only: SetAbstraction 3-32-64-128+max16, PointNet 131-128-256 and its "
+                             "256-512-16+max tail (W2 streamed by TMA), inv_pool 16-256-1024-16384 (streamed GEMM, TMA ring), "
+                             "decoder 144-128-64-32-3; no library GEMM in the timed region"},
             "clocks": clk, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
-            "roofline": roofline, "cpu_baseline": cpu_base,
+            "roofline": roofline, "cpu_baseline": cpu_base, "configs": configs,
             "quality": {"mean_chamfer": float(torch.cat(metrics)[:, 0].mean()),
                         "mean_d1_psnr_db": float(torch.cat(metrics)[:, 1].mean())},
         }))

@@ -271,9 +271,12 @@ int pcc_fold_first_bf16(const float *local, int n_local, int64_t ld_local, const
  * and of xyz, torch.cat): out[b * M + j, :] = [feat[b, idx[b, j], 0..C) | xyz[b, idx[b, j], 0..3) | 0 ...] as bf16 rows of
  * kpad columns (kpad % 8 == 0) -- the A operand of pcc_linear_bf16.  feat [B, N, C] fp32 or NULL (C = 0), xyz [B, N, 3] fp32 or
  * NULL, idx [B, M] int64; negative indices read point 0 (pointnet_sa_module.py:27).
+ * centre (nullable) [B, M / nsample, 3] fp32: the query every run of `nsample` rows was grouped around; when given, the xyz
+ * columns hold fl(xyz[idx] - centre) -- the recentred grouping of pppe_pcd_ae.PointNetSetAbstraction
+ * (/root/reference/pppe_pcd_ae.py:599-607: knn_points(return_nn) - new_xyz, index_points of the features, torch.cat).
  */
 int pcc_gather_concat_bf16(const float *feat, int C, const float *xyz, const int64_t *idx, int B, int N, int64_t M, int kpad,
-                           void *out, void *stream);
+                           void *out, const float *centre, int nsample, void *stream);
 
 /*
  * The remaining eval.py metrics, computed from outputs of pcc_knn_f32 / pcc_chamfer_fwd_f32.

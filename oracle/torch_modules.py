@@ -3,7 +3,7 @@ the C oracle.  TEST INFRASTRUCTURE ONLY (tests/, smoke(), bench.py cpu_baseline 
 
 Every function takes the reference's state_dict (same keys) and follows the cited lines; the layouts and op
 order are the reference's (channel-first F.conv2d on [B, C, K, S]), so the outputs match the reference modules
-run on CPU with the oracle ops injected (tests/test_modules_cpu.py checks that when /root/reference is present).
+run on CPU with the oracle ops injected (tests/test_oracle.py::test_torch_modules_match_reference_ae_golden pins that against tests/golden/ae_modules.npz).
 """
 import math
 

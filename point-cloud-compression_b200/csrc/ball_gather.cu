@@ -117,7 +117,8 @@ __device__ __forceinline__ unsigned pack2_bf16(float lo, float hi) {
 // chunks with the rows unrolled, so several rows' feature loads are in flight at once.
 __global__ void __launch_bounds__(256)
 gather_concat_bf16_kernel(const float *__restrict__ feat, int C, const float *__restrict__ xyz, const int64_t *__restrict__ idx,
-                          long long rows, int N, long long M, int kpad, uint4 *__restrict__ out) {
+                          long long rows, int N, long long M, int kpad, uint4 *__restrict__ out,
+                          const float *__restrict__ centre, int nsample) {
     constexpr int R = 4;
     const int chunks = kpad >> 3, lane = threadIdx.x & 31;
     const bool vec = feat && (C & 7) == 0;
@@ -137,6 +138,9 @@ gather_concat_bf16_kernel(const float *__restrict__ feat, int C, const float *__
             for (int i = 0; i < R; ++i) {
                 const float *f = feat ? feat + src[i] * C : nullptr;
                 const float *p = xyz ? xyz + src[i] * 3 : nullptr;
+                // recentred grouping (pppe_pcd_ae.py:600): row r belongs to query r / nsample, whose xyz is subtracted in fp32
+                const long long rr = r0 + i < rows ? r0 + i : rows - 1;
+                const float *cq = centre ? centre + (rr / nsample) * 3 : nullptr;
                 float v[8];
                 if (vec && c0 + 8 <= C) {
                     const float4 a = __ldg(reinterpret_cast<const float4 *>(f + c0));
@@ -146,7 +150,9 @@ gather_concat_bf16_kernel(const float *__restrict__ feat, int C, const float *__
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
                         const int c = c0 + e;
-                        v[e] = (f && c < C) ? __ldg(f + c) : (p && c >= C && c < C + 3) ? __ldg(p + (c - C)) : 0.0f;
+                        v[e] = (f && c < C) ? __ldg(f + c)
+                               : (p && c >= C && c < C + 3) ? (cq ? __fsub_rn(__ldg(p + (c - C)), __ldg(cq + (c - C))) : __ldg(p + (c - C)))
+                                                            : 0.0f;
                     }
                 }
                 q[i].x = pack2_bf16(v[0], v[1]);
@@ -210,7 +216,7 @@ PCC_API int pcc_gather_bwd_f32(const float *grad_out, const int64_t *idx, int B,
 }
 
 PCC_API int pcc_gather_concat_bf16(const float *feat, int C, const float *xyz, const int64_t *idx, int B, int N, int64_t M, int kpad,
-                                   void *out, void *stream) {
+                                   void *out, const float *centre, int nsample, void *stream) {
     using namespace pcc;
     PCC_REQUIRE((feat || xyz) && idx && out, "pcc_gather_concat_bf16: null pointer");
     PCC_REQUIRE(B >= 0 && N >= 1 && M >= 0 && C >= 0 && (feat || C == 0), "pcc_gather_concat_bf16: bad shape");
@@ -218,9 +224,10 @@ PCC_API int pcc_gather_concat_bf16(const float *feat, int C, const float *xyz, c
                 C + (xyz ? 3 : 0));
     PCC_REQUIRE(reinterpret_cast<uintptr_t>(out) % 16 == 0 && (!feat || reinterpret_cast<uintptr_t>(feat) % 16 == 0),
                 "pcc_gather_concat_bf16: feat / out must be 16-byte aligned");
+    PCC_REQUIRE(!centre || (xyz && nsample >= 1 && M % nsample == 0), "pcc_gather_concat_bf16: centre needs xyz and nsample | M");
     const long long rows = static_cast<long long>(B) * M;
     if (rows == 0) return 0;
     gather_concat_bf16_kernel<<<grid_for(rows * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        feat, C, xyz, idx, rows, N, M, kpad, static_cast<uint4 *>(out));
+        feat, C, xyz, idx, rows, N, M, kpad, static_cast<uint4 *>(out), centre, centre ? nsample : 1);
     return check_launch("gather_concat_bf16_kernel");
 }

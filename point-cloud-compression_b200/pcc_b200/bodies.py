@@ -183,6 +183,26 @@ def ae_decode(mod, latent_q):
     return out.view(BS, k, -1)
 
 
+def linear_stack_forward(seq, x):
+    """An nn.Sequential of Linear (+ ReLU) layers applied to [rows, d] -- AE.inv_pool called on its own, as decompress.py:96 does
+    (`ae.inv_pool(latent_quantized)`): every Linear on the streamed tensor-core GEMM, reference layout [rows, out_features],
+    fp32 dtype (the values are the bf16 activations the fused decode uses)."""
+    def build():
+        mods, out = list(seq), []
+        for i, m in enumerate(mods):
+            if isinstance(m, nn.Linear):
+                bias = m.bias if m.bias is not None else torch.zeros(m.out_features, device=m.weight.device)
+                out.append((m.weight, bias, i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU)))
+            elif not isinstance(m, nn.ReLU):
+                raise ValueError(f"pcc_b200: {type(m).__name__} inside a Linear stack is not a layer the kernels take")
+        return out
+    layers = _cached(seq, "linear_stack", build)
+    d = x.shape[-1]
+    lat = torch.nn.functional.pad(x.detach().reshape(-1, d).to(torch.bfloat16), (0, (-d) % 64))
+    out = mlp_ops.stream_chain(lat, layers)
+    return out.float().reshape(x.shape[:-1] + (out.shape[-1],))
+
+
 def ae_forward(mod, xyz):
     """AE.AE.forward (AE.py:34-55): xyz [BS, K, 3] -> (new_xyz [BS, k, 3], latent, latent_quantized)."""
     latent, latent_q = ae_encode(mod, xyz.contiguous())
@@ -299,3 +319,71 @@ def pppf_forward(mod, xyz):
     latent_q = z.round()                                                            # :142
     dec = mlp_ops.linear_small(latent_q, mod.dec_proj.weight, mod.dec_proj.bias)    # :145
     return folding_forward(mod.decoder, dec), latent, latent_q
+
+
+# ---- pppe_pcd_ae.PointNet2EncoderFull ("fast pppe_pcd_ae compress", BASELINE cfg5) -----------------------------------------------
+def pppe_sa_layers(mod):
+    """pppe_pcd_ae.PointNetSetAbstraction.mlp_stack: Sequential(Conv2d(bias=False), BatchNorm2d, ReLU) per layer, or
+    Sequential(Conv2d, ReLU) with bn=False (pppe_pcd_ae.py:556-561, 582-586); eval-mode BatchNorm folded into the conv."""
+    return _cached(mod, "pppe_stack", lambda: [_seq_layer(s) for s in mod.mlp_stack])
+
+
+def pppe_sa_points(mod, xyz, feat=None):
+    """pppe_pcd_ae.PointNetSetAbstraction.forward (pppe_pcd_ae.py:588-618), channel-last: xyz [B, N, 3], feat [B, N, C] or None
+    -> (new_xyz [B, S, 3], new features [B, S, C_out] fp32).  FPS start from the CPU RNG (pn_kit.py:321), kNN(K) of every centre,
+    recentred xyz [| gathered features], shared MLP, max over the K neighbours."""
+    B, N, _ = xyz.shape
+    S, K = mod.npoint, mod.K
+    new_xyz = xyz if S == N else ops.gather(xyz, pn_kit_ops.farthest_point_sample_batch(xyz, S))      # :596-600
+    layers = list(pppe_sa_layers(mod))
+    if feat is None:
+        _, _, grouped = ops.knn(new_xyz, xyz, K, return_nn=True, centre_sub=True, nn_only=True)       # :602-603
+        out = mlp_ops.run_chain(grouped.reshape(B * S * K, 3), layers, group=K)                      # :614-617
+    else:
+        _, idx, _ = ops.knn(new_xyz, xyz, K)                                                          # :602
+        C = feat.shape[2]
+
+        def rot():   # the reference concatenates [xyz | features] (:609); the grouping kernel emits [features | xyz]
+            w0 = layers[0][0]
+            return torch.cat((w0[:, 3:], w0[:, :3]), dim=1).detach().contiguous()
+
+        layers[0] = (_cached(mod, "pppe_rot_w0", rot), layers[0][1], layers[0][2])
+        a = mlp_ops.gather_concat_bf16(feat, xyz, idx, (C + 3 + 63) // 64 * 64, centre=new_xyz, nsample=K)   # :603-609
+        out = mlp_ops.stream_chain(a, layers, group=K)                                                # :614-617
+    return new_xyz, out.reshape(B, S, -1)
+
+
+def pppe_msg_points(mod, xyz, feat=None):
+    """pppe_pcd_ae.PointNetSetAbstractionMSG.forward (pppe_pcd_ae.py:627-633): every branch samples its own centres (one CPU-RNG
+    draw each); the LAST branch's centres are handed on; features concatenated along the channel axis."""
+    outs, new_xyz = [], None
+    for b in mod.branches:
+        new_xyz, f = pppe_sa_points(b, xyz, feat)
+        outs.append(f)
+    return new_xyz, torch.cat(outs, dim=2)
+
+
+def _pppe_level(mod, xyz, feat):
+    return pppe_msg_points(mod, xyz, feat) if hasattr(mod, "branches") else pppe_sa_points(mod, xyz, feat)
+
+
+def pppe_sa_forward(mod, xyz, points=None):
+    """Reference layouts: xyz [B, N, 3], points [B, C, N] or None -> (new_xyz [B, S, 3], new_points [B, C_out, S])."""
+    xyz = xyz.detach().float().contiguous()
+    feat = points.detach().float().permute(0, 2, 1).contiguous() if points is not None else None
+    new_xyz, f = _pppe_level(mod, xyz, feat)
+    return new_xyz, f.permute(0, 2, 1)
+
+
+def pppe_encoder_forward(mod, x):
+    """pppe_pcd_ae.PointNet2EncoderFull.forward (pppe_pcd_ae.py:672-690): x [B, N, 3] -> (latent [B, latent_dim], pooled features
+    [B, C_out]).  The levels hand channel-last features to each other (no permutes in between)."""
+    xyz, feat = x.detach().float().contiguous(), None
+    for sa in mod.sa_modules:
+        xyz, feat = _pppe_level(sa, xyz, feat)
+    global_feat = feat.max(dim=1)[0]                                                                  # :683
+    conv0, bn, conv3 = mod.global_conv[0], mod.global_conv[1], mod.global_conv[3]
+    w0, b0 = _cached(mod, "pppe_global", lambda: _fold(conv0, bn))
+    h = mlp_ops.linear_small(global_feat, w0, b0, relu=True)                                          # :660-665, 685
+    latent = mlp_ops.linear_small(h, _w2d(conv3), conv3.bias)
+    return latent, global_feat

@@ -359,8 +359,9 @@ def stream_chain(x, layers, group=0):
     return x
 
 
-def gather_concat_bf16(feat, xyz, idx, kpad):
-    """Rows [feat[b, idx] | xyz[b, idx] | 0...] in bf16, kpad columns (pointnet_sa_module.py:73-85 grouping + cat)."""
+def gather_concat_bf16(feat, xyz, idx, kpad, centre=None, nsample=1):
+    """Rows [feat[b, idx] | xyz[b, idx] | 0...] in bf16, kpad columns (pointnet_sa_module.py:73-85 grouping + cat).
+    centre [B, M / nsample, 3]: subtract the query's xyz from the xyz columns (pppe_pcd_ae.py:599-607 recentred grouping)."""
     lib = _lib.load()
     _check(idx)
     B = idx.shape[0]
@@ -374,9 +375,12 @@ def gather_concat_bf16(feat, xyz, idx, kpad):
         C = feat.shape[2]
     if xyz is not None:
         xyz = xyz.float().contiguous()
+    if centre is not None:
+        centre = centre.float().contiguous()
     out = torch.empty((B * M, kpad), dtype=torch.bfloat16, device=idx.device)
     with torch.cuda.device(idx.device):
         _lib.check(lib.pcc_gather_concat_bf16(feat.data_ptr() if feat is not None else None, C,
                                               xyz.data_ptr() if xyz is not None else None, idx.data_ptr(), B, N, M, kpad,
-                                              out.data_ptr(), torch.cuda.current_stream().cuda_stream), "pcc_gather_concat_bf16")
+                                              out.data_ptr(), centre.data_ptr() if centre is not None else None, int(nsample),
+                                              torch.cuda.current_stream().cuda_stream), "pcc_gather_concat_bf16")
     return out

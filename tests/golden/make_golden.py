@@ -9,6 +9,7 @@
 * ref_eval.npz        -- eval.py's calc_uc run from the reference's own source (extracted with ast), and the oracle's
                          p2plane PSNR (Open3D absent: unpinned).
 * ref_entropy.npz     -- outputs of the REFERENCE's own pn_kit.pmf_to_cdf / estimate_bits_from_pmf on seeded PMFs.
+* pppe_modules.npz    -- outputs of the REFERENCE's own pppe_pcd_ae.PointNet2EncoderFull on CPU (kNN served by the oracle).
 * p3d_ops.npz         -- outputs of the oracle restatement of the PyTorch3D ops (knn_points, ball_query,
                          sample_farthest_points, chamfer_distance) on seeded inputs, cross-checked here against
                          an independent torch brute-force statement before being written.  PyTorch3D itself
@@ -141,6 +142,25 @@ def pppf_modules():
     print("pppf_modules.npz:", {k: tuple(v.shape) for k, v in dict(f1=f1, f2=f2, f3=f3, recon=recon, latent=latent).items()})
 
 
+def pppe_modules():
+    """Outputs of the REFERENCE's pppe_pcd_ae.PointNet2EncoderFull (MSG + 2 SS set-abstraction levels, global head) in eval mode
+    on CPU, kNN served by the oracle, FPS = the reference's own pn_kit function with its CPU-RNG start draws (seed 11 first)."""
+    ref = ref_loader.load("pppe_pcd_ae")
+    model = ref.PointNet2EncoderFull(latent_dim=256)
+    model.load_state_dict(synth.seeded_module_state(model, 23))
+    model.eval()
+    x = torch.from_numpy(synth.modelnet_like(2, 2048, seed=71))
+    with torch.no_grad():
+        torch.manual_seed(11)
+        latent, pooled = model(x)
+        torch.manual_seed(11)
+        xyz1, f1 = model.sa_modules[0](x, None)
+        xyz2, f2 = model.sa_modules[1](xyz1, f1)
+    np.savez_compressed(os.path.join(HERE, "pppe_modules.npz"), x=x.numpy(), latent=latent.numpy(), pooled=pooled.numpy(),
+                        xyz1=xyz1.numpy(), f1=f1.numpy(), xyz2=xyz2.numpy(), f2=f2.numpy())
+    print("pppe_modules.npz:", {k: tuple(v.shape) for k, v in dict(latent=latent, pooled=pooled, f1=f1, f2=f2).items()})
+
+
 def ae_modules():
     """Outputs of the REFERENCE's AE.AE (SetAbstraction + PointNet encoder, inv_pool + MLP decoder) on CPU."""
     ref = ref_loader.load("AE")
@@ -259,6 +279,7 @@ if __name__ == "__main__":
     ref_fps_gather()
     p3d_ops()
     pppf_modules()
+    pppe_modules()
     ae_modules()
     ref_octree()
     ref_eval()

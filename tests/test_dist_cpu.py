@@ -13,10 +13,15 @@ def _worker(rank, world, port, n_total, q):
     sys.path[:0] = [ROOT, os.path.join(ROOT, "point-cloud-compression_b200")]
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from pcc_b200.dist import gather_rows, shard_range
+    from pcc_b200.dist import gather_rows, shard_range, sharded_rows
     b, e = shard_range(n_total, rank, world)
     local = torch.arange(b, e, dtype=torch.float64)[:, None] * torch.tensor([1.0, 10.0, 100.0], dtype=torch.float64)
     full = gather_rows(local, n_total)
+    # the scene-scale split (cfg5): every rank evaluates its slice of the query rows, one all-gather returns the whole table
+    calls = []
+    table = sharded_rows(lambda lo, hi: (calls.append((lo, hi)), torch.arange(lo, hi, dtype=torch.int64)[:, None].repeat(1, 4) * 3)[1],
+                         n_total)
+    assert calls == [(b, e)] and torch.equal(table, torch.arange(n_total, dtype=torch.int64)[:, None].repeat(1, 4) * 3)
     q.put((rank, full.tolist()))   # plain lists: a shared-memory tensor would need this process alive until it is received
     dist.destroy_process_group()
 

@@ -77,6 +77,34 @@ def test_pppf_encoder_decoder_vs_reference_module_golden(pcc, golden_dir):
         torch.set_grad_enabled(True)
 
 
+def test_pppe_encoder_vs_reference_module_golden(pcc, golden_dir):
+    """pcc_b200.pppe.PointNet2EncoderFull ("fast pppe_pcd_ae compress", cfg5) against the outputs of the REFERENCE's own
+    pppe_pcd_ae.PointNet2EncoderFull: FPS centres exact (same CPU-RNG draws), per-level features and the latent within the
+    bf16 tolerance; every level also judged on the reference's own inputs."""
+    from pcc_b200 import pppe
+    g = np.load(os.path.join(golden_dir, "pppe_modules.npz"))
+    model = pppe.PointNet2EncoderFull(latent_dim=256)
+    model.load_state_dict(synth.seeded_module_state(model, 23))
+    model = model.cuda().eval()
+    x = torch.from_numpy(g["x"]).cuda()
+    with torch.no_grad():
+        torch.manual_seed(11)
+        xyz1, f1 = model.sa_modules[0](x, None)
+        assert np.array_equal(xyz1.cpu().numpy(), g["xyz1"])
+        assert rel(f1.cpu().numpy(), g["f1"]) < FEATURE_RTOL
+        xyz2, f2 = model.sa_modules[1](torch.from_numpy(g["xyz1"]).cuda(), torch.from_numpy(g["f1"]).cuda())
+        assert np.array_equal(xyz2.cpu().numpy(), g["xyz2"])             # third CPU-RNG draw of the sequence
+        assert rel(f2.cpu().numpy(), g["f2"]) < FEATURE_RTOL
+        torch.manual_seed(11)
+        latent, pooled = model(x)
+        assert rel(pooled.cpu().numpy(), g["pooled"]) < 3e-2
+        assert rel(latent.cpu().numpy(), g["latent"]) < 3e-2
+        q, cond = pppe.compress(model, x, latent_bins=7)
+        assert q.shape == (2, 256) and float(q.min()) >= 0 and float(q.max()) <= 6 and torch.equal(q, q.round())
+    with pytest.raises(NotImplementedError):
+        model.train()(x)
+
+
 def test_pointnet_ops_wrapper_matches_reference_names(pcc):
     """PointnetPPOps (pointnet_sa_module.py:8-34): argument order and return types."""
     xyz = torch.from_numpy(synth.shapenet_like(2, 512, seed=3)).cuda()

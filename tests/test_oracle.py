@@ -225,9 +225,10 @@ sys.path.insert(0, {root!r})
 from oracle import ref_loader
 ref_loader.install_stubs()
 sys.path.insert(0, {path_first!r})
-import AE, PPPF_AE
+import AE, PPPF_AE, pppe_pcd_ae
 out = {{}}
 for name, m in (("AE.AE", AE.AE(256, 128, 16, 7)), ("AE.prob", AE.ConditionalProbabilityModel(7, 16)),
+                ("pppe.encoder", pppe_pcd_ae.PointNet2EncoderFull(latent_dim=256)),
                 ("PPPF_AE.PPPF_AE", PPPF_AE.PPPF_AE(K=512, k=0, d=16, L=7)), ("PPPF_AE.prob", PPPF_AE.ConditionalProbabilityModel(7, 16)),
                 ("PPPF_AE.AE", PPPF_AE.AE(K=256, k=0, d=16, L=7))):
     out[name] = {{k: list(v.shape) for k, v in m.state_dict().items()}}
@@ -249,7 +250,7 @@ def test_standins_match_reference_state_dict_keys():
 
 def test_standin_forwards_reproduce_reference_goldens(golden_dir):
     """The stand-ins' eager forward bodies, run on CPU with the oracle ops, reproduce the outputs of the real reference's
-    AE.AE and PPPF_AE.PPPF_AE (the committed goldens) -- so "stand-in under install() == reference under install()"."""
+    AE.AE, PPPF_AE.PPPF_AE and pppe_pcd_ae.PointNet2EncoderFull (the committed goldens) -- so "stand-in under install() == reference under install()"."""
     import subprocess
     import sys
     here = os.path.dirname(os.path.abspath(__file__))
@@ -262,7 +263,13 @@ from oracle import ref_loader
 from tools import synth
 ref_loader.install_stubs()
 sys.path.insert(0, {os.path.join(here, "standins")!r})
-import AE, PPPF_AE
+import AE, PPPF_AE, pppe_pcd_ae
+g = np.load({os.path.join(golden_dir, "pppe_modules.npz")!r})
+m = pppe_pcd_ae.PointNet2EncoderFull(latent_dim=256); m.load_state_dict(synth.seeded_module_state(m, 23)); m.eval()
+with torch.no_grad():
+    torch.manual_seed(11)
+    latent, pooled = m(torch.from_numpy(g["x"]))
+assert np.abs(latent.numpy() - g["latent"]).max() < 1e-5 and np.abs(pooled.numpy() - g["pooled"]).max() < 1e-5
 g = np.load({os.path.join(golden_dir, "ae_modules.npz")!r})
 m = AE.AE(256, 128, 16, 7); m.load_state_dict(synth.seeded_state_dict(synth.ae_shapes(128, 16, 7), 11)); m.eval()
 with torch.no_grad():
