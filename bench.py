@@ -217,11 +217,14 @@ def run_b200(args):
         return wrapper
 
     from pcc_b200 import mlp_ops
-    orig_fused, orig_knn = mlp_ops.fused_chain, pcc_b200.ops.knn
-    sa_timed, knn_timed = timed("sa_chain", orig_fused), timed("knn_in_patch", orig_knn)
-    mlp_ops.fused_chain = lambda inputs, layers, group=0, out_dtype=torch.float32: (
-        sa_timed if group == 16 else orig_fused)(inputs, layers, group, out_dtype)
-    pcc_b200.ops.knn = lambda q, p, K, *a, **kw: (knn_timed if K == 16 else orig_knn)(q, p, K, *a, **kw)
+    mlp_ops.sa_chain_indexed = timed("sa_chain", mlp_ops.sa_chain_indexed)      # pcc_sa_chain_indexed (ws::sa_chain2_kernel<1>)
+    pcc_b200.ops.knn_patch_u8 = timed("knn_in_patch", pcc_b200.ops.knn_patch_u8)  # pcc_knn_patch_u8 (knn_filter_kernel<16>)
+    if os.environ.get("PCC_SA_GROUPED"):   # A/B runs of the general route (development only)
+        orig_fused, orig_knn = mlp_ops.fused_chain, pcc_b200.ops.knn
+        sa_timed, knn_timed = timed("sa_chain", orig_fused), timed("knn_in_patch", orig_knn)
+        mlp_ops.fused_chain = lambda inputs, layers, group=0, out_dtype=torch.float32: (
+            sa_timed if group == 16 else orig_fused)(inputs, layers, group, out_dtype)
+        pcc_b200.ops.knn = lambda q, p, K, *a, **kw: (knn_timed if K == 16 else orig_knn)(q, p, K, *a, **kw)
     pcc_b200.ops.chamfer_forward = timed("chamfer", pcc_b200.ops.chamfer_forward)
     mlp_ops.pn_tail = timed("pn_tail", mlp_ops.pn_tail)
 
@@ -357,7 +360,7 @@ def run_b200(args):
             others = {}
             if "knn_in_patch" in kernel_ms:  # in-patch kNN (K=16 of 256): 8 un-fused FP32 ops per pair
                 pairs = BATCH * (N_POINTS * ALPHA // K_PATCH) * K_PATCH * K_PATCH
-                others["knn_thread_kernel"] = {"ms_per_launch": kernel_ms["knn_in_patch"], "pair_evals": pairs, "bound": "fp32 issue",
+                others["knn_filter_kernel"] = {"ms_per_launch": kernel_ms["knn_in_patch"], "pair_evals": pairs, "bound": "fp32 issue",
                                                "useful_frac": pairs * 8.0 / (kernel_ms["knn_in_patch"] / 1e3) / fp32_peak}
             if "chamfer" in kernel_ms:       # exact grid-pruned Chamfer: algorithmic pairs = P1 * P2 per cloud, mostly culled
                 pairs = 1.0 * BATCH * N_POINTS * N_POINTS

@@ -267,6 +267,20 @@ int pcc_fold_first_bf16(const float *local, int n_local, int64_t ld_local, const
                         int64_t M, int n_pts, int C, int relu, void *out, int64_t ld_out, void *stream);
 
 /*
+ * pn_kit.SetAbstraction with S == N (/root/reference/pn_kit.py:181-207 as AE.sa calls it, AE.py:38) in two launches that
+ * never materialise the grouped tensor: the in-patch kNN table as bytes, then the shared MLP gathering from the patch itself.
+ * pcc_knn_patch_u8: patches [BS, P, 3] fp32, K in {8, 16}, K <= P <= 256 -> out_idx [BS, P, K] uint8: the K nearest points of
+ *   every point inside its own patch, (d2, idx) order, bit-exact to pytorch3d.ops.knn_points (pn_kit.py:190).
+ * pcc_sa_chain_indexed: position (point g, neighbour n) = patches[patch(g) * P + idx8[g, n]] - patches[g] (pn_kit.py:191, fp32
+ *   subtraction) -> 3 -> 32 -> 64 -> 128 (ReLU) -> max over the 16 neighbours (pn_kit.py:196-207); layers as for pcc_mlp_chain
+ *   (layer 0 needs w_f32 / b_f32).  out [points, 128] fp32 (out_dtype 0) or bf16 (1).  Any other shape: PCC_ERR_UNSUPPORTED
+ *   (the general route is pcc_knn_f32 with out_nn + pcc_mlp_chain).  Result bit-identical to that route.
+ */
+int pcc_knn_patch_u8(const float *patches, int BS, int P, int K, uint8_t *out_idx, void *stream);
+int pcc_sa_chain_indexed(const float *patches, const uint8_t *idx8, int64_t points, int pts_per_patch, const PccMlpLayer *layers,
+                         int n_layers, void *out, int out_dtype, void *stream);
+
+/*
  * Grouping of one PointNet++ set-abstraction level (/root/reference/pointnet_sa_module.py:73-85: group_points of the features
  * and of xyz, torch.cat): out[b * M + j, :] = [feat[b, idx[b, j], 0..C) | xyz[b, idx[b, j], 0..3) | 0 ...] as bf16 rows of
  * kpad columns (kpad % 8 == 0) -- the A operand of pcc_linear_bf16.  feat [B, N, C] fp32 or NULL (C = 0), xyz [B, N, 3] fp32 or

@@ -119,6 +119,10 @@ struct SaParams {
     int out_bf16;
     int n_tiles;
     long long *dbg;            // bring-up aid (NULL in production): clock64() ticks of CTA 0's MMA thread and epilogue thread 0
+    // indexed form (sa_chain2_kernel<1>): position (point g, neighbour n) reads pts[patch(g) * P + idx8[16 g + n]] - pts[g]
+    const unsigned char *idx8; // [points, 16] neighbour indices inside the point's own patch
+    int pts_per_patch;         // P <= 256
+    int pts_shift;             // log2(P) when P is a power of two, else -1
 };
 
 namespace sa {
@@ -134,6 +138,12 @@ constexpr int OFF_W0 = OFF_BAR + 64;                 // float4 (w0, w1, w2, bias
 constexpr int SMEM = OFF_W0 + 512 + 1024;            // + alignment slack
 constexpr int THREADS = 320;                         // 2 groups of 4 epilogue warps + one MMA warp per slot
 constexpr int TMEM_COLS = 256;                       // 128 per slot
+// indexed form only: recentred neighbour coordinates of the next tiles, SoA x[128] y[128] z[128], 2 slots x 2 buffers, and
+// one "filled" barrier per buffer
+constexpr int OFF_XYZ = OFF_W0 + 512;
+constexpr int XYZ_BUF = 3 * P * 4;                   // 1536
+constexpr int OFF_BAR2 = OFF_XYZ + 4 * XYZ_BUF;      // 4 mbarriers
+constexpr int SMEM_IDX = OFF_BAR2 + 32 + 1024;
 static_assert(OFF_SLOT % 1024 == 0 && SLOT_BYTES % 1024 == 0, "slab alignment");
 }  // namespace sa
 
@@ -322,7 +332,10 @@ __global__ void __launch_bounds__(sa::THREADS, 2) sa_chain_kernel(const __grid_c
 //   epilogue group of slot s, per tile:  wait MMA1 -> epilogue 1 (acc -> X2) -> signal -> wait MMA2 -> epilogue 2 (max over 16
 //       neighbours -> out) -> signal "accumulator free"
 // ======================================================================================================================
-template <int DUMMY>
+// IDX = 1: the kernel takes the patches themselves ([points, 3], prm.xyz) and the in-patch kNN table as bytes (prm.idx8) and
+// forms the recentred neighbour coordinates on the fly -- the [points, 16, 3] fp32 tensor (100 MB per 32-cloud step, written by
+// the kNN kernel and read straight back here) never exists.  Same fp32 subtraction, so the result is bit-identical.
+template <int IDX>
 __global__ void __launch_bounds__(sa::THREADS, 2) sa_chain2_kernel(const __grid_constant__ SaParams prm) {
     using namespace sa;
     extern __shared__ unsigned char smem_raw[];
@@ -330,6 +343,7 @@ __global__ void __launch_bounds__(sa::THREADS, 2) sa_chain2_kernel(const __grid_
     const uint32_t sb = smem_u32(smem);
     const int tid = threadIdx.x, warp = __shfl_sync(FULL_MASK, tid >> 5, 0), lane = tid & 31;
     const uint32_t bar_acc = sb + OFF_BAR, bar_act = sb + OFF_BAR + 16, bar_x1 = sb + OFF_BAR + 32;  // [2] each
+    const uint32_t bar_xyz = sb + OFF_BAR2;                                                           // [2 slots][2 buffers] (IDX)
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BAR + 48);
 
     copy_to_smem(smem + OFF_W1, prm.w1p, 64 * KP1 * 2, tid, THREADS);
@@ -342,6 +356,9 @@ __global__ void __launch_bounds__(sa::THREADS, 2) sa_chain2_kernel(const __grid_
             mbar_init(bar_acc + 8 * s, 1);
             mbar_init(bar_act + 8 * s, 4);
             mbar_init(bar_x1 + 8 * s, 1);
+        }
+        if constexpr (IDX) {
+            for (int i = 0; i < 4; ++i) mbar_init(bar_xyz + 8 * i, 4);
         }
     }
     const uint32_t tmem_base = tmem_alloc_and_sync(tmem_slot, TMEM_COLS, warp, 8);
@@ -368,6 +385,20 @@ __global__ void __launch_bounds__(sa::THREADS, 2) sa_chain2_kernel(const __grid_
                 py[i] = __ldg(src + 1);
                 pz[i] = __ldg(src + 2);
             }
+        };
+        // IDX: the slot's epilogue group gathers and recentres the next tiles' neighbours into small shared buffers (k-th tile
+        // of the slot -> buffer k & 1, its barrier completes once per two tiles); this warp only reads 12 floats per lane
+        uint32_t kx = 0;
+        auto take_xyz = [&]() {
+            mbar_wait(bar_xyz + 8 * (2 * s + (kx & 1u)), (kx >> 1) & 1u);
+            const float *xb = reinterpret_cast<const float *>(smem + OFF_XYZ + (2 * s + (kx & 1u)) * XYZ_BUF);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                px[i] = xb[lane + 32 * i];
+                py[i] = xb[P + lane + 32 * i];
+                pz[i] = xb[2 * P + lane + 32 * i];
+            }
+            ++kx;
         };
         // layer 0 of positions lane + 32 i0 and lane + 32 (i0 + 1): 2 x 32 channels -> X1 (4 16-byte chunks per position)
         auto issue_mma2 = [&]() {
@@ -409,11 +440,11 @@ __global__ void __launch_bounds__(sa::THREADS, 2) sa_chain2_kernel(const __grid_
         };
         long long tile = 2ll * blockIdx.x + s;
         if (tile < n_tiles) {
-            load_xyz(tile);
+            if constexpr (IDX) take_xyz(); else load_xyz(tile);
             layer0_pair(0);
             layer0_pair(2);
             fence_async_smem();
-            if (tile + tstride < n_tiles) load_xyz(tile + tstride);
+            if constexpr (!IDX) { if (tile + tstride < n_tiles) load_xyz(tile + tstride); }
         }
         for (; tile < n_tiles; tile += tstride) {
             mbar_wait(bar_act + 8 * s, ph_act);   // the accumulator is free (epilogue 2 of the previous tile has read it)
@@ -433,10 +464,11 @@ __global__ void __launch_bounds__(sa::THREADS, 2) sa_chain2_kernel(const __grid_
             mma2_pending = true;
             if (more) {
                 tc_fence_after();
+                if constexpr (IDX) take_xyz();
                 layer0_pair(0);                     // (issues layer 2 from inside as soon as X2 is ready)
                 layer0_pair(2);
                 fence_async_smem();
-                if (tile + 2 * tstride < n_tiles) load_xyz(tile + 2 * tstride);
+                if constexpr (!IDX) { if (tile + 2 * tstride < n_tiles) load_xyz(tile + 2 * tstride); }
             }
             if (mma2_pending) {
                 mbar_wait(bar_act + 8 * s, ph_act);
@@ -455,7 +487,52 @@ __global__ void __launch_bounds__(sa::THREADS, 2) sa_chain2_kernel(const __grid_
         float *out_f = prm.out_bf16 ? nullptr : static_cast<float *>(prm.out);
         __nv_bfloat16 *out_h = prm.out_bf16 ? static_cast<__nv_bfloat16 *>(prm.out) : nullptr;
         if (lane == 0) mbar_arrive1(bar_act + 8 * s);   // the accumulator starts out free
+        // IDX: thread t of the group owns position t of a tile = neighbour (t & 15) of point 8 * tile + (t >> 4); it gathers
+        // that neighbour from the point's own patch and recentres it (pn_kit.py:190-191), two tiles ahead of the epilogues
+        const int t = row;
+        unsigned nbyte = 0u;                 // neighbour byte of the tile whose gather is issued next
+        float gc[3], gn[3];                  // centre / neighbour coordinates in flight
+        uint32_t kg = 0;                     // tiles of this slot gathered so far
+        auto load_byte = [&](long long tl) { nbyte = __ldg(prm.idx8 + tl * P + t); };
+        auto issue_gather = [&](long long tl) {
+            const unsigned g0 = static_cast<unsigned>(tl) * 8u;      // a tile is 8 points x 16 neighbours; P % 8 == 0: one patch
+            const unsigned pbase = prm.pts_shift >= 0 ? (g0 >> prm.pts_shift) << prm.pts_shift
+                                                      : g0 / static_cast<unsigned>(prm.pts_per_patch) * static_cast<unsigned>(prm.pts_per_patch);
+            const float *c = prm.xyz + static_cast<size_t>(g0 + (t >> 4)) * 3;
+            const float *n = prm.xyz + static_cast<size_t>(pbase + nbyte) * 3;
+#pragma unroll
+            for (int e = 0; e < 3; ++e) {
+                gc[e] = __ldg(c + e);
+                gn[e] = __ldg(n + e);
+            }
+        };
+        auto finish_gather = [&]() {
+            float *xb = reinterpret_cast<float *>(smem + OFF_XYZ + (2 * s + (kg & 1u)) * XYZ_BUF);
+#pragma unroll
+            for (int e = 0; e < 3; ++e) xb[e * P + t] = __fsub_rn(gn[e], gc[e]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive1(bar_xyz + 8 * (2 * s + (kg & 1u)));
+            ++kg;
+        };
+        if constexpr (IDX) {
+            const long long t0 = 2ll * blockIdx.x + s;
+            if (t0 < n_tiles) {
+                load_byte(t0);
+                issue_gather(t0);
+                if (t0 + tstride < n_tiles) load_byte(t0 + tstride);
+                finish_gather();
+                if (t0 + tstride < n_tiles) {
+                    issue_gather(t0 + tstride);
+                    if (t0 + 2 * tstride < n_tiles) load_byte(t0 + 2 * tstride);
+                    finish_gather();
+                }
+            }
+        }
         for (long long tile = 2ll * blockIdx.x + s; tile < n_tiles; tile += tstride) {
+            if constexpr (IDX) {            // the tile after next: loads in flight under the wait for layer 1 and its epilogue
+                if (tile + 2 * tstride < n_tiles) issue_gather(tile + 2 * tstride);
+                if (tile + 3 * tstride < n_tiles) load_byte(tile + 3 * tstride);
+            }
             // ---- layer 1 epilogue: 64 channels of my position -> X2 (one 128-byte row of the slab) ----
             mbar_wait(bar_acc + 8 * s, ph_acc);
             ph_acc ^= 1u;
@@ -473,6 +550,9 @@ __global__ void __launch_bounds__(sa::THREADS, 2) sa_chain2_kernel(const __grid_
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive1(bar_act + 8 * s);
+            if constexpr (IDX) {
+                if (tile + 2 * tstride < n_tiles) finish_gather();
+            }
             // ---- layer 2 epilogue (T-form): lane = channel `row`, columns = positions; max over each run of 16 ----
             mbar_wait(bar_acc + 8 * s, ph_acc);
             ph_acc ^= 1u;
@@ -1005,6 +1085,43 @@ int ws_dispatch(const PccMlpInput *in, int n_inputs, int64_t rows, const PccMlpL
 }
 
 }  // namespace pcc
+
+PCC_API int pcc_sa_chain_indexed(const float *patches, const uint8_t *idx8, int64_t points, int pts_per_patch, const PccMlpLayer *layers,
+                                 int n_layers, void *out, int out_dtype, void *stream) {
+    using namespace pcc;
+    using namespace pcc::ws;
+    PCC_REQUIRE(patches && idx8 && layers && out, "pcc_sa_chain_indexed: null pointer");
+    PCC_REQUIRE(points >= 0 && points < (1ll << 28) && (out_dtype == 0 || out_dtype == 1), "pcc_sa_chain_indexed: bad points / out_dtype");
+    static const int sa_dims[] = {3, 32, 64, 128}, sa_relu[] = {1, 1, 1};
+    if (!dims_are(layers, n_layers, sa_dims, sa_relu, 3) || !layers[0].w_f32 || !layers[0].b_f32 || pts_per_patch < 8 ||
+        pts_per_patch > 256 || pts_per_patch % 8 != 0 || points % pts_per_patch != 0) {
+        set_error("pcc_sa_chain_indexed: only the SetAbstraction shape 3-32-64-128 (ReLU), K = 16, patches of 8..256 points (multiple of 8)");
+        return PCC_ERR_UNSUPPORTED;
+    }
+    if (points == 0) return 0;
+    SaParams p{};
+    p.xyz = patches;
+    p.ld = 3;
+    p.w0 = layers[0].w_f32;
+    p.b0 = layers[0].b_f32;
+    p.w1p = layers[1].packed_w;
+    p.w2p = layers[2].packed_w;
+    p.out = out;
+    p.out_bf16 = out_dtype;
+    p.n_tiles = static_cast<int>(points / 8);
+    p.dbg = nullptr;
+    p.idx8 = idx8;
+    p.pts_per_patch = pts_per_patch;
+    p.pts_shift = -1;
+    for (int sh = 3; sh <= 8; ++sh)
+        if ((1 << sh) == pts_per_patch) p.pts_shift = sh;
+    if (int r = set_smem(sa_chain2_kernel<1>, sa::SMEM_IDX)) return r;
+    const int sms = num_sms();
+    const int pairs = (p.n_tiles + 1) / 2;
+    const int grid = pairs < 2 * sms ? pairs : 2 * sms;
+    sa_chain2_kernel<1><<<grid, sa::THREADS, sa::SMEM_IDX, static_cast<cudaStream_t>(stream)>>>(p);
+    return check_launch("sa_chain2_kernel<indexed>");
+}
 
 /* bring-up aid, not part of the public header: device buffer of 1024 int64 for clock64() ticks of the SA chain's CTA 0 */
 PCC_API void pcc_debug_ws_timing(long long *buf) { pcc::g_ws_dbg = buf; }

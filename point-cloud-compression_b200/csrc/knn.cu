@@ -19,6 +19,8 @@
 //   shared-memory broadcasts, results staged through shared memory so global writes are coalesced.
 //
 // Both kernels are CUDA-core / shared-memory bound: inputs are 12 B per point, read once per CTA.
+#include <stdlib.h>
+
 #include "pcc_common.cuh"
 
 namespace pcc {
@@ -634,6 +636,270 @@ knn_thread_kernel(const float *__restrict__ q, const float *__restrict__ p, int 
     }
 }
 
+
+// ---- thread-per-query kernel, filter form (K <= 16) ------------------------------------------------------------------
+// Same contract and the same exact result as knn_thread_kernel; what changes is how few instructions a (query, candidate)
+// pair costs.  The exact d2 takes 8 dependent-rounding FP32 operations + a shared-memory load; here a pair is first seen
+// through B = |c|^2 - 2 q.c (3 FFMA on a (x, y, z, |c|^2) tile: d2 = B + |q|^2 up to a PROVEN rounding bound E), twice:
+//   pass 1  32 strided group minima of B, sorted in registers; the KT-th smallest, tau, satisfies
+//           (K-th smallest exact d2) <= tau + |q|^2 + E                       (KT candidates have B <= tau)
+//   pass 2  a candidate can be one of the K nearest only if B <= tau + 2 E: its index is parked in a per-thread queue
+//           (~21 of 256 pass for K = 16)
+//   final   the parked candidates' EXACT d2 (dist2_rn, the reference arithmetic) are packed with their queue slot into
+//           32-bit keys ((d2 bits - base) << 5 | slot: slots are in index order, so the unsigned key order is the
+//           (d2, idx) order) and sorted by a 32-key register network -- no data-dependent control flow, no insertion chain.
+// Error bound (u = 2^-24, R = (|q| + |c|)^2 <= 2 (|q|^2 + max|c|^2)): the three FFMA and the two squared norms contribute
+// <= 9.2 u R against the real-number d2, the reference's rounded d2 differs from it by <= 5.1 u R, so
+// |B + |q|^2 - d2_rn| <= 2^-20 R <= 2^-19 (|q|^2 + max|c|^2); the kernel uses twice that.  A warp whose queues overflow
+// (heavy ties, tiny candidate sets) or whose keys do not fit 27 bits of d2 range falls back to the exact insertion scan.
+template <int KT>
+__global__ void __launch_bounds__(KT_THREADS, 4)
+knn_filter_kernel(const float *__restrict__ q, const float *__restrict__ p, int P1, int P2, int K,
+                  float *__restrict__ out_d2, int64_t *__restrict__ out_idx, float *__restrict__ out_nn,
+                  unsigned char *__restrict__ out_idx8, int centre_sub, float nn_scale) {
+    static_assert(KT <= 16, "filter form: K <= 16");
+    constexpr int STAGE_LD = KT + 1;
+    constexpr int PB = 64;                                    // queue depth: 32 keys of the sorting network + overflow slots
+    constexpr int FT = 256;                                   // candidates per search (byte queue entries)
+    constexpr int TILE_BYTES = FT * 16;
+    constexpr int STAGE_BYTES = KT_THREADS * STAGE_LD * 4;
+    __shared__ __align__(16) unsigned char smem_raw[TILE_BYTES > STAGE_BYTES ? TILE_BYTES : STAGE_BYTES];
+    __shared__ float sq[KT_THREADS * 3];
+    __shared__ unsigned char pend_i[PB][KT_THREADS];
+    __shared__ float s_cmax[KT_THREADS / 32];
+    float4 *tile = reinterpret_cast<float4 *>(smem_raw);
+    unsigned *stage = reinterpret_cast<unsigned *>(smem_raw);
+
+    const int b = blockIdx.y;
+    const int q0 = blockIdx.x * KT_THREADS;
+    const int qi = q0 + threadIdx.x;
+    const bool active = qi < P1;
+    const float *pc_ = p + static_cast<size_t>(b) * P2 * 3;
+
+    float qx = 0.f, qy = 0.f, qz = 0.f;
+    if (active) {
+        const float *qp = q + (static_cast<size_t>(b) * P1 + qi) * 3;
+        qx = qp[0];
+        qy = qp[1];
+        qz = qp[2];
+    }
+    sq[threadIdx.x * 3 + 0] = qx;
+    sq[threadIdx.x * 3 + 1] = qy;
+    sq[threadIdx.x * 3 + 2] = qz;
+    const int tn = P2;   // the dispatch guarantees P2 <= FT
+    float cm = 0.f;
+    for (int pt = threadIdx.x; pt < tn; pt += KT_THREADS) {
+        const float *s = pc_ + static_cast<size_t>(pt) * 3;
+        const float x = s[0], y = s[1], z = s[2];
+        const float w = fmaf(z, z, fmaf(y, y, x * x));
+        tile[pt] = make_float4(x, y, z, w);
+        cm = fmaxf(cm, w);
+    }
+    cm = __uint_as_float(__reduce_max_sync(FULL_MASK, __float_as_uint(cm)));   // w >= +0: the bit patterns order like the values
+    if ((threadIdx.x & 31) == 0) s_cmax[threadIdx.x >> 5] = cm;
+    __syncthreads();
+    float cmax2 = s_cmax[0];
+#pragma unroll
+    for (int i = 1; i < KT_THREADS / 32; ++i) cmax2 = fmaxf(cmax2, s_cmax[i]);
+    const float qn = fmaf(qz, qz, fmaf(qy, qy, qx * qx));
+    const float E = fmaf(qn + cmax2, 3.814697265625e-6f /* 2^-18 */, 1e-30f);
+    const float mx = -2.0f * qx, my = -2.0f * qy, mz = -2.0f * qz;
+    auto approx = [&](const float4 c) { return fmaf(mx, c.x, fmaf(my, c.y, fmaf(mz, c.z, c.w))); };
+
+    float thr = __int_as_float(0x7f800000);   // +inf: everything passes (tiny candidate sets)
+    if (tn >= 64) {
+        constexpr int G = 32;
+        float m[G];
+#pragma unroll
+        for (int g0 = 0; g0 < G; ++g0) m[g0] = __int_as_float(0x7f800000);
+        const int full = tn / G * G;
+        for (int j0 = 0; j0 < full; j0 += G) {
+#pragma unroll
+            for (int g0 = 0; g0 < G; ++g0) m[g0] = fminf(m[g0], approx(tile[j0 + g0]));
+        }
+#pragma unroll
+        for (int k = 2; k <= G; k <<= 1) {
+#pragma unroll
+            for (int jj = k >> 1; jj > 0; jj >>= 1) {
+#pragma unroll
+                for (int i = 0; i < G; ++i) {
+                    const int l = i ^ jj;
+                    if (l > i) {
+                        const float lo = fminf(m[i], m[l]), hi = fmaxf(m[i], m[l]);
+                        const bool up = (i & k) == 0;
+                        m[i] = up ? lo : hi;
+                        m[l] = up ? hi : lo;
+                    }
+                }
+            }
+        }
+        thr = m[KT - 1] + 2.0f * E;
+    }
+
+    // pass 2: one bit per candidate that passes (LDS + 3 FFMA + compare + a predicated OR with a constant per pair), 32
+    // candidates per word; the set bits of each word are unpacked into the thread's byte queue (indices < 256).  A word that
+    // would not fit the PB-deep queue marks the thread as overflowed (exact scan below).
+    unsigned char *const pq0 = &pend_i[0][threadIdx.x];
+    unsigned char *pq = pq0;
+    bool over = false;
+    for (int j0 = 0; j0 < tn; j0 += 32) {
+        unsigned w = 0u;
+        if (j0 + 32 <= tn) {
+#pragma unroll
+            for (int u = 0; u < 32; ++u)
+                if (approx(tile[j0 + u]) <= thr) w |= 1u << u;
+        } else {
+            for (int u = 0; j0 + u < tn; ++u)
+                if (approx(tile[j0 + u]) <= thr) w |= 1u << u;
+        }
+        if (pq + __popc(w) * KT_THREADS > pq0 + PB * KT_THREADS) {
+            over = true;
+            w = 0u;
+        }
+        while (w != 0u) {
+            *pq = static_cast<unsigned char>(j0 + __ffs(w) - 1);
+            w &= w - 1u;
+            pq += KT_THREADS;
+        }
+    }
+    const int pc = static_cast<int>(pq - pq0) / KT_THREADS;
+
+    float dl[KT];
+    unsigned il[KT];
+    // final selection on the exact distances: the first 32 parked candidates through the sorting network
+    constexpr int NS = 32;
+    unsigned key[NS];
+    unsigned dmax = 0u;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        key[s] = 0xffffffffu;
+        if (s < pc) {
+            const float4 c = tile[pend_i[s][threadIdx.x]];
+            key[s] = __float_as_uint(dist2_rn(qx, qy, qz, c.x, c.y, c.z));
+            dmax = max(dmax, key[s]);
+        }
+    }
+    // keys: rel = 0 for d2 == +0, d2 bits - base + 1 otherwise; needs 1 <= rel < 2^27 for every non-zero candidate
+    const unsigned base = dmax > 0x07fffffeu ? dmax - 0x07fffffdu : 1u;   // dmax - base + 1 <= 2^27 - 2
+    bool fits = !over;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        if (s < pc) {
+            const unsigned bits = key[s];
+            fits = fits && (bits == 0u || bits >= base);
+            key[s] = ((bits == 0u ? 0u : bits - base + 1u) << 5) | static_cast<unsigned>(s);
+        }
+    }
+    auto insert = [&](float d, unsigned j) {   // sorted insertion, strict compares: equal distances keep index order
+        if (d < dl[KT - 1]) {
+            dl[KT - 1] = d;
+            il[KT - 1] = j;
+#pragma unroll
+            for (int s = KT - 1; s > 0; --s) {
+                const bool sw = dl[s] < dl[s - 1];
+                const float dlo = sw ? dl[s] : dl[s - 1], dhi = sw ? dl[s - 1] : dl[s];
+                const unsigned ilo = sw ? il[s] : il[s - 1], ihi = sw ? il[s - 1] : il[s];
+                dl[s - 1] = dlo;
+                dl[s] = dhi;
+                il[s - 1] = ilo;
+                il[s] = ihi;
+            }
+        }
+    };
+    if (fits) {
+#pragma unroll
+        for (int k = 2; k <= NS; k <<= 1) {
+#pragma unroll
+            for (int jj = k >> 1; jj > 0; jj >>= 1) {
+#pragma unroll
+                for (int i = 0; i < NS; ++i) {
+                    const int l = i ^ jj;
+                    if (l > i) {
+                        const unsigned lo = min(key[i], key[l]), hi = max(key[i], key[l]);
+                        const bool up = (i & k) == 0;
+                        key[i] = up ? lo : hi;
+                        key[l] = up ? hi : lo;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < KT; ++s) {
+            const unsigned rel = key[s] >> 5;
+            const bool have = s < pc;
+            dl[s] = have ? __uint_as_float(rel == 0u ? 0u : rel - 1u + base) : __int_as_float(0x7f800000);
+            il[s] = have ? pend_i[key[s] & 31u][threadIdx.x] : 0u;
+        }
+        for (int s = NS; s < pc; ++s) {          // the few candidates beyond the network's 32 keys (index order: ties stay right)
+            const unsigned j = pend_i[s][threadIdx.x];
+            const float4 c = tile[j];
+            insert(dist2_rn(qx, qy, qz, c.x, c.y, c.z), j);
+        }
+    } else {
+        // exact insertion scan over every candidate that passes the filter (heavy ties, key range, tiny sets): rare
+#pragma unroll
+        for (int s = 0; s < KT; ++s) {
+            dl[s] = __int_as_float(0x7f800000);
+            il[s] = 0u;
+        }
+        for (int j = 0; j < tn; ++j) {
+            const float4 c = tile[j];
+            if (approx(c) <= thr) insert(dist2_rn(qx, qy, qz, c.x, c.y, c.z), static_cast<unsigned>(j));
+        }
+    }
+    __syncthreads();  // tile no longer needed: reuse as output staging
+
+    const int nq = min(KT_THREADS, P1 - q0);
+    const int valid = P2 < K ? P2 : K;
+    const size_t obase = (static_cast<size_t>(b) * P1 + q0) * K;
+    if (out_d2) {
+#pragma unroll
+        for (int s = 0; s < KT; ++s) stage[threadIdx.x * STAGE_LD + s] = s < valid ? __float_as_uint(dl[s]) : 0u;
+        __syncthreads();
+        for (int e = threadIdx.x; e < nq * K; e += KT_THREADS) {
+            const int ql = e / K, k = e - ql * K;
+            out_d2[obase + e] = __uint_as_float(stage[ql * STAGE_LD + k]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int s = 0; s < KT; ++s) stage[threadIdx.x * STAGE_LD + s] = s < valid ? il[s] : 0u;
+    __syncthreads();
+    if (out_idx) {
+        for (int e = threadIdx.x; e < nq * K; e += KT_THREADS) {
+            const int ql = e / K, k = e - ql * K;
+            out_idx[obase + e] = static_cast<int64_t>(stage[ql * STAGE_LD + k]);
+        }
+    }
+    if (out_idx8 && active) {   // P2 <= 256, K == KT: neighbour indices as bytes, one 8 / 16-byte store per query
+        unsigned pk[KT / 4];
+#pragma unroll
+        for (int i = 0; i < KT / 4; ++i)
+            pk[i] = (il[4 * i] & 255u) | ((il[4 * i + 1] & 255u) << 8) | ((il[4 * i + 2] & 255u) << 16) | (il[4 * i + 3] << 24);
+        unsigned *dst = reinterpret_cast<unsigned *>(out_idx8 + obase + static_cast<size_t>(threadIdx.x) * KT);
+        if constexpr (KT == 16) *reinterpret_cast<uint4 *>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        else *reinterpret_cast<uint2 *>(dst) = make_uint2(pk[0], pk[1]);
+    }
+    if (out_nn) {
+        for (int e = threadIdx.x; e < nq * K * 3; e += KT_THREADS) {
+            const int pk = e / 3, c = e - pk * 3;
+            const int ql = K == KT ? pk / KT : pk / K, k = pk - ql * K;
+            float v = pc_[static_cast<size_t>(stage[ql * STAGE_LD + k]) * 3 + c];
+            if (centre_sub) v = __fsub_rn(v, sq[ql * 3 + c]);
+            if (nn_scale != 1.0f) v = __fmul_rn(v, nn_scale);
+            out_nn[obase * 3 + e] = v;
+        }
+    }
+}
+
+template <int KT>
+static int launch_filter(const float *q, const float *p, int B, int P1, int P2, int K, float *out_d2, int64_t *out_idx,
+                         float *out_nn, unsigned char *out_idx8, int centre_sub, float nn_scale, cudaStream_t st) {
+    dim3 grid((P1 + KT_THREADS - 1) / KT_THREADS, B);
+    knn_filter_kernel<KT><<<grid, KT_THREADS, 0, st>>>(q, p, P1, P2, K, out_d2, out_idx, out_nn, out_idx8, centre_sub, nn_scale);
+    return check_launch("knn_filter_kernel");
+}
+
 template <int KT>
 static int launch_thread(const float *q, const float *p, int B, int P1, int P2, int K, float *out_d2,
                          int64_t *out_idx, float *out_nn, int centre_sub, float nn_scale, cudaStream_t st) {
@@ -656,6 +922,10 @@ PCC_API int pcc_knn_f32(const float *q, const float *p, int B, int P1, int P2, i
 
     const long long nq = static_cast<long long>(B) * P1;
     if (K <= 32 && P2 <= KNN_TILE && nq >= 32768) {
+        static const bool old_form = getenv("PCC_KNN_THREAD_OLD") != nullptr;   // A/B switch for the measurements in profiles/
+        const bool filt = !old_form && P2 <= 256;   // filter form: candidate sets that fit byte indices (the in-patch searches)
+        if (filt && K <= 8) return launch_filter<8>(q, p, B, P1, P2, K, out_d2, out_idx, out_nn, nullptr, centre_sub, nn_scale, st);
+        if (filt && K <= 16) return launch_filter<16>(q, p, B, P1, P2, K, out_d2, out_idx, out_nn, nullptr, centre_sub, nn_scale, st);
         if (K <= 8) return launch_thread<8>(q, p, B, P1, P2, K, out_d2, out_idx, out_nn, centre_sub, nn_scale, st);
         if (K <= 16) return launch_thread<16>(q, p, B, P1, P2, K, out_d2, out_idx, out_nn, centre_sub, nn_scale, st);
         return launch_thread<32>(q, p, B, P1, P2, K, out_d2, out_idx, out_nn, centre_sub, nn_scale, st);
@@ -690,4 +960,19 @@ PCC_API int pcc_knn_f32(const float *q, const float *p, int B, int P1, int P2, i
     dim3 grid((P1 + W - 1) / W, B);
     knn_warp_kernel<W><<<grid, W * 32, smem, st>>>(q, p, P1, P2, K, cap, out_d2, out_idx, out_nn, centre_sub, nn_scale);
     return check_launch("knn_warp_kernel");
+}
+
+PCC_API int pcc_knn_patch_u8(const float *patches, int BS, int P, int K, uint8_t *out_idx, void *stream) {
+    using namespace pcc;
+    PCC_REQUIRE(patches && out_idx, "pcc_knn_patch_u8: null pointer");
+    PCC_REQUIRE(BS >= 0 && BS <= 65535 && P >= 1, "pcc_knn_patch_u8: bad shape BS=%d P=%d", BS, P);
+    if ((K != 8 && K != 16) || P > 256 || P < K) {
+        set_error("pcc_knn_patch_u8: K must be 8 or 16 and K <= P <= 256 (byte indices)");
+        return PCC_ERR_UNSUPPORTED;
+    }
+    PCC_REQUIRE(reinterpret_cast<uintptr_t>(out_idx) % 16 == 0, "pcc_knn_patch_u8: out_idx must be 16-byte aligned");
+    if (BS == 0) return 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (K == 8) return launch_filter<8>(patches, patches, BS, P, P, K, nullptr, nullptr, nullptr, out_idx, 0, 1.0f, st);
+    return launch_filter<16>(patches, patches, BS, P, P, K, nullptr, nullptr, nullptr, out_idx, 0, 1.0f, st);
 }

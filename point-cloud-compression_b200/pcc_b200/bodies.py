@@ -10,12 +10,15 @@ through the names the reference gives them and runs the batched d
 There is no library GEMM and no CPU path in here: a shape the kernels do not take raises (PCC_ERR_UNSUPPORTED ->
 ValueError).  Element-wise glue (sigmoid, round, softmax, max over a tiny axis) is torch.
 """
+import os
+
 import torch
 import torch.nn as nn
 
 from . import mlp_ops, ops, pn_kit_ops
 
 _BN_TYPES = (nn.BatchNorm1d, nn.BatchNorm2d)
+_GROUPED_SA = bool(os.environ.get("PCC_SA_GROUPED"))   # A/B switch for the measurements in profiles/: the general (grouped tensor) route
 
 
 def training_pass(mod):
@@ -105,8 +108,14 @@ def sa_points(mod, xyz, out_dtype=torch.float32):
         new_xyz = xyz
     else:                                                                          # pn_kit.py:184 (CPU-RNG start index)
         new_xyz = ops.gather(xyz, pn_kit_ops.farthest_point_sample_batch(xyz, S))
+    layers = sa_layers(mod)
+    if S == P and BS <= 65535 and mlp_ops.sa_indexed_supported(P, mod.K, layers) and not _GROUPED_SA:
+        # the AE's shape: kNN table as bytes, then the chain gathers the recentred neighbours from the patch itself -- the
+        # [BS, S, K, 3] grouped tensor is never written (same fp32 arithmetic: bit-identical to the general route below)
+        feat = mlp_ops.sa_chain_indexed(xyz, ops.knn_patch_u8(xyz, mod.K), layers, out_dtype=out_dtype)     # :190-207
+        return new_xyz, feat.reshape(BS, S, -1)
     _, _, grouped = ops.knn(new_xyz, xyz, mod.K, return_nn=True, centre_sub=True, nn_only=True)  # :190-191  [BS,S,K,3]
-    feat = mlp_ops.fused_chain(grouped.reshape(BS * S * mod.K, 3), sa_layers(mod), group=mod.K, out_dtype=out_dtype)
+    feat = mlp_ops.fused_chain(grouped.reshape(BS * S * mod.K, 3), layers, group=mod.K, out_dtype=out_dtype)
     return new_xyz, feat.reshape(BS, S, -1)
 
 

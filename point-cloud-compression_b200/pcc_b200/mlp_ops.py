@@ -123,6 +123,34 @@ def fused_chain(inputs, layers, group=0, out_dtype=torch.float32):
     return out
 
 
+def sa_indexed_supported(P, K, layers):
+    """Shapes pcc_sa_chain_indexed takes: pn_kit.SetAbstraction as the AE uses it (3 -> 32 -> 64 -> 128, ReLU, K = 16)."""
+    dims = [layers[0][0].shape[1]] + [w.shape[0] for w, _, _ in layers]
+    return (K == 16 and 16 <= P <= 256 and P % 8 == 0 and dims == [3, 32, 64, 128] and all(bool(r) for _, _, r in layers))
+
+
+def sa_chain_indexed(patches, idx8, layers, out_dtype=torch.float32):
+    """SetAbstraction shared MLP + max over the 16 neighbours, gathering the recentred neighbours from the patch itself:
+    patches [BS, P, 3] fp32, idx8 [BS, P, 16] uint8 (ops.knn_patch_u8) -> [BS * P, 128]."""
+    lib = _lib.load()
+    _check(patches)
+    BS, P, _ = patches.shape
+    patches = patches.float().contiguous()
+    idx8 = idx8.contiguous()
+    arr = (_lib.PccMlpLayer * len(layers))()
+    keep = []
+    for i, (w, b, relu) in enumerate(layers):
+        pw, wf, bf = _packed(w, b)
+        keep.append((pw, wf, bf))
+        arr[i] = _lib.PccMlpLayer(pw.data_ptr(), w.shape[1], w.shape[0], int(bool(relu)), wf.data_ptr(), bf.data_ptr())
+    out = torch.empty((BS * P, layers[-1][0].shape[0]), dtype=out_dtype, device=patches.device)
+    with torch.cuda.device(patches.device):
+        _lib.check(lib.pcc_sa_chain_indexed(patches.data_ptr(), idx8.data_ptr(), BS * P, P, arr, len(layers), out.data_ptr(),
+                                            0 if out_dtype == torch.float32 else 1, torch.cuda.current_stream().cuda_stream),
+                   "pcc_sa_chain_indexed")
+    return out
+
+
 _bf16_cache = {}
 
 

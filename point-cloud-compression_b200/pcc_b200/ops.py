@@ -111,6 +111,20 @@ def knn(p1, p2, K, return_nn=False, centre_sub=False, nn_scale=1.0, nn_only=Fals
     return d, i, nn
 
 
+def knn_patch_u8(patches, K):
+    """In-patch kNN table as bytes: patches [BS, P, 3] (K <= P <= 256, K in {8, 16}) -> uint8 [BS, P, K], the K nearest points of
+    every point inside its own patch in (d2, idx) order (pn_kit.py:190 with S == N); feeds mlp_ops.sa_chain_indexed."""
+    lib = _lib.load()
+    patches = _cuda_f32(patches, "patches")
+    BS, P, _ = patches.shape
+    out = torch.empty((BS, P, K), dtype=torch.uint8, device=patches.device)
+    if BS == 0:
+        return out
+    with torch.cuda.device(patches.device):
+        _lib.check(lib.pcc_knn_patch_u8(_ptr(patches), BS, P, K, _ptr(out), _stream()), "pcc_knn_patch_u8")
+    return out
+
+
 def ball_query(p1, p2, K, radius, return_dists=True):
     lib = _lib.load()
     p1, p2 = _cuda_f32(p1, "p1"), _cuda_f32(p2, "p2")

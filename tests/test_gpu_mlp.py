@@ -238,3 +238,25 @@ def test_gather_concat_bf16_matches_torch(mlp):
     assert torch.equal(out.view(B, M, 192), ref.to(torch.bfloat16))
     out2 = mlp.gather_concat_bf16(None, xyz, idx, 64)   # xyz only
     assert torch.equal(out2.view(B, M, 64)[:, :, :3], ref[:, :, C:C + 3].to(torch.bfloat16)) and not out2.view(B, M, 64)[:, :, 3:].any()
+
+
+@pytest.mark.parametrize("BS,P", [(64, 256), (5, 128), (3, 16), (300, 256)])
+def test_sa_chain_indexed_is_bit_identical_to_the_grouped_route(BS, P):
+    """pcc_sa_chain_indexed (patch + byte kNN table in, neighbours gathered and recentred inside the kernel) against the general
+    route (pcc_knn_f32 writes the recentred [BS, P, 16, 3] tensor, pcc_mlp_chain reads it): the same fp32 subtraction feeds the
+    same kernel body, so the features must be bit-identical, fp32 and bf16 outputs alike (pn_kit.py:190-207)."""
+    import __graft_entry__  # noqa: F401
+    from pcc_b200 import mlp_ops, ops
+    torch.manual_seed(BS)
+    x = (torch.rand(BS, P, 3, device="cuda") - 0.5) * 1.3
+    layers = [(torch.randn(32, 3, device="cuda") * 0.5, torch.randn(32, device="cuda") * 0.1, True),
+              (torch.randn(64, 32, device="cuda") * 0.2, torch.randn(64, device="cuda") * 0.1, True),
+              (torch.randn(128, 64, device="cuda") * 0.2, torch.randn(128, device="cuda") * 0.1, True)]
+    assert mlp_ops.sa_indexed_supported(P, 16, layers)
+    _, _, grouped = ops.knn(x, x, 16, return_nn=True, centre_sub=True, nn_only=True)
+    idx8 = ops.knn_patch_u8(x, 16)
+    for dt in (torch.float32, torch.bfloat16):
+        want = mlp_ops.fused_chain(grouped.reshape(BS * P * 16, 3), layers, group=16, out_dtype=dt)
+        got = mlp_ops.sa_chain_indexed(x, idx8, layers, out_dtype=dt)
+        assert got.shape == want.shape == (BS * P, 128) and torch.equal(got, want)
+    assert not mlp_ops.sa_indexed_supported(P, 8, layers) and not mlp_ops.sa_indexed_supported(300, 16, layers)

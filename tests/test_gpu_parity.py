@@ -168,7 +168,7 @@ def test_knn_block_kernel_selection_paths_vs_oracle(pcc, orc, kind, P2, K):
     assert np.array_equal(i.cpu().numpy(), oi) and np.array_equal(d.cpu().numpy(), od)
 
 
-@pytest.mark.parametrize("kind", ["uniform", "grid", "identical", "offset", "tiny", "line", "two_clusters", "qp_differ"])
+@pytest.mark.parametrize("kind", ["uniform", "grid", "identical", "offset", "tiny", "line", "two_clusters", "qp_differ", "near_dup"])
 def test_knn_in_patch_adversarial_vs_oracle(pcc, orc, kind):
     """256 x 256, K = 16 (pn_kit.py:190 as AE.py:16 calls it) on inputs that stress the a-priori threshold and the tie rules:
     exact ties, all-identical points, large offsets, tiny scales, collinear points, two far clusters, queries != candidates."""
@@ -188,6 +188,9 @@ def test_knn_in_patch_adversarial_vs_oracle(pcc, orc, kind):
     elif kind == "two_clusters":
         x[:, ::2] *= np.float32(1e-3)
         x[:, 1::2] = x[:, 1::2] * np.float32(1e-3) + np.float32(1.0)
+    elif kind == "near_dup":
+        x[:, 1::4] = x[:, 0::4] + rng.normal(0, 1e-6, x[:, 0::4].shape).astype(np.float32)   # d2 ~ 1e-12 beside d2 ~ 1e-2: the
+        #                                                     packed 27-bit key range of the filter kernel does not hold them
     q = x
     if kind == "qp_differ":
         q = np.ascontiguousarray(x[:, ::-1]) * np.float32(0.9)
@@ -205,6 +208,33 @@ def test_knn_thread_kernel_in_patch_vs_oracle(pcc, orc, BS, P, K):
     od, oi, onn = orc.knn_points(x, x, K, True, threads=8)
     assert np.array_equal(i.cpu().numpy(), oi) and np.array_equal(d.cpu().numpy(), od)
     assert np.array_equal(nn.cpu().numpy(), onn - x[:, :, None, :])
+
+
+@pytest.mark.parametrize("BS,P,K,kind", [(64, 256, 16, "uniform"), (2048, 256, 16, "patches"), (40, 128, 8, "grid"), (7, 200, 16, "identical"),
+                                         (3, 16, 16, "uniform"), (33, 256, 8, "near_dup")])
+def test_knn_patch_u8_vs_oracle(pcc, orc, BS, P, K, kind):
+    """pcc_knn_patch_u8 (the byte index table the indexed SetAbstraction chain reads): equal to the oracle's knn_points indices
+    on small / tie-heavy / degenerate patches and on the bench's real patches (32 clouds x 64 patches)."""
+    if kind == "patches":
+        xyz = cu(synth.modelnet_like(32, 8192, seed=4))
+        cen = pcc.index_points(xyz, pcc.ops.fps(xyz, 64, None, 1e10))
+        x = pcc.ops.knn(cen, xyz, 256, return_nn=True, centre_sub=True, nn_scale=2.0)[2].reshape(BS, P, 3).cpu().numpy()
+    elif kind == "grid":
+        x = synth.grid_quantised(BS, P, depth=3, seed=9) - np.float32(0.5)
+    else:
+        x = synth.uniform_cube(BS, P, seed=10) - np.float32(0.5)
+        if kind == "identical":
+            x[:] = x[:, :1]
+        if kind == "near_dup":
+            x[:, 1::4] = x[:, 0::4] + np.random.default_rng(3).normal(0, 1e-6, x[:, 0::4].shape).astype(np.float32)
+    i8 = pcc.ops.knn_patch_u8(cu(x), K)
+    assert i8.dtype == torch.uint8 and i8.shape == (BS, P, K)
+    _, oi, _ = orc.knn_points(x, x, K, False, threads=8)
+    assert np.array_equal(i8.cpu().numpy().astype(np.int64), oi)
+    with pytest.raises(ValueError):
+        pcc.ops.knn_patch_u8(cu(x), 12)                      # K must be 8 or 16
+    with pytest.raises(ValueError):
+        pcc.ops.knn_patch_u8(cu(synth.uniform_cube(2, 300, seed=1)), 16)   # byte indices: P <= 256
 
 
 def test_knn_patching_full_size_properties(pcc):

@@ -15,9 +15,9 @@ for l in lines[start + 1:]:
     if l.startswith(".text.") or l.startswith("//-----"):
         if off2line:
             break
-    m = re.search(r'//## File ".*?", line (\d+)', l)
+    m = re.search(r'//## File "(.*?)", line (\d+)', l)
     if m:
-        cur = int(m.group(1))
+        cur = (m.group(1).rsplit("/", 1)[-1], int(m.group(2)))
         continue
     m = re.match(r"\s*/\*([0-9a-f]{4,})\*/", l)
     if m:
@@ -40,12 +40,22 @@ for r in body:
     ln = off2line.get(int(r[0], 16) - base)
     by_exec[ln] += int(r[ia])
     by_samp[ln] += int(r[isamp])
-srcl = open(src).read().splitlines()
+import os
+_src_cache = {}
+def text(key):
+    if not key:
+        return "?"
+    f, ln = key
+    if f not in _src_cache:
+        path = os.path.join(os.path.dirname(src), f)
+        _src_cache[f] = open(path).read().splitlines() if os.path.exists(path) else []
+    lines_ = _src_cache[f]
+    return f"{f}:{ln}: " + (lines_[ln - 1].strip()[:100] if 0 < ln <= len(lines_) else "")
 te, ts = sum(by_exec.values()), sum(by_samp.values())
 print(f"total executed {te}  samples {ts}")
 print("--- by executed instructions")
 for ln, c in by_exec.most_common(28):
-    print(f"{100*c/te:5.1f}% exec {100*by_samp[ln]/ts:5.1f}% samp  L{ln}: {srcl[ln-1].strip()[:110] if ln else '?'}")
+    print(f"{100*c/te:5.1f}% exec {100*by_samp[ln]/ts:5.1f}% samp  {text(ln)}")
 print("--- by stall samples")
 for ln, c in by_samp.most_common(16):
-    print(f"{100*c/ts:5.1f}% samp {100*by_exec[ln]/te:5.1f}% exec  L{ln}: {srcl[ln-1].strip()[:110] if ln else '?'}")
+    print(f"{100*c/ts:5.1f}% samp {100*by_exec[ln]/te:5.1f}% exec  L{ln}: {srcl[ln-1].strip()[:110] if ln and ln <= len(srcl) else '?'}")
