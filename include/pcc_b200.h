@@ -267,6 +267,33 @@ int pcc_fold_first_bf16(const float *local, int n_local, int64_t ld_local, const
                         int64_t M, int n_pts, int C, int relu, void *out, int64_t ld_out, void *stream);
 
 /*
+ * Weight gradient of one shared-MLP layer (the backward of the Conv2d(1x1) / Linear layers the reference trains under autograd,
+ * /root/reference/train.py:193-221): c[Na, Nb] = a[M, Na]^T . b[M, Nb] (fp32, overwritten; row pitch ldc) and, when colsum is
+ * given, colsum[Na] = column sums of a (the bias gradient).  a = the output gradient, b = the layer's input, both bf16
+ * row-major with widths / pitches that are multiples of 8 elements, 16-byte aligned.  The contraction over the M rows runs on
+ * the tensor cores straight from the row-major tensors (MN-major operands); long M with a small Na x Nb is split over the SMs
+ * and reduced with fp32 atomics (the sum order is then not fixed: results are reproducible to fp32 rounding, not bit-exact).
+ */
+int pcc_wgrad_bf16(const void *a, int64_t lda, int Na, const void *b, int64_t ldb, int Nb, int64_t M, float *c, int64_t ldc,
+                   float *colsum, void *stream);
+
+/*
+ * Training forms of the streamed layer and of the pooling (the reference trains these layers under autograd,
+ * /root/reference/train.py:193-221; here every contraction of the forward AND backward pass is one of these kernels).
+ * pcc_linear_train_bf16: pcc_linear_bf16 with a bf16 [M, n_store] result (n_store % 8 == 0, <= N: columns past it are not
+ *   written -- narrow layers inside the 128-column granule) and an optional mask [M, >= n_store] bf16: out = 0 where mask <= 0,
+ *   i.e. the ReLU backward of the layer below fused into the data-gradient GEMM  dX = (dY . W) * [X > 0].
+ * pcc_groupmax_fwd_bf16: pooled[M / group, C] fp32 = max over each run of `group` rows of x [M, C] bf16 (row pitch ldx), arg =
+ *   the first row of the run that attains it (pn_kit.py:139-143, 207).  pcc_groupmax_bwd_bf16: dy [M, ld_dy] bf16 = dout routed
+ *   to the arg-max rows (and only where pooled > 0 when `pooled` is given: a ReLU preceded the max); columns C .. ld_dy are zero.
+ */
+int pcc_linear_train_bf16(const void *a, int64_t M, int K, int64_t lda, const void *w, int64_t ldw, const float *bias, int N, int relu,
+                          void *out, int64_t ld_out, int n_store, const void *mask, int64_t ld_mask, void *stream);
+int pcc_groupmax_fwd_bf16(const void *x, int64_t M, int C, int64_t ldx, int group, float *pooled, int16_t *arg, void *stream);
+int pcc_groupmax_bwd_bf16(const float *dout, const float *pooled, const int16_t *arg, int64_t M, int C, int group, void *dy,
+                          int64_t ld_dy, void *stream);
+
+/*
  * pn_kit.SetAbstraction with S == N (/root/reference/pn_kit.py:181-207 as AE.sa calls it, AE.py:38) in two launches that
  * never materialise the grouped tensor: the in-patch kNN table as bytes, then the shared MLP gathering from the patch itself.
  * pcc_knn_patch_u8: patches [BS, P, 3] fp32, K in {8, 16}, K <= P <= 256 -> out_idx [BS, P, K] uint8: the K nearest points of

@@ -40,7 +40,7 @@ __device__ __forceinline__ int cell_coord(float p, float mn, float inv_h, int G)
 // grid (B, 2); dynamic smem: (G^3 + 1) u32
 __global__ void __launch_bounds__(GRID_BUILD_THREADS)
 grid_build_kernel(const float *__restrict__ x, const float *__restrict__ y, int P1, int P2, int G, float4 *__restrict__ sorted,
-                  unsigned *__restrict__ starts, GridInfo *__restrict__ info) {
+                  unsigned *__restrict__ starts, GridInfo *__restrict__ info, unsigned *__restrict__ rowmask) {
     extern __shared__ unsigned cnt[];
     __shared__ float red[6][32];
     __shared__ unsigned wsum[32];
@@ -153,6 +153,15 @@ grid_build_kernel(const float *__restrict__ x, const float *__restrict__ y, int 
     }
     if (tid == 0) st_out[ncell] = static_cast<unsigned>(P);
     __syncthreads();
+    // bit y of rowmask[z]: the row of cells (z, y, *) holds at least one point (G <= 32; warp z covers slab z).  The far walk
+    // of grid_nn_kernel iterates over set bits instead of testing every row of its box.
+    {
+        const int z = warp, yy = lane;
+        const bool occ = z < G && yy < G && cnt[(z * G + yy) * G] != (yy + 1 < G || z + 1 < G ? cnt[(z * G + yy) * G + G] : static_cast<unsigned>(P));
+        const unsigned m = __ballot_sync(FULL_MASK, occ);
+        if (lane == 0) rowmask[(static_cast<size_t>(side) * B + b) * 32 + z] = z < G ? m : 0u;
+    }
+    __syncthreads();
 
     // ---- scatter (cnt now holds the running cursor of every cell; the order inside a cell does not affect any result) ----
     for (int i = tid; i < P; i += GRID_BUILD_THREADS) {
@@ -182,7 +191,8 @@ __device__ __forceinline__ float slab_gap(float q, float mn, float h, int c, flo
 // grid (ceil(max(P1,P2) / 128), B, n_dir): direction 0 = x queries against y's grid -> kx; direction 1 = y against x -> ky
 __global__ void __launch_bounds__(128)
 grid_nn_kernel(int P1, int P2, const float4 *__restrict__ sorted, const unsigned *__restrict__ starts,
-               const GridInfo *__restrict__ info, unsigned long long *__restrict__ kx, unsigned long long *__restrict__ ky) {
+               const GridInfo *__restrict__ info, const unsigned *__restrict__ rowmask, unsigned long long *__restrict__ kx,
+               unsigned long long *__restrict__ ky) {
     const int b = blockIdx.y, dir = blockIdx.z, B = gridDim.y;
     const int Pq = dir ? P2 : P1, Pc = dir ? P1 : P2;
     if (blockIdx.x * 128 >= Pq) return;
@@ -249,15 +259,17 @@ grid_nn_kernel(int P1, int P2, const float4 *__restrict__ sorted, const unsigned
         const int xa = max(cell_coord(lo[0], g.mnx, g.inv_h, G) - 1, 0), xb = min(cell_coord(hi[0], g.mnx, g.inv_h, G) + 1, G - 1);
         const int ya = max(cell_coord(lo[1], g.mny, g.inv_h, G) - 1, 0), yb = min(cell_coord(hi[1], g.mny, g.inv_h, G) + 1, G - 1);
         const int za = max(cell_coord(lo[2], g.mnz, g.inv_h, G) - 1, 0), zb = min(cell_coord(hi[2], g.mnz, g.inv_h, G) + 1, G - 1);
+        // lane z holds the occupancy bits of slab z's rows: empty rows (most of the box when the candidate cloud is clumpy --
+        // e.g. the reconstruction of an untrained decoder) are never visited, no table loads, no pruning test
+        const unsigned my_rows = __ldg(rowmask + (static_cast<size_t>(cside) * B + b) * 32 + (threadIdx.x & 31));
+        const unsigned ymask = (yb >= 31 ? 0xffffffffu : (1u << (yb + 1)) - 1u) & ~((1u << ya) - 1u);
         for (int z = za; z <= zb; ++z) {
-            // empty slabs and rows cost two uniform table loads instead of the whole pruning test (a clumpy candidate
-            // cloud -- e.g. the reconstruction of an untrained decoder -- leaves most of the walked box empty)
-            if (__ldg(st + (z * G + ya) * G) == __ldg(st + (z * G + yb + 1) * G)) continue;
+            unsigned rows = __shfl_sync(FULL_MASK, my_rows, z) & ymask;
+            if (rows == 0u) continue;
             const float gz = slab_gap(q.z, g.mnz, g.h, z, g.margin);
             if (__all_sync(FULL_MASK, !need || gz * gz * 0.9999f > key_d2(best))) continue;
-            for (int yy = ya; yy <= yb; ++yy) {
-                const unsigned row0 = static_cast<unsigned>((z * G + yy) * G);
-                if (__ldg(st + row0 + xa) == __ldg(st + row0 + xb + 1)) continue;
+            for (; rows != 0u; rows &= rows - 1u) {
+                const int yy = __ffs(rows) - 1;
                 const float gy = slab_gap(q.y, g.mny, g.h, yy, g.margin);
                 // a row is skipped only if it lies outside the ball of every unsettled query of the warp
                 const float rem = key_d2(best) - (gz * gz + gy * gy) * 0.9999f;
@@ -288,7 +300,7 @@ grid_nn_kernel(int P1, int P2, const float4 *__restrict__ sorted, const unsigned
 int64_t chamfer_grid_extra_bytes(int B, int P1, int P2, int G) {
     const int64_t pts = static_cast<int64_t>(B) * (static_cast<int64_t>(P1) + P2) * 16;
     const int64_t tab = 2ll * B * (static_cast<int64_t>(G) * G * G + 1) * 4;
-    return pts + ((tab + 15) / 16) * 16 + 2ll * B * static_cast<int64_t>(sizeof(GridInfo));
+    return pts + ((tab + 15) / 16) * 16 + 2ll * B * static_cast<int64_t>(sizeof(GridInfo)) + 2ll * B * 32 * 4;
 }
 
 int chamfer_grid_pick(int P1, int P2) {   // grid resolution, or 0: use the brute-force kernels
@@ -309,6 +321,7 @@ int chamfer_grid_run(const float *x, const float *y, int B, int P1, int P2, int 
     const int64_t tab = 2ll * B * (static_cast<int64_t>(G) * G * G + 1) * 4;
     unsigned *starts = reinterpret_cast<unsigned *>(static_cast<char *>(extra) + pts);
     GridInfo *info = reinterpret_cast<GridInfo *>(static_cast<char *>(extra) + pts + ((tab + 15) / 16) * 16);
+    unsigned *rowmask = reinterpret_cast<unsigned *>(info + 2ll * B);   // [2][B][32]
     const size_t smem = static_cast<size_t>(G) * G * G * 4 + 4;
     static bool attr_done_dev[64] = {false};   // per device: the attribute belongs to the device's copy of the kernel
     int attr_done_d = 0;
@@ -321,11 +334,11 @@ int chamfer_grid_run(const float *x, const float *y, int B, int P1, int P2, int 
         }
         attr_done_dev[attr_done_d] = true;
     }
-    grid_build_kernel<<<dim3(B, 2), GRID_BUILD_THREADS, smem, st>>>(x, y, P1, P2, G, sorted, starts, info);
+    grid_build_kernel<<<dim3(B, 2), GRID_BUILD_THREADS, smem, st>>>(x, y, P1, P2, G, sorted, starts, info, rowmask);
     int rc = check_launch("grid_build_kernel");
     if (rc) return rc;
     const int pmax = P1 > P2 ? P1 : P2;
-    grid_nn_kernel<<<dim3((pmax + 127) / 128, B, ky ? 2 : 1), 128, 0, st>>>(P1, P2, sorted, starts, info, kx, ky);
+    grid_nn_kernel<<<dim3((pmax + 127) / 128, B, ky ? 2 : 1), 128, 0, st>>>(P1, P2, sorted, starts, info, rowmask, kx, ky);
     return check_launch("grid_nn_kernel");
 }
 

@@ -49,6 +49,11 @@ struct Params {
     int N, K, n_n;      // n_n = N / BN
     long long n_tiles;
     int relu, group;
+    // training (bf16 output only): columns >= n_store are not written (narrow layers inside the 128-column granule); with a
+    // mask tensor [M, >= n_store] bf16 the output is zeroed where mask <= 0 -- the ReLU backward of the layer below, fused
+    const __nv_bfloat16 *mask;
+    long long ld_mask;
+    int n_store;
 };
 
 template <bool RELU>
@@ -67,7 +72,7 @@ __device__ __forceinline__ void stage_row_chunk32(uint32_t stg, int r, int c0, c
     }
 }
 
-template <int BN, bool POOL>
+template <int BN, bool POOL, bool MASK>
 __global__ void __launch_bounds__(THREADS, 1)
 linear_kernel(const __grid_constant__ Params prm, const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
               const __grid_constant__ CUtensorMap tm_o) {
@@ -207,6 +212,22 @@ linear_kernel(const __grid_constant__ Params prm, const __grid_constant__ CUtens
                         else atomicMax(reinterpret_cast<unsigned *>(o), __float_as_uint(mine));
                     }
                 } else {
+                    if constexpr (MASK) {   // zero the 8-column chunks' elements whose mask value (the activation below) is <= 0
+                        const long long r = m0 + row;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int c = n0 + col + 8 * i;
+                            uint4 mk = make_uint4(0u, 0u, 0u, 0u);
+                            if (r < prm.M && c + 8 <= prm.n_store) mk = __ldg(reinterpret_cast<const uint4 *>(prm.mask + r * prm.ld_mask + c));
+                            const uint32_t mw[4] = {mk.x, mk.y, mk.z, mk.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {   // bf16 > 0  <=>  sign clear and not zero
+                                const uint32_t lo = mw[e] & 0xffffu, hi = mw[e] >> 16;
+                                if (lo == 0u || lo >= 0x8000u) v[8 * i + 2 * e] = 0u;
+                                if (hi == 0u || hi >= 0x8000u) v[8 * i + 2 * e + 1] = 0u;
+                            }
+                        }
+                    }
                     if (prm.relu) stage_row_chunk32<true>(stg, row, col, v);
                     else stage_row_chunk32<false>(stg, row, col, v);
                 }
@@ -219,7 +240,8 @@ linear_kernel(const __grid_constant__ Params prm, const __grid_constant__ CUtens
                 named_bar_sync(2, EPI_THREADS);
                 if (tid == 0) {
 #pragma unroll
-                    for (int s = 0; s < BN / 64; ++s) tma_store_2d(&tm_o, n0 + s * 64, static_cast<int>(m0), stg + s * SLAB);
+                    for (int s = 0; s < BN / 64; ++s)
+                        if (n0 + s * 64 < prm.n_store) tma_store_2d(&tm_o, n0 + s * 64, static_cast<int>(m0), stg + s * SLAB);
                     tma_store_commit();
                 }
             }
@@ -231,25 +253,25 @@ linear_kernel(const __grid_constant__ Params prm, const __grid_constant__ CUtens
     if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
 }
 
-template <int BN, bool POOL>
+template <int BN, bool POOL, bool MASK = false>
 static int launch(const Params &p, const CUtensorMap &ta, const CUtensorMap &tw, const CUtensorMap &to, cudaStream_t st) {
     using L = Lay<BN>;
-    const cudaError_t e = cudaFuncSetAttribute(linear_kernel<BN, POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM);
+    const cudaError_t e = cudaFuncSetAttribute(linear_kernel<BN, POOL, MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM);
     if (e != cudaSuccess) {
         set_error("pcc_linear_bf16: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
         return static_cast<int>(e);
     }
     const long long sms = num_sms();
     const int grid = static_cast<int>(p.n_tiles < sms ? p.n_tiles : sms);
-    linear_kernel<BN, POOL><<<grid, THREADS, L::SMEM, st>>>(p, ta, tw, to);
+    linear_kernel<BN, POOL, MASK><<<grid, THREADS, L::SMEM, st>>>(p, ta, tw, to);
     return check_launch("linear_kernel");
 }
 
 }  // namespace gws
 }  // namespace pcc
 
-PCC_API int pcc_linear_bf16(const void *a, int64_t M, int K, int64_t lda, const void *w, int64_t ldw, const float *bias, int N, int relu,
-                            int group, void *out, int64_t ld_out, void *stream) {
+static int linear_run(const void *a, int64_t M, int K, int64_t lda, const void *w, int64_t ldw, const float *bias, int N, int relu,
+                      int group, void *out, int64_t ld_out, const void *mask, int64_t ld_mask, int n_store, void *stream) {
     using namespace pcc;
     PCC_REQUIRE(a && w && bias && out, "pcc_linear_bf16: null pointer");
     PCC_REQUIRE(M >= 1 && M < (1ll << 31) - 256, "pcc_linear_bf16: M=%lld out of range", static_cast<long long>(M));
@@ -267,9 +289,13 @@ PCC_API int pcc_linear_bf16(const void *a, int64_t M, int K, int64_t lda, const 
         PCC_REQUIRE(group == 32 || relu, "pcc_linear_bf16: pooling over more than 32 rows needs the ReLU (atomicMax on non-negative values)");
         PCC_REQUIRE(ld_out == N, "pcc_linear_bf16: the pooled output is dense [M / group, N] fp32");
     } else {
-        PCC_REQUIRE(ld_out >= N && ld_out % 8 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0,
+        PCC_REQUIRE(n_store >= 8 && n_store <= N && n_store % 8 == 0, "pcc_linear_bf16: n_store=%d must be a multiple of 8 in [8, N]", n_store);
+        PCC_REQUIRE(ld_out >= n_store && ld_out % 8 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0,
                     "pcc_linear_bf16: out must be 16-byte aligned bf16 with a row pitch that is a multiple of 8 elements");
+        PCC_REQUIRE(!mask || (ld_mask >= n_store && ld_mask % 8 == 0 && reinterpret_cast<uintptr_t>(mask) % 16 == 0),
+                    "pcc_linear_bf16: mask must be 16-byte aligned bf16 [M, >= n_store] with a row pitch that is a multiple of 8");
     }
+    PCC_REQUIRE(!pool || !mask, "pcc_linear_bf16: the mask applies to the bf16 output only");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int BN = (N % 256 == 0) ? 256 : 128;
     CUtensorMap ta, tw, to;
@@ -284,8 +310,8 @@ PCC_API int pcc_linear_bf16(const void *a, int64_t M, int K, int64_t lda, const 
                 return static_cast<int>(e);
             }
         }
-    } else if (int r = make_tmap_bf16_2d(&to, out, static_cast<uint64_t>(M), static_cast<uint64_t>(N), static_cast<uint64_t>(ld_out), 128)) {
-        return r;
+    } else if (int r = make_tmap_bf16_2d(&to, out, static_cast<uint64_t>(M), static_cast<uint64_t>(n_store), static_cast<uint64_t>(ld_out), 128)) {
+        return r;   // the store map ends at n_store: TMA clips the columns past it
     }
     gws::Params p{};
     p.bias = bias;
@@ -297,6 +323,20 @@ PCC_API int pcc_linear_bf16(const void *a, int64_t M, int K, int64_t lda, const 
     p.n_tiles = ((M + 127) / 128) * p.n_n;
     p.relu = relu;
     p.group = pool ? group : 0;
+    p.mask = static_cast<const __nv_bfloat16 *>(mask);
+    p.ld_mask = ld_mask;
+    p.n_store = pool ? N : n_store;
+    if (mask) return BN == 256 ? gws::launch<256, false, true>(p, ta, tw, to, st) : gws::launch<128, false, true>(p, ta, tw, to, st);
     if (BN == 256) return pool ? gws::launch<256, true>(p, ta, tw, to, st) : gws::launch<256, false>(p, ta, tw, to, st);
     return pool ? gws::launch<128, true>(p, ta, tw, to, st) : gws::launch<128, false>(p, ta, tw, to, st);
+}
+
+PCC_API int pcc_linear_bf16(const void *a, int64_t M, int K, int64_t lda, const void *w, int64_t ldw, const float *bias, int N, int relu,
+                            int group, void *out, int64_t ld_out, void *stream) {
+    return linear_run(a, M, K, lda, w, ldw, bias, N, relu, group, out, ld_out, nullptr, 0, N, stream);
+}
+
+PCC_API int pcc_linear_train_bf16(const void *a, int64_t M, int K, int64_t lda, const void *w, int64_t ldw, const float *bias, int N,
+                                  int relu, void *out, int64_t ld_out, int n_store, const void *mask, int64_t ld_mask, void *stream) {
+    return linear_run(a, M, K, lda, w, ldw, bias, N, relu, 0, out, ld_out, mask, ld_mask, n_store, stream);
 }

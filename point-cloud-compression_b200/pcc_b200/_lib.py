@@ -60,6 +60,10 @@ SIGNATURES.update({
     "pcc_fold_first_bf16": (_i, [_vp, _i, _i64, _vp, _i64, _vp, _i64, _i, _i, _i, _vp, _i64, _vp]),
     "pcc_gather_concat_bf16": (_i, [_vp, _i, _vp, _vp, _i, _i, _i64, _i, _vp, _vp, _i, _vp]),
     "pcc_knn_patch_u8": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "pcc_linear_train_bf16": (_i, [_vp, _i64, _i, _i64, _vp, _i64, _vp, _i, _i, _vp, _i64, _i, _vp, _i64, _vp]),
+    "pcc_groupmax_fwd_bf16": (_i, [_vp, _i64, _i, _i64, _i, _vp, _vp, _vp]),
+    "pcc_groupmax_bwd_bf16": (_i, [_vp, _vp, _vp, _i64, _i, _i, _vp, _i64, _vp]),
+    "pcc_wgrad_bf16": (_i, [_vp, _i64, _i, _vp, _i64, _i, _i64, _vp, _i64, _vp, _vp]),
     "pcc_sa_chain_indexed": (_i, [_vp, _vp, _i64, _i, ctypes.POINTER(PccMlpLayer), _i, _vp, _i, _vp]),
     "pcc_normals_pca_f32": (_i, [_vp, _i64, _i, _vp, _vp]),
     "pcc_p2plane_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),

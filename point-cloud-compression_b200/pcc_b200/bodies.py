@@ -218,6 +218,69 @@ def ae_forward(mod, xyz):
     return ae_decode(mod, latent_q), latent, latent_q
 
 
+# ---- training bodies: the same modules under autograd, every contraction (forward and backward) on the pcc kernels --------------
+def _grad_layers_stack(mod):
+    """(w, b, relu) of pn_kit.PointNet / MLP with autograd-tracked views of the parameters (no BatchNorm: the AE uses bn=False)."""
+    out = []
+    for seq in mod.mlp_Modules:
+        mods = list(seq)
+        if any(isinstance(m, _BN_TYPES) for m in mods):
+            raise NotImplementedError("pcc_b200 training bodies: BatchNorm inside a trained stack is not supported")
+        out.append((mods[0].weight.flatten(1), mods[0].bias, any(isinstance(m, nn.ReLU) for m in mods[1:])))
+    return out
+
+
+def ae_forward_train(mod, xyz):
+    """AE.AE.forward (AE.py:34-55) under autograd: xyz [BS, K, 3] -> (new_xyz [BS, k, 3], latent, latent_quantized); gradients reach
+    every parameter through the STE quantiser exactly as in the reference.  The grouping (in-patch kNN) carries no gradient."""
+    from . import train_ops as T
+    if getattr(mod.sa, "bn", False):
+        raise NotImplementedError("pcc_b200 training bodies: SetAbstraction(bn=True) is not supported")
+    xyz = xyz.contiguous()
+    BS, P, _ = xyz.shape
+    K = mod.sa.K
+    with torch.no_grad():
+        _, _, grouped = ops.knn(xyz, xyz, K, return_nn=True, centre_sub=True, nn_only=True)            # pn_kit.py:190-191
+    sa_l = [(getattr(mod.sa, f"conv{i}").weight.flatten(1), getattr(mod.sa, f"conv{i}").bias, True if i < 2 else bool(mod.sa.finalRelu))
+            for i in range(3)]
+    feat = T.mlp_train(T.pad_bf16(grouped.reshape(BS * P * K, 3), 64), sa_l, group=K, mode="pool")    # pn_kit.py:196-207  [BS*P, 128]
+    pn_l = _grad_layers_stack(mod.pn)
+    w0 = pn_l[0][0]
+    pn_l[0] = (torch.cat((w0[:, 3:], w0[:, :3]), dim=1), pn_l[0][1], pn_l[0][2])                      # AE.py:39 cat(xyz, feat) -> [feat | xyz]
+    F_ = feat.shape[1]
+    x0 = torch.cat((feat.to(torch.bfloat16), xyz.reshape(BS * P, 3).to(torch.bfloat16),
+                    torch.zeros((BS * P, (-(F_ + 3)) % 64), dtype=torch.bfloat16, device=xyz.device)), dim=1)
+    raw = T.mlp_train(x0, pn_l, group=P, mode="pool")                                                  # pn_kit.py:124-144  [BS, d]
+    spread = mod.L - 0.2
+    latent = torch.sigmoid(raw) * spread - spread / 2                                                  # AE.py:42-44
+    latent_q = mod.quantize(latent)                                                                    # AE.py:45 (STE)
+    k = mod.k
+    ip = [(mod.inv_pool[i].weight, mod.inv_pool[i].bias, True) for i in (0, 2, 4)]
+    lin = T.mlp_train(T.pad_bf16(latent_q, 64), ip, mode="bf16")                                        # AE.py:48  bf16 [BS, 128 * k]
+    ch = lin.shape[1] // k
+    lin_pts = lin.view(BS, ch, k).permute(0, 2, 1).reshape(BS * k, ch)                                  # AE.py:49
+    d = latent_q.shape[1]
+    x0d = torch.cat((lin_pts, latent_q.to(torch.bfloat16).repeat_interleave(k, dim=0),
+                     torch.zeros((BS * k, (-(ch + d)) % 64), dtype=torch.bfloat16, device=xyz.device)), dim=1)   # AE.py:50-51
+    out = T.mlp_train(x0d, _grad_layers_stack(mod.inv_mlp), mode="f32")                                 # AE.py:52
+    return out.view(BS, k, 3), latent, latent_q
+
+
+def prob_forward_train(mod, sampled_xyz):
+    """AE.ConditionalProbabilityModel.forward (AE.py:107-123) under autograd on the pcc kernels."""
+    from . import train_ops as T
+    B, S, _ = sampled_xyz.shape
+    xyz = sampled_xyz.detach().float().contiguous()
+    feature = T.mlp_train(T.pad_bf16(xyz.reshape(B * S, 3), 64), _grad_layers_stack(mod.model_pn), group=S, mode="pool")   # AE.py:112
+    m0, m2, m4 = mod.model_mlp[0], mod.model_mlp[2], mod.model_mlp[4]
+    F_ = feature.shape[1]
+    x0 = torch.cat((xyz.reshape(B * S, 3).to(torch.bfloat16), feature.to(torch.bfloat16).repeat_interleave(S, dim=0),
+                    torch.zeros((B * S, (-(F_ + 3)) % 64), dtype=torch.bfloat16, device=xyz.device)), dim=1)                # AE.py:115
+    logits = T.mlp_train(x0, [(m0.weight.flatten(1), m0.bias, True), (m2.weight.flatten(1), m2.bias, True),
+                              (m4.weight.flatten(1), m4.bias, False)], mode="f32")                                        # AE.py:116-118
+    return torch.softmax(logits.view(B, S, mod.d, mod.L), dim=3)                                                           # AE.py:119-121
+
+
 # ---- conditional probability models ---------------------------------------------------------------------------------------
 def _prob_tail(model_mlp, sampled_xyz, feature, d, L):
     """AE.py:115-121 / PPPF_AE.py:213-228: cat(xyz, tiled global feature) -> Conv2d 3+F -> 512 -> 512 -> d*L -> softmax over L.

@@ -412,3 +412,26 @@ def gather_concat_bf16(feat, xyz, idx, kpad, centre=None, nsample=1):
                                               out.data_ptr(), centre.data_ptr() if centre is not None else None, int(nsample),
                                               torch.cuda.current_stream().cuda_stream), "pcc_gather_concat_bf16")
     return out
+
+
+# ---- training: weight gradients (csrc/wgrad_ws.cu) ---------------------------------------------------------------------------
+def wgrad(dy, x, want_bias=True):
+    """dW [Na, Nb] = dy[M, Na]^T . x[M, Nb] (fp32) and db [Na] = column sums of dy: the weight / bias gradient of a layer
+    y = x W^T + b from the bf16 output gradient and the bf16 input activation, both row-major [M, *] (column counts multiples of
+    8).  Runs on the tensor cores without transposed copies (MN-major operands)."""
+    lib = _lib.load()
+    _check(dy)
+    for t in (dy, x):
+        if t.dtype != torch.bfloat16 or t.dim() != 2 or t.stride(1) != 1 or t.shape[1] % 8 or t.stride(0) % 8 or t.data_ptr() % 16:
+            raise ValueError("pcc_b200.wgrad: operands must be 16-byte aligned bf16 [M, C] with C % 8 == 0")
+    if dy.shape[0] != x.shape[0]:
+        raise ValueError("pcc_b200.wgrad: dy and x disagree on the number of rows")
+    M, Na = dy.shape
+    Nb = x.shape[1]
+    dw = torch.empty((Na, Nb), dtype=torch.float32, device=dy.device)
+    db = torch.empty((Na,), dtype=torch.float32, device=dy.device) if want_bias else None
+    with torch.cuda.device(dy.device):
+        _lib.check(lib.pcc_wgrad_bf16(dy.data_ptr(), dy.stride(0), Na, x.data_ptr(), x.stride(0), Nb, M, dw.data_ptr(), Nb,
+                                      db.data_ptr() if db is not None else None, torch.cuda.current_stream().cuda_stream),
+                   "pcc_wgrad_bf16")
+    return dw, db

@@ -60,8 +60,8 @@ class SetAbstraction(nn.Module):
         return bodies.sa_points(self, xyz, out_dtype)[1]
 
     def forward_points_train(self, xyz):
-        """Differentiable body (training): the kNN grouping runs on the pcc kernel (no gradient flows into it, SURVEY.md
-        3.3), the shared MLP is issued as fp32 library GEMMs under autograd, like the reference's default fp32 training."""
+        """fp32 torch body under autograd (library GEMMs) -- part of AE.forward_train_fp32, the arithmetic the kernel training
+        path is tested against: the kNN grouping runs on the pcc kernel (no gradient flows into it)."""
         BS, P, _ = xyz.shape
         _, _, grouped = ops.knn(xyz.detach(), xyz.detach(), self.K, return_nn=True, centre_sub=True, nn_only=True)
         h = grouped.reshape(BS * P * self.K, 3)
@@ -146,8 +146,13 @@ class AE(nn.Module):
         return bodies.ae_decode(self, latent_q)
 
     def forward_train(self, xyz):
-        """AE.forward (AE.py:34-55) under autograd: fp32 library GEMMs for the network bodies, pcc kernels for the
-        grouping; gradients reach every parameter through the STE quantiser exactly as in the reference."""
+        """AE.forward (AE.py:34-55) under autograd, forward and backward contractions on the pcc kernels (bodies.ae_forward_train:
+        bf16 operands, fp32 accumulation and weight gradients)."""
+        return bodies.ae_forward_train(self, xyz)
+
+    def forward_train_fp32(self, xyz):
+        """The same body as plain fp32 torch ops under autograd (library GEMMs): the reference arithmetic the kernel path is
+        tested against (tests/test_gpu_train.py); Trainer(kernels=False) trains with it."""
         BS = xyz.shape[0]
         feat = self.sa.forward_points_train(xyz)
         h = torch.cat((xyz, feat), dim=2).reshape(BS * xyz.shape[1], -1)          # AE.py:39
@@ -189,6 +194,9 @@ class ConditionalProbabilityModel(nn.Module):
                                        nn.Conv2d(512, d * L, 1))
 
     def forward_train(self, sampled_xyz):
+        return bodies.prob_forward_train(self, sampled_xyz)
+
+    def forward_train_fp32(self, sampled_xyz):
         B, S, _ = sampled_xyz.shape
         h = sampled_xyz.reshape(B * S, 3)
         for w, b, relu in self.model_pn.layers():

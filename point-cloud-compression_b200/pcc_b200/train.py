@@ -1,8 +1,10 @@
 """Training step of the IPDAE patch auto-encoder on the B200 ops: the body of train.py:148-247 for one batch.
 
 The data-parallel geometric stages (normalise, FPS, kNN patching, in-patch kNN, Chamfer forward / backward) are the pcc
-kernels; the network bodies run as fp32 library GEMMs under autograd (the reference trains in fp32 by default, SURVEY.md
-appendix B-6).  Multi-GPU: one process per GPU, whole clouds per rank, gradients all-reduced by DistributedDataParallel
+kernels, and so are the network bodies: every contraction of the forward and backward pass runs on the streamed tcgen05 GEMM,
+the MN-major weight-gradient kernel and the pooling kernels (train_ops.py: bf16 operands, fp32 accumulation and weight
+gradients, fp32 master weights -- the counterpart of the reference's autocast path, train.py:114,154).  Trainer(kernels=False)
+runs the same bodies as plain fp32 torch ops (library GEMMs): the arithmetic the kernel path is tested against.  Multi-GPU: one process per GPU, whole clouds per rank, gradients all-reduced by DistributedDataParallel
 over NCCL -- the only collective of the path.  The octree centre coder stays on the reference path; the step applies its
 quantisation rule on the device (see codec.py).
 """
@@ -35,14 +37,16 @@ def _matmul_tf32(enabled):
 
 class Trainer:
     def __init__(self, K=256, k=128, d=16, L=7, N0=1024, alpha=2, lr=0.0005, lamda=1e-6, rate_loss_enable_step=40000,
-                 centre_depth=6, device="cuda", ddp=False, state_dict=None, tf32=True, amp=False):
+                 centre_depth=6, device="cuda", ddp=False, state_dict=None, tf32=True, amp=False, kernels=True):
         self.K, self.k, self.d, self.L, self.N0, self.alpha = K, k, d, L, N0, alpha
         # The reference's network bodies are 1x1 Conv2d layers, which PyTorch runs through cuDNN with TF32 enabled by
         # default (torch.backends.cudnn.allow_tf32); the addmm form used here gets the same arithmetic only when the
         # matmul flag is switched on as well.  fp32 storage and accumulation, 10-bit operand mantissas.
         # The flag is set only around this trainer's own forward / backward (a context in step()), never process-wide: other
         # code in the process -- e.g. a probability model whose PMFs must be reproduced bit for bit -- keeps its setting.
-        self.tf32 = bool(tf32)
+        self.kernels = bool(kernels)
+        self.tf32 = bool(tf32) and not self.kernels      # tf32 / amp only concern the library-GEMM bodies (kernels=False)
+        amp = bool(amp) and not self.kernels
         # amp=True: the network bodies run under bf16 autocast -- the counterpart of the reference's fp16 autocast + GradScaler
         # path (train.py:114,154-160, taken when --device is the string 'cuda'); bf16 needs no loss scaling.
         self.amp = amp
@@ -51,19 +55,20 @@ class Trainer:
         if state_dict is not None:
             self.ae.load_state_dict(state_dict)
         self.prob = ConditionalProbabilityModel(L, d).to(device)
-        self.ae_fwd, self.prob_fwd = self.ae.forward_train, self.prob
+        name = "forward_train" if self.kernels else "forward_train_fp32"
+        self.ae_fwd, self.prob_fwd = getattr(self.ae, name), getattr(self.prob, name)
         if ddp:  # gradients of both models are all-reduced over NCCL, bucketed and overlapped with the backward pass
             from torch.nn.parallel import DistributedDataParallel as DDP
 
             class _Train(torch.nn.Module):
-                def __init__(self, ae):
+                def __init__(self, net):
                     super().__init__()
-                    self.ae = ae
+                    self.net = net
 
                 def forward(self, x):
-                    return self.ae.forward_train(x)
+                    return getattr(self.net, name)(x)
 
-            self._ddp_ae, self._ddp_prob = DDP(_Train(self.ae)), DDP(self.prob)
+            self._ddp_ae, self._ddp_prob = DDP(_Train(self.ae)), DDP(_Train(self.prob))
             self.ae_fwd, self.prob_fwd = self._ddp_ae, self._ddp_prob
         self.optimizer = torch.optim.Adam(list(self.ae.parameters()) + list(self.prob.parameters()), lr=lr)  # train.py:132-135
         self.global_step = 0

@@ -260,3 +260,25 @@ def test_sa_chain_indexed_is_bit_identical_to_the_grouped_route(BS, P):
         got = mlp_ops.sa_chain_indexed(x, idx8, layers, out_dtype=dt)
         assert got.shape == want.shape == (BS * P, 128) and torch.equal(got, want)
     assert not mlp_ops.sa_indexed_supported(P, 8, layers) and not mlp_ops.sa_indexed_supported(300, 16, layers)
+
+
+@pytest.mark.parametrize("M,Na,Nb", [(64, 128, 128), (8192, 128, 64), (100_000, 64, 32), (1_000_003 // 8 * 8, 128, 64), (2048, 1024, 256),
+                                     (5000, 16, 144), (333 * 8, 264, 200)])
+def test_wgrad_matches_fp32_contraction(M, Na, Nb):
+    """pcc_wgrad_bf16 (MN-major tensor-core contraction over the rows + the ones-block column sums) against dy^T x and dy.sum(0)
+    computed in fp64 from the same bf16 operands: fp32 accumulation, so the error is a few ulp of the largest partial sums."""
+    import __graft_entry__  # noqa: F401
+    from pcc_b200 import mlp_ops
+    torch.manual_seed(M % 1000 + Na)
+    dy = (torch.randn(M, Na, device="cuda") * 0.5).to(torch.bfloat16)
+    x = torch.relu(torch.randn(M, Nb, device="cuda")).to(torch.bfloat16)
+    dw, db = mlp_ops.wgrad(dy, x)
+    want_w = dy.double().t() @ x.double()
+    want_b = dy.double().sum(0)
+    scale = float((dy.double().abs().t() @ x.double().abs()).max())
+    assert dw.shape == (Na, Nb) and float((dw.double() - want_w).abs().max()) < 2e-5 * scale
+    assert float((db.double() - want_b).abs().max()) < 2e-5 * float(dy.double().abs().sum(0).max())
+    # strided operands (a column window of a wider activation) and no bias
+    if Na >= 64 and (Na // 2) % 8 == 0:
+        dw2, none = mlp_ops.wgrad(dy[:, :Na // 2], x, want_bias=False)
+        assert none is None and float((dw2.double() - want_w[:Na // 2]).abs().max()) < 2e-5 * scale

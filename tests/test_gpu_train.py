@@ -51,6 +51,116 @@ def test_training_forward_matches_fused_inference_forward():
     assert float((h.view(4, ae.k, 3) - rec_i).abs().max()) < 1e-2
 
 
+def _rel_l2(a, b):
+    return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
+
+
+def _r16(t):
+    """Round to bf16 and back (differentiable: the casts pass the gradient through) -- where the kernels store bf16."""
+    return t.to(torch.bfloat16).float()
+
+
+def _emu_stack(x0, layers, group=0, mode="f32"):
+    """torch statement of train_ops.mlp_train's FORWARD arithmetic under autograd: bf16 operands (weights and every stored
+    activation rounded to bf16), fp32 accumulation; the backward is torch's fp32 autograd of that forward."""
+    h = _r16(x0)
+    L = len(layers)
+    for i, (w, b, relu) in enumerate(layers):
+        h = h @ _r16(w).t() + (b if b is not None else 0)
+        if relu:
+            h = torch.relu(h)
+        if i + 1 < L or mode != "f32":
+            h = _r16(h)
+    if mode == "pool":
+        h = h.view(-1, group, h.shape[1]).max(dim=1)[0]
+    return h
+
+
+def _emu_ae_forward(ae, xyz):
+    from pcc_b200 import ops
+    BS, P, _ = xyz.shape
+    with torch.no_grad():
+        _, _, grouped = ops.knn(xyz, xyz, 16, return_nn=True, centre_sub=True, nn_only=True)
+    feat = _emu_stack(grouped.reshape(-1, 3), ae.sa.layers(), 16, "pool")
+    raw = _emu_stack(torch.cat((xyz.reshape(-1, 3), feat), dim=1), ae.pn.layers(), P, "pool")
+    spread = ae.L - 0.2
+    latent = torch.sigmoid(raw) * spread - spread / 2
+    lq = ae.quantize(latent)
+    lin = _emu_stack(lq, [(ae.inv_pool[i].weight, ae.inv_pool[i].bias, True) for i in (0, 2, 4)], mode="bf16").view(BS, -1, ae.k)
+    x = torch.cat((lin, lq.unsqueeze(-1).repeat((1, 1, ae.k))), dim=1).permute(0, 2, 1).reshape(BS * ae.k, -1)
+    return _emu_stack(x, ae.inv_mlp.layers()).view(BS, ae.k, 3), latent, lq
+
+
+def test_kernel_training_gradients_match_the_autograd_bodies():
+    """AE.forward_train (every forward / backward contraction on the pcc kernels: streamed tcgen05 GEMM, MN-major weight-gradient
+    kernel, pooling kernels) against two torch autograd statements of the same body, same weights / patches / loss:
+      (i) the bf16-operand model of its own arithmetic (_emu_ae_forward: same rounding points, so the same ReLU / arg-max
+          patterns; torch's backward keeps fp32 gradients where the kernels store bf16): every parameter gradient within 1e-2
+          relative L2 (measured: <= 6e-3);
+      (ii) the plain fp32 body AE.forward_train_fp32 (the reference's default arithmetic): outputs and loss within the bf16
+          tolerance, gradients with cosine > 0.85 -- a bf16 network flips ~1 % of the ReLU units and pooling winners whose
+          pre-activations are near ties, which is what separates ANY reduced-precision training from fp32 gradients at depth."""
+    import __graft_entry__  # noqa: F401
+    from pcc_b200.modules import AE, ConditionalProbabilityModel
+    torch.manual_seed(3)
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        ae = AE(256, 128, 16, 7)
+        ae.load_state_dict(synth.seeded_state_dict(synth.ae_shapes(128, 16, 7), 11))
+        ae = ae.cuda().train()
+        xyz = torch.from_numpy(synth.modelnet_like(1, 2048, seed=9)).cuda().view(8, 256, 3) - 0.5
+        target = torch.rand(8, 128, 3, device="cuda") - 0.5
+
+        def run(fwd):
+            ae.zero_grad(set_to_none=True)
+            out, latent, lq = fwd(xyz)
+            loss = (out - target).square().mean() + 1e-2 * latent.square().mean()
+            loss.backward()
+            return out.detach(), latent.detach(), float(loss), {n: p.grad.clone() for n, p in ae.named_parameters()}
+
+        o_ref, l_ref, loss_ref, g_ref = run(ae.forward_train_fp32)
+        o_emu, l_emu, loss_emu, g_emu = run(lambda x: _emu_ae_forward(ae, x))
+        lib = __import__("pcc_b200")._lib.load()
+        n0 = lib.pcc_launch_count()
+        o_k, l_k, loss_k, g_k = run(ae.forward_train)
+        assert lib.pcc_launch_count() - n0 >= 40            # 14 forward layers + pooling + 14 wgrad + 11 dgrad ...
+        assert float((l_k - l_emu).abs().max()) < 2e-3 and float((o_k - o_emu).abs().max()) < 2e-3     # same arithmetic
+        assert float((l_k - l_ref).abs().max()) < 2e-2 and float((o_k - o_ref).abs().max()) < 2e-2     # bf16 vs fp32
+        assert abs(loss_k - loss_ref) < 2e-2 * abs(loss_ref)
+        report = {}
+        for name, g in g_emu.items():
+            assert g_k[name].shape == g.shape and torch.isfinite(g_k[name]).all(), name
+            if float(g.norm()) < 1e-12:
+                continue
+            cos = float((g_k[name].double() * g_ref[name].double()).sum() /
+                        (g_k[name].double().norm() * g_ref[name].double().norm() + 1e-30))
+            report[name] = (_rel_l2(g_k[name], g), cos)
+        print({k: (round(a, 4), round(c, 4)) for k, (a, c) in report.items()})
+        for name, (r, cos) in report.items():
+            assert r < 1e-2 and cos > 0.85, (name, r, cos)
+        # the probability model (PointNet + 3-layer head, softmax) against its fp32 body: shallow, so the comparison is direct
+        prob = ConditionalProbabilityModel(7, 16).cuda().train()
+        centres = torch.rand(3, 64, 3, device="cuda")
+        sym = torch.randint(0, 7, (3, 64, 16, 1), device="cuda")
+
+        def run_p(fwd):
+            prob.zero_grad(set_to_none=True)
+            pmf = fwd(centres)
+            loss = -torch.log(pmf.gather(3, sym).clamp(min=1e-6)).mean()
+            loss.backward()
+            return pmf.detach(), {n: p.grad.clone() for n, p in prob.named_parameters()}
+
+        p_ref, gp_ref = run_p(prob.forward_train_fp32)
+        p_k, gp_k = run_p(prob.forward_train)
+        assert float((p_k - p_ref).abs().max()) < 1e-2
+        for name, g in gp_ref.items():
+            if float(g.norm()) > 1e-12:
+                assert _rel_l2(gp_k[name], g) < 0.15, (name, _rel_l2(gp_k[name], g))
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+
 def test_pppf_training_pass_and_fused_inference_agree():
     """PPPF_AE (PointNet++ SA x3 + FoldingNet, cfg3): with autograd on, the differentiable body runs (pcc kernels for sampling /
     ball query / grouping / Chamfer, torch layers for the MLPs); in eval mode it computes what the fused inference path computes,
