@@ -48,41 +48,45 @@ groupmax_fwd_kernel(const __nv_bfloat16 *__restrict__ x, long long ldx, long lon
     }
 }
 
-// thread = (row, 8-column chunk of the ld_dy-wide output); columns >= C are written as zeros (operand padding)
+// thread = (group, 8-column chunk of the ld_dy-wide output): the group's arg / dout / pooled values are read once and its g rows
+// are written from registers (consecutive threads -> consecutive 16-byte chunks of the same row: coalesced); columns >= C are
+// written as zeros (operand padding)
 __global__ void __launch_bounds__(256)
 groupmax_bwd_kernel(const float *__restrict__ dout, const float *__restrict__ pooled, const short *__restrict__ arg, long long M, int C,
                     int g, int out_chunks, __nv_bfloat16 *__restrict__ dy, long long ld_dy) {
-    const long long total = M * out_chunks;
+    const long long n_groups = M / g, total = n_groups * out_chunks;
     for (long long t = blockIdx.x * 256ll + threadIdx.x; t < total; t += static_cast<long long>(gridDim.x) * 256) {
-        const long long r = t / out_chunks;
-        const int ch = static_cast<int>(t - r * out_chunks);
-        uint4 o = make_uint4(0u, 0u, 0u, 0u);
-        if (ch * 8 < C) {
-            const long long gr = r / g;
-            const short j = static_cast<short>(r - gr * g);
-            const long long s = gr * C + ch * 8;
-            const uint4 a = __ldg(reinterpret_cast<const uint4 *>(arg + s));
-            const float4 d0 = __ldg(reinterpret_cast<const float4 *>(dout + s)), d1 = __ldg(reinterpret_cast<const float4 *>(dout + s + 4));
-            const float d[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
-            const unsigned aw[4] = {a.x, a.y, a.z, a.w};
-            float p[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
-            if (pooled) {
-                const float4 p0 = __ldg(reinterpret_cast<const float4 *>(pooled + s)), p1 = __ldg(reinterpret_cast<const float4 *>(pooled + s + 4));
-                p[0] = p0.x, p[1] = p0.y, p[2] = p0.z, p[3] = p0.w, p[4] = p1.x, p[5] = p1.y, p[6] = p1.z, p[7] = p1.w;
-            }
-            float v[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const short ae = static_cast<short>((e & 1) ? (aw[e >> 1] >> 16) : (aw[e >> 1] & 0xffffu));
-                v[e] = (ae == j && p[e] > 0.0f) ? d[e] : 0.0f;
-            }
-            __nv_bfloat162 h[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
-            o = make_uint4(*reinterpret_cast<unsigned *>(&h[0]), *reinterpret_cast<unsigned *>(&h[1]), *reinterpret_cast<unsigned *>(&h[2]),
-                           *reinterpret_cast<unsigned *>(&h[3]));
+        const long long gr = t / out_chunks;
+        const int ch = static_cast<int>(t - gr * out_chunks);
+        __nv_bfloat16 *dst = dy + gr * g * ld_dy + ch * 8;
+        if (ch * 8 >= C) {
+            for (int j = 0; j < g; ++j) *reinterpret_cast<uint4 *>(dst + j * ld_dy) = make_uint4(0u, 0u, 0u, 0u);
+            continue;
         }
-        *reinterpret_cast<uint4 *>(dy + r * ld_dy + ch * 8) = o;
+        const long long s = gr * C + ch * 8;
+        const uint4 a = __ldg(reinterpret_cast<const uint4 *>(arg + s));
+        const float4 d0 = __ldg(reinterpret_cast<const float4 *>(dout + s)), d1 = __ldg(reinterpret_cast<const float4 *>(dout + s + 4));
+        float d[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+        if (pooled) {   // a ReLU preceded the max: no gradient where the maximum is not positive
+            const float4 p0 = __ldg(reinterpret_cast<const float4 *>(pooled + s)), p1 = __ldg(reinterpret_cast<const float4 *>(pooled + s + 4));
+            const float p[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) d[e] = p[e] > 0.0f ? d[e] : 0.0f;
+        }
+        const unsigned aw[4] = {a.x, a.y, a.z, a.w};
+        int at[8];
+        unsigned hv[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            at[e] = static_cast<int>((e & 1) ? (aw[e >> 1] >> 16) : (aw[e >> 1] & 0xffffu));
+            hv[e] = static_cast<unsigned>(__bfloat16_as_ushort(__float2bfloat16_rn(d[e])));
+        }
+        for (int j = 0; j < g; ++j) {
+            unsigned w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) w[e] = (at[2 * e] == j ? hv[2 * e] : 0u) | ((at[2 * e + 1] == j ? hv[2 * e + 1] : 0u) << 16);
+            *reinterpret_cast<uint4 *>(dst + j * ld_dy) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
     }
 }
 
@@ -120,7 +124,7 @@ PCC_API int pcc_groupmax_bwd_bf16(const float *dout, const float *pooled, const 
                 "pcc_groupmax_bwd_bf16: pointers must be 16-byte aligned");
     if (M == 0) return 0;
     const int out_chunks = static_cast<int>(ld_dy / 8);
-    groupmax_bwd_kernel<<<grid_of(M * out_chunks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    groupmax_bwd_kernel<<<grid_of(M / group * out_chunks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         dout, pooled, arg, M, C, group, out_chunks, static_cast<__nv_bfloat16 *>(dy), ld_dy);
     return check_launch("groupmax_bwd_kernel");
 }

@@ -243,7 +243,8 @@ def ae_forward_train(mod, xyz):
         _, _, grouped = ops.knn(xyz, xyz, K, return_nn=True, centre_sub=True, nn_only=True)            # pn_kit.py:190-191
     sa_l = [(getattr(mod.sa, f"conv{i}").weight.flatten(1), getattr(mod.sa, f"conv{i}").bias, True if i < 2 else bool(mod.sa.finalRelu))
             for i in range(3)]
-    feat = T.mlp_train(T.pad_bf16(grouped.reshape(BS * P * K, 3), 64), sa_l, group=K, mode="pool")    # pn_kit.py:196-207  [BS*P, 128]
+    x1 = T.fold_first_train(grouped.reshape(BS * P * K, 3), sa_l[0][0], sa_l[0][1])                   # conv0 in fp32 on the CUDA cores
+    feat = T.mlp_train(x1, sa_l[1:], group=K, mode="pool", x0_is_relu=True)                           # pn_kit.py:196-207  [BS*P, 128]
     pn_l = _grad_layers_stack(mod.pn)
     w0 = pn_l[0][0]
     pn_l[0] = (torch.cat((w0[:, 3:], w0[:, :3]), dim=1), pn_l[0][1], pn_l[0][2])                      # AE.py:39 cat(xyz, feat) -> [feat | xyz]

@@ -70,8 +70,13 @@ class Trainer:
 
             self._ddp_ae, self._ddp_prob = DDP(_Train(self.ae)), DDP(_Train(self.prob))
             self.ae_fwd, self.prob_fwd = self._ddp_ae, self._ddp_prob
-        self.optimizer = torch.optim.Adam(list(self.ae.parameters()) + list(self.prob.parameters()), lr=lr)  # train.py:132-135
+        # capturable: the step counters live on the device, so the whole step (forward, backward, Adam) can be replayed as one
+        # CUDA graph (step_graphed); the update arithmetic is the reference's torch.optim.Adam (train.py:132-135)
+        self.optimizer = torch.optim.Adam(list(self.ae.parameters()) + list(self.prob.parameters()), lr=lr,
+                                          capturable=str(device).startswith("cuda"))
         self.global_step = 0
+        self.ddp = bool(ddp)
+        self._graph = None
 
     def step(self, batch_x, start_idx=None):
         """One optimisation step on batch_x [B,N,3] (device).  Returns dict(loss, chamfer, fbpp)."""
@@ -92,6 +97,40 @@ class Trainer:
                                 nn_only=True)                                     # train.py:185-192
         with _matmul_tf32(self.tf32):
             return self._network_step(batch_x, x, rec_centres, patches, scale, B, N, S)
+
+    def step_graphed(self, batch_x, start_idx):
+        """step() replayed as ONE captured CUDA graph (forward + Chamfer + backward + Adam: ~300 kernel launches whose host-side
+        issue time exceeds their device time).  Needs a fixed batch shape and an explicit start_idx (the CPU RNG draw cannot be
+        captured); the first call warms up with three eager steps and captures, a shape change or the rate-loss switch
+        (train.py:211-214) re-captures.  Returns the graph's static result tensors (overwritten by the next call).  Single
+        process only: under DistributedDataParallel the eager step runs (its gradient hooks are not captured)."""
+        if self.ddp:
+            return self.step(batch_x, start_idx)
+        lam_on = self.global_step >= self.rate_loss_enable_step
+        key = (tuple(batch_x.shape), lam_on)
+        if self._graph is None or self._graph["key"] != key:
+            from . import mlp_ops
+            sx, ss = batch_x.clone(), start_idx.clone()
+            side = torch.cuda.Stream(batch_x.device)
+            side.wait_stream(torch.cuda.current_stream(batch_x.device))
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    self.step(sx, ss)
+            torch.cuda.current_stream(batch_x.device).wait_stream(side)
+            self.optimizer.zero_grad(set_to_none=True)
+            mlp_ops._wpad_cache.clear()          # the bf16 weight copies must be re-made INSIDE the graph on every replay
+            mlp_ops._pack_cache.clear()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = self.step(sx, ss)
+            self._graph = dict(key=key, graph=g, x=sx, start=ss, out=out)
+            return out
+        gr = self._graph
+        gr["x"].copy_(batch_x, non_blocking=True)
+        gr["start"].copy_(start_idx, non_blocking=True)
+        gr["graph"].replay()
+        self.global_step += 1
+        return gr["out"]
 
     def _network_step(self, batch_x, x, rec_centres, patches, scale, B, N, S):
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.amp):

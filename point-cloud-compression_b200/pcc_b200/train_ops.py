@@ -79,46 +79,49 @@ class _MlpTrain(torch.autograd.Function):
     """x0 bf16 [M, K0p] -> the stack's output; see mlp_train."""
 
     @staticmethod
-    def forward(ctx, x0, group, relus, mode, *params):
+    def forward(ctx, x0, group, relus, mode, x0_is_relu, *params):
         L = len(relus)
         acts = [x0]
         for l in range(L - 1):
             acts.append(linear_train(acts[-1], params[2 * l], params[2 * l + 1], relus[l]))
         w, b = params[2 * (L - 1)], params[2 * (L - 1) + 1]
         cout = w.shape[0]
-        ctx.group, ctx.relus, ctx.mode, ctx.M = group, relus, mode, x0.shape[0]
-        ctx.extra = None
+        ctx.group, ctx.relus, ctx.mode, ctx.M, ctx.x0_is_relu = group, relus, mode, x0.shape[0], x0_is_relu
+        extra = []
         if mode == "pool":
             if cout % 8:
                 raise ValueError("pcc_b200.mlp_train: a pooled stack needs an output width that is a multiple of 8")
             last = linear_train(acts[-1], w, b, relus[-1])
-            pooled, arg = groupmax_fwd(last, cout, group)
-            ctx.extra = (arg, pooled if relus[-1] else None)
-            out = pooled
+            out, arg = groupmax_fwd(last, cout, group)
+            extra = [arg]
         elif mode == "bf16":
             out = linear_train(acts[-1], w, b, relus[-1])
-            if relus[-1]:
-                ctx.extra = (out,)
         else:   # "f32": values that must not be rounded (decoded coordinates, logits)
             out = mlp_ops.linear(acts[-1], w, b if b is not None else _zeros(cout, x0.device), relus[-1], out_f32=True).contiguous()
-            if relus[-1]:
-                ctx.extra = (out,)
-        ctx.acts = acts
-        ctx.params = params
+        ctx.has_bias = tuple(p is not None for p in params)
+        ctx.n_acts, ctx.n_extra = len(acts), len(extra)
+        # everything through save_for_backward (the output included: an attribute would make a reference cycle that keeps the
+        # parameters' AccumulateGrad nodes alive across steps and breaks CUDA-graph capture of the training step)
+        ctx.save_for_backward(*acts, *extra, out, *[p for p in params if p is not None])
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        params, acts, relus, L = ctx.params, ctx.acts, ctx.relus, len(ctx.relus)
+        saved = ctx.saved_tensors
+        acts = list(saved[:ctx.n_acts])
+        extra = saved[ctx.n_acts:ctx.n_acts + ctx.n_extra]
+        out = saved[ctx.n_acts + ctx.n_extra]
+        it = iter(saved[ctx.n_acts + ctx.n_extra + 1:])
+        params = [next(it) if h else None for h in ctx.has_bias]
+        relus, L = ctx.relus, len(ctx.relus)
         cout = params[2 * (L - 1)].shape[0]
         ld = _ru(cout, 64)
         if ctx.mode == "pool":
-            arg, pooled = ctx.extra
-            dy = groupmax_bwd(dout, pooled, arg, ctx.M, cout, ctx.group, ld)
+            dy = groupmax_bwd(dout, out if relus[-1] else None, extra[0], ctx.M, cout, ctx.group, ld)
         else:
             g = dout
-            if ctx.extra is not None:                      # ReLU on the last layer
-                g = g * (ctx.extra[0][:, :g.shape[1]] > 0)
+            if relus[-1]:                                  # ReLU on the last layer
+                g = g * (out[:, :g.shape[1]] > 0)
             if g.dtype == torch.bfloat16 and g.shape[1] == ld and g.is_contiguous():
                 dy = g
             else:
@@ -129,7 +132,7 @@ class _MlpTrain(torch.autograd.Function):
         for l in range(L - 1, -1, -1):
             w, b = params[2 * l], params[2 * l + 1]
             co, ci = w.shape
-            if ctx.needs_input_grad[4 + 2 * l] or (b is not None and ctx.needs_input_grad[5 + 2 * l]):
+            if ctx.needs_input_grad[5 + 2 * l] or (b is not None and ctx.needs_input_grad[6 + 2 * l]):
                 dw, db = mlp_ops.wgrad(dy[:, :_ru(co, 8)], acts[l], want_bias=b is not None)
                 grads[2 * l] = dw[:co, :ci].to(w.dtype)
                 if b is not None:
@@ -137,24 +140,50 @@ class _MlpTrain(torch.autograd.Function):
             if l > 0:
                 dy = linear_train(dy, w.t(), None, False, mask=acts[l] if relus[l - 1] else None, n_store=acts[l].shape[1])
             elif ctx.needs_input_grad[0]:
-                dx0 = linear_train(dy, w.t(), None, False, n_store=acts[0].shape[1])
-        return (dx0, None, None, None) + tuple(grads)
+                dx0 = linear_train(dy, w.t(), None, False, mask=acts[0] if ctx.x0_is_relu else None, n_store=acts[0].shape[1])
+        return (dx0, None, None, None, None) + tuple(grads)
 
 
-def mlp_train(x0, layers, group=0, mode="f32"):
+def mlp_train(x0, layers, group=0, mode="f32", x0_is_relu=False):
     """Differentiable shared-MLP stack on the pcc kernels.
 
     x0      bf16 [M, K0p]: the first layer's input, zero padded to a multiple of 64 columns (gradient: bf16, same shape);
     layers  [(weight [cout, cin], bias [cout] or None, relu)], fp32 parameters (cin_0 <= K0p; later layers read the previous
             layer's channels);
     group / mode   "pool": max over every run of `group` rows -> fp32 [M / group, cout];  "bf16": bf16 [M, roundup(cout, 64)]
-            (feeds another stack);  "f32": fp32 [M, cout]."""
+            (feeds another stack);  "f32": fp32 [M, cout];
+    x0_is_relu     x0 is itself the output of a ReLU layer (fold_first_train): its gradient is masked where x0 <= 0."""
     if mode == "pool" and group <= 1:
         raise ValueError("pcc_b200.mlp_train: mode 'pool' needs group > 1")
     flat = []
     for w, b, _ in layers:
         flat += [w, b]
-    return _MlpTrain.apply(x0, int(group), tuple(bool(r) for _, _, r in layers), mode, *flat)
+    return _MlpTrain.apply(x0, int(group), tuple(bool(r) for _, _, r in layers), mode, bool(x0_is_relu), *flat)
+
+
+class _FoldFirst(torch.autograd.Function):
+    """relu(local [M, n <= 4] fp32 . w [C, n]^T + b) -> bf16 [M, roundup(C, 64)] on the CUDA cores (csrc/small_ops.cu: the
+    coordinates are not rounded to bf16, as in the inference chain's first layer); backward: the incoming gradient is already
+    masked by the consumer (mlp_train(..., x0_is_relu=True)), dW / db come from the weight-gradient kernel."""
+
+    @staticmethod
+    def forward(ctx, local, w, b):
+        M = local.shape[0]
+        out = mlp_ops.fold_first(local, w, b.detach().float().reshape(1, -1), M, relu=True)
+        ctx.save_for_backward(torch.nn.functional.pad(local.detach().to(torch.bfloat16), (0, 8 - local.shape[1])))
+        ctx.shape = tuple(w.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        co, ci = ctx.shape
+        dw, db = mlp_ops.wgrad(dout[:, :_ru(co, 8)], ctx.saved_tensors[0])
+        return None, dw[:co, :ci], db[:co]
+
+
+def fold_first_train(local, w, b):
+    """First layer of a stack whose input is a few fp32 coordinates per row (SetAbstraction's recentred neighbours)."""
+    return _FoldFirst.apply(local.contiguous(), w, b)
 
 
 def pad_bf16(t, width):

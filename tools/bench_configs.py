@@ -62,10 +62,13 @@ def cfg2(clock, dev, world, sd):
     x = torch.from_numpy(synth.modelnet_like(32, 8192, seed=77 + (torch.distributed.get_rank() if world > 1 else 0))).to(dev)
     start = torch.zeros(32, dtype=torch.int64, device=dev)
     out = {}
-    ms = clock.ms(lambda: out.update(tr.step(x, start)), 5, 2)
+    eager_ms = clock.ms(lambda: out.update(tr.step(x, start)), 5, 2)
+    ms = eager_ms if world > 1 else clock.ms(lambda: out.update(tr.step_graphed(x, start)), 10, 2)
     n_grad = sum(p.numel() for p in list(tr.ae.parameters()) + list(tr.prob.parameters()))
-    res = {"workload": "IPDAE train step, 32 clouds x 8192 pts per rank, K=256: forward + Chamfer + backward + Adam (TF32 network bodies "
-                       "under autograd; FPS / kNN / Chamfer fwd+bwd on the pcc kernels)", "ms_per_step": ms,
+    res = {"workload": "IPDAE train step, 32 clouds x 8192 pts per rank, K=256: forward + Chamfer + backward + Adam; every "
+                       "contraction of the forward and backward pass on the pcc tensor-core kernels (bf16 operands, fp32 accumulation "
+                       "and weight gradients), FPS / kNN / Chamfer fwd+bwd on the pcc kernels; one CUDA-graph replay per step at 1 rank, "
+                       "launched kernel by kernel under DistributedDataParallel", "ms_per_step": ms, "ms_per_step_eager": eager_ms,
            "clouds_per_s": world * 32 / ms * 1e3, "scaling": "weak", "loss": float(out["loss"]),
            "collective": (f"DistributedDataParallel gradient all-reduce over NCCL, {n_grad * 4 / 1e6:.1f} MB fp32 per step"
                           if world > 1 else "none (1 rank)")}
