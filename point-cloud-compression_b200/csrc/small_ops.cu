@@ -62,36 +62,54 @@ linear_small_kernel(const float *__restrict__ x, long long ldx, const float *__r
     }
 }
 
+// thread = (row, 8-channel chunk): consecutive threads write consecutive 16-byte chunks (coalesced); the layer's weights sit in
+// shared memory as (w_j0..w_j3) float4 per channel; rows and chunks are split with 32-bit arithmetic inside a block's row window
 __global__ void __launch_bounds__(256)
 fold_first_kernel(const float *__restrict__ local, int n_local, long long ld_local, const float *__restrict__ w, long long ldw,
                   const float *__restrict__ per_cloud, long long M, int n_pts, int C, int relu, __nv_bfloat16 *__restrict__ out,
                   long long ldo) {
+    extern __shared__ float4 ws4[];   // [roundup(C, 8)]
     const int chunks = static_cast<int>(ldo >> 3);  // 8 channels (16 bytes) per thread
-    const long long total = M * chunks;
-    for (long long e = blockIdx.x * 256ll + threadIdx.x; e < total; e += gridDim.x * 256ll) {
-        const long long r = e / chunks;
-        const int c0 = static_cast<int>(e % chunks) * 8;
-        float l[4];
+    const int cpad = (C + 7) & ~7;
+    for (int c = threadIdx.x; c < cpad; c += 256) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < C) {
+            v.x = __ldg(w + static_cast<long long>(c) * ldw);
+            if (n_local > 1) v.y = __ldg(w + static_cast<long long>(c) * ldw + 1);
+            if (n_local > 2) v.z = __ldg(w + static_cast<long long>(c) * ldw + 2);
+            if (n_local > 3) v.w = __ldg(w + static_cast<long long>(c) * ldw + 3);
+        }
+        ws4[c] = v;
+    }
+    __syncthreads();
+    const int rows_per_pass = 256 / chunks > 0 ? 256 / chunks : 1;       // ldo <= 2048: every thread owns one (row, chunk)
+    const int my_row = threadIdx.x / chunks, my_chunk = threadIdx.x - my_row * chunks;
+    if (my_row >= rows_per_pass) return;
+    const int c0 = my_chunk * 8;
+    for (long long r = static_cast<long long>(blockIdx.x) * rows_per_pass + my_row; r < M; r += static_cast<long long>(gridDim.x) * rows_per_pass) {
+        uint32_t pk[4] = {0u, 0u, 0u, 0u};
+        if (c0 < C) {
+            const float *lp = local + r * ld_local;
+            const float l0 = __ldg(lp), l1 = n_local > 1 ? __ldg(lp + 1) : 0.f, l2 = n_local > 2 ? __ldg(lp + 2) : 0.f,
+                        l3 = n_local > 3 ? __ldg(lp + 3) : 0.f;
+            const float *pc = per_cloud + (n_pts >= M ? 0 : r / n_pts) * C;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) l[j] = j < n_local ? __ldg(local + r * ld_local + j) : 0.0f;
-        const float *pc = per_cloud + (r / n_pts) * C;
-        uint32_t pk[4];
+            for (int h = 0; h < 4; ++h) {
+                float v[2];
 #pragma unroll
-        for (int h = 0; h < 4; ++h) {
-            float v[2];
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const int c = c0 + 2 * h + q;
-                float a = 0.0f;
-                if (c < C) {
-                    a = __ldg(pc + c);
-                    for (int j = 0; j < n_local; ++j) a = fmaf(l[j], __ldg(w + static_cast<long long>(c) * ldw + j), a);
-                    if (relu) a = fmaxf(a, 0.0f);
+                for (int q = 0; q < 2; ++q) {
+                    const int c = c0 + 2 * h + q;
+                    float a = 0.0f;
+                    if (c < C) {
+                        const float4 wv = ws4[c];
+                        a = fmaf(l3, wv.w, fmaf(l2, wv.z, fmaf(l1, wv.y, fmaf(l0, wv.x, __ldg(pc + c)))));
+                        if (relu) a = fmaxf(a, 0.0f);
+                    }
+                    v[q] = a;
                 }
-                v[q] = a;
+                const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[0], v[1]);
+                pk[h] = *reinterpret_cast<const uint32_t *>(&b2);
             }
-            const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[0], v[1]);
-            pk[h] = *reinterpret_cast<const uint32_t *>(&b2);
         }
         *reinterpret_cast<uint4 *>(out + r * ldo + c0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
@@ -120,12 +138,15 @@ PCC_API int pcc_fold_first_bf16(const float *local, int n_local, int64_t ld_loca
                 static_cast<long long>(M), n_pts);
     PCC_REQUIRE(ld_out >= C && ld_out % 8 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0,
                 "pcc_fold_first_bf16: out must be 16-byte aligned with a row pitch that is a multiple of 8 elements");
+    PCC_REQUIRE(ld_out <= 2048 && C <= 2048, "pcc_fold_first_bf16: at most 2048 output channels");
     if (M == 0) return 0;
-    const long long total = M * (ld_out >> 3);
-    long long blocks = (total + 255) / 256;
+    const int chunks = static_cast<int>(ld_out >> 3);
+    const int rows_per_pass = 256 / chunks > 0 ? 256 / chunks : 1;
+    long long blocks = (M + rows_per_pass - 1) / rows_per_pass;
     const long long cap = static_cast<long long>(num_sms()) * 16;
     if (blocks > cap) blocks = cap;
-    fold_first_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    const size_t smem = static_cast<size_t>((C + 7) & ~7) * sizeof(float4);
+    fold_first_kernel<<<static_cast<unsigned>(blocks), 256, smem, static_cast<cudaStream_t>(stream)>>>(
         local, n_local, ld_local, w, ldw, per_cloud, M, n_pts, C, relu, static_cast<__nv_bfloat16 *>(out), ld_out);
     return check_launch("fold_first_kernel");
 }
