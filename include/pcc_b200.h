@@ -267,6 +267,16 @@ int pcc_fold_first_bf16(const float *local, int n_local, int64_t ld_local, const
                         int64_t M, int n_pts, int C, int relu, void *out, int64_t ld_out, void *stream);
 
 /*
+ * pcc_knn_f32 for scene-scale candidate clouds (compress.py:70-74 on a Stanford3D / S3DIS scene, pppe_pcd_ae.py:599 on a whole
+ * cloud): identical outputs, bit for bit, but the candidates are visited through a 32^3 uniform grid built over p (cell, then
+ * shell after shell, until the K-th distance is inside the scanned block) -- ~10^3 distance evaluations per query instead of P2.
+ * workspace: pcc_knn_grid_workspace_bytes(B, P2) bytes, 16-byte aligned, caller-owned.
+ */
+int64_t pcc_knn_grid_workspace_bytes(int B, int P2);
+int pcc_knn_grid_f32(const float *q, const float *p, int B, int P1, int P2, int K, float *out_d2, int64_t *out_idx, float *out_nn,
+                     int centre_sub, float nn_scale, void *workspace, void *stream);
+
+/*
  * Weight gradient of one shared-MLP layer (the backward of the Conv2d(1x1) / Linear layers the reference trains under autograd,
  * /root/reference/train.py:193-221): c[Na, Nb] = a[M, Na]^T . b[M, Nb] (fp32, overwritten; row pitch ldc) and, when colsum is
  * given, colsum[Na] = column sums of a (the bias gradient).  a = the output gradient, b = the layer's input, both bf16

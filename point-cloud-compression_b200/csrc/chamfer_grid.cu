@@ -19,23 +19,12 @@
 //                       then the warp walks the union of its unsettled queries' balls with uniform control flow
 #include <stdlib.h>
 
+#include "grid.cuh"
 #include "pcc_common.cuh"
 
 namespace pcc {
 
-struct GridInfo {
-    float mnx, mny, mnz, h, inv_h;
-    int G;
-    float margin;   // slack taken off every face / gap distance before it is trusted (rounding of cell assignment / faces)
-    int pad;
-};
-
 constexpr int GRID_BUILD_THREADS = 1024;
-
-__device__ __forceinline__ int cell_coord(float p, float mn, float inv_h, int G) {
-    const int c = static_cast<int>((p - mn) * inv_h);
-    return c < 0 ? 0 : (c >= G ? G - 1 : c);
-}
 
 // grid (B, 2); dynamic smem: (G^3 + 1) u32
 __global__ void __launch_bounds__(GRID_BUILD_THREADS)
@@ -301,6 +290,174 @@ int64_t chamfer_grid_extra_bytes(int B, int P1, int P2, int G) {
     const int64_t pts = static_cast<int64_t>(B) * (static_cast<int64_t>(P1) + P2) * 16;
     const int64_t tab = 2ll * B * (static_cast<int64_t>(G) * G * G + 1) * 4;
     return pts + ((tab + 15) / 16) * 16 + 2ll * B * static_cast<int64_t>(sizeof(GridInfo)) + 2ll * B * 32 * 4;
+}
+
+// ---- multi-CTA build for one big cloud (scene scale): the same grid as grid_build_kernel makes, spread over the SMs ----------
+__device__ __forceinline__ int ordered_int(float f) {   // monotone float -> int map (atomicMin / atomicMax on floats)
+    const int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float ordered_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+// grid (blocks, B): bb[b][0..2] = min, bb[b][4..6] = min of the negated coordinates, as ordered ints (memset to 0x7f7f7f7f)
+__global__ void __launch_bounds__(256)
+big_bbox_kernel(const float *__restrict__ pts, int P, int *__restrict__ bb) {
+    const int b = blockIdx.y;
+    const float *p = pts + static_cast<size_t>(b) * P * 3;
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < P; i += gridDim.x * 256) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float v = p[static_cast<size_t>(i) * 3 + a];
+            mn[a] = fminf(mn[a], v);
+            mx[a] = fmaxf(mx[a], v);
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[a] = fminf(mn[a], __shfl_xor_sync(FULL_MASK, mn[a], o));
+            mx[a] = fmaxf(mx[a], __shfl_xor_sync(FULL_MASK, mx[a], o));
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicMin(bb + b * 8 + a, ordered_int(mn[a]));
+            atomicMin(bb + b * 8 + 4 + a, ordered_int(-mx[a]));   // max as the min of the negated values: one memset pattern
+        }
+    }
+}
+
+__global__ void big_info_kernel(int *__restrict__ bb, int G, GridInfo *__restrict__ info, int B) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    float ext = 0.0f, lo[3], maxabs = 0.0f;
+    for (int a = 0; a < 3; ++a) {
+        const float m0 = ordered_float(bb[b * 8 + a]), m1 = -ordered_float(bb[b * 8 + 4 + a]);
+        lo[a] = m0;
+        ext = fmaxf(ext, m1 - m0);
+        maxabs = fmaxf(maxabs, fmaxf(fabsf(m0), fabsf(m1)));
+    }
+    GridInfo gi;
+    const bool ok = ext > 0.0f && ext < 3.0e38f;
+    gi.h = ok ? ext / static_cast<float>(G) : 1.0f;
+    gi.inv_h = ok ? static_cast<float>(G) / ext : 1.0f;
+    gi.mnx = lo[0];
+    gi.mny = lo[1];
+    gi.mnz = lo[2];
+    gi.G = G;
+    gi.margin = 1e-4f * gi.h + 1e-6f * maxabs;
+    gi.pad = 0;
+    info[b] = gi;
+}
+
+// grid (blocks, B): SCATTER = false: cell histogram into cnt; true: counting-sort scatter with cnt as the running cursors
+template <bool SCATTER>
+__global__ void __launch_bounds__(256)
+big_cells_kernel(const float *__restrict__ pts, int P, const GridInfo *__restrict__ info, unsigned *__restrict__ cnt, int ncell1,
+                 float4 *__restrict__ sorted) {
+    const int b = blockIdx.y;
+    const GridInfo g = info[b];
+    const int G = g.G;
+    const float *p = pts + static_cast<size_t>(b) * P * 3;
+    unsigned *c = cnt + static_cast<size_t>(b) * ncell1;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < P; i += gridDim.x * 256) {
+        const float px = p[static_cast<size_t>(i) * 3], py = p[static_cast<size_t>(i) * 3 + 1], pz = p[static_cast<size_t>(i) * 3 + 2];
+        const int cell = (cell_coord(pz, g.mnz, g.inv_h, G) * G + cell_coord(py, g.mny, g.inv_h, G)) * G + cell_coord(px, g.mnx, g.inv_h, G);
+        const unsigned pos = atomicAdd(c + cell, 1u);
+        if (SCATTER) sorted[static_cast<size_t>(b) * P + pos] = make_float4(px, py, pz, __uint_as_float(static_cast<unsigned>(i)));
+    }
+}
+
+// one CTA (1024 threads) per cloud: exclusive scan of the histogram -> starts (and the scatter's cursors), row occupancy masks
+__global__ void __launch_bounds__(GRID_BUILD_THREADS)
+big_scan_kernel(unsigned *__restrict__ cnt, unsigned *__restrict__ starts, unsigned *__restrict__ rowmask, int G, int P) {
+    __shared__ unsigned wsum[32];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ncell = G * G * G;
+    unsigned *c = cnt + static_cast<size_t>(b) * (ncell + 1);
+    unsigned *st_out = starts + static_cast<size_t>(b) * (ncell + 1);
+    const int seg = (ncell + 31) / 32;
+    const int s0 = warp * seg, s1 = min(ncell, s0 + seg);
+    unsigned carry = 0u;
+    for (int base = s0; base < s1; base += 32) {
+        const int i = base + lane;
+        const unsigned v = i < s1 ? c[i] : 0u;
+        unsigned inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(FULL_MASK, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (i < s1) c[i] = carry + inc - v;
+        carry += __shfl_sync(FULL_MASK, inc, 31);
+    }
+    if (lane == 0) wsum[warp] = carry;
+    __syncthreads();
+    if (warp == 0) {
+        const unsigned v = wsum[lane];
+        unsigned inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(FULL_MASK, inc, o);
+            if (lane >= o) inc += t;
+        }
+        wsum[lane] = inc - v;
+    }
+    __syncthreads();
+    const unsigned off = wsum[warp];
+    for (int i = s0 + lane; i < s1; i += 32) {
+        const unsigned v = c[i] + off;
+        c[i] = v;
+        st_out[i] = v;
+    }
+    if (tid == 0) st_out[ncell] = static_cast<unsigned>(P);
+    __syncthreads();
+    {
+        const int z = warp, yy = lane;
+        const bool occ = z < G && yy < G &&
+                         st_out[(z * G + yy) * G] != (yy + 1 < G || z + 1 < G ? st_out[(z * G + yy) * G + G] : static_cast<unsigned>(P));
+        const unsigned m = __ballot_sync(FULL_MASK, occ);
+        if (lane == 0) rowmask[static_cast<size_t>(b) * 32 + z] = z < G ? m : 0u;
+    }
+}
+
+// One side only (the candidate cloud of the scene-scale kNN, knn.cu): sorted [B, P] float4, starts [B, G^3 + 1], info [B],
+// rowmask [B, 32]
+int grid_build_single(const float *pts, int B, int P, int G, float4 *sorted, unsigned *starts, GridInfo *info, unsigned *rowmask,
+                      void *scratch, cudaStream_t st) {
+    if (scratch && P >= 32768) {
+        // big clouds: bounding box, histogram, scan and scatter as grid-wide kernels (a 1M-point cloud on one CTA takes ~1.1 ms)
+        const int ncell1 = G * G * G + 1;
+        unsigned *cnt = static_cast<unsigned *>(scratch);                       // [B][ncell1] histogram -> cursors
+        int *bb = reinterpret_cast<int *>(cnt + static_cast<size_t>(B) * ncell1);   // [B][8]
+        cudaError_t e = cudaMemsetAsync(cnt, 0, static_cast<size_t>(B) * ncell1 * 4, st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(bb, 0x7f, static_cast<size_t>(B) * 8 * 4, st);        // mins: large positive ordered ints
+        if (e != cudaSuccess) {
+            set_error("grid build: cudaMemsetAsync failed: %s", cudaGetErrorString(e));
+            return static_cast<int>(e);
+        }
+        const int blocks = min((P + 255) / 256, num_sms() * 8);
+        big_bbox_kernel<<<dim3(blocks, B), 256, 0, st>>>(pts, P, bb);
+        big_info_kernel<<<(B + 63) / 64, 64, 0, st>>>(bb, G, info, B);
+        big_cells_kernel<false><<<dim3(blocks, B), 256, 0, st>>>(pts, P, info, cnt, ncell1, nullptr);
+        big_scan_kernel<<<B, GRID_BUILD_THREADS, 0, st>>>(cnt, starts, rowmask, G, P);
+        big_cells_kernel<true><<<dim3(blocks, B), 256, 0, st>>>(pts, P, info, cnt, ncell1, sorted);
+        return check_launch("grid build (multi-CTA)");
+    }
+    static bool attr_done_dev[64] = {false};
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) d = 0;
+    if (!attr_done_dev[d]) {
+        const cudaError_t e = cudaFuncSetAttribute(grid_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 32 * 32 * 4 + 4);
+        if (e != cudaSuccess) {
+            set_error("grid build: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+            return static_cast<int>(e);
+        }
+        attr_done_dev[d] = true;
+    }
+    grid_build_kernel<<<dim3(B, 1), GRID_BUILD_THREADS, static_cast<size_t>(G) * G * G * 4 + 4, st>>>(pts, pts, P, P, G, sorted, starts, info,
+                                                                                                  rowmask);
+    return check_launch("grid_build_kernel");
 }
 
 int chamfer_grid_pick(int P1, int P2) {   // grid resolution, or 0: use the brute-force kernels

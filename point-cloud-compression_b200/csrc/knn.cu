@@ -21,6 +21,7 @@
 // Both kernels are CUDA-core / shared-memory bound: inputs are 12 B per point, read once per CTA.
 #include <stdlib.h>
 
+#include "grid.cuh"
 #include "pcc_common.cuh"
 
 namespace pcc {
@@ -192,6 +193,136 @@ knn_warp_kernel(const float *__restrict__ q, const float *__restrict__ p, int P1
         }
     }
     if (!active) return;
+    __syncwarp();
+    count = warp_select(keys, count, cap, K);
+
+    const size_t obase = (static_cast<size_t>(b) * P1 + qi) * K;
+    for (int k = lane; k < K; k += 32) {
+        float d = 0.0f;
+        unsigned idx = 0u;
+        if (k < count) {
+            const unsigned long long key = keys[k];
+            d = key_d2(key);
+            idx = key_idx(key);
+        }
+        if (out_d2) out_d2[obase + k] = d;
+        if (out_idx) out_idx[obase + k] = static_cast<int64_t>(idx);
+        if (out_nn) {
+            float nx = pc[static_cast<size_t>(idx) * 3 + 0], ny = pc[static_cast<size_t>(idx) * 3 + 1],
+                  nz = pc[static_cast<size_t>(idx) * 3 + 2];
+            if (centre_sub) {
+                nx = __fsub_rn(nx, qx);
+                ny = __fsub_rn(ny, qy);
+                nz = __fsub_rn(nz, qz);
+            }
+            if (nn_scale != 1.0f) {
+                nx = __fmul_rn(nx, nn_scale);
+                ny = __fmul_rn(ny, nn_scale);
+                nz = __fmul_rn(nz, nn_scale);
+            }
+            float *o = out_nn + (obase + k) * 3;
+            o[0] = nx;
+            o[1] = ny;
+            o[2] = nz;
+        }
+    }
+}
+
+// ---- warp-per-query kernel over a uniform grid (scene scale: P2 in the 10^5 .. 10^7 range) ------------------------------------
+// Same result as knn_warp_kernel, bit for bit (same un-fused d2, same (d2, idx) keys, same selection code); what changes is
+// which candidates are evaluated.  The candidate cloud is sorted by cell of a G^3 grid (grid_build_kernel, chamfer_grid.cu);
+// the warp scans the query's own cell, then shell after shell of cells around it (each row of a shell is one contiguous range
+// of the sorted array, or its two end cells), and stops when the K-th smallest d2 found so far is smaller than the squared
+// distance from the query to the nearest face of the scanned block that is still inside the grid (minus GridInfo::margin, with
+// the relative slack the Chamfer search uses): every point outside the block is then farther than all K kept -- ties included.
+// 7812 queries x 1M points, K = 256: ~1-3 k candidates per query instead of 10^6.
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+knn_grid_kernel(const float *__restrict__ q, const float *__restrict__ p, const float4 *__restrict__ sorted,
+                const unsigned *__restrict__ starts, const GridInfo *__restrict__ info, int P1, int P2, int K, int cap,
+                float *__restrict__ out_d2, int64_t *__restrict__ out_idx, float *__restrict__ out_nn, int centre_sub, float nn_scale) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned long long *all_keys = reinterpret_cast<unsigned long long *>(smem_raw);
+    const int b = blockIdx.y;
+    const unsigned lane = lane_id();
+    const int warp = threadIdx.x >> 5;
+    const int qi = blockIdx.x * WARPS + warp;
+    if (qi >= P1) return;                       // warps are independent: no block-level barrier below
+    const float *pc = p + static_cast<size_t>(b) * P2 * 3;
+    const float4 *cand = sorted + static_cast<size_t>(b) * P2;
+    const GridInfo g = info[b];
+    const int G = g.G;
+    const unsigned *st = starts + static_cast<size_t>(b) * (G * G * G + 1);
+    unsigned long long *keys = all_keys + static_cast<size_t>(warp) * cap;
+    const float *qp = q + (static_cast<size_t>(b) * P1 + qi) * 3;
+    const float qx = qp[0], qy = qp[1], qz = qp[2];
+    int count = 0;
+    unsigned long long thresh = KEY_MAX;
+    unsigned thresh_hi = 0xffffffffu;
+
+    auto reselect = [&]() {   // keep the K smallest of the buffer (ties at the K-th d2 kept when they fit), tighten the threshold
+        int kept = -1;
+        unsigned T = 0u;
+        __syncwarp();
+        if (cap <= 32 * PRUNE_NPL && count >= K) kept = warp_prune(keys, count, cap, K, T);
+        if (kept >= 0) {
+            count = kept;
+            thresh = (static_cast<unsigned long long>(T) << 32) | 0xffffffffull;
+        } else {
+            count = warp_select(keys, count, cap, K);
+            thresh = count >= K ? keys[K - 1] : KEY_MAX;
+        }
+        thresh_hi = static_cast<unsigned>(thresh >> 32);
+    };
+    auto consider = [&](unsigned d2_bits, unsigned idx, bool valid) {
+        const unsigned long long key = valid ? ((static_cast<unsigned long long>(d2_bits) << 32) | idx) : KEY_MAX;
+        const bool pass = key < thresh;
+        const unsigned m = __ballot_sync(FULL_MASK, pass);
+        if (m == 0u) return;
+        if (pass) keys[count + __popc(m & ((1u << lane) - 1u))] = key;
+        count += __popc(m);
+        if (count + 32 > cap) reselect();
+    };
+    auto scan = [&](unsigned a, unsigned e) {   // candidates [a, e) of the sorted array: one coalesced 16-byte load per lane
+        for (unsigned j0 = a; j0 < e; j0 += 32) {
+            const unsigned j = j0 + lane;
+            const bool valid = j < e;
+            const float4 c = __ldg(cand + (valid ? j : a));
+            const unsigned d = __float_as_uint(dist2_rn(qx, qy, qz, c.x, c.y, c.z));
+            if (!__any_sync(FULL_MASK, valid && d <= thresh_hi)) continue;
+            consider(d, __float_as_uint(c.w), valid);
+        }
+    };
+
+    const int cx = cell_coord(qx, g.mnx, g.inv_h, G), cy = cell_coord(qy, g.mny, g.inv_h, G), cz = cell_coord(qz, g.mnz, g.inv_h, G);
+    for (int R = 0; R < G; ++R) {
+        const int z0 = max(cz - R, 0), z1 = min(cz + R, G - 1), y0 = max(cy - R, 0), y1 = min(cy + R, G - 1);
+        const int xa = max(cx - R, 0), xb = min(cx + R, G - 1);
+        for (int z = z0; z <= z1; ++z)
+            for (int yy = y0; yy <= y1; ++yy) {
+                const unsigned row = static_cast<unsigned>((z * G + yy) * G);
+                if (z == cz - R || z == cz + R || yy == cy - R || yy == cy + R) {
+                    scan(__ldg(st + row + xa), __ldg(st + row + xb + 1));                       // a face row of the shell
+                } else {                                                                         // interior row: its two end cells
+                    if (cx - R >= 0) scan(__ldg(st + row + cx - R), __ldg(st + row + cx - R + 1));
+                    if (cx + R <= G - 1) scan(__ldg(st + row + cx + R), __ldg(st + row + cx + R + 1));
+                }
+            }
+        // every unscanned point lies beyond a face of the block that is inside the grid
+        float bound = INFINITY;
+        if (cx - R > 0) bound = fminf(bound, qx - (g.mnx + static_cast<float>(cx - R) * g.h));
+        if (cx + R + 1 < G) bound = fminf(bound, (g.mnx + static_cast<float>(cx + R + 1) * g.h) - qx);
+        if (cy - R > 0) bound = fminf(bound, qy - (g.mny + static_cast<float>(cy - R) * g.h));
+        if (cy + R + 1 < G) bound = fminf(bound, (g.mny + static_cast<float>(cy + R + 1) * g.h) - qy);
+        if (cz - R > 0) bound = fminf(bound, qz - (g.mnz + static_cast<float>(cz - R) * g.h));
+        if (cz + R + 1 < G) bound = fminf(bound, (g.mnz + static_cast<float>(cz + R + 1) * g.h) - qz);
+        if (bound == INFINITY) break;            // the block covers the grid
+        bound -= g.margin;
+        if (count >= K && bound > 0.0f) {
+            reselect();                          // thresh_hi = the K-th smallest d2 so far (its bit pattern)
+            if (count >= K && __uint_as_float(thresh_hi) < bound * bound * 0.99998f) break;
+        }
+    }
     __syncwarp();
     count = warp_select(keys, count, cap, K);
 
@@ -975,4 +1106,52 @@ PCC_API int pcc_knn_patch_u8(const float *patches, int BS, int P, int K, uint8_t
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (K == 8) return launch_filter<8>(patches, patches, BS, P, P, K, nullptr, nullptr, nullptr, out_idx, 0, 1.0f, st);
     return launch_filter<16>(patches, patches, BS, P, P, K, nullptr, nullptr, nullptr, out_idx, 0, 1.0f, st);
+}
+
+/* Scene-scale form: the same result as pcc_knn_f32 through a uniform grid over p (workspace from pcc_knn_grid_workspace_bytes). */
+PCC_API int64_t pcc_knn_grid_workspace_bytes(int B, int P2) {
+    const int64_t G = 32;
+    return static_cast<int64_t>(B) * P2 * 16 + ((static_cast<int64_t>(B) * (G * G * G + 1) * 4 + 15) / 16) * 16 +
+           static_cast<int64_t>(B) * static_cast<int64_t>(sizeof(pcc::GridInfo)) + static_cast<int64_t>(B) * 32 * 4 + 64 +
+           static_cast<int64_t>(B) * ((G * G * G + 1) + 8) * 4;
+}
+
+PCC_API int pcc_knn_grid_f32(const float *q, const float *p, int B, int P1, int P2, int K, float *out_d2, int64_t *out_idx,
+                             float *out_nn, int centre_sub, float nn_scale, void *workspace, void *stream) {
+    using namespace pcc;
+    PCC_REQUIRE(q && p && workspace && (out_d2 || out_idx || out_nn), "pcc_knn_grid_f32: null pointer");
+    PCC_REQUIRE(B >= 0 && P1 >= 0 && P2 >= 1 && P2 <= (1 << 24), "pcc_knn_grid_f32: bad shape B=%d P1=%d P2=%d", B, P1, P2);
+    PCC_REQUIRE(K >= 1 && K <= PCC_MAX_KNN_K, "pcc_knn_grid_f32: K=%d outside [1,%d]", K, PCC_MAX_KNN_K);
+    PCC_REQUIRE(B <= 65535 && reinterpret_cast<uintptr_t>(workspace) % 16 == 0, "pcc_knn_grid_f32: B > 65535 or unaligned workspace");
+    if (B == 0 || P1 == 0) return 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int G = 32;
+    char *w = static_cast<char *>(workspace);
+    float4 *sorted = reinterpret_cast<float4 *>(w);
+    w += static_cast<int64_t>(B) * P2 * 16;
+    unsigned *starts = reinterpret_cast<unsigned *>(w);
+    w += ((static_cast<int64_t>(B) * (G * G * G + 1) * 4 + 15) / 16) * 16;
+    GridInfo *info = reinterpret_cast<GridInfo *>(w);
+    unsigned *rowmask = reinterpret_cast<unsigned *>(info + B);
+    void *scratch = reinterpret_cast<void *>((reinterpret_cast<uintptr_t>(rowmask + static_cast<size_t>(B) * 32) + 15) & ~static_cast<uintptr_t>(15));
+    if (int r = grid_build_single(p, B, P2, G, sorted, starts, info, rowmask, scratch, st)) return r;
+    int kp = 32;
+    while (kp < K) kp <<= 1;
+    const int cap = 2 * kp;
+    constexpr int W = 8;
+    const size_t smem = static_cast<size_t>(W) * cap * sizeof(unsigned long long);
+    static bool attr_set_dev[64] = {false};
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) d = 0;
+    if (!attr_set_dev[d]) {
+        const cudaError_t e = cudaFuncSetAttribute(knn_grid_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, W * 2 * PCC_MAX_KNN_K * 8);
+        if (e != cudaSuccess) {
+            set_error("pcc_knn_grid_f32: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+            return static_cast<int>(e);
+        }
+        attr_set_dev[d] = true;
+    }
+    dim3 grid((P1 + W - 1) / W, B);
+    knn_grid_kernel<W><<<grid, W * 32, smem, st>>>(q, p, sorted, starts, info, P1, P2, K, cap, out_d2, out_idx, out_nn, centre_sub, nn_scale);
+    return check_launch("knn_grid_kernel");
 }

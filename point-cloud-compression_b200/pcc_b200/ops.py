@@ -6,6 +6,8 @@ include/pcc_b200.h.
 """
 import collections
 
+import os
+
 import torch
 
 from . import _lib
@@ -89,10 +91,15 @@ def assemble(patches, centres, patch_scale, center=None, longest=None, margin=0.
     return out
 
 
-def knn(p1, p2, K, return_nn=False, centre_sub=False, nn_scale=1.0, nn_only=False):
+_KNN_GRID_MIN_POINTS = 65536      # candidate clouds at least this large go through the grid form of the search
+_KNN_NO_GRID = bool(os.environ.get("PCC_KNN_NO_GRID"))   # A/B switch for the measurements in profiles/
+
+
+def knn(p1, p2, K, return_nn=False, centre_sub=False, nn_scale=1.0, nn_only=False, grid=None):
     """K nearest neighbours: (dists [B,P1,K] squared, idx int64 [B,P1,K], nn [B,P1,K,3] or None).
     nn_only=True skips the distance / index outputs (returns None for them): the grouping calls of the network bodies
-    use only the gathered, recentred neighbours."""
+    use only the gathered, recentred neighbours.  grid: None = the grid form of the search for scene-scale p2 (>= 65536 points),
+    True / False force / forbid it (tests: both forms give identical results)."""
     lib = _lib.load()
     p1, p2 = _cuda_f32(p1, "p1"), _cuda_f32(p2, "p2")
     _check_pair(p1, p2)
@@ -106,8 +113,14 @@ def knn(p1, p2, K, return_nn=False, centre_sub=False, nn_scale=1.0, nn_only=Fals
     if B == 0 or P1 == 0:   # nothing to search for: empty results, no launch (empty tensors have no storage to point at)
         return d, i, nn
     with torch.cuda.device(p1.device):
-        _lib.check(lib.pcc_knn_f32(_ptr(p1), _ptr(p2), B, P1, P2, K, _ptr(d), _ptr(i), _ptr(nn), int(centre_sub),
-                                   float(nn_scale), _stream()), "pcc_knn_f32")
+        if (P2 >= _KNN_GRID_MIN_POINTS and not _KNN_NO_GRID) if grid is None else grid:
+            # scene scale: the same search through a uniform grid over p2 (identical results; workspace owned by this call)
+            ws = torch.empty((lib.pcc_knn_grid_workspace_bytes(B, P2),), dtype=torch.uint8, device=p1.device)
+            _lib.check(lib.pcc_knn_grid_f32(_ptr(p1), _ptr(p2), B, P1, P2, K, _ptr(d), _ptr(i), _ptr(nn), int(centre_sub),
+                                            float(nn_scale), _ptr(ws), _stream()), "pcc_knn_grid_f32")
+        else:
+            _lib.check(lib.pcc_knn_f32(_ptr(p1), _ptr(p2), B, P1, P2, K, _ptr(d), _ptr(i), _ptr(nn), int(centre_sub),
+                                       float(nn_scale), _stream()), "pcc_knn_f32")
     return d, i, nn
 
 

@@ -144,6 +144,41 @@ def test_knn_scene_kernel_vs_oracle(pcc, orc, kind, P1, P2, K):
     assert np.array_equal(nn.cpu().numpy(), onn)
 
 
+@pytest.mark.parametrize("kind,P1,P2,K", [("scene", 300, 200_000, 256), ("uniform", 64, 70_000, 16), ("grid", 40, 100_000, 256),
+                                          ("identical", 5, 66_000, 100), ("outside", 33, 80_000, 32), ("scene", 9, 300_000, 1024),
+                                          ("clumps", 50, 120_000, 1), ("small", 20, 3000, 64)])
+def test_knn_grid_form_vs_brute_force_and_oracle(pcc, orc, kind, P1, P2, K):
+    """pcc_knn_grid_f32 (scene scale: cell, then shell after shell of a 32^3 grid until the K-th distance is inside the scanned
+    block) against the brute-force warp kernel on the same inputs -- distances, indices and gathered neighbours must be identical
+    -- and against the CPU oracle on a few queries: surface-like scenes, exact ties (grid-quantised, all-identical points),
+    queries outside the cloud's bounding box, far clumps (whole shells empty), K from 1 to 1024, and a cloud smaller than the
+    grid's cell count."""
+    rng = np.random.default_rng(P2 + K)
+    if kind == "scene":
+        p = synth.scene_like(P2, seed=P2)
+    elif kind == "grid":
+        p = synth.grid_quantised(1, P2, depth=5, seed=P2)
+    elif kind == "identical":
+        p = np.full((1, P2, 3), 0.25, np.float32)
+    elif kind == "clumps":
+        c = rng.uniform(0, 10, (6, 3)).astype(np.float32)
+        p = (c[rng.integers(0, 6, P2)] + rng.normal(0, 0.01, (P2, 3)).astype(np.float32))[None]
+    else:
+        p = synth.uniform_cube(1, P2, seed=P2)
+    q = p[:, rng.integers(0, P2, P1)].copy()
+    if kind == "outside":
+        q = (q * 3.0 - 1.0).astype(np.float32)
+    if kind == "clumps":
+        q[0, ::2] += np.float32(3.0)
+    q[0, 0] = p[0, 7]
+    d, i, nn = pcc.ops.knn(cu(q), cu(p), K, return_nn=True, centre_sub=True, nn_scale=2.0, grid=True)
+    bd, bi, bnn = pcc.ops.knn(cu(q), cu(p), K, return_nn=True, centre_sub=True, nn_scale=2.0, grid=False)
+    assert torch.equal(i, bi) and torch.equal(d, bd) and torch.equal(nn, bnn)
+    n = min(P1, 6)
+    od, oi, _ = orc.knn_points(q[:, :n], p, K, False, threads=8)
+    assert np.array_equal(i[:, :n].cpu().numpy(), oi) and np.array_equal(d[:, :n].cpu().numpy(), od)
+
+
 @pytest.mark.parametrize("kind,P2,K", [("identical", 8192, 256), ("two_values", 8192, 300), ("grid", 8192, 512),
                                        ("grid", 5000, 64), ("uniform", 4097, 512), ("half_dup", 6000, 256)])
 def test_knn_block_kernel_selection_paths_vs_oracle(pcc, orc, kind, P2, K):
