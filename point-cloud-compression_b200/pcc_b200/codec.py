@@ -227,7 +227,7 @@ class PatchCodec:
         return out + (c["octree"],) if return_octree else out
 
     @torch.no_grad()
-    def roundtrip_sweep(self, host_batches, start_idx=None, sink=None, graphed=False):
+    def roundtrip_sweep(self, host_batches, start_idx=None, sink=None, graphed=False, streams=1):
         """compress -> decompress -> eval over a stream of HOST batches (the per-file loops of compress.py:78-155 and
         eval.py:167-221 as one sweep).  `host_batches` yields pinned CPU tensors [B,N,3]; the upload of batch s + 1 runs
         on a copy stream while batch s is being processed (two device staging buffers), and `sink(s, latent_q, centres,
@@ -235,15 +235,19 @@ class PatchCodec:
         copies; it may return a CUDA event that marks the end of those copies.
         graphed=True replays one captured CUDA graph per staging buffer instead of launching the step's kernels one by one
         (needs a fixed batch shape and an explicit start_idx; the tensors handed to `sink` are then the graph's static outputs,
-        reused two batches later -- after the event `sink` returned).  Returns the number of batches; the caller synchronises."""
+        reused `max(2, streams)` batches later -- after the event `sink` returned).  streams=2..4 (graphed only) replays one graph
+        per staging buffer on its own compute stream, so the latency-bound head of batch s + 1 (FPS: 32 CTAs on 148 SMs, octree
+        coder) runs beside the tail of batch s.  Returns the number of batches; the caller synchronises."""
         dev = next(self.ae.parameters()).device
         main = torch.cuda.current_stream(dev)
         copy = getattr(self, "_copy_stream", None)
         if copy is None:
             copy = self._copy_stream = torch.cuda.Stream(dev)
         it = iter(host_batches)
-        bufs, ready, free = [None, None], [torch.cuda.Event(), torch.cuda.Event()], [None, None]
-        drained = [None, None]
+        streams = max(1, min(4, int(streams))) if graphed else 1
+        nbuf = max(2, streams)                  # staging buffers (and captured graphs): one per compute stream, at least two
+        bufs, ready, free = [None] * nbuf, [torch.cuda.Event() for _ in range(nbuf)], [None] * nbuf
+        drained = [None] * nbuf
 
         def upload(slot, host):
             if graphed and bufs[slot] is not None and tuple(bufs[slot].shape) != tuple(host.shape):
@@ -262,7 +266,7 @@ class PatchCodec:
         if graphed and nxt is not None:
             if start_idx is None:
                 raise ValueError("roundtrip_sweep(graphed=True) needs an explicit start_idx (the CPU RNG draw cannot be captured)")
-            cache = self._captured_sweep(nxt, start_idx, dev, main)
+            cache = self._captured_sweep(nxt, start_idx, dev, main, nbuf)
             bufs, graphs = list(cache["bufs"]), cache["graphs"]
             cache["start"].copy_(start_idx.to(dev), non_blocking=True)   # the graphs read the cache's own copy, never the caller's tensor
         # the first upload runs on the copy stream: it must not overtake main-stream work that may still be reading / about to
@@ -272,23 +276,34 @@ class PatchCodec:
             upload(0, nxt)
         s = 0
         while nxt is not None:
-            slot = s & 1
+            slot = s % nbuf
             nxt = next(it, None)
             if nxt is not None:
-                upload(slot ^ 1, nxt)
-            main.wait_event(ready[slot])
-            if graphs is not None:
-                if drained[slot] is not None:
-                    main.wait_event(drained[slot])     # the caller's copies of this graph's previous outputs are done
-                graphs[slot][0].replay()
-                lat, cen, met, _, octree = graphs[slot][1]
-            else:
-                lat, cen, met, _, octree = self.roundtrip(bufs[slot], start_idx, return_octree=True)
-            free[slot] = torch.cuda.Event()
-            free[slot].record(main)
-            if sink is not None:
-                drained[slot] = sink(s, lat, cen, met, octree)
+                upload((s + 1) % nbuf, nxt)
+            cs = main
+            if graphs is not None and streams > 1:
+                if len(getattr(self, "_compute_streams", [])) < streams:
+                    self._compute_streams = [torch.cuda.Stream(dev) for _ in range(4)]
+                cs = self._compute_streams[slot]
+                if s < nbuf:
+                    cs.wait_stream(main)
+            with torch.cuda.stream(cs):
+                cs.wait_event(ready[slot])
+                if graphs is not None:
+                    if drained[slot] is not None:
+                        cs.wait_event(drained[slot])     # the caller's copies of this graph's previous outputs are done
+                    graphs[slot][0].replay()
+                    lat, cen, met, _, octree = graphs[slot][1]
+                else:
+                    lat, cen, met, _, octree = self.roundtrip(bufs[slot], start_idx, return_octree=True)
+                free[slot] = torch.cuda.Event()
+                free[slot].record(cs)
+                if sink is not None:
+                    drained[slot] = sink(s, lat, cen, met, octree)
             s += 1
+        if graphs is not None and streams > 1:
+            for c in self._compute_streams:
+                main.wait_stream(c)
         return s
 
     def _weights_key(self):
@@ -302,14 +317,14 @@ class PatchCodec:
         from . import mlp_ops
         return (dict(mlp_ops._pack_cache), dict(mlp_ops._wpad_cache), dict(mlp_ops._bf16_cache))
 
-    def _captured_sweep(self, first, start_idx, dev, main):
-        """Two captured graphs of roundtrip() (one per staging buffer), re-captured whenever the batch shape, the centre mode or
-        any weight (version counter / storage) changes.  The cache owns everything the graphs point at: the staging buffers, its
+    def _captured_sweep(self, first, start_idx, dev, main, nbuf=2):
+        """`nbuf` captured graphs of roundtrip() (one per staging buffer), re-captured whenever the batch shape, the centre mode,
+        the buffer count or any weight (version counter / storage) changes.  The cache owns everything the graphs point at: the staging buffers, its
         own copy of start_idx, and the derived weight tensors."""
-        key = (tuple(first.shape), self.centre_mode, self._weights_key())
+        key = (tuple(first.shape), self.centre_mode, self._weights_key(), nbuf)
         cache = getattr(self, "_sweep_graphs", None)
         if cache is None or cache["key"] != key:
-            sb = [first.to(dev), first.to(dev)]     # static staging buffers, filled with real data for the capture
+            sb = [first.to(dev) for _ in range(nbuf)]   # static staging buffers, filled with real data for the capture
             st = start_idx.to(dev).clone()
             side = torch.cuda.Stream(dev)
             side.wait_stream(main)
@@ -318,7 +333,7 @@ class PatchCodec:
             main.wait_stream(side)
             torch.cuda.synchronize(dev)
             gs = []
-            for slot in range(2):
+            for slot in range(nbuf):
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
                     outs = self.roundtrip(sb[slot], st, return_octree=True)

@@ -125,6 +125,14 @@ def test_roundtrip_sweep_matches_per_batch_calls(setup):
     torch.cuda.synchronize()
     for s in range(5):
         assert all(torch.equal(a, b) for a, b in zip(got[s], eager[s]))
+    graphed = dict(got)
+    got.clear()
+    for n in (2, 3):                       # one graph per staging buffer, each on its own compute stream
+        got.clear()
+        assert codec.roundtrip_sweep(iter(host), start, sink, graphed=True, streams=n) == 5
+        torch.cuda.synchronize()
+        for s in range(5):
+            assert all(torch.equal(a, b) for a, b in zip(got[s], graphed[s]))
     for s, h in enumerate(host):
         lat, cen, met, _, octree = codec.roundtrip(h.cuda(), start, return_octree=True)
         assert torch.equal(got[s][0], lat.cpu()) and torch.equal(got[s][1], cen.cpu())
