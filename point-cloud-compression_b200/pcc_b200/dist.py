@@ -55,7 +55,7 @@ def sharded_rows(fn, n_rows, rank=None, world=None, group=None):
     return gather_rows(fn(b, e), n_rows, group=group)
 
 
-def scene_patches(xyz, npoint, K, start_idx=None, group=None, return_local_nn=False):
+def scene_patches(xyz, npoint, K, start_idx=None, group=None, return_local_nn=False, fps_idx=None):
     """compress.py:96-108 at scene scale (cfg5: one cloud of ~1M points) on `world` GPUs.  xyz [1, N, 3] is replicated on every
     rank.  FPS is 7812 dependent grid-wide arg-maxes and does not shard bit-exactly: rank 0 runs it and broadcasts the centre
     indices (the path's first collective, 8 B per centre); the kNN queries are split over the ranks against the replicated cloud
@@ -67,14 +67,15 @@ def scene_patches(xyz, npoint, K, start_idx=None, group=None, return_local_nn=Fa
     rank = dist.get_rank(group) if on else 0
     world = dist.get_world_size(group) if on else 1
     N = xyz.shape[1]
-    if start_idx is None:                                                         # pn_kit.py:321 (CPU RNG draw, rank 0's)
-        start_idx = torch.randint(0, N, (1,), dtype=torch.long)
-    if rank == 0:
-        fps_idx = ops.fps(xyz, npoint, start_idx.to(xyz.device), 1e10)
-    else:
-        fps_idx = torch.empty((1, npoint), dtype=torch.int64, device=xyz.device)
-    if on:
-        dist.broadcast(fps_idx, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    if fps_idx is None:                                                           # (given: only the kNN split runs -- timing)
+        if start_idx is None:                                                     # pn_kit.py:321 (CPU RNG draw, rank 0's)
+            start_idx = torch.randint(0, N, (1,), dtype=torch.long)
+        if rank == 0:
+            fps_idx = ops.fps(xyz, npoint, start_idx.to(xyz.device), 1e10)
+        else:
+            fps_idx = torch.empty((1, npoint), dtype=torch.int64, device=xyz.device)
+        if on:
+            dist.broadcast(fps_idx, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
     centres = ops.gather(xyz, fps_idx)                                            # [1, npoint, 3]
     b, e = shard_range(npoint, rank, world)
     local = {}
