@@ -1115,10 +1115,12 @@ PCC_API int pcc_sa_chain_indexed(const float *patches, const uint8_t *idx8, int6
     p.pts_shift = -1;
     for (int sh = 3; sh <= 8; ++sh)
         if ((1 << sh) == pts_per_patch) p.pts_shift = sh;
-    if (int r = set_smem(sa_chain2_kernel<1>, sa::SMEM_IDX)) return r;
     const int sms = num_sms();
     const int pairs = (p.n_tiles + 1) / 2;
     const int grid = pairs < 2 * sms ? pairs : 2 * sms;
+    // (a third form -- the epilogue group also computes the fp32 3 -> 32 layer of the next tile in its wait for layer 2, the MMA
+    // warp only issues -- was measured at 362 us against 312 us: the epilogue groups, not the MMA warps, pace the kernel)
+    if (int r = set_smem(sa_chain2_kernel<1>, sa::SMEM_IDX)) return r;
     sa_chain2_kernel<1><<<grid, sa::THREADS, sa::SMEM_IDX, static_cast<cudaStream_t>(stream)>>>(p);
     return check_launch("sa_chain2_kernel<indexed>");
 }
