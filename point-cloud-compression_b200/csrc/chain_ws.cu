@@ -1120,6 +1120,8 @@ PCC_API int pcc_sa_chain_indexed(const float *patches, const uint8_t *idx8, int6
     const int grid = pairs < 2 * sms ? pairs : 2 * sms;
     // (a third form -- the epilogue group also computes the fp32 3 -> 32 layer of the next tile in its wait for layer 2, the MMA
     // warp only issues -- was measured at 362 us against 312 us: the epilogue groups, not the MMA warps, pace the kernel)
+    // (eight epilogue warps per slot -- 18 warps per CTA at 56 registers, each slot's epilogues split over two groups, one
+    // 32-column tcgen05.ld in flight per warp -- was measured at 398 us against 310 us: more warps lose here, as in round 1)
     if (int r = set_smem(sa_chain2_kernel<1>, sa::SMEM_IDX)) return r;
     sa_chain2_kernel<1><<<grid, sa::THREADS, sa::SMEM_IDX, static_cast<cudaStream_t>(stream)>>>(p);
     return check_launch("sa_chain2_kernel<indexed>");
