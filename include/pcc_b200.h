@@ -277,6 +277,19 @@ int pcc_knn_grid_f32(const float *q, const float *p, int B, int P1, int P2, int 
                      int centre_sub, float nn_scale, void *workspace, void *stream);
 
 /*
+ * pn_kit.PointNet of the AE in one launch (/root/reference/pn_kit.py:124-144 as AE.py:39 calls it on cat((xyz, feat))):
+ * out[patch, cout] = max over the patch's 256 positions of W3 . relu(W2 . relu(W1 . relu(W0 . [feat | xyz] + b0) + b1) + b2) + b3,
+ * widths 131 -> 128 -> 256 -> 512 -> cout <= 16.  feat [rows, 128] bf16 (the SetAbstraction output), xyz [rows, 3] fp32,
+ * rows % 256 == 0.  w0f [128, 128] bf16 = the feature columns of the first layer, w0_packed = pcc_mlp_pack_weights_f32 of the
+ * rotated layer [feat | xyz] (cin = 131: xyz columns and bias), w1 [256, 128] / w2 [512, 256] bf16 row-major, b1 / b2 fp32,
+ * w3_packed = pcc_mlp_pack_weights_f32(cin = 512).  No intermediate activation reaches HBM (the two-launch route
+ * pcc_mlp_chain + pcc_pn_tail_bf16 writes and re-reads a [rows, 256] bf16 tensor).
+ */
+int pcc_pointnet_fused_bf16(const void *feat, int64_t rows, int64_t ld_feat, const float *xyz, int64_t ld_xyz, const void *w0f_bf16,
+                            const void *w0_packed, const void *w1_bf16, const float *b1, const void *w2_bf16, const float *b2,
+                            const void *w3_packed, int cout, int relu3, float *out, void *stream);
+
+/*
  * Weight gradient of one shared-MLP layer (the backward of the Conv2d(1x1) / Linear layers the reference trains under autograd,
  * /root/reference/train.py:193-221): c[Na, Nb] = a[M, Na]^T . b[M, Nb] (fp32, overwritten; row pitch ldc) and, when colsum is
  * given, colsum[Na] = column sums of a (the bias gradient).  a = the output gradient, b = the layer's input, both bf16

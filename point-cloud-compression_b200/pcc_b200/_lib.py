@@ -61,6 +61,7 @@ SIGNATURES.update({
     "pcc_gather_concat_bf16": (_i, [_vp, _i, _vp, _vp, _i, _i, _i64, _i, _vp, _vp, _i, _vp]),
     "pcc_knn_grid_workspace_bytes": (_i64, [_i, _i]),
     "pcc_knn_grid_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _f, _vp, _vp]),
+    "pcc_pointnet_fused_bf16": (_i, [_vp, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "pcc_knn_patch_u8": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "pcc_linear_train_bf16": (_i, [_vp, _i64, _i, _i64, _vp, _i64, _vp, _i, _i, _vp, _i64, _i, _vp, _i64, _vp]),
     "pcc_groupmax_fwd_bf16": (_i, [_vp, _i64, _i, _i64, _i, _vp, _vp, _vp]),

@@ -18,6 +18,7 @@ import torch.nn as nn
 from . import mlp_ops, ops, pn_kit_ops
 
 _BN_TYPES = (nn.BatchNorm1d, nn.BatchNorm2d)
+_TWO_LAUNCH_PN = bool(os.environ.get("PCC_PN_TWO_LAUNCH"))   # A/B switch: PointNet front + tail as two launches (round 1)
 _GROUPED_SA = bool(os.environ.get("PCC_SA_GROUPED"))   # A/B switch for the measurements in profiles/: the general (grouped tensor) route
 
 
@@ -137,7 +138,10 @@ def pointnet_xyz_feat(mod, xyz, feat):
         return torch.cat((w0[:, 3:], w0[:, :3]), dim=1).detach().contiguous()
 
     layers[0] = (_cached(mod, "rot_w0", rot), layers[0][1], layers[0][2])
-    return mlp_ops.run_chain([(feat.reshape(BS * P, F), 1), (xyz.reshape(BS * P, 3), 1)], layers, group=P)
+    f2, x2 = feat.reshape(BS * P, F), xyz.reshape(BS * P, 3)
+    if not _TWO_LAUNCH_PN and mlp_ops.pointnet_fused_supported(f2, x2, layers, P):
+        return mlp_ops.pointnet_fused(f2, x2, layers)                              # one launch, no [M, 256] activation in HBM
+    return mlp_ops.run_chain([(f2, 1), (x2, 1)], layers, group=P)
 
 
 def mlp_points(mod, x):

@@ -190,6 +190,37 @@ def pn_tail(x, layers):
     return out
 
 
+def pointnet_fused_supported(feat, xyz, layers, group):
+    """The one-launch PointNet of the AE: [feat 128 bf16 | xyz 3] -> 128 -> 256 -> 512 -> cout <= 16, ReLU on the first three,
+    max over runs of 256 rows."""
+    dims = [layers[0][0].shape[1]] + [w.shape[0] for w, _, _ in layers]
+    return (len(layers) == 4 and group == 256 and dims[:4] == [131, 128, 256, 512] and dims[4] <= 16 and
+            all(bool(r) for _, _, r in layers[:3]) and feat.dtype == torch.bfloat16 and feat.dim() == 2 and feat.shape[1] == 128 and
+            feat.stride(1) == 1 and feat.stride(0) % 8 == 0 and feat.data_ptr() % 16 == 0 and feat.shape[0] % 256 == 0 and
+            xyz.shape[0] == feat.shape[0] and xyz.shape[1] == 3)
+
+
+def pointnet_fused(feat, xyz, layers):
+    """pn_kit.PointNet on [feat | xyz] in one launch (csrc/pn_fused.cu); layers[0]'s weight columns are [feat (128) | xyz (3)]."""
+    lib = _lib.load()
+    (w0, b0, _), (w1, b1, _), (w2, b2, _), (w3, b3, relu3) = layers
+    w0f = _bf16(w0[:, :128])
+    pw0, _, _ = _packed(w0, b0)
+    w1h, w2h = _bf16(w1), _bf16(w2)
+    b1f, b2f = b1.detach().float().contiguous(), b2.detach().float().contiguous()
+    pw3, _, _ = _packed(w3, b3)
+    xyz = xyz.detach().float()
+    if xyz.stride(1) != 1:
+        xyz = xyz.contiguous()
+    out = torch.empty((feat.shape[0] // 256, w3.shape[0]), dtype=torch.float32, device=feat.device)
+    with torch.cuda.device(feat.device):
+        _lib.check(lib.pcc_pointnet_fused_bf16(feat.data_ptr(), feat.shape[0], feat.stride(0), xyz.data_ptr(), xyz.stride(0),
+                                               w0f.data_ptr(), pw0.data_ptr(), w1h.data_ptr(), b1f.data_ptr(), w2h.data_ptr(),
+                                               b2f.data_ptr(), pw3.data_ptr(), w3.shape[0], int(bool(relu3)), out.data_ptr(),
+                                               torch.cuda.current_stream().cuda_stream), "pcc_pointnet_fused_bf16")
+    return out
+
+
 def _split(layers, pooled=False):
     """Longest prefix of `layers` that fits the fused kernel."""
     dims = [layers[0][0].shape[1]] + [w.shape[0] for w, _, _ in layers]

@@ -282,3 +282,32 @@ def test_wgrad_matches_fp32_contraction(M, Na, Nb):
     if Na >= 64 and (Na // 2) % 8 == 0:
         dw2, none = mlp_ops.wgrad(dy[:, :Na // 2], x, want_bias=False)
         assert none is None and float((dw2.double() - want_w[:Na // 2]).abs().max()) < 2e-5 * scale
+
+
+@pytest.mark.parametrize("n_patches", [1, 3, 148, 300])
+def test_pointnet_fused_matches_the_two_launch_route(n_patches):
+    """pcc_pointnet_fused_bf16 (131 -> 128 -> 256 -> 512 -> 16 + max over the patch in one kernel, nothing in HBM in between)
+    against the round-1 route (warp-specialised front chain -> [M, 256] bf16 in HBM -> fused tail) and against an fp32 torch body:
+    the two kernels round at the same points except the second layer's bias (fp32 in the fused epilogue, bf16 in the front
+    chain's packed weights)."""
+    import __graft_entry__  # noqa: F401
+    from pcc_b200 import mlp_ops
+    torch.manual_seed(n_patches)
+    M = n_patches * 256
+    feat = torch.relu(torch.randn(M, 128, device="cuda")).to(torch.bfloat16)
+    xyz = (torch.rand(M, 3, device="cuda") - 0.5) * 1.2
+    dims = [131, 128, 256, 512, 16]
+    layers = [(torch.randn(o, i, device="cuda") / i ** 0.5, torch.randn(o, device="cuda") * 0.1, l < 3)
+              for l, (i, o) in enumerate(zip(dims[:-1], dims[1:]))]
+    assert mlp_ops.pointnet_fused_supported(feat, xyz, layers, 256)
+    got = mlp_ops.pointnet_fused(feat, xyz, layers)
+    two = mlp_ops.run_chain([(feat, 1), (xyz, 1)], layers, group=256)
+    h = torch.cat((feat.float(), xyz), dim=1)
+    for w, b, relu in layers:
+        h = h @ w.t() + b
+        h = torch.relu(h) if relu else h
+    want = h.view(n_patches, 256, 16).max(dim=1)[0]
+    scale = float(want.abs().max())
+    assert got.shape == two.shape == (n_patches, 16)
+    assert float((got - two).abs().max()) < 4e-3 * scale
+    assert float((got - want).abs().max()) < 3e-2 * scale
