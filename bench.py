@@ -201,7 +201,7 @@ def run_b200(args):
 
     # per-kernel timing hooks: CUDA events around the launches of the kernels that dominate the step, recorded live on
     # torch's current stream (the stream every pcc kernel is launched on)
-    events = {"sa_chain": [], "knn_in_patch": [], "chamfer": [], "pn_tail": []}
+    events = {"sa_chain": [], "knn_in_patch": [], "chamfer": [], "pn_tail": [], "pn_fused": []}
     record = {"on": False}
 
     def timed(name, fn):
@@ -227,6 +227,7 @@ def run_b200(args):
         pcc_b200.ops.knn = lambda q, p, K, *a, **kw: (knn_timed if K == 16 else orig_knn)(q, p, K, *a, **kw)
     pcc_b200.ops.chamfer_forward = timed("chamfer", pcc_b200.ops.chamfer_forward)
     mlp_ops.pn_tail = timed("pn_tail", mlp_ops.pn_tail)
+    mlp_ops.pointnet_fused = timed("pn_fused", mlp_ops.pointnet_fused)          # pcc_pointnet_fused_bf16 (pnf2::pn_fused_kernel)
 
     def barrier():
         if dist is not None:
@@ -394,6 +395,11 @@ def run_b200(args):
                                             "achieved_tflops": fl / (kernel_ms["pn_tail"] / 1e3) / 1e12,
                                             "frac": fl / (kernel_ms["pn_tail"] / 1e3) / 1e12 / tf_peak}
             traffic, traffic_src = sa_traffic()
+            if "pn_fused" in kernel_ms:      # PointNet 131-128-256-512-16 + max in one kernel: tensor pipe, every weight streamed from L2
+                fl = BATCH * (N_POINTS * ALPHA // K_PATCH) * K_PATCH * 2.0 * (131 * 128 + 128 * 256 + 256 * 512 + 512 * D_LATENT)
+                others["pn_fused_kernel"] = {"ms_per_launch": kernel_ms["pn_fused"], "bound": "tensor",
+                                             "achieved_tflops": fl / (kernel_ms["pn_fused"] / 1e3) / 1e12,
+                                             "frac": fl / (kernel_ms["pn_fused"] / 1e3) / 1e12 / tf_peak}
             roofline = {"kernel": "ws::sa_chain2_kernel -- SetAbstraction shared MLP 3-32-64-128 + max over 16 neighbours (tcgen05)",
                         "bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src + " bf16_tflops_sustained (kernel timed inside a long step)",

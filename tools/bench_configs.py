@@ -134,7 +134,7 @@ def cfg5(clock, dev, rank, world, n_points=1_000_000, npoint=7812, K=256):
     enc.load_state_dict(synth.seeded_module_state(enc, 23))
     enc = enc.to(dev).eval()
     torch.manual_seed(11)
-    enc_ms = clock.ms(lambda: pppe.compress(enc, xyz, latent_bins=7), 3, 1)
+    enc_ms = clock.ms(lambda: pppe.compress(enc, xyz, latent_bins=7), 5, 2)
     res.update({"workload": f"one S3DIS-shaped scene of {n_points} pts: FPS -> {npoint} centres (rank 0 + broadcast), kNN K={K} with the "
                             f"queries split over {world} rank(s) against the replicated cloud + all-gather of the index table; "
                             "pppe_pcd_ae PointNet2EncoderFull + quantiser on the whole scene",
