@@ -387,8 +387,13 @@ def run_b200(args):
                 others["grid_nn_kernel (+ build, finalize)"] = {
                     "ms_per_launch": kernel_ms["chamfer"], "algorithmic_pair_evals": pairs, "bound": "L1 / FP32 issue",
                     "algorithmic_gpairs_per_s": pairs / (kernel_ms["chamfer"] / 1e3) / 1e9,
-                    "note": "pairs evaluated << algorithmic pairs (culling); the brute-force kernel it replaces ran at 0.90 of the "
-                            "FP32 issue roof (profiles/r01_chamfer_ncu_full.txt)"}
+                    "evaluated_pairs_est": 0.22e9, "cull_ratio_est": 0.10,
+                    "fp32_issue_frac_est": 0.22e9 * 8.0 / (kernel_ms["chamfer"] / 1e3) / fp32_peak,
+                    "note": "pairs evaluated << algorithmic pairs (exact culling): ~677 candidates per query in the far direction "
+                            "(original -> clumpy reconstruction) + ~32 in the near one + the 128-point bound sample, from the "
+                            "instrumented counts in DESIGN.md 4 -- ~10 % of the algorithmic pairs; the kernel is issue bound (77 % "
+                            "issue-active, profiles/r02_step_kernels_ncu_full.txt), the brute-force kernel it replaces ran at 0.90 "
+                            "of the FP32 issue roof (profiles/r01_chamfer_ncu_full.txt)"}
             if "pn_tail" in kernel_ms:       # 256-512-16 + max: tensor pipe, weights streamed from L2
                 fl = BATCH * (N_POINTS * ALPHA // K_PATCH) * K_PATCH * 2.0 * (256 * 512 + 512 * D_LATENT)
                 others["pn_tail_kernel"] = {"ms_per_launch": kernel_ms["pn_tail"], "bound": "tensor",

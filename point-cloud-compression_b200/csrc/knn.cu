@@ -1125,7 +1125,9 @@ PCC_API int pcc_knn_grid_f32(const float *q, const float *p, int B, int P1, int 
     PCC_REQUIRE(B <= 65535 && reinterpret_cast<uintptr_t>(workspace) % 16 == 0, "pcc_knn_grid_f32: B > 65535 or unaligned workspace");
     if (B == 0 || P1 == 0) return 0;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int G = 32;
+    // cells per axis: 32 for scenes; small clouds get ~2 points per cell so that a K = 256 ball spans a handful of shells
+    static const int g_env = getenv("PCC_KNN_GRID_G") ? atoi(getenv("PCC_KNN_GRID_G")) : 0;   // tuning knob (profiles/)
+    const int G = (g_env >= 4 && g_env <= 32) ? g_env : (P2 >= 200000 ? 32 : P2 >= 30000 ? 24 : 16);
     char *w = static_cast<char *>(workspace);
     float4 *sorted = reinterpret_cast<float4 *>(w);
     w += static_cast<int64_t>(B) * P2 * 16;

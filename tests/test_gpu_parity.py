@@ -179,6 +179,22 @@ def test_knn_grid_form_vs_brute_force_and_oracle(pcc, orc, kind, P1, P2, K):
     assert np.array_equal(i[:, :n].cpu().numpy(), oi) and np.array_equal(d[:, :n].cpu().numpy(), od)
 
 
+def test_scene_patches_single_process_equals_direct_ops(pcc, orc):
+    """dist.scene_patches (cfg5: FPS on rank 0 + broadcast, kNN queries split over ranks + all-gather) in a single process is
+    the plain FPS + kNN; its FPS prefix is checked against the oracle, the returned local patches against the gathered table."""
+    from pcc_b200 import dist as pdist
+    xyz = cu(synth.scene_like(150_000, seed=31))
+    start = torch.tensor([4321], dtype=torch.int64)
+    fps_idx, knn_idx, (b, e, nn) = pdist.scene_patches(xyz, 600, 64, start, return_local_nn=True)
+    assert (b, e) == (0, 600) and fps_idx.shape == (1, 600) and knn_idx.shape == (1, 600, 64) and nn.shape == (1, 600, 64, 3)
+    assert np.array_equal(fps_idx[0, :120].cpu().numpy(), orc.fps(xyz.cpu().numpy(), 120, start.numpy(), 1e10, threads=8)[0])
+    cen = pcc.ops.gather(xyz, fps_idx)
+    d, i, want_nn = pcc.ops.knn(cen, xyz, 64, return_nn=True, centre_sub=True)
+    assert torch.equal(i, knn_idx) and torch.equal(want_nn, nn)
+    again = pdist.scene_patches(xyz, 600, 64, fps_idx=fps_idx)          # the kNN leg alone (bench cfg5 times it this way)
+    assert torch.equal(again[0], fps_idx) and torch.equal(again[1], knn_idx)
+
+
 @pytest.mark.parametrize("kind,P2,K", [("identical", 8192, 256), ("two_values", 8192, 300), ("grid", 8192, 512),
                                        ("grid", 5000, 64), ("uniform", 4097, 512), ("half_dup", 6000, 256)])
 def test_knn_block_kernel_selection_paths_vs_oracle(pcc, orc, kind, P2, K):
