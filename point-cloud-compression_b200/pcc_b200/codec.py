@@ -337,7 +337,9 @@ class PatchCodec:
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
                     outs = self.roundtrip(sb[slot], st, return_octree=True)
+                g.replay()                          # first replay uploads the graph: keep that out of the caller's sweep
                 gs.append((g, outs))
+            torch.cuda.synchronize(dev)
             cache = self._sweep_graphs = dict(key=key, bufs=sb, graphs=gs, start=st, keep=self._derived_tensors(),
                                               ae_cache=[dict(m.__dict__.get("_pcc_cache", {})) for m in self.ae.modules()])
         return cache
@@ -363,6 +365,8 @@ class PatchCodec:
         with torch.cuda.graph(graph):
             outs = self.roundtrip(xs, ss)
         launches = int(lib.pcc_launch_count() - n0)    # kernels of this library inside one replay
+        graph.replay()                                 # the first replay uploads the graph
+        torch.cuda.synchronize(dev)
         wkey, keep = self._weights_key(), self._derived_tensors()   # the graph points at these packed weights
 
         def run(xyz, start_idx):
