@@ -7,8 +7,8 @@
 //       for every grid point, so W[:, n_local:] . latent is a per-cloud vector), the pooled-feature part of
 //       AE.ConditionalProbabilityModel's first Conv2d (AE.py:115-116).  These are weight-bandwidth bound (every weight is used
 //       M <= a few hundred times), so they run on the CUDA cores in fp32 -- which also keeps the value that is about to be
-//       ROUNDED to a symbol (enc_proj) in the reference's precision.  Every output is one serial k-ascending FMA chain, so a
-//       row's result does not depend on how many rows are in the call (batch invariance: the entropy coder needs the decoder to
+//       ROUNDED to a symbol (enc_proj) in the reference's precision.  Every output is one fixed-order sum (32 strided FMA chains
+//       + a shuffle tree), so a row's result does not depend on how many rows are in the call (batch invariance: the entropy coder needs the decoder to
 //       reproduce the encoder's PMFs bit for bit whatever the batch size).
 //
 //   pcc_fold_first_bf16    out[r, c] = relu(per_cloud[r / n_pts, c] + sum_j local[r, j] * w[c, j])   (bf16 rows)
@@ -22,42 +22,45 @@
 namespace pcc {
 namespace {
 
-constexpr int LS_TM = 8, LS_TN = 64, LS_KC = 64, LS_THREADS = 128;
+constexpr int LS_TM = 8, LS_WARPS = 4, LS_THREADS = LS_WARPS * 32;
 
+// One WARP per (output column n, block of LS_TM rows): lane l owns k = l, l + 32, ... (the weight row is read once, coalesced,
+// and reused for the 8 rows), partial sums are combined by a fixed xor-shuffle tree.  Every output is the same fixed-order sum
+// whatever M is (batch invariance: the entropy coder needs the decoder to reproduce the encoder's PMFs bit for bit), and the
+// M x N outputs spread over M / 8 x N warps -- the serial-chain form of round 2's first version kept 64 CTAs busy for 110 us on
+// FoldingNet's 1024-wide latent.
 __global__ void __launch_bounds__(LS_THREADS)
 linear_small_kernel(const float *__restrict__ x, long long ldx, const float *__restrict__ w, long long ldw,
                     const float *__restrict__ bias, int M, int K, int N, int relu, float *__restrict__ out, long long ldo) {
-    __shared__ float xs[LS_TM][LS_KC];
-    __shared__ float ws[LS_TN][LS_KC + 1];
-    const int m0 = blockIdx.y * LS_TM, n0 = blockIdx.x * LS_TN;
-    const int col = threadIdx.x & (LS_TN - 1), rg = threadIdx.x / LS_TN;  // 2 row groups of 4 rows
-    float acc[4];
-    const float b = (bias && n0 + col < N) ? __ldg(bias + n0 + col) : 0.0f;
+    const int lane = threadIdx.x & 31;
+    const int n = blockIdx.x * LS_WARPS + (threadIdx.x >> 5);
+    const int m0 = blockIdx.y * LS_TM;
+    if (n >= N) return;
+    const float *wr = w + static_cast<long long>(n) * ldw;
+    float acc[LS_TM];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) acc[i] = b;
-    for (int k0 = 0; k0 < K; k0 += LS_KC) {
-        for (int e = threadIdx.x; e < LS_TM * LS_KC; e += LS_THREADS) {
-            const int r = e / LS_KC, k = e % LS_KC;
-            xs[r][k] = (m0 + r < M && k0 + k < K) ? __ldg(x + static_cast<long long>(m0 + r) * ldx + k0 + k) : 0.0f;
-        }
-        for (int e = threadIdx.x; e < LS_TN * LS_KC; e += LS_THREADS) {
-            const int c = e / LS_KC, k = e % LS_KC;
-            ws[c][k] = (n0 + c < N && k0 + k < K) ? __ldg(w + static_cast<long long>(n0 + c) * ldw + k0 + k) : 0.0f;
-        }
-        __syncthreads();
-        const int kn = K - k0 < LS_KC ? K - k0 : LS_KC;  // the zero tail is not accumulated: the chain is exactly k = 0..K-1
-        for (int k = 0; k < kn; ++k) {
-            const float wv = ws[col][k];
+    for (int i = 0; i < LS_TM; ++i) acc[i] = 0.0f;
+    for (int k = lane; k < K; k += 32) {
+        const float wv = __ldg(wr + k);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) acc[i] = fmaf(xs[rg * 4 + i][k], wv, acc[i]);
+        for (int i = 0; i < LS_TM; ++i) {
+            const int r = m0 + i < M ? m0 + i : M - 1;   // rows past the end replay the last row and are not stored
+            acc[i] = fmaf(__ldg(x + static_cast<long long>(r) * ldx + k), wv, acc[i]);
         }
-        __syncthreads();
     }
-    if (n0 + col < N) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int r = m0 + rg * 4 + i;
-            if (r < M) out[static_cast<long long>(r) * ldo + n0 + col] = relu ? fmaxf(acc[i], 0.0f) : acc[i];
+    for (int i = 0; i < LS_TM; ++i) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(FULL_MASK, acc[i], o);
+    }
+    if (lane == 0) {
+        const float b = bias ? __ldg(bias + n) : 0.0f;
+#pragma unroll
+        for (int i = 0; i < LS_TM; ++i) {
+            if (m0 + i < M) {
+                const float v = acc[i] + b;
+                out[static_cast<long long>(m0 + i) * ldo + n] = relu ? fmaxf(v, 0.0f) : v;
+            }
         }
     }
 }
@@ -124,7 +127,7 @@ PCC_API int pcc_linear_small_f32(const float *x, int M, int K, int64_t ldx, cons
     PCC_REQUIRE(x && w && out, "pcc_linear_small_f32: null pointer");
     PCC_REQUIRE(M >= 1 && M <= 65535 * LS_TM && K >= 1 && N >= 1, "pcc_linear_small_f32: M=%d K=%d N=%d out of range", M, K, N);
     PCC_REQUIRE(ldx >= K && ldw >= K && ld_out >= N, "pcc_linear_small_f32: row pitch smaller than the row");
-    const dim3 grid((N + LS_TN - 1) / LS_TN, (M + LS_TM - 1) / LS_TM);
+    const dim3 grid((N + LS_WARPS - 1) / LS_WARPS, (M + LS_TM - 1) / LS_TM);
     linear_small_kernel<<<grid, LS_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(x, ldx, w, ldw, bias, M, K, N, relu, out, ld_out);
     return check_launch("linear_small_kernel");
 }

@@ -62,7 +62,7 @@ def cfg2(clock, dev, world, sd):
     x = torch.from_numpy(synth.modelnet_like(32, 8192, seed=77 + (torch.distributed.get_rank() if world > 1 else 0))).to(dev)
     start = torch.zeros(32, dtype=torch.int64, device=dev)
     out = {}
-    eager_ms = clock.ms(lambda: out.update(tr.step(x, start)), 5, 2)
+    eager_ms = clock.ms(lambda: out.update(tr.step(x, start)), 8, 4)
     ms = eager_ms if world > 1 else clock.ms(lambda: out.update(tr.step_graphed(x, start)), 10, 2)
     n_grad = sum(p.numel() for p in list(tr.ae.parameters()) + list(tr.prob.parameters()))
     res = {"workload": "IPDAE train step, 32 clouds x 8192 pts per rank, K=256: forward + Chamfer + backward + Adam; every "
