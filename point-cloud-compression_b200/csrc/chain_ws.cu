@@ -145,6 +145,19 @@ constexpr int XYZ_BUF = 3 * P * 4;                   // 1536
 constexpr int OFF_BAR2 = OFF_XYZ + 4 * XYZ_BUF;      // 4 mbarriers
 constexpr int SMEM_IDX = OFF_BAR2 + 32 + 1024;
 static_assert(OFF_SLOT % 1024 == 0 && SLOT_BYTES % 1024 == 0, "slab alignment");
+// sa_chain2_kernel's layout for NS accumulator slots per CTA (NS = 2 is the layout above)
+template <int NS>
+struct Lay {
+    static constexpr int OFF_BAR = OFF_SLOT + NS * SLOT_BYTES;   // 3 x NS mbarriers + the TMEM address word
+    static constexpr int OFF_W0 = OFF_BAR + 32 * NS;
+    static constexpr int SMEM = OFF_W0 + 512 + 1024;
+    static constexpr int THREADS = 160 * NS;                     // per slot: 4 epilogue warps + one MMA warp
+    static constexpr int TMEM_COLS = 128 * NS;
+    static constexpr int OFF_XYZ = OFF_W0 + 512;
+    static constexpr int OFF_BAR2 = OFF_XYZ + 2 * NS * XYZ_BUF;  // 2 x NS mbarriers
+    static constexpr int SMEM_IDX = OFF_BAR2 + 16 * NS + 1024;
+};
+static_assert(Lay<2>::OFF_BAR == OFF_BAR && Lay<2>::OFF_W0 == OFF_W0 && Lay<2>::SMEM == SMEM && Lay<2>::SMEM_IDX == SMEM_IDX, "Lay<2>");
 }  // namespace sa
 
 template <bool TIMED>
@@ -335,47 +348,65 @@ __global__ void __launch_bounds__(sa::THREADS, 2) sa_chain_kernel(const __grid_c
 // IDX = 1: the kernel takes the patches themselves ([points, 3], prm.xyz) and the in-patch kNN table as bytes (prm.idx8) and
 // forms the recentred neighbour coordinates on the fly -- the [points, 16, 3] fp32 tensor (100 MB per 32-cloud step, written by
 // the kNN kernel and read straight back here) never exists.  Same fp32 subtraction, so the result is bit-identical.
-template <int IDX>
-__global__ void __launch_bounds__(sa::THREADS, 2) sa_chain2_kernel(const __grid_constant__ SaParams prm) {
+// PCC_SA_TICKS (a build flag, never set in the shipped library): clock64() of CTA 0 / slot 0 -- epilogue thread 0 at dbg[0..],
+// the MMA warp's lane 0 at dbg[2048..]; read by tools/time_sa_ticks.py
+#ifdef PCC_SA_TICKS
+#define SA_TICK(base) do { if (ticker && tick < 2000) prm.dbg[(base) + tick++] = clock64(); } while (0)
+#else
+#define SA_TICK(base) do { } while (0)
+#endif
+template <int IDX, int NS>
+__global__ void __launch_bounds__(sa::Lay<NS>::THREADS, NS == 2 ? 2 : 1) sa_chain2_kernel(const __grid_constant__ SaParams prm) {
     using namespace sa;
+    // NS accumulator slots per CTA: 2 (two CTAs per SM) or 4 (one CTA per SM, whose four MMA warps land on four different
+    // SM sub-partitions -- with 2 + 2 the MMA warps of both CTAs share sub-partitions 0 and 1)
+    using L = Lay<NS>;
+    constexpr int OFF_BAR = L::OFF_BAR, OFF_W0 = L::OFF_W0, OFF_XYZ = L::OFF_XYZ, OFF_BAR2 = L::OFF_BAR2, THREADS = L::THREADS;
+    constexpr int TMEM_COLS = L::TMEM_COLS, EW = 4 * NS;   // EW: epilogue warps
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     const uint32_t sb = smem_u32(smem);
     const int tid = threadIdx.x, warp = __shfl_sync(FULL_MASK, tid >> 5, 0), lane = tid & 31;
-    const uint32_t bar_acc = sb + OFF_BAR, bar_act = sb + OFF_BAR + 16, bar_x1 = sb + OFF_BAR + 32;  // [2] each
-    const uint32_t bar_xyz = sb + OFF_BAR2;                                                           // [2 slots][2 buffers] (IDX)
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BAR + 48);
+    const uint32_t bar_acc = sb + OFF_BAR, bar_act = sb + OFF_BAR + 8 * NS;  // [NS] each
+    const uint32_t bar_xyz = sb + OFF_BAR2;                                                           // [NS slots][2 buffers] (IDX)
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BAR + 24 * NS);
 
     copy_to_smem(smem + OFF_W1, prm.w1p, 64 * KP1 * 2, tid, THREADS);
     copy_to_smem(smem + OFF_W2, prm.w2p, 128 * KP2 * 2, tid, THREADS);
     fill_ones_block(smem + OFF_ONES, tid, THREADS);
-    for (int e = tid; e < 32 * 4; e += THREADS)
-        reinterpret_cast<float *>(smem + OFF_W0)[e] = (e & 3) < 3 ? prm.w0[(e >> 2) * 3 + (e & 3)] : prm.b0[e >> 2];
+    // layer-0 weights as channel PAIRS for the packed fp32 FMA: pair j = channels (2j, 2j + 1) -> {wx wx' | wy wy' | wz wz' | b b'}
+    for (int e = tid; e < 32 * 4; e += THREADS) {
+        const int ch = 2 * (e >> 3) + (e & 1), comp = (e >> 1) & 3;
+        reinterpret_cast<float *>(smem + OFF_W0)[e] = comp < 3 ? prm.w0[ch * 3 + comp] : prm.b0[ch];
+    }
     if (tid == 0) {
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < NS; ++s) {
             mbar_init(bar_acc + 8 * s, 1);
             mbar_init(bar_act + 8 * s, 4);
-            mbar_init(bar_x1 + 8 * s, 1);
         }
         if constexpr (IDX) {
-            for (int i = 0; i < 4; ++i) mbar_init(bar_xyz + 8 * i, 4);
+            for (int i = 0; i < 2 * NS; ++i) mbar_init(bar_xyz + 8 * i, 4);
         }
     }
-    const uint32_t tmem_base = tmem_alloc_and_sync(tmem_slot, TMEM_COLS, warp, 8);
+    const uint32_t tmem_base = tmem_alloc_and_sync(tmem_slot, TMEM_COLS, warp, EW);
     const int n_tiles = prm.n_tiles;
-    const int tstride = 2 * gridDim.x;
+    const int tstride = NS * gridDim.x;
+#ifdef PCC_SA_TICKS
+    const bool ticker = prm.dbg && blockIdx.x == 0 && (tid == 0 || tid == 32 * EW);   // slot 0: epilogue thread 0, MMA lane 0
+    int tick = 0, tick2 = 0;
+#endif
 
-    if (warp >= 8) {
-        // ---- MMA warp of slot s: issues both layers' MMAs and computes layer 0 of the next tile ----
-        const int s = warp - 8;
+    if (warp >= EW) {
+        // ---- MMA warp of slot s: issues layer 1 and computes layer 0 of the next tile (layer 2 is issued by the slot's epilogue
+        // group the moment X2 is complete: polling for that from inside layer 0 cost this warp ~150 clocks per poll) ----
+        const int s = warp - EW;
         const uint32_t acc = __shfl_sync(FULL_MASK, tmem_base, 0) + s * 128;
-        const uint32_t id64 = umma_idesc(128, 64), id128 = umma_idesc(128, 128);
+        const uint32_t id64 = umma_idesc(128, 64);
         const uint64_t d_ones = desc_k16(sb + OFF_ONES);
-        const uint64_t d_w1 = desc_w(sb + OFF_W1, KP1, 0), d_w2 = desc_w(sb + OFF_W2, KP2, 0);
+        const uint64_t d_w1 = desc_w(sb + OFF_W1, KP1, 0);
         const uint32_t x1 = sb + OFF_SLOT + s * SLOT_BYTES + SL_X1;
         const uint64_t d_x1 = umma_desc_sw128(x1);
-        const uint64_t d_x2 = umma_desc_sw128(sb + OFF_SLOT + s * SLOT_BYTES + SL_X2);
-        const float4 *w0s = reinterpret_cast<const float4 *>(smem + OFF_W0);
+        const uint32_t w0s = sb + OFF_W0;   // (explicit ld.shared below: through the re-aligned generic pointer these were LD.E)
         float px[4], py[4], pz[4];   // lane owns positions lane + 32 i of the tile
         auto load_xyz = [&](long long tile) {
 #pragma unroll
@@ -391,91 +422,80 @@ __global__ void __launch_bounds__(sa::THREADS, 2) sa_chain2_kernel(const __grid_
         uint32_t kx = 0;
         auto take_xyz = [&]() {
             mbar_wait(bar_xyz + 8 * (2 * s + (kx & 1u)), (kx >> 1) & 1u);
-            const float *xb = reinterpret_cast<const float *>(smem + OFF_XYZ + (2 * s + (kx & 1u)) * XYZ_BUF);
+            // (plain generic loads on purpose: with ld.shared here and st.shared in finish_gather the kernel measured 247 us against
+            // 224 us -- this warp has slack, and its layer 0 then starts later, out of the way of the slot's layer-1 epilogue)
+            const float *xg = reinterpret_cast<const float *>(smem + OFF_XYZ + (2 * s + (kx & 1u)) * XYZ_BUF);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                px[i] = xb[lane + 32 * i];
-                py[i] = xb[P + lane + 32 * i];
-                pz[i] = xb[2 * P + lane + 32 * i];
+                px[i] = xg[lane + 32 * i];
+                py[i] = xg[P + lane + 32 * i];
+                pz[i] = xg[2 * P + lane + 32 * i];
             }
             ++kx;
         };
-        // layer 0 of positions lane + 32 i0 and lane + 32 (i0 + 1): 2 x 32 channels -> X1 (4 16-byte chunks per position)
-        auto issue_mma2 = [&]() {
-            tc_fence_after();
-            if (elect_one()) {  // T-form: D^T[128 channels, 128 positions]
+        uint32_t ph_act = 0;
+        // layer 0 (3 -> 32, fp32) of the lane's four positions, two channels per instruction (fma.rn.f32x2: each half is the same
+        // IEEE fma as the scalar form, so the result is bit-identical), one 16-byte chunk (8 channels) of X1 per position at a time
+        auto layer0_tile = [&]() {
+            uint64_t qx[4], qy[4], qz[4];
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) umma_bf16(acc, d_w2 + 16 * ks, d_x2 + 2 * ks, id128, ks > 0);
-                umma_bf16(acc, d_w2 + 64, d_ones, id128, 1u);
-                umma_commit(bar_acc + 8 * s);
+            for (int i = 0; i < 4; ++i) {
+                qx[i] = dup_f32x2(px[i]);
+                qy[i] = dup_f32x2(py[i]);
+                qz[i] = dup_f32x2(pz[i]);
             }
-            __syncwarp();
-        };
-        uint32_t ph_act = 0, ph_x1 = 0;
-        bool mma2_pending = false;   // layer 2 of the current tile still has to be issued: polled inside layer 0
-        auto layer0_pair = [&](int i0) {
-            uint32_t pk[2][16];
 #pragma unroll
-            for (int c = 0; c < 16; ++c) {
-                if ((c & 3) == 0 && mma2_pending && __any_sync(FULL_MASK, mbar_test(bar_act + 8 * s, ph_act))) {   // X2 ready
-                    ph_act ^= 1u;
-                    issue_mma2();
-                    mma2_pending = false;
+            for (int c8 = 0; c8 < 4; ++c8) {
+                uint32_t pk[4][4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const ulonglong2 wxy = ld_shared_v2u64(w0s + 32 * (4 * c8 + j)), wzb = ld_shared_v2u64(w0s + 32 * (4 * c8 + j) + 16);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        pk[i][j] = pack_relu_bf16x2_pair(fma_f32x2(wzb.x, qz[i], fma_f32x2(wxy.y, qy[i], fma_f32x2(wxy.x, qx[i], wzb.y))));
                 }
-                const float4 wa = w0s[2 * c], wb = w0s[2 * c + 1];
 #pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    const float a = fmaf(wa.z, pz[i0 + i], fmaf(wa.y, py[i0 + i], fmaf(wa.x, px[i0 + i], wa.w)));
-                    const float b = fmaf(wb.z, pz[i0 + i], fmaf(wb.y, py[i0 + i], fmaf(wb.x, px[i0 + i], wb.w)));
-                    pk[i][c] = pack_relu_bf16x2(a, b);
+                for (int i = 0; i < 4; ++i) {
+                    const int p = lane + 32 * i;
+                    st_shared_v4(x1 + p * 128 + ((c8 ^ (p & 7)) << 4), pk[i][0], pk[i][1], pk[i][2], pk[i][3]);
                 }
             }
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const int p = lane + 32 * (i0 + i);
-#pragma unroll
-                for (int c8 = 0; c8 < 4; ++c8)
-                    st_shared_v4(x1 + p * 128 + ((c8 ^ (p & 7)) << 4), pk[i][4 * c8], pk[i][4 * c8 + 1], pk[i][4 * c8 + 2], pk[i][4 * c8 + 3]);
-            }
         };
-        long long tile = 2ll * blockIdx.x + s;
+        long long tile = static_cast<long long>(NS) * blockIdx.x + s;
         if (tile < n_tiles) {
             if constexpr (IDX) take_xyz(); else load_xyz(tile);
-            layer0_pair(0);
-            layer0_pair(2);
+            layer0_tile();
             fence_async_smem();
             if constexpr (!IDX) { if (tile + tstride < n_tiles) load_xyz(tile + tstride); }
         }
         for (; tile < n_tiles; tile += tstride) {
-            mbar_wait(bar_act + 8 * s, ph_act);   // the accumulator is free (epilogue 2 of the previous tile has read it)
+            SA_TICK(2048);   // 0 top
+            const bool more = tile + tstride < n_tiles;
+            mbar_wait(bar_act + 8 * s, ph_act);   // accumulator columns 0..63 are free (epilogue 2 of the previous tile has read them)
             ph_act ^= 1u;
+            SA_TICK(2048);   // 1 accumulator free
             tc_fence_after();
             if (elect_one()) {
                 umma_bf16(acc, d_x1, d_w1, id64, 0u);
                 umma_bf16(acc, d_x1 + 2, d_w1 + 16, id64, 1u);
                 umma_bf16(acc, d_ones, d_w1 + 32, id64, 1u);
-                umma_commit(bar_x1 + 8 * s);
                 umma_commit(bar_acc + 8 * s);
             }
             __syncwarp();
-            const bool more = tile + tstride < n_tiles;
-            mbar_wait(bar_x1 + 8 * s, ph_x1);       // layer 1 has consumed X1: the next tile's layer 0 may overwrite it
-            ph_x1 ^= 1u;
-            mma2_pending = true;
+            SA_TICK(2048);   // 2 layer 1 issued
+            if constexpr (IDX) { if (more) take_xyz(); }   // (layer 0 of this tile is done with px/py/pz: the loads land under the wait)
+            SA_TICK(2048);   // 3 xyz taken
+            // layer 1 has consumed X1 (the same completion the epilogue group waits for: bar_acc completes twice per tile,
+            // layer 1 on even phases): the next tile's layer 0 may overwrite it
+            mbar_wait(bar_acc + 8 * s, 0u);
+            SA_TICK(2048);   // 4 X1 consumed
             if (more) {
                 tc_fence_after();
-                if constexpr (IDX) take_xyz();
-                layer0_pair(0);                     // (issues layer 2 from inside as soon as X2 is ready)
-                layer0_pair(2);
+                layer0_tile();
                 fence_async_smem();
                 if constexpr (!IDX) { if (tile + 2 * tstride < n_tiles) load_xyz(tile + 2 * tstride); }
             }
-            if (mma2_pending) {
-                mbar_wait(bar_act + 8 * s, ph_act);
-                ph_act ^= 1u;
-                issue_mma2();
-                mma2_pending = false;
-            }
+            SA_TICK(2048);   // 5 layer 0 of the next tile done
         }
     } else {
         // ---- epilogue group g = warp / 4 serves slot g; warp q = warp % 4 owns TMEM lanes 32q.. ----
@@ -484,6 +504,10 @@ __global__ void __launch_bounds__(sa::THREADS, 2) sa_chain2_kernel(const __grid_
         const uint32_t acc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + s * 128;
         const uint32_t slot = sb + OFF_SLOT + s * SLOT_BYTES;
         uint32_t ph_acc = 0;
+        // layer 2 is issued from here: warp (s & 3) of the group (a different SM sub-partition per slot), one elected lane
+        const uint32_t id128 = umma_idesc(128, 128);
+        const uint64_t d_ones = desc_k16(sb + OFF_ONES), d_w2 = desc_w(sb + OFF_W2, KP2, 0), d_x2 = umma_desc_sw128(slot + SL_X2);
+        const uint32_t acc_slot = tmem_base + s * 128;
         float *out_f = prm.out_bf16 ? nullptr : static_cast<float *>(prm.out);
         __nv_bfloat16 *out_h = prm.out_bf16 ? static_cast<__nv_bfloat16 *>(prm.out) : nullptr;
         if (lane == 0) mbar_arrive1(bar_act + 8 * s);   // the accumulator starts out free
@@ -507,15 +531,15 @@ __global__ void __launch_bounds__(sa::THREADS, 2) sa_chain2_kernel(const __grid_
             }
         };
         auto finish_gather = [&]() {
-            float *xb = reinterpret_cast<float *>(smem + OFF_XYZ + (2 * s + (kg & 1u)) * XYZ_BUF);
+            float *xg = reinterpret_cast<float *>(smem + OFF_XYZ + (2 * s + (kg & 1u)) * XYZ_BUF);
 #pragma unroll
-            for (int e = 0; e < 3; ++e) xb[e * P + t] = __fsub_rn(gn[e], gc[e]);
+            for (int e = 0; e < 3; ++e) xg[e * P + t] = __fsub_rn(gn[e], gc[e]);
             __syncwarp();
             if (lane == 0) mbar_arrive1(bar_xyz + 8 * (2 * s + (kg & 1u)));
             ++kg;
         };
         if constexpr (IDX) {
-            const long long t0 = 2ll * blockIdx.x + s;
+            const long long t0 = static_cast<long long>(NS) * blockIdx.x + s;
             if (t0 < n_tiles) {
                 load_byte(t0);
                 issue_gather(t0);
@@ -528,7 +552,8 @@ __global__ void __launch_bounds__(sa::THREADS, 2) sa_chain2_kernel(const __grid_
                 }
             }
         }
-        for (long long tile = 2ll * blockIdx.x + s; tile < n_tiles; tile += tstride) {
+        for (long long tile = static_cast<long long>(NS) * blockIdx.x + s; tile < n_tiles; tile += tstride) {
+            SA_TICK(0);   // 0 top
             if constexpr (IDX) {            // the tile after next: loads in flight under the wait for layer 1 and its epilogue
                 if (tile + 2 * tstride < n_tiles) issue_gather(tile + 2 * tstride);
                 if (tile + 3 * tstride < n_tiles) load_byte(tile + 3 * tstride);
@@ -537,6 +562,7 @@ __global__ void __launch_bounds__(sa::THREADS, 2) sa_chain2_kernel(const __grid_
             mbar_wait(bar_acc + 8 * s, ph_acc);
             ph_acc ^= 1u;
             tc_fence_after();
+            SA_TICK(0);   // 1 layer 1 accumulator ready
             {
                 uint32_t v0[32], v1[32];
                 tmem_ld32_issue(acc, v0);
@@ -546,17 +572,38 @@ __global__ void __launch_bounds__(sa::THREADS, 2) sa_chain2_kernel(const __grid_
                 tmem_ld32_wait(v1);
                 store_row_chunks<32, true>(slot + SL_X2, row, 32, v1);
             }
+            SA_TICK(0);   // 2 X2 stored
             fence_async_smem();
             tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive1(bar_act + 8 * s);
-            if constexpr (IDX) {
+            // the four warps of the group: X2 is complete (and layer 1's accumulator read); literal ids, so that ptxas
+            // reserves NS + 1 hardware barriers and not all 16
+            if (s == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+            else if (s == 1) asm volatile("bar.sync 2, 128;" ::: "memory");
+            else if (s == 2) asm volatile("bar.sync 3, 128;" ::: "memory");
+            else asm volatile("bar.sync 4, 128;" ::: "memory");
+            if (q == (s & 3)) {
+#ifdef PCC_SA_TICKS
+                if (ticker && tick2 < 500) prm.dbg[4096 + tick2++] = clock64();
+#endif
+                tc_fence_after();
+                if (elect_one()) {  // T-form: D^T[128 channels, 128 positions]
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) umma_bf16(acc_slot, d_w2 + 16 * ks, d_x2 + 2 * ks, id128, ks > 0);
+                    umma_bf16(acc_slot, d_w2 + 64, d_ones, id128, 1u);
+                    umma_commit(bar_acc + 8 * s);
+                }
+                __syncwarp();
+            }
+            SA_TICK(0);   // 3 layer 2 issued
+            if constexpr (IDX) {            // (late: the loads issued at the top of the iteration have landed by now)
                 if (tile + 2 * tstride < n_tiles) finish_gather();
             }
+            SA_TICK(0);   // 4 gather finished
             // ---- layer 2 epilogue (T-form): lane = channel `row`, columns = positions; max over each run of 16 ----
             mbar_wait(bar_acc + 8 * s, ph_acc);
             ph_acc ^= 1u;
             tc_fence_after();
+            SA_TICK(0);   // 5 layer 2 accumulator ready
             const long long o = tile * 8 * 128 + row;
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
@@ -576,12 +623,13 @@ __global__ void __launch_bounds__(sa::THREADS, 2) sa_chain2_kernel(const __grid_
                     if (out_h) out_h[o + (j * 4 + g) * 128] = __float2bfloat16_rn(mm); else out_f[o + (j * 4 + g) * 128] = mm;
                 }
             }
-            tc_fence_before();
+            SA_TICK(0);   // 6 pooled rows stored
+            tc_fence_before();   // (the reads of columns 64..127 are ordered before the group's next bar.sync -> layer 2 of the next tile)
             __syncwarp();
             if (lane == 0) mbar_arrive1(bar_act + 8 * s);   // accumulator free
         }
     }
-    tmem_free(tmem_base, TMEM_COLS, warp, 8);
+    tmem_free(tmem_base, TMEM_COLS, warp, EW);
 }
 
 // ======================================================================================================================
@@ -1032,8 +1080,8 @@ int ws_dispatch(const PccMlpInput *in, int n_inputs, int64_t rows, const PccMlpL
             if (int r = set_smem(sa_chain_kernel<true>, sa::SMEM)) return r;
             sa_chain_kernel<true><<<grid, sa::THREADS, sa::SMEM, st>>>(p);
         } else if (!form1) {
-            if (int r = set_smem(sa_chain2_kernel<0>, sa::SMEM)) return r;
-            sa_chain2_kernel<0><<<grid, sa::THREADS, sa::SMEM, st>>>(p);
+            if (int r = set_smem(sa_chain2_kernel<0, 2>, sa::SMEM)) return r;
+            sa_chain2_kernel<0, 2><<<grid, sa::THREADS, sa::SMEM, st>>>(p);
             *handled = true;
             return check_launch("sa_chain2_kernel");
         } else {
@@ -1109,21 +1157,31 @@ PCC_API int pcc_sa_chain_indexed(const float *patches, const uint8_t *idx8, int6
     p.out = out;
     p.out_bf16 = out_dtype;
     p.n_tiles = static_cast<int>(points / 8);
-    p.dbg = nullptr;
+    p.dbg = g_ws_dbg;
     p.idx8 = idx8;
     p.pts_per_patch = pts_per_patch;
     p.pts_shift = -1;
     for (int sh = 3; sh <= 8; ++sh)
         if ((1 << sh) == pts_per_patch) p.pts_shift = sh;
     const int sms = num_sms();
-    const int pairs = (p.n_tiles + 1) / 2;
-    const int grid = pairs < 2 * sms ? pairs : 2 * sms;
     // (a third form -- the epilogue group also computes the fp32 3 -> 32 layer of the next tile in its wait for layer 2, the MMA
     // warp only issues -- was measured at 362 us against 312 us: the epilogue groups, not the MMA warps, pace the kernel)
     // (eight epilogue warps per slot -- 18 warps per CTA at 56 registers, each slot's epilogues split over two groups, one
     // 32-column tcgen05.ld in flight per warp -- was measured at 398 us against 310 us: more warps lose here, as in round 1)
-    if (int r = set_smem(sa_chain2_kernel<1>, sa::SMEM_IDX)) return r;
-    sa_chain2_kernel<1><<<grid, sa::THREADS, sa::SMEM_IDX, static_cast<cudaStream_t>(stream)>>>(p);
+    static const int slots = [] {
+        const char *e = getenv("PCC_SA_SLOTS");
+        return e && atoi(e) == 2 ? 2 : 4;
+    }();
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (slots == 4) {
+        const int quads = (p.n_tiles + 3) / 4;
+        if (int r = set_smem(sa_chain2_kernel<1, 4>, sa::Lay<4>::SMEM_IDX)) return r;
+        sa_chain2_kernel<1, 4><<<quads < sms ? quads : sms, sa::Lay<4>::THREADS, sa::Lay<4>::SMEM_IDX, st>>>(p);
+    } else {
+        const int pairs = (p.n_tiles + 1) / 2;
+        if (int r = set_smem(sa_chain2_kernel<1, 2>, sa::SMEM_IDX)) return r;
+        sa_chain2_kernel<1, 2><<<pairs < 2 * sms ? pairs : 2 * sms, sa::THREADS, sa::SMEM_IDX, st>>>(p);
+    }
     return check_launch("sa_chain2_kernel<indexed>");
 }
 

@@ -39,6 +39,7 @@ __device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
 }
 
+// (a suspend-time hint on try_wait -- "sleep up to 4 us" -- was measured: no change for the chain kernels, 6 % slower for pn_fused)
 __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
     uint32_t ok;
     uint32_t spins = 0;
@@ -148,10 +149,31 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+__device__ __forceinline__ ulonglong2 ld_shared_v2u64(uint32_t addr) {   // read-only data (weights): not volatile, may be hoisted
+    ulonglong2 v;
+    asm("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "r"(addr));
+    return v;
+}
 // bf16x2 pack with the ReLU folded into the conversion (F2FP.RELU): low half = lo, high half = hi
 __device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {
     uint32_t r;
     asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+// packed fp32: two independent IEEE fma.rn per instruction (FFMA2), operands are {lo, hi} register pairs
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ uint64_t dup_f32x2(float x) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ uint32_t pack_relu_bf16x2_pair(uint64_t v) {   // low half of the result = low float of the pair
+    uint32_t r;
+    asm("{\n\t.reg .f32 lo, hi;\n\tmov.b64 {lo, hi}, %1;\n\tcvt.rn.relu.bf16x2.f32 %0, hi, lo;\n\t}\n" : "=r"(r) : "l"(v));
     return r;
 }
 __device__ __forceinline__ float fmax3(float a, float b, float c) {

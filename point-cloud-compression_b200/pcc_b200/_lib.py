@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpcc_b200.so")
+# PCC_B200_LIB: development aid -- load another build of the same library (A/B runs of a kernel variant)
+LIB_PATH = os.environ.get("PCC_B200_LIB") or os.path.join(_HERE, "libpcc_b200.so")
 
 _vp = ctypes.c_void_p
 _i = ctypes.c_int

@@ -25,7 +25,8 @@ for l in lines[start + 1:]:
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hdr = next(r for r in rows if r and r[0] == "Address")
-ia, isamp = hdr.index("Instructions Executed"), hdr.index("# Samples")
+ia = hdr.index("Instructions Executed")
+isamp = hdr.index("# Samples") if "# Samples" in hdr else hdr.index("Warp Stall Sampling (All Samples)")
 want = sys.argv[5] if len(sys.argv) > 5 else ""
 body, take = [], False
 for r in rows:
@@ -51,11 +52,11 @@ def text(key):
         _src_cache[f] = open(path).read().splitlines() if os.path.exists(path) else []
     lines_ = _src_cache[f]
     return f"{f}:{ln}: " + (lines_[ln - 1].strip()[:100] if 0 < ln <= len(lines_) else "")
-te, ts = sum(by_exec.values()), sum(by_samp.values())
+te, ts = sum(by_exec.values()), (sum(by_samp.values()) or 1)
 print(f"total executed {te}  samples {ts}")
 print("--- by executed instructions")
 for ln, c in by_exec.most_common(28):
     print(f"{100*c/te:5.1f}% exec {100*by_samp[ln]/ts:5.1f}% samp  {text(ln)}")
 print("--- by stall samples")
 for ln, c in by_samp.most_common(16):
-    print(f"{100*c/ts:5.1f}% samp {100*by_exec[ln]/te:5.1f}% exec  L{ln}: {srcl[ln-1].strip()[:110] if ln and ln <= len(srcl) else '?'}")
+    print(f"{100*c/ts:5.1f}% samp {100*by_exec[ln]/te:5.1f}% exec  {text(ln)}")
