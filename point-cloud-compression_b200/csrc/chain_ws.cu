@@ -114,6 +114,8 @@ struct SaParams {
     const float *xyz;
     long long ld;
     const float *w0, *b0;      // fp32 [32,3], [32]
+    const float *b2;           // fp32 [128] or NULL (sa_chain2_kernel): layer 2's bias, added after the max in the epilogue; NULL:
+                               // the bf16 bias column of the packed weights goes through one more MMA, as in layers 1
     const void *w1p, *w2p;     // packed [64 x 48], [128 x 80]
     void *out;
     int out_bf16;
@@ -508,6 +510,7 @@ __global__ void __launch_bounds__(sa::Lay<NS>::THREADS, NS == 2 ? 2 : 1) sa_chai
         const uint32_t id128 = umma_idesc(128, 128);
         const uint64_t d_ones = desc_k16(sb + OFF_ONES), d_w2 = desc_w(sb + OFF_W2, KP2, 0), d_x2 = umma_desc_sw128(slot + SL_X2);
         const uint32_t acc_slot = tmem_base + s * 128;
+        const float bias2 = prm.b2 ? __ldg(prm.b2 + row) : 0.0f;
         float *out_f = prm.out_bf16 ? nullptr : static_cast<float *>(prm.out);
         __nv_bfloat16 *out_h = prm.out_bf16 ? static_cast<__nv_bfloat16 *>(prm.out) : nullptr;
         if (lane == 0) mbar_arrive1(bar_act + 8 * s);   // the accumulator starts out free
@@ -589,7 +592,7 @@ __global__ void __launch_bounds__(sa::Lay<NS>::THREADS, NS == 2 ? 2 : 1) sa_chai
                 if (elect_one()) {  // T-form: D^T[128 channels, 128 positions]
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) umma_bf16(acc_slot, d_w2 + 16 * ks, d_x2 + 2 * ks, id128, ks > 0);
-                    umma_bf16(acc_slot, d_w2 + 64, d_ones, id128, 1u);
+                    if (!prm.b2) umma_bf16(acc_slot, d_w2 + 64, d_ones, id128, 1u);
                     umma_commit(bar_acc + 8 * s);
                 }
                 __syncwarp();
@@ -619,7 +622,8 @@ __global__ void __launch_bounds__(sa::Lay<NS>::THREADS, NS == 2 ? 2 : 1) sa_chai
                     float mm = fmax3(__uint_as_float(v[b]), __uint_as_float(v[b + 1]), __uint_as_float(v[b + 2]));
 #pragma unroll
                     for (int i = 3; i < 15; i += 2) mm = fmax3(mm, __uint_as_float(v[b + i]), __uint_as_float(v[b + i + 1]));
-                    mm = fmax3(mm, __uint_as_float(v[b + 15]), 0.0f);  // the ReLU commutes with the max
+                    // the bias (one per channel = per lane) and the ReLU commute with the max over the 16 neighbours
+                    mm = fmaxf(fmaxf(mm, __uint_as_float(v[b + 15])) + bias2, 0.0f);
                     if (out_h) out_h[o + (j * 4 + g) * 128] = __float2bfloat16_rn(mm); else out_f[o + (j * 4 + g) * 128] = mm;
                 }
             }
@@ -1067,6 +1071,7 @@ int ws_dispatch(const PccMlpInput *in, int n_inputs, int64_t rows, const PccMlpL
         p.ld = in[0].ld;
         p.w0 = layers[0].w_f32;
         p.b0 = layers[0].b_f32;
+        p.b2 = layers[2].b_f32;
         p.w1p = layers[1].packed_w;
         p.w2p = layers[2].packed_w;
         p.out = out;
@@ -1152,6 +1157,7 @@ PCC_API int pcc_sa_chain_indexed(const float *patches, const uint8_t *idx8, int6
     p.ld = 3;
     p.w0 = layers[0].w_f32;
     p.b0 = layers[0].b_f32;
+    p.b2 = layers[2].b_f32;
     p.w1p = layers[1].packed_w;
     p.w2p = layers[2].packed_w;
     p.out = out;
