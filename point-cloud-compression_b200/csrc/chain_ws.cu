@@ -369,7 +369,7 @@ __global__ void __launch_bounds__(sa::Lay<NS>::THREADS, NS == 2 ? 2 : 1) sa_chai
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     const uint32_t sb = smem_u32(smem);
     const int tid = threadIdx.x, warp = __shfl_sync(FULL_MASK, tid >> 5, 0), lane = tid & 31;
-    const uint32_t bar_acc = sb + OFF_BAR, bar_act = sb + OFF_BAR + 8 * NS;  // [NS] each
+    const uint32_t bar_acc = sb + OFF_BAR, bar_act = sb + OFF_BAR + 8 * NS, bar_x1 = sb + OFF_BAR + 16 * NS;  // [NS] each
     const uint32_t bar_xyz = sb + OFF_BAR2;                                                           // [NS slots][2 buffers] (IDX)
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BAR + 24 * NS);
 
@@ -385,6 +385,7 @@ __global__ void __launch_bounds__(sa::Lay<NS>::THREADS, NS == 2 ? 2 : 1) sa_chai
         for (int s = 0; s < NS; ++s) {
             mbar_init(bar_acc + 8 * s, 1);
             mbar_init(bar_act + 8 * s, 4);
+            mbar_init(bar_x1 + 8 * s, 1);
         }
         if constexpr (IDX) {
             for (int i = 0; i < 2 * NS; ++i) mbar_init(bar_xyz + 8 * i, 4);
@@ -435,7 +436,7 @@ __global__ void __launch_bounds__(sa::Lay<NS>::THREADS, NS == 2 ? 2 : 1) sa_chai
             }
             ++kx;
         };
-        uint32_t ph_act = 0;
+        uint32_t ph_act = 0, ph_x1 = 0;
         // layer 0 (3 -> 32, fp32) of the lane's four positions, two channels per instruction (fma.rn.f32x2: each half is the same
         // IEEE fma as the scalar form, so the result is bit-identical), one 16-byte chunk (8 channels) of X1 per position at a time
         auto layer0_tile = [&]() {
@@ -481,15 +482,18 @@ __global__ void __launch_bounds__(sa::Lay<NS>::THREADS, NS == 2 ? 2 : 1) sa_chai
                 umma_bf16(acc, d_x1, d_w1, id64, 0u);
                 umma_bf16(acc, d_x1 + 2, d_w1 + 16, id64, 1u);
                 umma_bf16(acc, d_ones, d_w1 + 32, id64, 1u);
+                umma_commit(bar_x1 + 8 * s);
                 umma_commit(bar_acc + 8 * s);
             }
             __syncwarp();
             SA_TICK(2048);   // 2 layer 1 issued
             if constexpr (IDX) { if (more) take_xyz(); }   // (layer 0 of this tile is done with px/py/pz: the loads land under the wait)
             SA_TICK(2048);   // 3 xyz taken
-            // layer 1 has consumed X1 (the same completion the epilogue group waits for: bar_acc completes twice per tile,
-            // layer 1 on even phases): the next tile's layer 0 may overwrite it
-            mbar_wait(bar_acc + 8 * s, 0u);
+            // layer 1 has consumed X1: the next tile's layer 0 may overwrite it.  (Its own barrier, one phase per tile: waiting
+            // for the even phases of bar_acc instead deadlocks if this warp is ever delayed past layer 2's completion, which
+            // flips bar_acc's parity back -- seen as a rare launch failure under the 4-stream replay)
+            mbar_wait(bar_x1 + 8 * s, ph_x1);
+            ph_x1 ^= 1u;
             SA_TICK(2048);   // 4 X1 consumed
             if (more) {
                 tc_fence_after();

@@ -394,7 +394,7 @@ namespace pcc {
 int64_t chamfer_grid_extra_bytes(int B, int P1, int P2, int G);
 int chamfer_grid_pick(int P1, int P2);
 int chamfer_grid_run(const float *x, const float *y, int B, int P1, int P2, int G, unsigned long long *kx,
-                     unsigned long long *ky, void *extra, cudaStream_t st);
+                     unsigned long long *ky, bool want_idx, void *extra, cudaStream_t st);
 static int chamfer_path() {   // PCC_CHAMFER_PATH=brute forces the brute-force kernels (A/B measurements)
     static const int v = [] {
         const char *e = getenv("PCC_CHAMFER_PATH");
@@ -438,7 +438,7 @@ PCC_API int pcc_chamfer_fwd_f32(const float *x, const float *y, int B, int P1, i
     const int G = chamfer_path() ? 0 : chamfer_grid_pick(P1, P2);
     if (G) {
         const uintptr_t extra = (reinterpret_cast<uintptr_t>(ky + static_cast<size_t>(B) * P2) + 15) & ~static_cast<uintptr_t>(15);
-        const int rc = chamfer_grid_run(x, y, B, P1, P2, G, kx, ky, reinterpret_cast<void *>(extra), st);
+        const int rc = chamfer_grid_run(x, y, B, P1, P2, G, kx, ky, out_ix || out_iy, reinterpret_cast<void *>(extra), st);
         if (rc) return rc;
     } else {
         // one-pass kernel: pick the column split that balances the grid over the SMs (~4 resident CTAs each)

@@ -27,6 +27,9 @@ namespace pcc {
 constexpr int GRID_BUILD_THREADS = 1024;
 
 // grid (B, 2); dynamic smem: (G^3 + 1) u32
+// PAIRED: the sorted points are stored two by two, 32 bytes per pair {x0 x1 y0 y1 z0 z1 i0 i1}, every cloud padded to an even
+// count with a point at +inf -- the operand layout of the packed-fp32 distance loop of grid_nn_d2_kernel
+template <bool PAIRED>
 __global__ void __launch_bounds__(GRID_BUILD_THREADS)
 grid_build_kernel(const float *__restrict__ x, const float *__restrict__ y, int P1, int P2, int G, float4 *__restrict__ sorted,
                   unsigned *__restrict__ starts, GridInfo *__restrict__ info, unsigned *__restrict__ rowmask) {
@@ -37,7 +40,9 @@ grid_build_kernel(const float *__restrict__ x, const float *__restrict__ y, int 
     const int b = blockIdx.x, side = blockIdx.y, B = gridDim.x;
     const int P = side ? P2 : P1;
     const float *pts = side ? y + static_cast<size_t>(b) * P2 * 3 : x + static_cast<size_t>(b) * P1 * 3;
-    float4 *out = sorted + (side ? static_cast<size_t>(B) * P1 + static_cast<size_t>(b) * P2 : static_cast<size_t>(b) * P1);
+    const size_t S1 = PAIRED ? (static_cast<size_t>(P1) + 1) & ~static_cast<size_t>(1) : P1;
+    const size_t S2 = PAIRED ? (static_cast<size_t>(P2) + 1) & ~static_cast<size_t>(1) : P2;
+    float4 *out = sorted + (side ? static_cast<size_t>(B) * S1 + static_cast<size_t>(b) * S2 : static_cast<size_t>(b) * S1);
     const int ncell = G * G * G;
     unsigned *st_out = starts + (static_cast<size_t>(side) * B + b) * (ncell + 1);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -157,7 +162,20 @@ grid_build_kernel(const float *__restrict__ x, const float *__restrict__ y, int 
         const float px = pts[static_cast<size_t>(i) * 3], py = pts[static_cast<size_t>(i) * 3 + 1], pz = pts[static_cast<size_t>(i) * 3 + 2];
         const int cx = cell_coord(px, g.mnx, g.inv_h, G), cy = cell_coord(py, g.mny, g.inv_h, G), cz = cell_coord(pz, g.mnz, g.inv_h, G);
         const unsigned pos = atomicAdd(&cnt[(cz * G + cy) * G + cx], 1u);
-        out[pos] = make_float4(px, py, pz, __uint_as_float(static_cast<unsigned>(i)));
+        if (PAIRED) {
+            float *o = reinterpret_cast<float *>(out) + static_cast<size_t>(pos >> 1) * 8 + (pos & 1u);
+            o[0] = px;
+            o[2] = py;
+            o[4] = pz;
+            o[6] = __uint_as_float(static_cast<unsigned>(i));
+        } else {
+            out[pos] = make_float4(px, py, pz, __uint_as_float(static_cast<unsigned>(i)));
+        }
+    }
+    if (PAIRED && (P & 1) && tid == 0) {   // the odd cloud's last pair: a point no query can be near
+        float *o = reinterpret_cast<float *>(out) + static_cast<size_t>(P >> 1) * 8 + 1;
+        o[0] = o[2] = o[4] = INFINITY;
+        o[6] = __uint_as_float(0xffffffffu);
     }
 }
 
@@ -286,8 +304,172 @@ grid_nn_kernel(int P1, int P2, const float4 *__restrict__ sorted, const unsigned
     keys[__float_as_uint(q.w)] = best;
 }
 
+// ---- distance-only form (the caller wants no indices: eval.py's Chamfer / D1 PSNR, AE.get_loss without a backward pass) ----------
+// Same search, same visited candidates (a superset: ranges are widened to whole pairs), same un-fused d2 per candidate -- so the
+// same minima, bit for bit -- but the running best is a float and the distance of TWO candidates costs 8 packed fp32
+// instructions (add / mul .f32x2: each half is the IEEE operation of dist2_rn; (c - q)^2 == (q - c)^2 exactly), 4 scalar adds and
+// one 3-input min: 7.3 issue slots per candidate against 14.7 for the keyed loop, which was issue bound.
+__device__ __forceinline__ unsigned long long add_f32x2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long mul_f32x2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long dup_neg_f32x2(float x) {
+    unsigned long long r;
+    const float n = -x;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(n));
+    return r;
+}
+__device__ __forceinline__ float2 unpack_f32x2(unsigned long long v) {
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+__device__ __forceinline__ float fmin3(float a, float b, float c) {
+    float r;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+__device__ __forceinline__ float pair_min(float bd, ulonglong2 xy, unsigned long long zz, unsigned long long nqx, unsigned long long nqy,
+                                          unsigned long long nqz) {
+    const unsigned long long dx = add_f32x2(xy.x, nqx), dy = add_f32x2(xy.y, nqy), dz = add_f32x2(zz, nqz);
+    // the three squares packed, the two sums per candidate scalar: ptxas (12.9) contracts mul.rn.f32x2 + add.rn.f32x2 into
+    // FFMA2 whatever --fmad says, which would change the rounding of dist2_rn; it never fuses across the scalar add.rn
+    const float2 sx = unpack_f32x2(mul_f32x2(dx, dx)), sy = unpack_f32x2(mul_f32x2(dy, dy)), sz = unpack_f32x2(mul_f32x2(dz, dz));
+    return fmin3(bd, __fadd_rn(__fadd_rn(sx.x, sy.x), sz.x), __fadd_rn(__fadd_rn(sx.y, sy.y), sz.y));
+}
+// candidates [a, e) of a paired array, widened to whole pairs; pairs j, j + step, ... (step > 1: the strided sample).  Four pairs
+// are loaded before the first is used: the loop is load-latency bound otherwise (55 % of its stall samples on the first add)
+__device__ __forceinline__ void scan_pairs(const float4 *__restrict__ cand, unsigned a, unsigned e, unsigned long long nqx,
+                                           unsigned long long nqy, unsigned long long nqz, float &bd, unsigned step = 1u) {
+    if (a >= e) return;   // (an empty range with an odd start would otherwise widen to one pair)
+    const unsigned long long *c = reinterpret_cast<const unsigned long long *>(cand);
+    unsigned j = a >> 1;
+    const unsigned je = (e + 1u) >> 1;
+    for (; j + 3u * step < je; j += 4u * step) {
+        ulonglong2 xy[4];
+        unsigned long long zz[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const unsigned long long *p = c + 4 * static_cast<size_t>(j + u * step);
+            xy[u] = __ldg(reinterpret_cast<const ulonglong2 *>(p));
+            zz[u] = __ldg(p + 2);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) bd = pair_min(bd, xy[u], zz[u], nqx, nqy, nqz);
+    }
+#pragma unroll 1
+    for (; j < je; j += step) {
+        const unsigned long long *p = c + 4 * static_cast<size_t>(j);
+        bd = pair_min(bd, __ldg(reinterpret_cast<const ulonglong2 *>(p)), __ldg(p + 2), nqx, nqy, nqz);
+    }
+}
+
+// grid and arguments as grid_nn_kernel; `sorted` is the PAIRED array; kx / ky receive pack_key(d2, 0)
+__global__ void __launch_bounds__(128)
+grid_nn_d2_kernel(int P1, int P2, const float4 *__restrict__ sorted, const unsigned *__restrict__ starts,
+                  const GridInfo *__restrict__ info, const unsigned *__restrict__ rowmask, unsigned long long *__restrict__ kx,
+                  unsigned long long *__restrict__ ky) {
+    const int b = blockIdx.y, dir = blockIdx.z, B = gridDim.y;
+    const int Pq = dir ? P2 : P1, Pc = dir ? P1 : P2;
+    if (blockIdx.x * 128 >= Pq) return;
+    const int qi_raw = blockIdx.x * 128 + threadIdx.x;
+    const int qi = qi_raw < Pq ? qi_raw : Pq - 1;   // lanes past the end replay the last query (warp-uniform step 2) and do not store
+    const size_t S1 = (static_cast<size_t>(P1) + 1) & ~static_cast<size_t>(1), S2 = (static_cast<size_t>(P2) + 1) & ~static_cast<size_t>(1);
+    const float4 *qpts = sorted + (dir ? static_cast<size_t>(B) * S1 + static_cast<size_t>(b) * S2 : static_cast<size_t>(b) * S1);
+    const float4 *cand = sorted + (dir ? static_cast<size_t>(b) * S1 : static_cast<size_t>(B) * S1 + static_cast<size_t>(b) * S2);
+    const int cside = dir ? 0 : 1;
+    const GridInfo g = info[static_cast<size_t>(cside) * B + b];
+    const int G = g.G;
+    const unsigned *st = starts + (static_cast<size_t>(cside) * B + b) * (G * G * G + 1);
+    unsigned long long *keys = dir ? ky + static_cast<size_t>(b) * P2 : kx + static_cast<size_t>(b) * P1;
+
+    const float *qf = reinterpret_cast<const float *>(qpts) + static_cast<size_t>(qi >> 1) * 8 + (qi & 1);
+    const float qx = qf[0], qy = qf[2], qz = qf[4];
+    const unsigned qw = __float_as_uint(qf[6]);
+    const unsigned long long nqx = dup_neg_f32x2(qx), nqy = dup_neg_f32x2(qy), nqz = dup_neg_f32x2(qz);
+    const int cx = cell_coord(qx, g.mnx, g.inv_h, G), cy = cell_coord(qy, g.mny, g.inv_h, G), cz = cell_coord(qz, g.mnz, g.inv_h, G);
+    float bd = INFINITY;
+    // ---- step 1: the 3x3x3 block around the query's cell (the nine table look-ups first: they are independent loads) ----
+    {
+        const int xa = max(cx - 1, 0), xb = min(cx + 1, G - 1);
+        unsigned ra[9], re[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            const int z = cz + k / 3 - 1, yy = cy + k % 3 - 1;
+            const bool in = z >= 0 && z < G && yy >= 0 && yy < G;
+            const unsigned row = static_cast<unsigned>((z * G + yy) * G);
+            ra[k] = in ? __ldg(st + row + xa) : 0u;
+            re[k] = in ? __ldg(st + row + xb + 1) : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < 9; ++k) scan_pairs(cand, ra[k], re[k], nqx, nqy, nqz, bd);
+    }
+    // (bounds and margins: see grid_nn_kernel)
+    float bound = INFINITY;
+    if (cx - 1 > 0) bound = fminf(bound, qx - (g.mnx + static_cast<float>(cx - 1) * g.h));
+    if (cx + 2 < G) bound = fminf(bound, (g.mnx + static_cast<float>(cx + 2) * g.h) - qx);
+    if (cy - 1 > 0) bound = fminf(bound, qy - (g.mny + static_cast<float>(cy - 1) * g.h));
+    if (cy + 2 < G) bound = fminf(bound, (g.mny + static_cast<float>(cy + 2) * g.h) - qy);
+    if (cz - 1 > 0) bound = fminf(bound, qz - (g.mnz + static_cast<float>(cz - 1) * g.h));
+    if (cz + 2 < G) bound = fminf(bound, (g.mnz + static_cast<float>(cz + 2) * g.h) - qz);
+    bound -= g.margin;
+    const bool done = bound == INFINITY || (bd != INFINITY && bound > 0.0f && bd < bound * bound * 0.99998f);
+    const bool need = !done;
+    if (__any_sync(FULL_MASK, need)) {
+        if (__any_sync(FULL_MASK, need && bd == INFINITY)) {
+            // upper bound from a strided sample of the candidates (<= 128 points, the same for every lane)
+            // (<= 64 pairs, every (Pc / 128 + 1)-th pair: a strided sample of the candidates, the same for every lane)
+            scan_pairs(cand, 0u, static_cast<unsigned>(Pc), nqx, nqy, nqz, bd, static_cast<unsigned>(Pc) / 128u + 1u);
+        }
+        const float R = need ? sqrtf(bd) * 1.0001f + g.margin : 0.0f;
+        float lo[3] = {need ? qx - R : INFINITY, need ? qy - R : INFINITY, need ? qz - R : INFINITY};
+        float hi[3] = {need ? qx + R : -INFINITY, need ? qy + R : -INFINITY, need ? qz + R : -INFINITY};
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                lo[a] = fminf(lo[a], __shfl_xor_sync(FULL_MASK, lo[a], o));
+                hi[a] = fmaxf(hi[a], __shfl_xor_sync(FULL_MASK, hi[a], o));
+            }
+        }
+        const int xa = max(cell_coord(lo[0], g.mnx, g.inv_h, G) - 1, 0), xb = min(cell_coord(hi[0], g.mnx, g.inv_h, G) + 1, G - 1);
+        const int ya = max(cell_coord(lo[1], g.mny, g.inv_h, G) - 1, 0), yb = min(cell_coord(hi[1], g.mny, g.inv_h, G) + 1, G - 1);
+        const int za = max(cell_coord(lo[2], g.mnz, g.inv_h, G) - 1, 0), zb = min(cell_coord(hi[2], g.mnz, g.inv_h, G) + 1, G - 1);
+        const unsigned my_rows = __ldg(rowmask + (static_cast<size_t>(cside) * B + b) * 32 + (threadIdx.x & 31));
+        const unsigned ymask = (yb >= 31 ? 0xffffffffu : (1u << (yb + 1)) - 1u) & ~((1u << ya) - 1u);
+        for (int z = za; z <= zb; ++z) {
+            unsigned rows = __shfl_sync(FULL_MASK, my_rows, z) & ymask;
+            if (rows == 0u) continue;
+            const float gz = slab_gap(qz, g.mnz, g.h, z, g.margin);
+            if (__all_sync(FULL_MASK, !need || gz * gz * 0.9999f > bd)) continue;
+            for (; rows != 0u; rows &= rows - 1u) {
+                const int yy = __ffs(rows) - 1;
+                const float gy = slab_gap(qy, g.mny, g.h, yy, g.margin);
+                const float rem = bd - (gz * gz + gy * gy) * 0.9999f;
+                const bool hit = need && rem >= 0.0f;
+                if (!__any_sync(FULL_MASK, hit)) continue;
+                const float rx = hit ? sqrtf(rem) * 1.0001f + g.margin : 0.0f;
+                const int lx = hit ? cell_coord(qx - rx, g.mnx, g.inv_h, G) : G;
+                const int hx = hit ? cell_coord(qx + rx, g.mnx, g.inv_h, G) : -1;
+                const int xa2 = max(xa, __reduce_min_sync(FULL_MASK, lx)), xb2 = min(xb, __reduce_max_sync(FULL_MASK, hx));
+                if (xa2 > xb2) continue;
+                const unsigned row = static_cast<unsigned>((z * G + yy) * G);
+                scan_pairs(cand, __ldg(st + row + xa2), __ldg(st + row + xb2 + 1), nqx, nqy, nqz, bd);
+            }
+        }
+    }
+    if (qi_raw >= Pq) return;
+    keys[qw] = pack_key(bd, 0u);
+}
+
 int64_t chamfer_grid_extra_bytes(int B, int P1, int P2, int G) {
-    const int64_t pts = static_cast<int64_t>(B) * (static_cast<int64_t>(P1) + P2) * 16;
+    const int64_t pts = static_cast<int64_t>(B) * (((static_cast<int64_t>(P1) + 1) & ~1ll) + ((static_cast<int64_t>(P2) + 1) & ~1ll)) * 16;
     const int64_t tab = 2ll * B * (static_cast<int64_t>(G) * G * G + 1) * 4;
     return pts + ((tab + 15) / 16) * 16 + 2ll * B * static_cast<int64_t>(sizeof(GridInfo)) + 2ll * B * 32 * 4;
 }
@@ -448,14 +630,14 @@ int grid_build_single(const float *pts, int B, int P, int G, float4 *sorted, uns
     int d = 0;
     if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) d = 0;
     if (!attr_done_dev[d]) {
-        const cudaError_t e = cudaFuncSetAttribute(grid_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 32 * 32 * 4 + 4);
+        const cudaError_t e = cudaFuncSetAttribute(grid_build_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 32 * 32 * 4 + 4);
         if (e != cudaSuccess) {
             set_error("grid build: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
             return static_cast<int>(e);
         }
         attr_done_dev[d] = true;
     }
-    grid_build_kernel<<<dim3(B, 1), GRID_BUILD_THREADS, static_cast<size_t>(G) * G * G * 4 + 4, st>>>(pts, pts, P, P, G, sorted, starts, info,
+    grid_build_kernel<false><<<dim3(B, 1), GRID_BUILD_THREADS, static_cast<size_t>(G) * G * G * 4 + 4, st>>>(pts, pts, P, P, G, sorted, starts, info,
                                                                                                   rowmask);
     return check_launch("grid_build_kernel");
 }
@@ -472,9 +654,11 @@ int chamfer_grid_pick(int P1, int P2) {   // grid resolution, or 0: use the brut
 
 // extra = 16-byte aligned workspace region behind the two key arrays (chamfer_grid_extra_bytes); fills kx and (if ky) ky
 int chamfer_grid_run(const float *x, const float *y, int B, int P1, int P2, int G, unsigned long long *kx,
-                     unsigned long long *ky, void *extra, cudaStream_t st) {
+                     unsigned long long *ky, bool want_idx, void *extra, cudaStream_t st) {
     float4 *sorted = static_cast<float4 *>(extra);
-    const int64_t pts = static_cast<int64_t>(B) * (static_cast<int64_t>(P1) + P2) * 16;
+    const int64_t pts = static_cast<int64_t>(B) * (((static_cast<int64_t>(P1) + 1) & ~1ll) + ((static_cast<int64_t>(P2) + 1) & ~1ll)) * 16;
+    static const bool keyed_only = getenv("PCC_CHAMFER_KEYED") != nullptr;   // A/B: the keyed kernel also when no index is wanted
+    const bool d2_only = !want_idx && !keyed_only;
     const int64_t tab = 2ll * B * (static_cast<int64_t>(G) * G * G + 1) * 4;
     unsigned *starts = reinterpret_cast<unsigned *>(static_cast<char *>(extra) + pts);
     GridInfo *info = reinterpret_cast<GridInfo *>(static_cast<char *>(extra) + pts + ((tab + 15) / 16) * 16);
@@ -484,18 +668,22 @@ int chamfer_grid_run(const float *x, const float *y, int B, int P1, int P2, int 
     int attr_done_d = 0;
     if (cudaGetDevice(&attr_done_d) != cudaSuccess || attr_done_d < 0 || attr_done_d >= 64) attr_done_d = 0;
     if (!attr_done_dev[attr_done_d]) {
-        const cudaError_t e = cudaFuncSetAttribute(grid_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 32 * 32 * 4 + 4);
+        cudaError_t e = cudaFuncSetAttribute(grid_build_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 32 * 32 * 4 + 4);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(grid_build_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 32 * 32 * 4 + 4);
         if (e != cudaSuccess) {
             set_error("chamfer grid: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
             return static_cast<int>(e);
         }
         attr_done_dev[attr_done_d] = true;
     }
-    grid_build_kernel<<<dim3(B, 2), GRID_BUILD_THREADS, smem, st>>>(x, y, P1, P2, G, sorted, starts, info, rowmask);
+    if (d2_only) grid_build_kernel<true><<<dim3(B, 2), GRID_BUILD_THREADS, smem, st>>>(x, y, P1, P2, G, sorted, starts, info, rowmask);
+    else grid_build_kernel<false><<<dim3(B, 2), GRID_BUILD_THREADS, smem, st>>>(x, y, P1, P2, G, sorted, starts, info, rowmask);
     int rc = check_launch("grid_build_kernel");
     if (rc) return rc;
     const int pmax = P1 > P2 ? P1 : P2;
-    grid_nn_kernel<<<dim3((pmax + 127) / 128, B, ky ? 2 : 1), 128, 0, st>>>(P1, P2, sorted, starts, info, rowmask, kx, ky);
+    const dim3 grid((pmax + 127) / 128, B, ky ? 2 : 1);
+    if (d2_only) grid_nn_d2_kernel<<<grid, 128, 0, st>>>(P1, P2, sorted, starts, info, rowmask, kx, ky);
+    else grid_nn_kernel<<<grid, 128, 0, st>>>(P1, P2, sorted, starts, info, rowmask, kx, ky);
     return check_launch("grid_nn_kernel");
 }
 

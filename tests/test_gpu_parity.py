@@ -402,7 +402,7 @@ def _adversarial_pair(kind, P1, P2, seed):
 
 
 @pytest.mark.parametrize("kind", ["ties", "identical", "outliers", "offset", "disjoint", "line"])
-@pytest.mark.parametrize("P1,P2", [(4096, 4096), (1024, 2500)])
+@pytest.mark.parametrize("P1,P2", [(4096, 4096), (1024, 2500), (2049, 1025)])
 def test_chamfer_grid_path_adversarial_vs_oracle(pcc, orc, kind, P1, P2):
     """The grid-pruned search (clouds >= 1024 points) must return exactly what the exhaustive search returns."""
     x, y = _adversarial_pair(kind, P1, P2, seed=P1 + len(kind))
@@ -411,6 +411,10 @@ def test_chamfer_grid_path_adversarial_vs_oracle(pcc, orc, kind, P1, P2):
     assert np.array_equal(r["dx"].cpu().numpy(), dx) and np.array_equal(r["dy"].cpu().numpy(), dy)
     assert np.array_equal(r["ix"].cpu().numpy(), ix) and np.array_equal(r["iy"].cpu().numpy(), iy)
     assert abs(r["loss"].item() - loss) <= CHAMFER_RTOL * abs(loss) + 1e-30
+    # the distance-only form (no index wanted: packed-fp32 loop over paired candidates) returns the same minima, bit for bit
+    n = pcc.ops.chamfer_forward(cu(x), cu(y), want_idx=False)
+    assert np.array_equal(n["dx"].cpu().numpy(), dx) and np.array_equal(n["dy"].cpu().numpy(), dy)
+    assert torch.equal(n["per_cloud"], r["per_cloud"]) and torch.equal(n["loss"], r["loss"])
 
 
 def test_chamfer_full_batch_properties(pcc):
@@ -425,6 +429,9 @@ def test_chamfer_full_batch_properties(pcc):
     d, i = pcc.ops.nn1(x, y)
     assert torch.equal(d, a["dx"]) and torch.equal(i, a["ix"])
     assert abs(a["per_cloud"].double().mean().item() - a["loss"].item()) <= 1e-6 * a["loss"].item()
+    n = pcc.ops.chamfer_forward(x, y, want_idx=False)     # eval.py's form: distances only
+    assert torch.equal(n["dx"], a["dx"]) and torch.equal(n["dy"], a["dy"]) and torch.equal(n["per_cloud"], a["per_cloud"])
+    assert n["ix"] is None and n["iy"] is None
 
 
 def test_d1_psnr_inner_step(pcc, orc, g_p3d):
