@@ -243,12 +243,20 @@ def ae_forward_train(mod, xyz):
     xyz = xyz.contiguous()
     BS, P, _ = xyz.shape
     K = mod.sa.K
-    with torch.no_grad():
-        _, _, grouped = ops.knn(xyz, xyz, K, return_nn=True, centre_sub=True, nn_only=True)            # pn_kit.py:190-191
     sa_l = [(getattr(mod.sa, f"conv{i}").weight.flatten(1), getattr(mod.sa, f"conv{i}").bias, True if i < 2 else bool(mod.sa.finalRelu))
             for i in range(3)]
-    x1 = T.fold_first_train(grouped.reshape(BS * P * K, 3), sa_l[0][0], sa_l[0][1])                   # conv0 in fp32 on the CUDA cores
-    feat = T.mlp_train(x1, sa_l[1:], group=K, mode="pool", x0_is_relu=True)                           # pn_kit.py:196-207  [BS*P, 128]
+    fused = (K == 16 and P <= 256 and P % 8 == 0 and sa_l[2][2] and [tuple(w.shape) for w, _, _ in sa_l] == [(32, 3), (64, 32), (128, 64)]
+             and all(b is not None for _, b, _ in sa_l) and not os.environ.get("PCC_SA_TRAIN_UNFUSED"))
+    if fused:
+        # one forward kernel (the inference one: no activation is kept) and one backward kernel that recomputes them per tile
+        with torch.no_grad():
+            idx8 = ops.knn_patch_u8(xyz, K)                                                            # pn_kit.py:190
+        feat = T.sa_indexed_train(xyz, idx8, sa_l)                                                     # pn_kit.py:191-207  [BS*P, 128]
+    else:
+        with torch.no_grad():
+            _, _, grouped = ops.knn(xyz, xyz, K, return_nn=True, centre_sub=True, nn_only=True)        # pn_kit.py:190-191
+        x1 = T.fold_first_train(grouped.reshape(BS * P * K, 3), sa_l[0][0], sa_l[0][1])               # conv0 in fp32 on the CUDA cores
+        feat = T.mlp_train(x1, sa_l[1:], group=K, mode="pool", x0_is_relu=True)                       # pn_kit.py:196-207  [BS*P, 128]
     pn_l = _grad_layers_stack(mod.pn)
     w0 = pn_l[0][0]
     pn_l[0] = (torch.cat((w0[:, 3:], w0[:, :3]), dim=1), pn_l[0][1], pn_l[0][2])                      # AE.py:39 cat(xyz, feat) -> [feat | xyz]

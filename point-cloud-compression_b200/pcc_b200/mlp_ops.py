@@ -151,6 +151,28 @@ def sa_chain_indexed(patches, idx8, layers, out_dtype=torch.float32):
     return out
 
 
+def sa_chain_indexed_bwd(patches, idx8, params, grad_out):
+    """Parameter gradients of sa_chain_indexed (csrc/sa_bwd.cu): params = (w0 [32,3], b0, w1 [64,32], b1, w2 [128,64], b2) fp32,
+    grad_out [BS * P, 128] -> six fp32 tensors shaped like params."""
+    lib = _lib.load()
+    _check(patches)
+    BS, P, _ = patches.shape
+    patches = patches.float().contiguous()
+    idx8 = idx8.contiguous()
+    ps = [t.detach().float().contiguous() for t in params]
+    if [tuple(t.shape) for t in ps] != [(32, 3), (32,), (64, 32), (64,), (128, 64), (128,)]:
+        raise ValueError("pcc_b200.sa_chain_indexed_bwd: the stack must be 3 -> 32 -> 64 -> 128")
+    g = grad_out.detach().float().contiguous()
+    if tuple(g.shape) != (BS * P, 128):
+        raise ValueError("pcc_b200.sa_chain_indexed_bwd: grad_out must be [BS * P, 128]")
+    grads = [torch.zeros_like(t) for t in ps]
+    with torch.cuda.device(patches.device):
+        _lib.check(lib.pcc_sa_chain_indexed_bwd(patches.data_ptr(), idx8.data_ptr(), BS * P, P, *[t.data_ptr() for t in ps], g.data_ptr(),
+                                                *[t.data_ptr() for t in grads], torch.cuda.current_stream().cuda_stream),
+                   "pcc_sa_chain_indexed_bwd")
+    return grads
+
+
 _bf16_cache = {}
 
 

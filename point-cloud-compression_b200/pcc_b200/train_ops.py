@@ -186,6 +186,31 @@ def fold_first_train(local, w, b):
     return _FoldFirst.apply(local.contiguous(), w, b)
 
 
+class _SaIndexed(torch.autograd.Function):
+    """pn_kit.SetAbstraction's shared MLP + max over the neighbours as one forward kernel (mlp_ops.sa_chain_indexed, the inference
+    kernel: nothing is kept but the inputs) and one backward kernel that recomputes the activations (csrc/sa_bwd.cu)."""
+
+    @staticmethod
+    def forward(ctx, patches, idx8, w0, b0, w1, b1, w2, b2):
+        layers = [(w0.detach(), b0.detach(), True), (w1.detach(), b1.detach(), True), (w2.detach(), b2.detach(), True)]
+        out = mlp_ops.sa_chain_indexed(patches, idx8, layers, out_dtype=torch.float32)
+        ctx.save_for_backward(patches, idx8, w0, b0, w1, b1, w2, b2)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        patches, idx8, *params = ctx.saved_tensors
+        grads = mlp_ops.sa_chain_indexed_bwd(patches, idx8, params, dout)
+        return (None, None) + tuple(g.to(p.dtype).reshape(p.shape) for g, p in zip(grads, params))
+
+
+def sa_indexed_train(patches, idx8, layers):
+    """Differentiable SetAbstraction stack (3 -> 32 -> 64 -> 128, ReLU everywhere, max over the 16 in-patch neighbours of idx8):
+    patches [BS, P, 3] fp32 (no gradient), layers [(weight, bias, True)] x 3 -> fp32 [BS * P, 128]."""
+    (w0, b0, _), (w1, b1, _), (w2, b2, _) = layers
+    return _SaIndexed.apply(patches, idx8, w0, b0, w1, b1, w2, b2)
+
+
 def pad_bf16(t, width):
     """fp32 / bf16 [M, C] -> bf16 [M, width] with zero columns past C (differentiable)."""
     t = t.to(torch.bfloat16)

@@ -82,8 +82,11 @@ def _emu_ae_forward(ae, xyz):
     with torch.no_grad():
         _, _, grouped = ops.knn(xyz, xyz, 16, return_nn=True, centre_sub=True, nn_only=True)
     sa = ae.sa.layers()
-    x1 = _r16(torch.relu(grouped.reshape(-1, 3) @ sa[0][0].t() + sa[0][1]))      # conv0: fp32 on the CUDA cores, stored as bf16
-    feat = _emu_stack(x1, sa[1:], 16, "pool")
+    # the fused SetAbstraction kernels (chain_ws.cu / sa_bwd.cu): conv0 in fp32 stored as bf16, conv1's bias as a bf16 operand, conv2's
+    # accumulators stay fp32 through the max, its bias (fp32) and the ReLU come after the max
+    x1 = _r16(torch.relu(grouped.reshape(-1, 3) @ sa[0][0].t() + sa[0][1]))
+    x2 = _r16(torch.relu(x1 @ _r16(sa[1][0]).t() + _r16(sa[1][1])))
+    feat = torch.relu((x2 @ _r16(sa[2][0]).t()).view(-1, 16, sa[2][0].shape[0]).max(dim=1)[0] + sa[2][1])
     raw = _emu_stack(torch.cat((xyz.reshape(-1, 3), feat), dim=1), ae.pn.layers(), P, "pool")
     spread = ae.L - 0.2
     latent = torch.sigmoid(raw) * spread - spread / 2
@@ -225,3 +228,40 @@ def test_trainer_ddp_world_size_one_nccl():
         if created:
             dist.destroy_process_group()
     assert all(np.isfinite(ddp_losses)) and np.allclose(ddp_losses, plain, rtol=1e-4)
+
+
+def test_sa_fused_backward_matches_autograd_of_the_bf16_model():
+    """train_ops.sa_indexed_train: forward = the inference SetAbstraction kernel, backward = csrc/sa_bwd.cu (activations recomputed
+    per tile, weight gradients accumulated in TMEM) against torch autograd on the bf16-operand statement of the same forward
+    (pn_kit.py:190-207): outputs within bf16 rounding, every parameter gradient within 1e-2 relative L2 (the kernel stores dY2,
+    dX2 and dX1 as bf16 where torch keeps fp32)."""
+    import __graft_entry__  # noqa: F401
+    from pcc_b200 import ops, train_ops
+    torch.manual_seed(5)
+    BS, P = 24, 256                                            # 6144 points = 768 tiles: several tiles per slot, ragged over the CTAs
+    patches = (torch.from_numpy(synth.modelnet_like(1, BS * P, seed=21)).cuda().view(BS, P, 3) - 0.5).contiguous()
+    idx8 = ops.knn_patch_u8(patches, 16)
+    g = torch.Generator().manual_seed(7)
+    ws = []
+    for cin, cout in ((3, 32), (32, 64), (64, 128)):
+        ws.append((torch.randn(cout, cin, generator=g) / cin ** 0.5).cuda().requires_grad_())
+        ws.append((0.1 * torch.randn(cout, generator=g)).cuda().requires_grad_())
+    G = torch.randn(BS * P, 128, generator=g).cuda()
+
+    out = train_ops.sa_indexed_train(patches, idx8, [(ws[0], ws[1], True), (ws[2], ws[3], True), (ws[4], ws[5], True)])
+    (out * G).sum().backward()
+    got = [w.grad.clone() for w in ws]
+    for w in ws:
+        w.grad = None
+
+    nb = torch.gather(patches, 1, idx8.long().reshape(BS, P * 16, 1).expand(-1, -1, 3)).view(BS, P, 16, 3)
+    local = (nb - patches.unsqueeze(2)).reshape(-1, 3)                                    # pn_kit.py:191
+    x1 = _r16(torch.relu(local @ ws[0].t() + ws[1]))
+    x2 = _r16(torch.relu(x1 @ _r16(ws[2]).t() + _r16(ws[3])))
+    y2 = x2 @ _r16(ws[4]).t()
+    ref = torch.relu(y2.view(-1, 16, 128).max(dim=1)[0] + ws[5])
+    (ref * G).sum().backward()
+    assert (out - ref).abs().max().item() <= 2e-2 * ref.abs().max().item()
+    for name, a, w in zip(("w0", "b0", "w1", "b1", "w2", "b2"), got, ws):
+        r = (a - w.grad).norm().item() / w.grad.norm().item()
+        assert r < 1e-2, f"{name}: relative L2 error {r:.3e}"
