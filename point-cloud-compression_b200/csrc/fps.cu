@@ -16,6 +16,8 @@
 //   over C = ceil(N/8192) co-resident CTAs (cooperative launch), still register resident; per iteration each
 //   CTA publishes its best candidate as tagged 64-bit words in its own slot and polls the other CTAs' slots
 //   (no atomics, no fences: see the comment above the kernel).
+#include <stdlib.h>
+
 #include "pcc_common.cuh"
 
 namespace pcc {
@@ -187,7 +189,11 @@ fps_block_kernel(const float *__restrict__ xyz, int N, int npoint, const int64_t
 // and, not kept: one polling thread per slot instead of one warp (4.16 at C = 123: more pollers, more contention), eight
 // replicas of the table (no better), a reducer CTA that republishes the winner to an outbox (3.8 us already at C = 2) and
 // two-level groups of 8..32 CTAs (5.4-5.7 us at C = 123): a second, dependent store -> poll hop costs 1.3 us or more, far more
-// than the polling traffic it saves.
+// than the polling traffic it saves.  Round 2 repeated that with thread-block clusters of 8 (cooperative + cluster launch, 16
+// clusters for 1M points): (a) candidates pushed into every peer's shared memory (st.shared::cluster, local polling), the
+// cluster winner through a 16-slot global table: 5.76 us / iteration; (b) the flat global table polled by one CTA per cluster
+// only, which pushes the winner to its peers over DSMEM: 5.15 us -- against 4.40 us for this kernel on the same box.  Both were
+// bit-exact against the oracle and both lose: the dependent DSMEM hop costs more than the polling traffic it removes.
 // Instrumented with clock64 (1.97 GHz): CTA-local update + block arg-max 2020 clocks; publish -> every slot fresh 3300 clocks at
 // C = 13 (one slot per lane: the bare store -> visible -> polled latency across the two dies) and 7750 at C = 123; barrier +
 // unpacking the coordinates 215 (the instrumented kernel is ~30 % slower than the plain one: read these as proportions).
@@ -389,8 +395,8 @@ PCC_API int pcc_fps_f32(const float *xyz, int B, int N, int npoint, const int64_
         set_error("pcc_fps_f32: N=%d exceeds the co-resident capacity %d", N, sms * GRID_PTS_PER_CTA);
         return PCC_ERR_UNSUPPORTED;
     }
-    const int clouds_per_launch = sms / C;
     unsigned long long *ws = static_cast<unsigned long long *>(workspace);   // 2 x 32 bytes per CTA of a launch
+    const int clouds_per_launch = sms / C;
     for (int c0 = 0; c0 < B; c0 += clouds_per_launch) {
         int nc = B - c0 < clouds_per_launch ? B - c0 : clouds_per_launch;
         cudaError_t e = cudaMemsetAsync(ws, 0, sizeof(unsigned long long) * 8 * nc * C, st);

@@ -89,6 +89,15 @@ def test_fps_multi_cta_iteration_tag_wrap(pcc, orc):
         assert np.array_equal(got, orc.fps(xyz, 4200, start, 1e10, threads=8))
 
 
+def test_fps_multi_cta_18_ctas_ties_and_wrap(pcc, orc):
+    """140,000 points = 18 CTAs per cloud, two clouds (7 co-resident clouds per launch would fit: the batch loop), 2,200
+    iterations (one tag wrap), grid-quantised points (exact ties everywhere) and uniform ones, every index against the oracle."""
+    xyz = np.concatenate((synth.grid_quantised(1, 140_000, depth=6, seed=91), synth.uniform_cube(1, 140_000, seed=92)), axis=0)
+    start = np.array([5, 139_999], np.int64)
+    got = pcc.ops.fps(cu(xyz), 2200, cu(start), 1e10).cpu().numpy()
+    assert np.array_equal(got, orc.fps(xyz, 2200, start, 1e10, threads=8))
+
+
 @pytest.mark.parametrize("name", ["sfp", "sfp_pad", "sfp_ties"])
 def test_sample_farthest_points_golden(pcc, g_p3d, name):
     pts, idx = pcc.sample_farthest_points(cu(g_p3d[f"{name}_x"]), K=int(g_p3d[f"{name}_K"]))
