@@ -384,16 +384,18 @@ def run_b200(args):
                                                "useful_frac": pairs * 8.0 / (kernel_ms["knn_in_patch"] / 1e3) / fp32_peak}
             if "chamfer" in kernel_ms:       # exact grid-pruned Chamfer: algorithmic pairs = P1 * P2 per cloud, mostly culled
                 pairs = 1.0 * BATCH * N_POINTS * N_POINTS
-                others["grid_nn_kernel (+ build, finalize)"] = {
-                    "ms_per_launch": kernel_ms["chamfer"], "algorithmic_pair_evals": pairs, "bound": "L1 / FP32 issue",
+                others["grid_nn_d2_kernel (+ build, finalize)"] = {
+                    "ms_per_launch": kernel_ms["chamfer"], "algorithmic_pair_evals": pairs, "bound": "FP32 pipe / load latency",
                     "algorithmic_gpairs_per_s": pairs / (kernel_ms["chamfer"] / 1e3) / 1e9,
-                    "evaluated_pairs_est": 0.22e9, "cull_ratio_est": 0.10,
-                    "fp32_issue_frac_est": 0.22e9 * 8.0 / (kernel_ms["chamfer"] / 1e3) / fp32_peak,
+                    "evaluated_pairs_est": 0.25e9, "cull_ratio_est": 0.12,
+                    "fp32_issue_frac_est": 0.25e9 * 8.0 / (kernel_ms["chamfer"] / 1e3) / fp32_peak,
                     "note": "pairs evaluated << algorithmic pairs (exact culling): ~677 candidates per query in the far direction "
-                            "(original -> clumpy reconstruction) + ~32 in the near one + the 128-point bound sample, from the "
-                            "instrumented counts in DESIGN.md 4 -- ~10 % of the algorithmic pairs; the kernel is issue bound (77 % "
-                            "issue-active, profiles/r02_step_kernels_ncu_full.txt), the brute-force kernel it replaces ran at 0.90 "
-                            "of the FP32 issue roof (profiles/r01_chamfer_ncu_full.txt)"}
+                            "(original -> clumpy reconstruction) + ~32 in the near one + the 128-point bound sample (instrumented "
+                            "counts, DESIGN.md 4), widened to whole pairs -- ~12 % of the algorithmic pairs.  eval.py wants no "
+                            "indices, so the distance-only kernel runs: two candidates per packed-fp32 instruction, 7.3 issue slots "
+                            "per candidate instead of 14.7 (profiles/r02_step_kernels_ncu_full.txt: FMA pipe ~45 %, issue ~60 %, "
+                            "stalls on the candidate loads); the brute-force kernel it replaces ran at 0.90 of the FP32 issue roof "
+                            "(profiles/r01_chamfer_ncu_full.txt)"}
             if "pn_tail" in kernel_ms:       # 256-512-16 + max: tensor pipe, weights streamed from L2
                 fl = BATCH * (N_POINTS * ALPHA // K_PATCH) * K_PATCH * 2.0 * (256 * 512 + 512 * D_LATENT)
                 others["pn_tail_kernel"] = {"ms_per_launch": kernel_ms["pn_tail"], "bound": "tensor",
@@ -410,8 +412,10 @@ def run_b200(args):
                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src + " bf16_tflops_sustained (kernel timed inside a long step)",
                         "ms_per_launch": ms, "flop_per_launch": flop,
                         "note": "K is 32..64 per layer, so the kernel is paced by the MMA -> epilogue -> MMA hand-offs of its four "
-                                "tiles in flight per SM (TMEM: 128 accumulator columns per tile) and by the per-warp latency of the "
-                                "epilogue / fp32 layer-0 code, not by the tensor pipe; see DESIGN.md 4 and profiles/",
+                                "tiles in flight per SM (all 512 TMEM columns: 128 accumulator columns per tile) -- tensor pipe and "
+                                "tensor-core shared-memory reads are ~45-50 % busy each, issue ~55 % (profiles/r02_step_kernels_ncu_full.txt); "
+                                "round 2: one 640-thread CTA per SM with four slots, fma.rn.f32x2 layer 0, layer 2 issued by the "
+                                "epilogue group (0.40 -> 0.59); see DESIGN.md 4",
                         "other_kernels": others}
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
