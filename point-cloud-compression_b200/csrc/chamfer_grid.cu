@@ -309,6 +309,10 @@ grid_nn_kernel(int P1, int P2, const float4 *__restrict__ sorted, const unsigned
 // same minima, bit for bit -- but the running best is a float and the distance of TWO candidates costs 8 packed fp32
 // instructions (add / mul .f32x2: each half is the IEEE operation of dist2_rn; (c - q)^2 == (q - c)^2 exactly), 4 scalar adds and
 // one 3-input min: 7.3 issue slots per candidate against 14.7 for the keyed loop, which was issue bound.
+// (Measured beside it: the plain float4 layout with (x, y) of ONE candidate packed -- 8 issue slots per candidate, no paired
+// scatter in the build: 260 us against 238 us on the bench's clumpy reconstructions, 107 us against ~125 us on close clouds where
+// the 3x3x3 step and the build dominate (keyed kernel: 286 / 119 us).  Looking one row ahead with the table look-ups of the far
+// walk, and double-buffering the candidate batches, changed nothing / lost 4 %.)
 __device__ __forceinline__ unsigned long long add_f32x2(unsigned long long a, unsigned long long b) {
     unsigned long long r;
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
