@@ -324,6 +324,15 @@ def mlp_chain_groupmax(x, layers, group):
 _wpad_cache = {}
 
 
+def invalidate_weight_caches():
+    """Drop every cached bf16 / packed copy of a weight.  The caches are keyed on the parameters' version counters, which an
+    in-place update made outside autograd's book-keeping does not bump -- torch.optim.Adam(fused=True) is one: the trainer calls
+    this around every optimiser step, and so should anybody who writes into a parameter's storage by other means."""
+    _pack_cache.clear()
+    _wpad_cache.clear()
+    _bf16_cache.clear()
+
+
 def _w_bf16_padded(w, b, kpad, npad):
     """[cout, cin] parameter (+ bias) -> cached (bf16 [npad, kpad] with zero rows / columns past the data, fp32 bias [npad])."""
     bw, bb = _base(w), _base(b)
