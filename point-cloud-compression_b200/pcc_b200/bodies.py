@@ -32,7 +32,9 @@ def has_train_mode_bn(mod):
 
 
 def _state_key(mod):
-    return tuple((t.data_ptr(), t._version) for t in list(mod.parameters()) + list(mod.buffers()))
+    # (storage, version) of every parameter / buffer + the epoch that mlp_ops.invalidate_weight_caches() bumps (updates that do
+    # not touch the version counters, e.g. torch's fused optimiser kernels)
+    return (mlp_ops._weights_epoch,) + tuple((t.data_ptr(), t._version) for t in list(mod.parameters()) + list(mod.buffers()))
 
 
 def _cached(mod, name, build):

@@ -322,12 +322,15 @@ def mlp_chain_groupmax(x, layers, group):
 
 # ---- streamed tensor-core GEMM layers (csrc/gemm_ws.cu): weights too large to sit beside the activations ---------------
 _wpad_cache = {}
+_weights_epoch = 0
 
 
 def invalidate_weight_caches():
     """Drop every cached bf16 / packed copy of a weight.  The caches are keyed on the parameters' version counters, which an
     in-place update made outside autograd's book-keeping does not bump -- torch.optim.Adam(fused=True) is one: the trainer calls
     this around every optimiser step, and so should anybody who writes into a parameter's storage by other means."""
+    global _weights_epoch
+    _weights_epoch += 1        # part of bodies._state_key: per-module derived weights and captured graphs are rebuilt too
     _pack_cache.clear()
     _wpad_cache.clear()
     _bf16_cache.clear()

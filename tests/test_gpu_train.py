@@ -265,3 +265,32 @@ def test_sa_fused_backward_matches_autograd_of_the_bf16_model():
     for name, a, w in zip(("w0", "b0", "w1", "b1", "w2", "b2"), got, ws):
         r = (a - w.grad).norm().item() / w.grad.norm().item()
         assert r < 1e-2, f"{name}: relative L2 error {r:.3e}"
+
+
+def test_inference_after_fused_optimiser_steps_sees_the_new_weights():
+    """torch's fused Adam kernel updates parameters without bumping their version counters, which every weight cache keys on:
+    the trainer invalidates them (mlp_ops.invalidate_weight_caches).  The fused inference forward of the SAME module, and a
+    captured round-trip graph, must follow the trained weights."""
+    import __graft_entry__  # noqa: F401
+    from pcc_b200.codec import PatchCodec
+    from pcc_b200.train import Trainer
+    torch.manual_seed(2)
+    tr = Trainer(K=256, k=128, d=16, L=7, lr=1e-2, state_dict=synth.seeded_state_dict(synth.ae_shapes(128, 16, 7), 11))
+    x = torch.from_numpy(synth.modelnet_like(2, 2048, seed=61)).cuda()
+    start = torch.zeros(2, dtype=torch.int64, device="cuda")
+    codec = PatchCodec(tr.ae.eval(), centre_mode="coded")
+    run = codec.graphed_roundtrip(2, 2048)
+    # [2] = the per-cloud metrics (Chamfer, D1 PSNR, MSE) of the reconstruction: they move with every weight of the decoder
+    before, before_g = codec.roundtrip(x, start)[2].clone(), run(x, start)[2].clone()
+    assert torch.equal(before, before_g)
+    for _ in range(3):
+        tr.step(x, start)
+    tr.ae.eval()
+    with pytest.raises(RuntimeError):                          # the old capture points at the old packed weights
+        run(x, start)
+    run = codec.graphed_roundtrip(2, 2048)
+    after, after_g = codec.roundtrip(x, start)[2].clone(), run(x, start)[2].clone()
+    assert torch.equal(after, after_g)
+    assert not torch.equal(after, before)                      # three steps at lr = 1e-2 move the reconstruction
+    fresh = PatchCodec(tr.ae, centre_mode="coded")             # nothing cached in this object
+    assert torch.equal(fresh.roundtrip(x, start)[2], after)
