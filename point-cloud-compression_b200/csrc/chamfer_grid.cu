@@ -329,11 +329,6 @@ __device__ __forceinline__ unsigned long long dup_neg_f32x2(float x) {
     asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(n));
     return r;
 }
-__device__ __forceinline__ float2 unpack_f32x2(unsigned long long v) {
-    float2 r;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
-    return r;
-}
 __device__ __forceinline__ float fmin3(float a, float b, float c) {
     float r;
     asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));

@@ -46,4 +46,23 @@ constexpr unsigned FULL_MASK = 0xffffffffu;
 
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
 
+// packed fp32 (sm_100): two independent IEEE operations per instruction, operands are {lo, hi} register pairs.  They issue at
+// half rate -- no extra FP32 throughput, half the issue slots.  NOTE: ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into
+// FFMA2 whatever --fmad says; code that needs un-fused sums keeps them scalar (chamfer_grid.cu).
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ uint64_t dup_f32x2(float x) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float2 unpack_f32x2(uint64_t v) {
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+
 }  // namespace pcc

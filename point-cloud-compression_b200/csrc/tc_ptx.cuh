@@ -4,6 +4,8 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 
+#include "pcc_common.cuh"
+
 namespace pcc {
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------
@@ -158,17 +160,6 @@ __device__ __forceinline__ ulonglong2 ld_shared_v2u64(uint32_t addr) {   // read
 __device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {
     uint32_t r;
     asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-    return r;
-}
-// packed fp32: two independent IEEE fma.rn per instruction (FFMA2), operands are {lo, hi} register pairs
-__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
-    uint64_t r;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-    return r;
-}
-__device__ __forceinline__ uint64_t dup_f32x2(float x) {
-    uint64_t r;
-    asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(x));
     return r;
 }
 __device__ __forceinline__ uint32_t pack_relu_bf16x2_pair(uint64_t v) {   // low half of the result = low float of the pair
