@@ -230,15 +230,17 @@ def test_trainer_ddp_world_size_one_nccl():
     assert all(np.isfinite(ddp_losses)) and np.allclose(ddp_losses, plain, rtol=1e-4)
 
 
-def test_sa_fused_backward_matches_autograd_of_the_bf16_model():
+@pytest.mark.parametrize("BS,P", [(24, 256), (3, 200), (1, 16)])
+def test_sa_fused_backward_matches_autograd_of_the_bf16_model(BS, P):
     """train_ops.sa_indexed_train: forward = the inference SetAbstraction kernel, backward = csrc/sa_bwd.cu (activations recomputed
     per tile, weight gradients accumulated in TMEM) against torch autograd on the bf16-operand statement of the same forward
     (pn_kit.py:190-207): outputs within bf16 rounding, every parameter gradient within 1e-2 relative L2 (the kernel stores dY2,
-    dX2 and dX1 as bf16 where torch keeps fp32)."""
+    dX2 and dX1 as bf16 where torch keeps fp32).  24 x 256: 768 tiles, several per slot and ragged over the CTAs; 3 x 200: a patch
+    size that is not a power of two (75 tiles: one slot of the last CTA stays empty); 1 x 16: the smallest legal shape (one patch
+    of K points, two tiles, one CTA)."""
     import __graft_entry__  # noqa: F401
     from pcc_b200 import ops, train_ops
     torch.manual_seed(5)
-    BS, P = 24, 256                                            # 6144 points = 768 tiles: several tiles per slot, ragged over the CTAs
     patches = (torch.from_numpy(synth.modelnet_like(1, BS * P, seed=21)).cuda().view(BS, P, 3) - 0.5).contiguous()
     idx8 = ops.knn_patch_u8(patches, 16)
     g = torch.Generator().manual_seed(7)
