@@ -122,14 +122,20 @@ gather_concat_bf16_kernel(const float *__restrict__ feat, int C, const float *__
     constexpr int R = 4;
     const int chunks = kpad >> 3, lane = threadIdx.x & 31;
     const bool vec = feat && (C & 7) == 0;
+    // rows < 2^31 (checked by the launcher): the two divisions per row are 32-bit (the 64-bit form was ~100 instructions each,
+    // more than the rest of the row's work)
+    const unsigned Mu = static_cast<unsigned>(M), nsu = static_cast<unsigned>(nsample);
     for (long long r0 = (blockIdx.x * 8ll + (threadIdx.x >> 5)) * R; r0 < rows; r0 += static_cast<long long>(gridDim.x) * 8 * R) {
         long long src[R];
+        const float *cq[R];
 #pragma unroll
         for (int i = 0; i < R; ++i) {
-            const long long r = r0 + i < rows ? r0 + i : rows - 1;
+            const unsigned r = static_cast<unsigned>(r0 + i < rows ? r0 + i : rows - 1);
             long long j = __ldg(idx + r);
             j = j < 0 ? 0 : j;
-            src[i] = (r / M) * N + j;
+            src[i] = static_cast<long long>(r / Mu) * N + j;
+            // recentred grouping (pppe_pcd_ae.py:600): row r belongs to query r / nsample, whose xyz is subtracted in fp32
+            cq[i] = centre ? centre + static_cast<size_t>(r / nsu) * 3 : nullptr;
         }
         for (int ch = lane; ch < chunks; ch += 32) {
             const int c0 = ch * 8;
@@ -138,9 +144,6 @@ gather_concat_bf16_kernel(const float *__restrict__ feat, int C, const float *__
             for (int i = 0; i < R; ++i) {
                 const float *f = feat ? feat + src[i] * C : nullptr;
                 const float *p = xyz ? xyz + src[i] * 3 : nullptr;
-                // recentred grouping (pppe_pcd_ae.py:600): row r belongs to query r / nsample, whose xyz is subtracted in fp32
-                const long long rr = r0 + i < rows ? r0 + i : rows - 1;
-                const float *cq = centre ? centre + (rr / nsample) * 3 : nullptr;
                 float v[8];
                 if (vec && c0 + 8 <= C) {
                     const float4 a = __ldg(reinterpret_cast<const float4 *>(f + c0));
@@ -151,7 +154,7 @@ gather_concat_bf16_kernel(const float *__restrict__ feat, int C, const float *__
                     for (int e = 0; e < 8; ++e) {
                         const int c = c0 + e;
                         v[e] = (f && c < C) ? __ldg(f + c)
-                               : (p && c >= C && c < C + 3) ? (cq ? __fsub_rn(__ldg(p + (c - C)), __ldg(cq + (c - C))) : __ldg(p + (c - C)))
+                               : (p && c >= C && c < C + 3) ? (cq[i] ? __fsub_rn(__ldg(p + (c - C)), __ldg(cq[i] + (c - C))) : __ldg(p + (c - C)))
                                                             : 0.0f;
                     }
                 }
@@ -227,6 +230,7 @@ PCC_API int pcc_gather_concat_bf16(const float *feat, int C, const float *xyz, c
     PCC_REQUIRE(!centre || (xyz && nsample >= 1 && M % nsample == 0), "pcc_gather_concat_bf16: centre needs xyz and nsample | M");
     const long long rows = static_cast<long long>(B) * M;
     if (rows == 0) return 0;
+    PCC_REQUIRE(rows < (1ll << 31), "pcc_gather_concat_bf16: %lld rows exceed 2^31", rows);
     gather_concat_bf16_kernel<<<grid_for(rows * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         feat, C, xyz, idx, rows, N, M, kpad, static_cast<uint4 *>(out), centre, centre ? nsample : 1);
     return check_launch("gather_concat_bf16_kernel");
