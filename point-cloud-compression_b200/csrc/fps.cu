@@ -15,10 +15,11 @@
 // fps_grid_kernel: clouds with N > 8192 (the 1M-point scene).  The cloud is spread
 //   over C = ceil(N/8192) co-resident CTAs (cooperative launch), still register resident; per iteration each
 //   CTA publishes its best candidate as tagged 64-bit words in its own slot and polls the other CTAs' slots
-//   (no atomics, no fences: see the comment above the kernel).
+//   (no atomics, no fences: see the comment above the kernel).  From 65,536 points on the bucketed form of
+//   fps_bucket.cu takes over (same output, one CTA per cloud, exact spatial skipping); PCC_FPS_PATH=grid keeps this one.
 #include <stdlib.h>
 
-#include "pcc_common.cuh"
+#include "fps.cuh"
 
 namespace pcc {
 
@@ -94,20 +95,6 @@ __device__ __forceinline__ void select_slot(const float (&px)[PPT], const float 
             y = py[p];
             z = pz[p];
         }
-}
-
-// Optional fused epilogue: the sampled point itself (the index_points gather that follows every FPS call), optionally
-// snapped to the octree grid: floor(c / cube) * cube + cube / 2 (octree_np.getDecodeFromPc, octree_np.py:114-133).
-__device__ __forceinline__ void store_centre(float *o, float x, float y, float z, float cube) {
-    if (cube > 0.0f) {
-        const float h = __fmul_rn(cube, 0.5f);
-        x = __fadd_rn(__fmul_rn(floorf(__fdiv_rn(x, cube)), cube), h);
-        y = __fadd_rn(__fmul_rn(floorf(__fdiv_rn(y, cube)), cube), h);
-        z = __fadd_rn(__fmul_rn(floorf(__fdiv_rn(z, cube)), cube), h);
-    }
-    o[0] = x;
-    o[1] = y;
-    o[2] = z;
 }
 
 template <int THREADS, int PPT>
@@ -369,6 +356,7 @@ static int launch_block(const float *xyz, int B, int N, int npoint, const int64_
 PCC_API int64_t pcc_fps_workspace_bytes(int B, int N, int npoint) {
     (void)npoint;
     if (N <= pcc::GRID_PTS_PER_CTA || B <= 0) return 0;
+    if (pcc::fps_bucket_takes(N)) return pcc::fps_bucket_workspace_bytes(B, N);
     return static_cast<int64_t>(sizeof(pcc::FpsGridWs)) * pcc::num_sms();
 }
 
@@ -389,6 +377,8 @@ PCC_API int pcc_fps_f32(const float *xyz, int B, int N, int npoint, const int64_
 
     // multi-CTA path: C co-resident CTAs per cloud, as many clouds per cooperative launch as fit.
     PCC_REQUIRE(workspace, "pcc_fps_f32: N=%d needs a workspace of pcc_fps_workspace_bytes()", N);
+    // scene scale: Morton buckets with exact skipping, one CTA per cloud (fps_bucket.cu)
+    if (fps_bucket_takes(N)) return fps_bucket_run(xyz, B, N, npoint, start_idx, init_dist, out_idx, out_xyz, quant_cube, workspace, st);
     const int sms = num_sms();
     const int C = (N + GRID_PTS_PER_CTA - 1) / GRID_PTS_PER_CTA;
     if (C > sms || static_cast<long long>(C) * GRID_PTS_PER_CTA > GRID_IDX_MASK) {

@@ -98,6 +98,71 @@ def test_fps_multi_cta_18_ctas_ties_and_wrap(pcc, orc):
     assert np.array_equal(got, orc.fps(xyz, 2200, start, 1e10, threads=8))
 
 
+class _fps_path:
+    """PCC_FPS_PATH for the duration of a block ("bucket": fps_bucket.cu whenever it fits; "grid": the co-resident kernel)."""
+    def __init__(self, value):
+        self.value = value
+
+    def __enter__(self):
+        self.old = os.environ.get("PCC_FPS_PATH")
+        os.environ["PCC_FPS_PATH"] = self.value
+
+    def __exit__(self, *exc):
+        if self.old is None:
+            os.environ.pop("PCC_FPS_PATH", None)
+        else:
+            os.environ["PCC_FPS_PATH"] = self.old
+
+
+@pytest.mark.parametrize("case", ["scene", "ties", "uniform_pads", "duplicates", "identical", "two_clouds", "tiny"])
+def test_fps_bucket_form_vs_oracle(pcc, orc, case):
+    """The scene-scale form (Morton buckets + exact skipping, fps_bucket.cu) forced on clouds the oracle finishes in seconds:
+    every index against the oracle -- exact ties (grid-quantised points), a ragged last bucket, duplicated points (running
+    distance 0 early), one point repeated N times, two clouds per launch, the smallest cloud that reaches this path."""
+    if case == "scene":
+        xyz, S = synth.scene_like(60_000, seed=5), 3000
+    elif case == "ties":
+        xyz, S = synth.grid_quantised(1, 70_000, depth=5, seed=7), 2500
+    elif case == "uniform_pads":
+        xyz, S = synth.uniform_cube(1, 20_001, seed=8), 1500
+    elif case == "duplicates":
+        base = synth.uniform_cube(1, 3000, seed=9)
+        xyz, S = np.tile(base, (1, 5, 1)), 3500          # every point five times: 500 picks at distance 0 at the end
+    elif case == "identical":
+        xyz, S = np.full((1, 9000, 3), 0.25, np.float32), 40
+    elif case == "two_clouds":
+        xyz, S = np.concatenate((synth.scene_like(30_000, seed=1), synth.uniform_cube(1, 30_000, seed=2) * 3.0), 0), 1200
+    else:
+        xyz, S = synth.uniform_cube(1, 8200, seed=3), 300      # just above the single-CTA kernel's 8192 points
+    B, N = xyz.shape[:2]
+    start = np.array([(7919 * (b + 1)) % N for b in range(B)], np.int64)
+    with _fps_path("bucket"):
+        got, got_xyz = pcc.ops.fps(cu(xyz), S, cu(start), 1e10, return_xyz=True)
+    got = got.cpu().numpy()
+    assert np.array_equal(got, orc.fps(xyz, S, start, 1e10, threads=8))
+    assert np.array_equal(got_xyz.cpu().numpy(), np.take_along_axis(xyz, got[:, :, None], 1))
+
+
+def test_fps_bucket_form_pytorch3d_contract(pcc, orc):
+    """sample_farthest_points' contract on the bucketed form: start at index 0, FLT_MAX, -1 padding when K > N."""
+    xyz = synth.uniform_cube(2, 9000, seed=4)
+    with _fps_path("bucket"):
+        idx = pcc.ops.fps(cu(xyz), 9100, None, float(np.finfo(np.float32).max)).cpu().numpy()
+    want = orc.fps(xyz, 9000, np.zeros(2, np.int64), float(np.finfo(np.float32).max), threads=8)
+    assert np.array_equal(idx[:, :9000], want) and (idx[:, 9000:] == -1).all()
+
+
+def test_fps_bucket_form_equals_grid_form_at_scene_scale(pcc):
+    """1,000,000 points -> 7812 centres: the bucketed form (default from 65,536 points) against the co-resident multi-CTA
+    kernel on every iteration (the oracle prefix is test_scene_scale_cfg5's)."""
+    xyz = cu(synth.scene_like(1_000_000, seed=3))
+    start = cu(np.array([12345], np.int64))
+    a = pcc.ops.fps(xyz, 7812, start, 1e10)
+    with _fps_path("grid"):
+        b = pcc.ops.fps(xyz, 7812, start, 1e10)
+    assert torch.equal(a, b)
+
+
 @pytest.mark.parametrize("name", ["sfp", "sfp_pad", "sfp_ties"])
 def test_sample_farthest_points_golden(pcc, g_p3d, name):
     pts, idx = pcc.sample_farthest_points(cu(g_p3d[f"{name}_x"]), K=int(g_p3d[f"{name}_K"]))
