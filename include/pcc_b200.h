@@ -49,8 +49,11 @@ int64_t pcc_launch_count(void);
  * out_xyz (nullable) [B, npoint, 3]: the sampled points themselves -- the index_points / gather call that follows every
  * reference FPS call (compress.py:96, pointnet_sa_module.py:68) -- snapped to the octree grid when quant_cube > 0
  * (floor(c / cube) * cube + cube / 2, octree_np.py:114-133); padded entries are 0.
- * Clouds with N > 8192 are spread over several co-resident CTAs and need a device `workspace` of
- * pcc_fps_workspace_bytes(B, N, npoint) bytes (0 for N <= 8192 -> NULL allowed).
+ * Clouds with N > 8192 need a device `workspace` of pcc_fps_workspace_bytes(B, N, npoint) bytes (0 for N <= 8192 -> NULL
+ * allowed): they are spread over several co-resident CTAs; long samplings (npoint >= ~N / 1024) of clouds of 196,608 to
+ * 1,048,575 points (the 1M-point scene) continue, after a head of such iterations, on one CTA per cloud that keeps the cloud
+ * sorted along a Hilbert curve in buckets and skips, exactly, every bucket the new centre cannot reach (about 25 bytes of
+ * workspace per point) -- the same indices either way.
  */
 int64_t pcc_fps_workspace_bytes(int B, int N, int npoint);
 int pcc_fps_f32(const float *xyz, int B, int N, int npoint, const int64_t *start_idx, float init_dist,

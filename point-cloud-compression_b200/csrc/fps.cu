@@ -15,8 +15,9 @@
 // fps_grid_kernel: clouds with N > 8192 (the 1M-point scene).  The cloud is spread
 //   over C = ceil(N/8192) co-resident CTAs (cooperative launch), still register resident; per iteration each
 //   CTA publishes its best candidate as tagged 64-bit words in its own slot and polls the other CTAs' slots
-//   (no atomics, no fences: see the comment above the kernel).  From 65,536 points on the bucketed form of
-//   fps_bucket.cu takes over (same output, one CTA per cloud, exact spatial skipping); PCC_FPS_PATH=grid keeps this one.
+//   (no atomics, no fences: see the comment above the kernel).  For big clouds and long samplings the bucketed form of
+//   fps_bucket.cu takes over after a head of iterations of this kernel (same output, one CTA per cloud, exact spatial
+//   skipping); PCC_FPS_PATH=grid keeps this one throughout.
 #include <stdlib.h>
 
 #include "fps.cuh"
@@ -181,6 +182,9 @@ fps_block_kernel(const float *__restrict__ xyz, int N, int npoint, const int64_t
 // cluster winner through a 16-slot global table: 5.76 us / iteration; (b) the flat global table polled by one CTA per cluster
 // only, which pushes the winner to its peers over DSMEM: 5.15 us -- against 4.40 us for this kernel on the same box.  Both were
 // bit-exact against the oracle and both lose: the dependent DSMEM hop costs more than the polling traffic it removes.
+// Also measured and not kept: polling all of a lane's slots together (five loads in flight per round, first words only, the
+// winner's coordinate words fetched by one lane afterwards) instead of one slot after the other -- 6.0 us per iteration against
+// 4.7 at 123 CTAs, 3.3 against 1.9 at 13: every round re-reads every slot, and that traffic is what the exchange is bound by.
 // Instrumented with clock64 (1.97 GHz): CTA-local update + block arg-max 2020 clocks; publish -> every slot fresh 3300 clocks at
 // C = 13 (one slot per lane: the bare store -> visible -> polled latency across the two dies) and 7750 at C = 123; barrier +
 // unpacking the coordinates 215 (the instrumented kernel is ~30 % slower than the plain one: read these as proportions).
@@ -203,12 +207,13 @@ __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long
     return v;
 }
 
-template <bool WIDE>
+template <bool WIDE, bool HEAD>   // HEAD: the first centres of a longer row, running distances handed over at exit (fps_bucket.cu)
 __global__ void __launch_bounds__(GRID_THREADS, 1)
 fps_grid_kernel(const float *__restrict__ xyz, int N, int npoint, const int64_t *__restrict__ start_idx,
                 float init_dist, int64_t *__restrict__ out_idx, unsigned long long *ws, int ctas_per_cloud, int cloud0,
-                float *__restrict__ out_xyz, float quant_cube) {
+                float *__restrict__ out_xyz, float quant_cube, int out_stride_arg, float *__restrict__ md_out) {
     constexpr int NWARPS = GRID_THREADS / 32;
+    const int out_stride = HEAD ? out_stride_arg : npoint;
     __shared__ FpsSlots slots;
     __shared__ unsigned long long s_w0, s_w1, s_w2;
     const int cloud_local = blockIdx.x / ctas_per_cloud;
@@ -216,7 +221,7 @@ fps_grid_kernel(const float *__restrict__ xyz, int N, int npoint, const int64_t 
     const int b = cloud0 + cloud_local;
     const int tid = threadIdx.x;
     const float *pc = xyz + static_cast<size_t>(b) * N * 3;
-    int64_t *out = out_idx + static_cast<size_t>(b) * npoint;
+    int64_t *out = out_idx + static_cast<size_t>(b) * out_stride;   // out_stride >= npoint: a prefix of a longer row (hand-over)
     unsigned long long *table = ws + static_cast<size_t>(cloud_local) * 8 * ctas_per_cloud;   // [2][ctas_per_cloud][4]
     const int base = part * GRID_PTS_PER_CTA;
 
@@ -239,7 +244,7 @@ fps_grid_kernel(const float *__restrict__ xyz, int N, int npoint, const int64_t 
         for (int k = k_n + tid; k < npoint; k += GRID_THREADS) {
             out[k] = -1;
             if (out_xyz) {
-                float *o = out_xyz + (static_cast<size_t>(b) * npoint + k) * 3;
+                float *o = out_xyz + (static_cast<size_t>(b) * out_stride + k) * 3;
                 o[0] = o[1] = o[2] = 0.0f;
             }
         }
@@ -254,7 +259,7 @@ fps_grid_kernel(const float *__restrict__ xyz, int N, int npoint, const int64_t 
     for (int i = 0; i < k_n; ++i) {
         if (part == 0 && tid == 0) {
             out[i] = far;
-            if (out_xyz) store_centre(out_xyz + (static_cast<size_t>(b) * npoint + i) * 3, cx, cy, cz, quant_cube);
+            if (out_xyz) store_centre(out_xyz + (static_cast<size_t>(b) * out_stride + i) * 3, cx, cy, cz, quant_cube);
         }
         if (i == k_n - 1) break;
         unsigned bits;
@@ -342,6 +347,13 @@ fps_grid_kernel(const float *__restrict__ xyz, int N, int npoint, const int64_t 
         // s_w0..2 are rewritten only after the next block_argmax's __syncthreads, which every thread reaches
         // after reading it here.
     }
+    if (HEAD && md_out) {   // hand-over to the bucketed form: running distances after the centres out[0 .. k_n - 2]
+#pragma unroll
+        for (int p = 0; p < GRID_PPT; ++p) {
+            const int g = base + p * GRID_THREADS + tid;
+            if (g < N) md_out[static_cast<size_t>(b) * N + g] = md[p];
+        }
+    }
 }
 
 template <int THREADS, int PPT>
@@ -351,13 +363,49 @@ static int launch_block(const float *xyz, int B, int N, int npoint, const int64_
     return check_launch("fps_block_kernel");
 }
 
+// multi-CTA path: C co-resident CTAs per cloud, as many clouds per cooperative launch as fit.  `out_stride` >= npoint is the row
+// length of out_idx / out_xyz (the bucketed form lets this kernel write the head of a longer row); `md_out` (nullable) [B, N]
+// receives the running distances at exit.  `workspace`: pcc_fps_grid_workspace_bytes().
+int64_t fps_grid_workspace_bytes() { return static_cast<int64_t>(sizeof(FpsGridWs)) * num_sms(); }
+
+int fps_grid_run(const float *xyz, int B, int N, int npoint, const int64_t *start_idx, float init_dist, int64_t *out_idx,
+                 float *out_xyz, float quant_cube, int out_stride, float *md_out, void *workspace, cudaStream_t st) {
+    const int sms = num_sms();
+    const int C = (N + GRID_PTS_PER_CTA - 1) / GRID_PTS_PER_CTA;
+    if (C > sms || static_cast<long long>(C) * GRID_PTS_PER_CTA > GRID_IDX_MASK) {
+        set_error("pcc_fps_f32: N=%d exceeds the co-resident capacity %d", N, sms * GRID_PTS_PER_CTA);
+        return PCC_ERR_UNSUPPORTED;
+    }
+    unsigned long long *ws = static_cast<unsigned long long *>(workspace);   // 2 x 32 bytes per CTA of a launch
+    const int clouds_per_launch = sms / C;
+    for (int c0 = 0; c0 < B; c0 += clouds_per_launch) {
+        int nc = B - c0 < clouds_per_launch ? B - c0 : clouds_per_launch;
+        cudaError_t e = cudaMemsetAsync(ws, 0, sizeof(unsigned long long) * 8 * nc * C, st);
+        if (e != cudaSuccess) {
+            set_error("pcc_fps_f32: memset failed: %s", cudaGetErrorString(e));
+            return static_cast<int>(e);
+        }
+        int ctas = C, cloud0 = c0;
+        void *args[] = {&xyz, &N, &npoint, &start_idx, &init_dist, &out_idx, &ws, &ctas, &cloud0, &out_xyz, &quant_cube, &out_stride, &md_out};
+        const bool head = md_out != nullptr || out_stride != npoint;
+        void *fn = C <= GRID_WIDE_MAX_CTAS ? (head ? reinterpret_cast<void *>(fps_grid_kernel<true, true>) : reinterpret_cast<void *>(fps_grid_kernel<true, false>))
+                                           : (head ? reinterpret_cast<void *>(fps_grid_kernel<false, true>) : reinterpret_cast<void *>(fps_grid_kernel<false, false>));
+        e = cudaLaunchCooperativeKernel(fn, dim3(nc * C), dim3(GRID_THREADS),
+                                        args, 0, st);
+        if (e != cudaSuccess) {
+            set_error("pcc_fps_f32: cooperative launch failed: %s", cudaGetErrorString(e));
+            return static_cast<int>(e);
+        }
+    }
+    return check_launch("fps_grid_kernel");
+}
+
 }  // namespace pcc
 
 PCC_API int64_t pcc_fps_workspace_bytes(int B, int N, int npoint) {
-    (void)npoint;
     if (N <= pcc::GRID_PTS_PER_CTA || B <= 0) return 0;
-    if (pcc::fps_bucket_takes(N)) return pcc::fps_bucket_workspace_bytes(B, N);
-    return static_cast<int64_t>(sizeof(pcc::FpsGridWs)) * pcc::num_sms();
+    if (pcc::fps_bucket_takes(N, npoint)) return pcc::fps_bucket_workspace_bytes(B, N);
+    return pcc::fps_grid_workspace_bytes();
 }
 
 PCC_API int pcc_fps_f32(const float *xyz, int B, int N, int npoint, const int64_t *start_idx, float init_dist,
@@ -375,34 +423,9 @@ PCC_API int pcc_fps_f32(const float *xyz, int B, int N, int npoint, const int64_
     if (N <= 4096) return launch_block<1024, 4>(xyz, B, N, npoint, start_idx, init_dist, out_idx, out_xyz, quant_cube, st);
     if (N <= 8192) return launch_block<1024, 8>(xyz, B, N, npoint, start_idx, init_dist, out_idx, out_xyz, quant_cube, st);
 
-    // multi-CTA path: C co-resident CTAs per cloud, as many clouds per cooperative launch as fit.
     PCC_REQUIRE(workspace, "pcc_fps_f32: N=%d needs a workspace of pcc_fps_workspace_bytes()", N);
-    // scene scale: Morton buckets with exact skipping, one CTA per cloud (fps_bucket.cu)
-    if (fps_bucket_takes(N)) return fps_bucket_run(xyz, B, N, npoint, start_idx, init_dist, out_idx, out_xyz, quant_cube, workspace, st);
-    const int sms = num_sms();
-    const int C = (N + GRID_PTS_PER_CTA - 1) / GRID_PTS_PER_CTA;
-    if (C > sms || static_cast<long long>(C) * GRID_PTS_PER_CTA > GRID_IDX_MASK) {
-        set_error("pcc_fps_f32: N=%d exceeds the co-resident capacity %d", N, sms * GRID_PTS_PER_CTA);
-        return PCC_ERR_UNSUPPORTED;
-    }
-    unsigned long long *ws = static_cast<unsigned long long *>(workspace);   // 2 x 32 bytes per CTA of a launch
-    const int clouds_per_launch = sms / C;
-    for (int c0 = 0; c0 < B; c0 += clouds_per_launch) {
-        int nc = B - c0 < clouds_per_launch ? B - c0 : clouds_per_launch;
-        cudaError_t e = cudaMemsetAsync(ws, 0, sizeof(unsigned long long) * 8 * nc * C, st);
-        if (e != cudaSuccess) {
-            set_error("pcc_fps_f32: memset failed: %s", cudaGetErrorString(e));
-            return static_cast<int>(e);
-        }
-        int ctas = C, cloud0 = c0;
-        void *args[] = {&xyz, &N, &npoint, &start_idx, &init_dist, &out_idx, &ws, &ctas, &cloud0, &out_xyz, &quant_cube};
-        void *fn = C <= GRID_WIDE_MAX_CTAS ? reinterpret_cast<void *>(fps_grid_kernel<true>) : reinterpret_cast<void *>(fps_grid_kernel<false>);
-        e = cudaLaunchCooperativeKernel(fn, dim3(nc * C), dim3(GRID_THREADS),
-                                        args, 0, st);
-        if (e != cudaSuccess) {
-            set_error("pcc_fps_f32: cooperative launch failed: %s", cudaGetErrorString(e));
-            return static_cast<int>(e);
-        }
-    }
-    return check_launch("fps_grid_kernel");
+    // scene scale: Morton buckets with exact skipping, one CTA per cloud (fps_bucket.cu), after a head of co-resident iterations
+    if (fps_bucket_takes(N, npoint))
+        return fps_bucket_run(xyz, B, N, npoint, start_idx, init_dist, out_idx, out_xyz, quant_cube, workspace, st);
+    return fps_grid_run(xyz, B, N, npoint, start_idx, init_dist, out_idx, out_xyz, quant_cube, npoint, nullptr, workspace, st);
 }

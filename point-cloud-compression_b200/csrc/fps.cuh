@@ -18,8 +18,15 @@ __device__ __forceinline__ void store_centre(float *o, float x, float y, float z
     o[2] = z;
 }
 
-// Scene-scale form (fps_bucket.cu): spatial buckets with exact skipping, one CTA per cloud.
-bool fps_bucket_takes(int N);                       // shape gate of the bucketed form
+// Co-resident multi-CTA form (fps.cu), N > 8192.  out_stride >= npoint is the row length of out_idx / out_xyz; md_out (nullable)
+// [B, N] receives the running distances at exit (after the centres out[0 .. npoint - 2]).
+int64_t fps_grid_workspace_bytes();
+int fps_grid_run(const float *xyz, int B, int N, int npoint, const int64_t *start_idx, float init_dist, int64_t *out_idx,
+                 float *out_xyz, float quant_cube, int out_stride, float *md_out, void *workspace, cudaStream_t st);
+
+// Scene-scale form (fps_bucket.cu): spatial buckets with exact skipping, one CTA per cloud, after a head of iterations of the
+// co-resident form.
+bool fps_bucket_takes(int N, int npoint);           // shape gate of the bucketed form
 int64_t fps_bucket_workspace_bytes(int B, int N);
 int fps_bucket_run(const float *xyz, int B, int N, int npoint, const int64_t *start_idx, float init_dist, int64_t *out_idx,
                    float *out_xyz, float quant_cube, void *workspace, cudaStream_t st);

@@ -99,26 +99,35 @@ def test_fps_multi_cta_18_ctas_ties_and_wrap(pcc, orc):
 
 
 class _fps_path:
-    """PCC_FPS_PATH for the duration of a block ("bucket": fps_bucket.cu whenever it fits; "grid": the co-resident kernel)."""
-    def __init__(self, value):
-        self.value = value
+    """PCC_FPS_PATH ("bucket": fps_bucket.cu whenever it fits; "grid": the co-resident kernel) and PCC_FPS_HEAD (iterations the
+    co-resident kernel runs before it hands over to the bucketed form; "0": none) for the duration of a block."""
+    def __init__(self, path, head=None):
+        self.want = {"PCC_FPS_PATH": path, "PCC_FPS_HEAD": head}
 
     def __enter__(self):
-        self.old = os.environ.get("PCC_FPS_PATH")
-        os.environ["PCC_FPS_PATH"] = self.value
+        self.old = {k: os.environ.get(k) for k in self.want}
+        for k, v in self.want.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
 
     def __exit__(self, *exc):
-        if self.old is None:
-            os.environ.pop("PCC_FPS_PATH", None)
-        else:
-            os.environ["PCC_FPS_PATH"] = self.old
+        for k, v in self.old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
 
 
+@pytest.mark.parametrize("head", ["0", None, "37"])
 @pytest.mark.parametrize("case", ["scene", "ties", "uniform_pads", "duplicates", "identical", "two_clouds", "tiny"])
-def test_fps_bucket_form_vs_oracle(pcc, orc, case):
+def test_fps_bucket_form_vs_oracle(pcc, orc, case, head):
     """The scene-scale form (Morton buckets + exact skipping, fps_bucket.cu) forced on clouds the oracle finishes in seconds:
     every index against the oracle -- exact ties (grid-quantised points), a ragged last bucket, duplicated points (running
-    distance 0 early), one point repeated N times, two clouds per launch, the smallest cloud that reaches this path."""
+    distance 0 early), one point repeated N times, two clouds per launch, the smallest cloud that reaches this path; alone
+    (head "0"), after the default head of co-resident iterations (128 at these sizes, when the sampling is >= 512 long) and
+    after an odd one (the hand-over of the running distances and of the last picked centre)."""
     if case == "scene":
         xyz, S = synth.scene_like(60_000, seed=5), 3000
     elif case == "ties":
@@ -136,7 +145,7 @@ def test_fps_bucket_form_vs_oracle(pcc, orc, case):
         xyz, S = synth.uniform_cube(1, 8200, seed=3), 300      # just above the single-CTA kernel's 8192 points
     B, N = xyz.shape[:2]
     start = np.array([(7919 * (b + 1)) % N for b in range(B)], np.int64)
-    with _fps_path("bucket"):
+    with _fps_path("bucket", head):
         got, got_xyz = pcc.ops.fps(cu(xyz), S, cu(start), 1e10, return_xyz=True)
     got = got.cpu().numpy()
     assert np.array_equal(got, orc.fps(xyz, S, start, 1e10, threads=8))
@@ -153,8 +162,8 @@ def test_fps_bucket_form_pytorch3d_contract(pcc, orc):
 
 
 def test_fps_bucket_form_equals_grid_form_at_scene_scale(pcc):
-    """1,000,000 points -> 7812 centres: the bucketed form (default from 65,536 points) against the co-resident multi-CTA
-    kernel on every iteration (the oracle prefix is test_scene_scale_cfg5's)."""
+    """1,000,000 points -> 7812 centres: the default route (244 co-resident iterations, then the bucketed form) against the
+    co-resident multi-CTA kernel alone on every iteration (the oracle prefix is test_scene_scale_cfg5's)."""
     xyz = cu(synth.scene_like(1_000_000, seed=3))
     start = cu(np.array([12345], np.int64))
     a = pcc.ops.fps(xyz, 7812, start, 1e10)
