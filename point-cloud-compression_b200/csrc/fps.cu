@@ -404,7 +404,7 @@ int fps_grid_run(const float *xyz, int B, int N, int npoint, const int64_t *star
 
 PCC_API int64_t pcc_fps_workspace_bytes(int B, int N, int npoint) {
     if (N <= pcc::GRID_PTS_PER_CTA || B <= 0) return 0;
-    if (pcc::fps_bucket_takes(N, npoint)) return pcc::fps_bucket_workspace_bytes(B, N);
+    if (pcc::fps_bucket_takes(B, N, npoint)) return pcc::fps_bucket_workspace_bytes(B, N);
     return pcc::fps_grid_workspace_bytes();
 }
 
@@ -425,7 +425,7 @@ PCC_API int pcc_fps_f32(const float *xyz, int B, int N, int npoint, const int64_
 
     PCC_REQUIRE(workspace, "pcc_fps_f32: N=%d needs a workspace of pcc_fps_workspace_bytes()", N);
     // scene scale: Morton buckets with exact skipping, one CTA per cloud (fps_bucket.cu), after a head of co-resident iterations
-    if (fps_bucket_takes(N, npoint))
+    if (fps_bucket_takes(B, N, npoint))
         return fps_bucket_run(xyz, B, N, npoint, start_idx, init_dist, out_idx, out_xyz, quant_cube, workspace, st);
     return fps_grid_run(xyz, B, N, npoint, start_idx, init_dist, out_idx, out_xyz, quant_cube, npoint, nullptr, workspace, st);
 }

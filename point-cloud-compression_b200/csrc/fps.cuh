@@ -26,7 +26,7 @@ int fps_grid_run(const float *xyz, int B, int N, int npoint, const int64_t *star
 
 // Scene-scale form (fps_bucket.cu): spatial buckets with exact skipping, one CTA per cloud, after a head of iterations of the
 // co-resident form.
-bool fps_bucket_takes(int N, int npoint);           // shape gate of the bucketed form
+bool fps_bucket_takes(int B, int N, int npoint);          // shape gate of the bucketed form
 int64_t fps_bucket_workspace_bytes(int B, int N);
 int fps_bucket_run(const float *xyz, int B, int N, int npoint, const int64_t *start_idx, float init_dist, int64_t *out_idx,
                    float *out_xyz, float quant_cube, void *workspace, cudaStream_t st);

@@ -536,12 +536,18 @@ static int head_iterations(int N, int npoint) {
     return (k0 >= 2 && k_n >= 4 * k0) ? k0 : 0;
 }
 
-bool fps_bucket_takes(int N, int npoint) {
+bool fps_bucket_takes(int B, int N, int npoint) {
     const char *e = getenv("PCC_FPS_PATH");   // "grid": the co-resident multi-CTA kernel; "bucket": this form whenever it fits
     if (e && e[0] == 'g') return false;
     if (N >= fpsb::NB_MAX * fpsb::BS) return false;   // N < 2^20: the index field of the arg-max key
     if (e && e[0] == 'b') return true;
-    return N >= 196608 && head_iterations(N, npoint) > 0;   // measured: the co-resident kernel wins on smaller / shorter jobs
+    if (N < 196608) return false;                     // measured: the co-resident kernel wins on smaller clouds
+    if (head_iterations(N, npoint) > 0) return true;  // long samplings
+    // short samplings: this form runs one CTA per cloud side by side; the co-resident kernel needs ceil(N / 8192) SMs per cloud
+    // and takes the clouds it cannot fit one launch after the other (1M points: 2.4 ms per cloud for 512 centres against 2.7 ms
+    // for any number of clouds here -- the two branches of the pppe encoder's first level)
+    const int per_launch = num_sms() / ((N + 8191) / 8192);
+    return B > 1 && per_launch < 2;
 }
 
 int64_t fps_bucket_workspace_bytes(int B, int N) {

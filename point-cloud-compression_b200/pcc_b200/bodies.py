@@ -415,13 +415,17 @@ def pppe_sa_layers(mod):
     return _cached(mod, "pppe_stack", lambda: [_seq_layer(s) for s in mod.mlp_stack])
 
 
-def pppe_sa_points(mod, xyz, feat=None):
+def pppe_sa_points(mod, xyz, feat=None, centres_idx=None):
     """pppe_pcd_ae.PointNetSetAbstraction.forward (pppe_pcd_ae.py:588-618), channel-last: xyz [B, N, 3], feat [B, N, C] or None
     -> (new_xyz [B, S, 3], new features [B, S, C_out] fp32).  FPS start from the CPU RNG (pn_kit.py:321), kNN(K) of every centre,
-    recentred xyz [| gathered features], shared MLP, max over the K neighbours."""
+    recentred xyz [| gathered features], shared MLP, max over the K neighbours.  `centres_idx` [B, S]: the sampling, when the
+    caller has already run it (the MSG level batches its branches' samplings)."""
     B, N, _ = xyz.shape
     S, K = mod.npoint, mod.K
-    new_xyz = xyz if S == N else ops.gather(xyz, pn_kit_ops.farthest_point_sample_batch(xyz, S))      # :596-600
+    if S == N:
+        new_xyz = xyz
+    else:
+        new_xyz = ops.gather(xyz, centres_idx if centres_idx is not None else pn_kit_ops.farthest_point_sample_batch(xyz, S))   # :596-600
     layers = list(pppe_sa_layers(mod))
     if feat is None:
         _, _, grouped = ops.knn(new_xyz, xyz, K, return_nn=True, centre_sub=True, nn_only=True)       # :602-603
@@ -440,12 +444,26 @@ def pppe_sa_points(mod, xyz, feat=None):
     return new_xyz, out.reshape(B, S, -1)
 
 
+# Above this many points a cloud's sampling occupies most of the GPU (co-resident CTAs, 8192 points each): samplings of the same
+# cloud are then cheaper as ONE batched call, which the scene-scale form runs side by side on one SM each (fps_bucket.cu).
+_MSG_BATCHED_FPS_MIN_POINTS = 196608
+
+
 def pppe_msg_points(mod, xyz, feat=None):
     """pppe_pcd_ae.PointNetSetAbstractionMSG.forward (pppe_pcd_ae.py:627-633): every branch samples its own centres (one CPU-RNG
-    draw each); the LAST branch's centres are handed on; features concatenated along the channel axis."""
+    draw each, in branch order); the LAST branch's centres are handed on; features concatenated along the channel axis.  On
+    scene-sized clouds the branches' samplings -- independent sequences over the same points -- run as one batched FPS call."""
+    B, N, _ = xyz.shape
+    branches = list(mod.branches)
+    samplings = [None] * len(branches)
+    nps = {b.npoint for b in branches}
+    if len(branches) > 1 and len(nps) == 1 and N >= _MSG_BATCHED_FPS_MIN_POINTS and branches[0].npoint != N:
+        starts = torch.cat([torch.randint(0, N, (B,), dtype=torch.long) for _ in branches])       # pn_kit.py:321, one draw per branch
+        idx = ops.fps(xyz.repeat(len(branches), 1, 1), branches[0].npoint, starts.to(xyz.device), 1e10)
+        samplings = list(idx.reshape(len(branches), B, -1).unbind(0))
     outs, new_xyz = [], None
-    for b in mod.branches:
-        new_xyz, f = pppe_sa_points(b, xyz, feat)
+    for b, ci in zip(branches, samplings):
+        new_xyz, f = pppe_sa_points(b, xyz, feat, ci)
         outs.append(f)
     return new_xyz, torch.cat(outs, dim=2)
 

@@ -105,6 +105,27 @@ def test_pppe_encoder_vs_reference_module_golden(pcc, golden_dir):
         model.train()(x)
 
 
+def test_pppe_msg_level_batches_its_samplings_on_scene_sized_clouds(pcc, monkeypatch):
+    """Above 196,608 points the MSG level runs its branches' farthest-point samplings as ONE batched call (same CPU-RNG draws in
+    the same order): centres and features are bit-identical to the branch-by-branch route."""
+    from pcc_b200 import bodies, pppe
+    model = pppe.PointNet2EncoderFull(latent_dim=256)
+    model.load_state_dict(synth.seeded_module_state(model, 23))
+    msg = model.cuda().eval().sa_modules[0]
+    assert hasattr(msg, "branches") and len(msg.branches) == 2
+    x = torch.from_numpy(synth.scene_like(200_000, seed=2)).cuda()
+    with torch.no_grad():
+        torch.manual_seed(5)
+        xyz_a, f_a = bodies.pppe_msg_points(msg, x)
+        nxt_a = int(torch.randint(0, 1000, (1,)))
+        monkeypatch.setattr(bodies, "_MSG_BATCHED_FPS_MIN_POINTS", 1 << 30)
+        torch.manual_seed(5)
+        xyz_b, f_b = bodies.pppe_msg_points(msg, x)
+        nxt_b = int(torch.randint(0, 1000, (1,)))
+    assert torch.equal(xyz_a, xyz_b) and torch.equal(f_a, f_b)
+    assert nxt_a == nxt_b                                               # the CPU generator advanced by the same draws
+
+
 def test_pointnet_ops_wrapper_matches_reference_names(pcc):
     """PointnetPPOps (pointnet_sa_module.py:8-34): argument order and return types."""
     xyz = torch.from_numpy(synth.shapenet_like(2, 512, seed=3)).cuda()

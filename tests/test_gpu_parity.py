@@ -161,6 +161,17 @@ def test_fps_bucket_form_pytorch3d_contract(pcc, orc):
     assert np.array_equal(idx[:, :9000], want) and (idx[:, 9000:] == -1).all()
 
 
+def test_fps_short_batched_sampling_of_big_clouds_takes_the_bucket_form(pcc):
+    """Two 620,000-point clouds, 96 centres each: the co-resident kernel fits one such cloud per launch, so the default route is
+    the bucketed form (one CTA per cloud, side by side) although the sampling is short -- same indices as the co-resident kernel."""
+    xyz = cu(np.concatenate((synth.scene_like(620_000, seed=8), synth.uniform_cube(1, 620_000, seed=9) * 5.0), 0))
+    start = cu(np.array([7, 619_999], np.int64))
+    a = pcc.ops.fps(xyz, 96, start, 1e10)
+    with _fps_path("grid"):
+        b = pcc.ops.fps(xyz, 96, start, 1e10)
+    assert torch.equal(a, b)
+
+
 def test_fps_bucket_form_equals_grid_form_at_scene_scale(pcc):
     """1,000,000 points -> 7812 centres: the default route (244 co-resident iterations, then the bucketed form) against the
     co-resident multi-CTA kernel alone on every iteration (the oracle prefix is test_scene_scale_cfg5's)."""
