@@ -172,6 +172,21 @@ def test_fps_short_batched_sampling_of_big_clouds_takes_the_bucket_form(pcc):
     assert torch.equal(a, b)
 
 
+@pytest.mark.parametrize("kind", ["plane", "line", "dups", "offset", "tiny", "lattice", "aniso"])
+def test_fps_bucket_form_degenerate_geometry(pcc, orc, kind):
+    """Degenerate boxes and arithmetic corners of the skip test (tools/soak_fps.py runs the long version): a plane and a line (zero
+    extent along an axis), points repeated seven times, coordinates at 1e6 (fp32 spacing 0.06), an extent of 1e-21 (every square
+    underflows: nothing may be skipped), a lattice (ties everywhere), a 10^4 : 1 anisotropic cloud -- against the oracle, alone and
+    after a three-iteration head."""
+    from tools import soak_fps
+    xyz = soak_fps.cloud(kind, 20_000, np.random.default_rng(17))[None]
+    start = np.array([4242], np.int64)
+    want = orc.fps(xyz, 500, start, 1e10, threads=8)
+    for head in ("0", "3"):
+        with _fps_path("bucket", head):
+            assert np.array_equal(pcc.ops.fps(cu(xyz), 500, cu(start), 1e10).cpu().numpy(), want), head
+
+
 def test_fps_bucket_form_equals_grid_form_at_scene_scale(pcc):
     """1,000,000 points -> 7812 centres: the default route (244 co-resident iterations, then the bucketed form) against the
     co-resident multi-CTA kernel alone on every iteration (the oracle prefix is test_scene_scale_cfg5's)."""
