@@ -999,6 +999,203 @@ dec_chain_kernel(const __grid_constant__ DecParams prm, const __grid_constant__ 
     tmem_free(tmem_base, TMEM_COLS, warp, 8);
 }
 
+// ---- DEC with two tiles in flight per SM -------------------------------------------------------------------------------------
+// The one-tile kernel above is a chain of four MMA -> epilogue hand-offs per tile with nothing else to run on the SM (issue 9 %,
+// tensor 18 %, DRAM 18 %).  Here a CTA carries TWO independent chains ("slots"): per slot 8 epilogue warps, one MMA warp, one TMA
+// producer warp, 128 TMEM columns and its own barriers, so one slot's epilogue runs under the other's MMAs.  To fit twice in
+// shared memory a slot keeps only [latent block | lin | X1]: X2 is written over X1's first slab and X3 over its second -- each
+// only after the MMAs that read the bytes underneath have completed (the epilogue that writes waits for exactly that commit).
+namespace dec2 {
+using dec::KP0;
+using dec::KP1;
+using dec::KP2;
+using dec::KP3;
+using dec::OFF_ONES;
+using dec::OFF_W0;
+using dec::OFF_W1;
+using dec::OFF_W2;
+using dec::OFF_W3;
+constexpr int SLOTS = 2;
+constexpr int S_XLAT = 0, S_LIN = K16, S_X1 = S_LIN + 2 * SLAB;     // X2 = S_X1, X3 = S_X1 + SLAB
+constexpr int SLOT_BYTES = S_X1 + 2 * SLAB;                          // 69632
+constexpr int OFF_SLOT = OFF_ONES + K16;                             // 70656 = 69 * 1024
+constexpr int OFF_BAR = OFF_SLOT + SLOTS * SLOT_BYTES;               // 209920
+constexpr int SMEM = OFF_BAR + 128 + 1024;
+constexpr int EPI_WARPS = 8;
+constexpr int MMA_WARP0 = SLOTS * EPI_WARPS, TMA_WARP0 = MMA_WARP0 + SLOTS;
+constexpr int THREADS = (TMA_WARP0 + SLOTS) * 32;                    // 640
+constexpr int TMEM_COLS = 128 * SLOTS;
+static_assert(OFF_SLOT % 1024 == 0 && SLOT_BYTES % 1024 == 0 && S_LIN % 1024 == 0 && S_X1 % 1024 == 0, "swizzled slabs are 1 KB aligned");
+}  // namespace dec2
+
+__global__ void __launch_bounds__(dec2::THREADS, 1)
+dec_chain2_kernel(const __grid_constant__ DecParams prm, const __grid_constant__ CUtensorMap tm_lin) {
+    using namespace dec2;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    const uint32_t sb = smem_u32(smem);
+    const int tid = threadIdx.x, warp = __shfl_sync(FULL_MASK, tid >> 5, 0), lane = tid & 31;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BAR + 96);
+
+    copy_to_smem(smem + OFF_W0, prm.w0p, 128 * KP0 * 2, tid, THREADS);
+    copy_to_smem(smem + OFF_W1, prm.w1p, 64 * KP1 * 2, tid, THREADS);
+    copy_to_smem(smem + OFF_W2, prm.w2p, 32 * KP2 * 2, tid, THREADS);
+    copy_to_smem(smem + OFF_W3, prm.w3p, 16 * KP3 * 2, tid, THREADS);
+    fill_ones_block(smem + OFF_ONES, tid, THREADS);
+    if (tid == 0) {
+#pragma unroll
+        for (int sl = 0; sl < SLOTS; ++sl) {
+            mbar_init(sb + OFF_BAR + 32 * sl, 9);         // in: 8 epilogue warps (latent block) + the producer's expect_tx
+            mbar_init(sb + OFF_BAR + 32 * sl + 8, 1);     // empty: lin consumed
+            mbar_init(sb + OFF_BAR + 32 * sl + 16, 1);    // acc: a layer's MMAs completed
+            mbar_init(sb + OFF_BAR + 32 * sl + 24, 8);    // act: the next layer's input is in shared memory
+        }
+    }
+    const uint32_t tmem_base = tmem_alloc_and_sync(tmem_slot, TMEM_COLS, warp, MMA_WARP0);
+    const int n_tiles = prm.n_tiles;
+    // role and slot of this warp; slot sl takes tiles blockIdx.x + gridDim.x * (2 j + sl)
+    const int sl = warp < MMA_WARP0 ? warp / EPI_WARPS : (warp < TMA_WARP0 ? warp - MMA_WARP0 : warp - TMA_WARP0);
+    const uint32_t ss = sb + OFF_SLOT + sl * SLOT_BYTES;
+    const uint32_t bar_in = sb + OFF_BAR + 32 * sl, bar_empty = bar_in + 8, bar_acc = bar_in + 16, bar_act = bar_in + 24;
+    const int tile0 = blockIdx.x + gridDim.x * sl, tstep = gridDim.x * SLOTS;
+
+    if (warp >= TMA_WARP0) {
+        if (lane == 0) {
+            uint32_t ph = 1;
+            for (int tile = tile0; tile < n_tiles; tile += tstep) {
+                mbar_wait(bar_empty, ph);
+                ph ^= 1u;
+                mbar_arrive_expect_tx(bar_in, 2 * SLAB);
+                tma_load_2d(ss + S_LIN, &tm_lin, 0, tile * P, bar_in);
+                tma_load_2d(ss + S_LIN + SLAB, &tm_lin, 64, tile * P, bar_in);
+            }
+        }
+    } else if (warp >= MMA_WARP0) {
+        // ---- MMA issuer of slot sl: warp-uniform control flow, one elected lane issues ----
+        const uint32_t tb = __shfl_sync(FULL_MASK, tmem_base, 0) + 128u * sl;
+        uint32_t ph_in = 0, ph_act = 0;
+        const uint32_t id128 = umma_idesc(128, 128), id64 = umma_idesc(128, 64), id32 = umma_idesc(128, 32), id16 = umma_idesc(128, 16);
+        const uint64_t d_lin = umma_desc_sw128(ss + S_LIN), d_x1 = umma_desc_sw128(ss + S_X1), d_x2 = d_x1,
+                       d_x3 = umma_desc_sw128(ss + S_X1 + SLAB);
+        const uint64_t d_w0 = desc_w(sb + OFF_W0, KP0, 0), d_w1 = desc_w(sb + OFF_W1, KP1, 0), d_w2 = desc_w(sb + OFF_W2, KP2, 0),
+                       d_w3 = desc_w(sb + OFF_W3, KP3, 0);
+        const uint64_t d_xlat = desc_k16(ss + S_XLAT), d_ones = desc_k16(sb + OFF_ONES);
+        for (int tile = tile0; tile < n_tiles; tile += tstep) {
+            mbar_wait(bar_in, ph_in);
+            ph_in ^= 1u;
+            tc_fence_after();
+            if (elect_one()) {
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks)
+                    umma_bf16(tb, d_lin + (ks >> 2) * (SLAB >> 4) + (ks & 3) * 2, d_w0 + 16 * ks, id128, ks > 0);
+                umma_bf16(tb, d_xlat, d_w0 + 16 * 8, id128, 1u);
+                umma_bf16(tb, d_ones, d_w0 + 16 * 9, id128, 1u);
+                umma_commit(bar_acc);
+                umma_commit(bar_empty);
+            }
+            __syncwarp();
+            mbar_wait(bar_act, ph_act);   // layer 1: 128 -> 64
+            ph_act ^= 1u;
+            tc_fence_after();
+            if (elect_one()) {
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks)
+                    umma_bf16(tb, d_x1 + (ks >> 2) * (SLAB >> 4) + (ks & 3) * 2, d_w1 + 16 * ks, id64, ks > 0);
+                umma_bf16(tb, d_ones, d_w1 + 16 * 8, id64, 1u);
+                umma_commit(bar_acc);
+            }
+            __syncwarp();
+            mbar_wait(bar_act, ph_act);   // layer 2: 64 -> 32
+            ph_act ^= 1u;
+            tc_fence_after();
+            if (elect_one()) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) umma_bf16(tb, d_x2 + ks * 2, d_w2 + 16 * ks, id32, ks > 0);
+                umma_bf16(tb, d_ones, d_w2 + 16 * 4, id32, 1u);
+                umma_commit(bar_acc);
+            }
+            __syncwarp();
+            mbar_wait(bar_act, ph_act);   // layer 3: 32 -> 3 (N = 16)
+            ph_act ^= 1u;
+            tc_fence_after();
+            if (elect_one()) {
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) umma_bf16(tb, d_x3 + ks * 2, d_w3 + 16 * ks, id16, ks > 0);
+                umma_bf16(tb, d_ones, d_w3 + 16 * 2, id16, 1u);
+                umma_commit(bar_acc);
+            }
+            __syncwarp();
+        }
+    } else {
+        const int q = warp & 3, h = (warp >> 2) & 1;
+        const int row = q * 32 + lane;
+        const int et = tid - sl * (EPI_WARPS * 32);   // thread of the slot's epilogue group
+        const uint32_t lane_base = tmem_base + 128u * sl + (static_cast<uint32_t>(q * 32) << 16);
+        uint32_t ph_acc = 0;
+        auto arrive_act = [&]() {
+            fence_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive1(bar_act);
+        };
+        auto wait_acc = [&]() {
+            mbar_wait(bar_acc, ph_acc);
+            ph_acc ^= 1u;
+            tc_fence_after();
+        };
+        for (int tile = tile0; tile < n_tiles; tile += tstep) {
+            if (et < P) {  // every row of the tile carries the same latent (AE.py:51 tiles it over the k points)
+                const float4 *lp = reinterpret_cast<const float4 *>(prm.lat + static_cast<long long>(tile) * prm.ld_lat);
+                uint32_t w[8];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4 f = __ldg(lp + i);
+                    w[2 * i] = bf16_bits(f.x) | (bf16_bits(f.y) << 16);
+                    w[2 * i + 1] = bf16_bits(f.z) | (bf16_bits(f.w) << 16);
+                }
+                store_k16_row(ss + S_XLAT, et, w);
+            }
+            fence_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive1(bar_in);
+            wait_acc();   // layer 0: 64 channels per warp -> X1 slab h
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                uint32_t v[32];
+                tmem_ld32(lane_base + h * 64 + j * 32, v);
+                store_row_chunks<32, true>(ss + S_X1, row, h * 64 + j * 32, v);
+            }
+            arrive_act();
+            wait_acc();   // layer 1: 32 channels per warp -> X2, over X1's first slab (layer 1 has read it)
+            {
+                uint32_t v[32];
+                tmem_ld32(lane_base + h * 32, v);
+                store_row_chunks<32, true>(ss + S_X1, row, h * 32, v);
+            }
+            arrive_act();
+            wait_acc();   // layer 2: 16 channels per warp -> X3, over X1's second slab
+            {
+                uint32_t v[16];
+                tmem_ld16(lane_base + h * 16, v);
+                store_row_chunks<16, true>(ss + S_X1 + SLAB, row, h * 16, v);
+            }
+            arrive_act();
+            wait_acc();   // layer 3: x, y, z of this position (no ReLU)
+            if (h == 0) {
+                uint32_t v[4];
+                tmem_ld4(lane_base, v);
+                float *o = prm.out + (static_cast<long long>(tile) * P + row) * 3;
+                o[0] = __uint_as_float(v[0]);
+                o[1] = __uint_as_float(v[1]);
+                o[2] = __uint_as_float(v[2]);
+            }
+            tc_fence_before();
+        }
+    }
+    tmem_free(tmem_base, TMEM_COLS, warp, MMA_WARP0);
+}
+
 // ---- host side ---------------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1135,6 +1332,14 @@ int ws_dispatch(const PccMlpInput *in, int n_inputs, int64_t rows, const PccMlpL
         p.w3p = layers[3].packed_w;
         p.out = static_cast<float *>(out);
         p.n_tiles = n_tiles;
+        static const bool one_slot = getenv("PCC_DEC_SLOTS") != nullptr && getenv("PCC_DEC_SLOTS")[0] == '1';   // A/B
+        if (n_tiles > sms && !one_slot) {   // more than one tile per SM: two tiles in flight per CTA
+            if (int r = set_smem(dec_chain2_kernel, dec2::SMEM)) return r;
+            const int grid = (n_tiles + 1) / 2 < sms ? (n_tiles + 1) / 2 : sms;
+            dec_chain2_kernel<<<grid, dec2::THREADS, dec2::SMEM, st>>>(p, tm_lin);
+            *handled = true;
+            return check_launch("dec_chain2_kernel");
+        }
         if (int r = set_smem(dec_chain_kernel, dec::SMEM)) return r;
         const int grid = n_tiles < sms ? n_tiles : sms;
         dec_chain_kernel<<<grid, dec::THREADS, dec::SMEM, st>>>(p, tm_lin);

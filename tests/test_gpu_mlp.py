@@ -124,6 +124,33 @@ def test_input_segments_bf16_and_broadcast(mlp):
     assert (yb.float() - ym2).abs().max().item() / ym2.abs().max().item() < 1e-2  # one extra bf16 rounding of the output
 
 
+@pytest.mark.parametrize("patches", [149, 301, 2048])
+def test_decoder_chain_two_tiles_in_flight(mlp, patches):
+    """More tiles than SMs: the decoder chain runs as dec_chain2_kernel (two independent tile chains per CTA, X2 / X3 written over
+    X1's slabs).  Against the bf16-operand model, and -- same MMAs, same epilogue arithmetic -- bit-identical to the one-tile
+    kernel, which a fresh process selects with PCC_DEC_SLOTS=1 (odd tile counts: the two slots of a CTA get different numbers of
+    tiles, some none)."""
+    import subprocess, sys, os, tempfile
+    layers = make_layers([144, 128, 64, 32, 3], [True, True, True, False], seed=9)
+    k = 128
+    g = torch.Generator(device="cuda").manual_seed(patches)
+    lin = (torch.rand(patches * k, 128, device="cuda", generator=g) - 0.5).bfloat16()
+    lat = torch.randint(-3, 4, (patches, 16), device="cuda", generator=g).float()
+    y = mlp.fused_chain([(lin, 1), (lat, k)], layers)
+    x = torch.cat((lin.float(), lat.repeat_interleave(k, dim=0)), dim=1)
+    ym = ref_chain(x, layers, 0, model_bf16=True)
+    assert (y - ym).abs().max().item() / ym.abs().max().item() < MODEL_RTOL
+    if patches == 301:
+        with tempfile.TemporaryDirectory() as d:
+            torch.save({"lin": lin.cpu(), "lat": lat.cpu(), "layers": [(w.cpu(), b.cpu(), r) for w, b, r in layers]}, os.path.join(d, "in.pt"))
+            code = ("import sys, torch; sys.path[:0] = [%r, %r]; import __graft_entry__; from pcc_b200 import mlp_ops; "
+                    "t = torch.load(%r); layers = [(w.cuda(), b.cuda(), r) for w, b, r in t['layers']]; "
+                    "y = mlp_ops.fused_chain([(t['lin'].cuda(), 1), (t['lat'].cuda(), 128)], layers); torch.save(y.cpu(), %r)"
+                    % (os.getcwd(), os.path.join(os.getcwd(), "point-cloud-compression_b200"), os.path.join(d, "in.pt"), os.path.join(d, "out.pt")))
+            subprocess.run([sys.executable, "-c", code], check=True, env=dict(os.environ, PCC_DEC_SLOTS="1"), timeout=300)
+            assert torch.equal(torch.load(os.path.join(d, "out.pt")), y.cpu())
+
+
 def test_wide_fp32_segment_single_layer_and_run_chain_planner(mlp):
     """PointnetSAModule SA3-like: [gathered features fp32 256ch | xyz 3ch] -> 256 -> 256 -> 512 -> 1024, max over 128.
     The planner runs the layers that fit as fused launches and the rest on the streamed tcgen05 GEMM."""
