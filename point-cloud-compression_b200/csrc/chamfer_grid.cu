@@ -313,22 +313,6 @@ grid_nn_kernel(int P1, int P2, const float4 *__restrict__ sorted, const unsigned
 // scatter in the build: 260 us against 238 us on the bench's clumpy reconstructions, 107 us against ~125 us on close clouds where
 // the 3x3x3 step and the build dominate (keyed kernel: 286 / 119 us).  Looking one row ahead with the table look-ups of the far
 // walk, and double-buffering the candidate batches, changed nothing / lost 4 %.)
-__device__ __forceinline__ unsigned long long add_f32x2(unsigned long long a, unsigned long long b) {
-    unsigned long long r;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ unsigned long long mul_f32x2(unsigned long long a, unsigned long long b) {
-    unsigned long long r;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ unsigned long long dup_neg_f32x2(float x) {
-    unsigned long long r;
-    const float n = -x;
-    asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(n));
-    return r;
-}
 __device__ __forceinline__ float fmin3(float a, float b, float c) {
     float r;
     asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));

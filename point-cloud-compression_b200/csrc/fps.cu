@@ -65,19 +65,44 @@ __device__ __forceinline__ void block_argmax(FpsSlots &s, int buf, unsigned bits
 }
 
 // Update the PPT register-resident points of this thread against centre c and return the thread's best.
+// Even PPT: two points per packed-fp32 instruction for the three differences and the three squares (each half is the IEEE
+// operation of dist2_rn: p + (-c) == p - c exactly); the two sums per point stay scalar -- ptxas contracts mul.rn.f32x2 +
+// add.rn.f32x2 into FFMA2 whatever --fmad says, which would change dist2_rn's rounding.  10 issue slots per pair instead of 16:
+// the single-CTA kernel is issue bound (~150 instructions per thread and iteration on a full SM).
 template <int PPT>
 __device__ __forceinline__ void fps_local_update(const float (&px)[PPT], const float (&py)[PPT],
                                                  const float (&pz)[PPT], float (&md)[PPT], float cx, float cy,
                                                  float cz, unsigned &bits, int &slot) {
     float best = -1.0f;
     slot = 0;
+    if constexpr (PPT % 2 == 0) {
+        const unsigned long long ncx = dup_neg_f32x2(cx), ncy = dup_neg_f32x2(cy), ncz = dup_neg_f32x2(cz);
 #pragma unroll
-    for (int p = 0; p < PPT; ++p) {
-        const float d = dist2_rn(px[p], py[p], pz[p], cx, cy, cz);
-        md[p] = fminf(md[p], d);  // == `if (d < md) md = d` (pn_kit.py:327-328) for non-NaN inputs
-        if (md[p] > best) {       // strict: the lowest p (lowest global index) keeps a tie
-            best = md[p];
-            slot = p;
+        for (int p = 0; p < PPT; p += 2) {
+            const unsigned long long dx = add_f32x2(pack_f32x2(px[p], px[p + 1]), ncx), dy = add_f32x2(pack_f32x2(py[p], py[p + 1]), ncy),
+                                     dz = add_f32x2(pack_f32x2(pz[p], pz[p + 1]), ncz);
+            const float2 sx = unpack_f32x2(mul_f32x2(dx, dx)), sy = unpack_f32x2(mul_f32x2(dy, dy)), sz = unpack_f32x2(mul_f32x2(dz, dz));
+            const float d0 = __fadd_rn(__fadd_rn(sx.x, sy.x), sz.x), d1 = __fadd_rn(__fadd_rn(sx.y, sy.y), sz.y);
+            md[p] = fminf(md[p], d0);
+            md[p + 1] = fminf(md[p + 1], d1);
+            if (md[p] > best) {       // strict: the lowest p (lowest global index) keeps a tie
+                best = md[p];
+                slot = p;
+            }
+            if (md[p + 1] > best) {
+                best = md[p + 1];
+                slot = p + 1;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int p = 0; p < PPT; ++p) {
+            const float d = dist2_rn(px[p], py[p], pz[p], cx, cy, cz);
+            md[p] = fminf(md[p], d);  // == `if (d < md) md = d` (pn_kit.py:327-328) for non-NaN inputs
+            if (md[p] > best) {       // strict: the lowest p (lowest global index) keeps a tie
+                best = md[p];
+                slot = p;
+            }
         }
     }
     bits = __float_as_uint(best);

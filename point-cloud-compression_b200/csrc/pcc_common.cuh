@@ -59,6 +59,27 @@ __device__ __forceinline__ uint64_t dup_f32x2(float x) {
     asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(x));
     return r;
 }
+__device__ __forceinline__ unsigned long long add_f32x2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long mul_f32x2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long dup_neg_f32x2(float x) {
+    unsigned long long r;
+    const float n = -x;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(n));
+    return r;
+}
+__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
 __device__ __forceinline__ float2 unpack_f32x2(uint64_t v) {
     float2 r;
     asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
