@@ -253,7 +253,7 @@ def ae_forward_train(mod, xyz):
         # one forward kernel (the inference one: no activation is kept) and one backward kernel that recomputes them per tile
         with torch.no_grad():
             idx8 = ops.knn_patch_u8(xyz, K)                                                            # pn_kit.py:190
-        feat = T.sa_indexed_train(xyz, idx8, sa_l)                                                     # pn_kit.py:191-207  [BS*P, 128]
+        feat = T.sa_indexed_train(xyz, idx8, sa_l, out_bf16=True)                                      # pn_kit.py:191-207  bf16 [BS*P, 128]
     else:
         with torch.no_grad():
             _, _, grouped = ops.knn(xyz, xyz, K, return_nn=True, centre_sub=True, nn_only=True)        # pn_kit.py:190-191

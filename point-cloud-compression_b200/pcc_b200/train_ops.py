@@ -191,9 +191,9 @@ class _SaIndexed(torch.autograd.Function):
     kernel: nothing is kept but the inputs) and one backward kernel that recomputes the activations (csrc/sa_bwd.cu)."""
 
     @staticmethod
-    def forward(ctx, patches, idx8, w0, b0, w1, b1, w2, b2):
+    def forward(ctx, patches, idx8, w0, b0, w1, b1, w2, b2, out_bf16):
         layers = [(w0.detach(), b0.detach(), True), (w1.detach(), b1.detach(), True), (w2.detach(), b2.detach(), True)]
-        out = mlp_ops.sa_chain_indexed(patches, idx8, layers, out_dtype=torch.float32)
+        out = mlp_ops.sa_chain_indexed(patches, idx8, layers, out_dtype=torch.bfloat16 if out_bf16 else torch.float32)
         ctx.save_for_backward(patches, idx8, w0, b0, w1, b1, w2, b2)
         return out
 
@@ -201,14 +201,15 @@ class _SaIndexed(torch.autograd.Function):
     def backward(ctx, dout):
         patches, idx8, *params = ctx.saved_tensors
         grads = mlp_ops.sa_chain_indexed_bwd(patches, idx8, params, dout)
-        return (None, None) + tuple(g.to(p.dtype).reshape(p.shape) for g, p in zip(grads, params))
+        return (None, None) + tuple(g.to(p.dtype).reshape(p.shape) for g, p in zip(grads, params)) + (None,)
 
 
-def sa_indexed_train(patches, idx8, layers):
+def sa_indexed_train(patches, idx8, layers, out_bf16=False):
     """Differentiable SetAbstraction stack (3 -> 32 -> 64 -> 128, ReLU everywhere, max over the 16 in-patch neighbours of idx8):
-    patches [BS, P, 3] fp32 (no gradient), layers [(weight, bias, True)] x 3 -> fp32 [BS * P, 128]."""
+    patches [BS, P, 3] fp32 (no gradient), layers [(weight, bias, True)] x 3 -> [BS * P, 128], fp32 or -- out_bf16: the kernel rounds
+    its fp32 result once, exactly what a `.to(torch.bfloat16)` of the fp32 output would hold, without the 268 MB fp32 round trip."""
     (w0, b0, _), (w1, b1, _), (w2, b2, _) = layers
-    return _SaIndexed.apply(patches, idx8, w0, b0, w1, b1, w2, b2)
+    return _SaIndexed.apply(patches, idx8, w0, b0, w1, b1, w2, b2, bool(out_bf16))
 
 
 def pad_bf16(t, width):
