@@ -339,13 +339,14 @@ int pcc_sa_chain_indexed(const float *patches, const uint8_t *idx8, int64_t poin
  * (/root/reference/train.py:193-221 -> pn_kit.py:196-207) -- in one kernel that recomputes the activations tile by tile
  * (csrc/sa_bwd.cu) instead of storing them in the forward pass.  patches / idx8 / points / pts_per_patch as in the forward call;
  * w0 [32, 3], b0 [32], w1 [64, 32], b1 [64], w2 [128, 64], b2 [128] fp32 (the master weights; operands are rounded to bf16 as in
- * the forward kernel); grad_out [points, 128] fp32 = dLoss / d(out).  The gradients are ADDED into dw0 .. db2 (fp32, same shapes):
- * zero them first.  The grouped coordinates are data, so there is no input gradient.
+ * the forward kernel); grad_out = dLoss / d(out): `points` rows of 128 values, grad_ld elements apart (>= 128), fp32 (grad_dtype 0)
+ * or bf16 (grad_dtype 1: the slice of the next stack's input gradient autograd hands back, read in place).  The gradients are ADDED
+ * into dw0 .. db2 (fp32, same shapes): zero them first.  The grouped coordinates are data, so there is no input gradient.
  */
 int pcc_sa_chain_indexed_bwd(const float *patches, const uint8_t *idx8, int64_t points, int pts_per_patch, const float *w0,
                              const float *b0, const float *w1, const float *b1, const float *w2, const float *b2,
-                             const float *grad_out, float *dw0, float *db0, float *dw1, float *db1, float *dw2, float *db2,
-                             void *stream);
+                             const void *grad_out, int grad_dtype, int64_t grad_ld, float *dw0, float *db0, float *dw1, float *db1,
+                             float *dw2, float *db2, void *stream);
 
 /*
  * Grouping of one PointNet++ set-abstraction level (/root/reference/pointnet_sa_module.py:73-85: group_points of the features

@@ -50,7 +50,9 @@ constexpr int TMEM_COLS = 512;            // per slot: 128 (tile accumulator) + 
 struct Params {
     const float *xyz;            // patches [BS * Pp, 3]
     const unsigned char *idx8;   // [points, 16]
-    const float *g;              // [points, 128] gradient of the pooled output
+    const float *g;              // [points, 128] gradient of the pooled output: fp32 rows of g_ld elements, or ...
+    const __nv_bfloat16 *g16;    // ... bf16 rows (non-NULL: autograd hands the PointNet stack's input gradient over as a bf16 slice)
+    long long g_ld;
     const float *w0, *b0, *w1, *b1, *w2, *b2;
     float *dw0, *db0, *dw1, *db1, *dw2, *db2;   // accumulated with atomics (zeroed by the caller)
     int n_tiles, pts_per_patch, pts_shift;
@@ -236,7 +238,10 @@ __global__ void __launch_bounds__(THREADS, 1) sa_bwd_kernel(const __grid_constan
         for (long long tile = tile0; tile < n_tiles; tile += tstride) {
             float gq[8];                                       // pooled gradient of my channel, the tile's 8 points (used in P2)
 #pragma unroll
-            for (int p = 0; p < 8; ++p) gq[p] = __ldg(prm.g + (tile * 8 + p) * 128 + row);
+            for (int p = 0; p < 8; ++p) {
+                const long long o = (static_cast<long long>(tile) * 8 + p) * prm.g_ld + row;
+                gq[p] = prm.g16 ? __bfloat162float(prm.g16[o]) : __ldg(prm.g + o);
+            }
             // ---- P0: recentre, layer 0 (fp32), X1+ row ----
             {
                 const float lx = __fsub_rn(gn[0], gc[0]), ly = __fsub_rn(gn[1], gc[1]), lz = __fsub_rn(gn[2], gc[2]);
@@ -395,19 +400,23 @@ __global__ void __launch_bounds__(THREADS, 1) sa_bwd_kernel(const __grid_constan
 // Weight gradients of the SetAbstraction stack whose forward pass is pcc_sa_chain_indexed: see include/pcc_b200.h
 PCC_API int pcc_sa_chain_indexed_bwd(const float *patches, const unsigned char *idx8, int64_t points, int pts_per_patch, const float *w0,
                                      const float *b0, const float *w1, const float *b1, const float *w2, const float *b2,
-                                     const float *grad_out, float *dw0, float *db0, float *dw1, float *db1, float *dw2, float *db2,
-                                     void *stream) {
+                                     const void *grad_out, int grad_dtype, int64_t grad_ld, float *dw0, float *db0, float *dw1, float *db1,
+                                     float *dw2, float *db2, void *stream) {
     using namespace pcc;
     PCC_REQUIRE(patches && idx8 && w0 && b0 && w1 && b1 && w2 && b2 && grad_out && dw0 && db0 && dw1 && db1 && dw2 && db2,
                 "pcc_sa_chain_indexed_bwd: null pointer");
     PCC_REQUIRE(points >= 0 && points % 8 == 0 && pts_per_patch >= 8 && pts_per_patch <= 256 && pts_per_patch % 8 == 0 &&
                     points % pts_per_patch == 0 && points / 8 < (1ll << 28),
                 "pcc_sa_chain_indexed_bwd: bad shape points=%lld pts_per_patch=%d", static_cast<long long>(points), pts_per_patch);
+    PCC_REQUIRE((grad_dtype == 0 || grad_dtype == 1) && grad_ld >= 128, "pcc_sa_chain_indexed_bwd: grad_dtype=%d grad_ld=%lld", grad_dtype,
+                static_cast<long long>(grad_ld));
     if (points == 0) return 0;
     sab::Params p{};
     p.xyz = patches;
     p.idx8 = idx8;
-    p.g = grad_out;
+    p.g = grad_dtype == 0 ? static_cast<const float *>(grad_out) : nullptr;
+    p.g16 = grad_dtype == 1 ? static_cast<const __nv_bfloat16 *>(grad_out) : nullptr;
+    p.g_ld = grad_ld;
     p.w0 = w0; p.b0 = b0; p.w1 = w1; p.b1 = b1; p.w2 = w2; p.b2 = b2;
     p.dw0 = dw0; p.db0 = db0; p.dw1 = dw1; p.db1 = db1; p.dw2 = dw2; p.db2 = db2;
     p.n_tiles = static_cast<int>(points / 8);

@@ -69,7 +69,7 @@ SIGNATURES.update({
     "pcc_groupmax_bwd_bf16": (_i, [_vp, _vp, _vp, _i64, _i, _i, _vp, _i64, _vp]),
     "pcc_wgrad_bf16": (_i, [_vp, _i64, _i, _vp, _i64, _i, _i64, _vp, _i64, _vp, _vp]),
     "pcc_sa_chain_indexed": (_i, [_vp, _vp, _i64, _i, ctypes.POINTER(PccMlpLayer), _i, _vp, _i, _vp]),
-    "pcc_sa_chain_indexed_bwd": (_i, [_vp, _vp, _i64, _i] + [_vp] * 14),
+    "pcc_sa_chain_indexed_bwd": (_i, [_vp, _vp, _i64, _i] + [_vp] * 7 + [_i, _i64] + [_vp] * 7),
     "pcc_normals_pca_f32": (_i, [_vp, _i64, _i, _vp, _vp]),
     "pcc_p2plane_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "pcc_uc_f32": (_i, [_vp, _vp, _i, _i, _vp, _vp]),

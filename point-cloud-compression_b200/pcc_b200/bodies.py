@@ -271,9 +271,18 @@ def ae_forward_train(mod, xyz):
     latent_q = mod.quantize(latent)                                                                    # AE.py:45 (STE)
     k = mod.k
     ip = [(mod.inv_pool[i].weight, mod.inv_pool[i].bias, True) for i in (0, 2, 4)]
-    lin = T.mlp_train(T.pad_bf16(latent_q, 64), ip, mode="bf16")                                        # AE.py:48  bf16 [BS, 128 * k]
-    ch = lin.shape[1] // k
-    lin_pts = lin.view(BS, ch, k).permute(0, 2, 1).reshape(BS * k, ch)                                  # AE.py:49
+    # AE.py:49 views the last Linear's output as [channels, k] per patch and permutes it to [k, channels]; permuting that layer's
+    # ROWS instead (as ae_decode does for inference) moves 2 x 67 MB of weights per step where the activation and its gradient
+    # were 2 x 2 x 67 MB of strided copies, and the GEMM writes the layout the decoder reads
+    l4 = mod.inv_pool[4]
+    ch = l4.out_features // k
+    if os.environ.get("PCC_TRAIN_PERMUTE_ACT"):   # A/B: the reference's own order of operations
+        lin = T.mlp_train(T.pad_bf16(latent_q, 64), ip, mode="bf16")                                    # AE.py:48  bf16 [BS, 128 * k]
+        lin_pts = lin.view(BS, ch, k).permute(0, 2, 1).reshape(BS * k, ch)                              # AE.py:49
+    else:
+        ip[2] = (l4.weight.view(ch, k, -1).permute(1, 0, 2).reshape(ch * k, -1), l4.bias.view(ch, k).t().reshape(-1), True)
+        lin = T.mlp_train(T.pad_bf16(latent_q, 64), ip, mode="bf16")                                    # AE.py:48  bf16 [BS, k * 128]
+        lin_pts = lin.view(BS * k, ch)                                                                  # AE.py:49
     d = latent_q.shape[1]
     x0d = torch.cat((lin_pts, latent_q.to(torch.bfloat16).repeat_interleave(k, dim=0),
                      torch.zeros((BS * k, (-(ch + d)) % 64), dtype=torch.bfloat16, device=xyz.device)), dim=1)   # AE.py:50-51

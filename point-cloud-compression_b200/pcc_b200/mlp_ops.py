@@ -162,12 +162,15 @@ def sa_chain_indexed_bwd(patches, idx8, params, grad_out):
     ps = [t.detach().float().contiguous() for t in params]
     if [tuple(t.shape) for t in ps] != [(32, 3), (32,), (64, 32), (64,), (128, 64), (128,)]:
         raise ValueError("pcc_b200.sa_chain_indexed_bwd: the stack must be 3 -> 32 -> 64 -> 128")
-    g = grad_out.detach().float().contiguous()
+    g = grad_out.detach()
     if tuple(g.shape) != (BS * P, 128):
         raise ValueError("pcc_b200.sa_chain_indexed_bwd: grad_out must be [BS * P, 128]")
+    if g.dtype not in (torch.float32, torch.bfloat16) or g.stride(1) != 1 or g.stride(0) < 128:
+        g = g.float().contiguous()   # fp32 or bf16 rows are read in place (a column slice of a wider gradient included)
     grads = [torch.zeros_like(t) for t in ps]
     with torch.cuda.device(patches.device):
         _lib.check(lib.pcc_sa_chain_indexed_bwd(patches.data_ptr(), idx8.data_ptr(), BS * P, P, *[t.data_ptr() for t in ps], g.data_ptr(),
+                                                0 if g.dtype == torch.float32 else 1, g.stride(0),
                                                 *[t.data_ptr() for t in grads], torch.cuda.current_stream().cuda_stream),
                    "pcc_sa_chain_indexed_bwd")
     return grads

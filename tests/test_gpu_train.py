@@ -268,6 +268,17 @@ def test_sa_fused_backward_matches_autograd_of_the_bf16_model(BS, P):
         r = (a - w.grad).norm().item() / w.grad.norm().item()
         assert r < 1e-2, f"{name}: relative L2 error {r:.3e}"
 
+    # the gradient as autograd hands it over in the AE: a bf16 column slice of the PointNet stack's [M, 192] input gradient, read in
+    # place -- the same six tensors as from an fp32 contiguous copy of those values
+    from pcc_b200 import mlp_ops
+    wide = torch.zeros(BS * P, 192, dtype=torch.bfloat16, device="cuda")
+    wide[:, :128] = G.to(torch.bfloat16)
+    params = [w.detach() for w in ws]
+    in_place = mlp_ops.sa_chain_indexed_bwd(patches, idx8, params, wide[:, :128])
+    copied = mlp_ops.sa_chain_indexed_bwd(patches, idx8, params, wide[:, :128].float().contiguous())
+    for a, b in zip(in_place, copied):   # the CTAs add their partial sums with fp32 atomics: the order, not the values, differs
+        assert (a - b).norm().item() <= 1e-5 * b.norm().item()
+
 
 def test_inference_after_fused_optimiser_steps_sees_the_new_weights():
     """torch's fused Adam kernel updates parameters without bumping their version counters, which every weight cache keys on:

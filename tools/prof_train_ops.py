@@ -13,7 +13,10 @@ start = torch.zeros(32, dtype=torch.int64, device="cuda")
 for _ in range(3):
     tr.step(x, start)
 torch.cuda.synchronize()
-with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True) as prof:
     tr.step(x, start)
     torch.cuda.synchronize()
 print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=70))
+# the aten ops with their input shapes: which tensors the glue kernels (copies, casts, cat) move
+print(prof.key_averages(group_by_input_shape=True).table(sort_by="self_cuda_time_total", row_limit=30, max_name_column_width=40,
+                                                         max_shapes_column_width=90))
