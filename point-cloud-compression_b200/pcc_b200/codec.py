@@ -102,6 +102,29 @@ class PatchCodec:
         return ops.eval_metrics(r["dx"], r["per_cloud"], bbox)                    # eval.py:84,88-92,199-205 in one kernel
 
     @torch.no_grad()
+    def evaluate_sweep(self, pairs, n_streams=2):
+        """eval.py's loop over a test set (eval.py:167-221): `pairs` yields (decomp [b, N, 3], original [b, N, 3]) chunks on the
+        device; returns the [sum b, 3] metrics table of `evaluate`, chunk after chunk.  Consecutive chunks run on alternating
+        streams: the grid build of a chunk (one 1024-thread CTA per cloud and side, latency bound, one per SM) shares the SMs with
+        the nearest-neighbour kernel of the chunk before it (small CTAs without shared memory) instead of waiting for it."""
+        dev = None
+        rows, streams, main = [], [], None
+        for ci, (y, x) in enumerate(pairs):
+            if main is None:
+                dev = x.device
+                main = torch.cuda.current_stream(dev)
+                streams = [torch.cuda.Stream(dev) for _ in range(max(1, int(n_streams)))]
+            st = streams[ci % len(streams)]
+            st.wait_stream(main)             # the chunk was produced on the caller's stream
+            with torch.cuda.stream(st):
+                y.record_stream(st)
+                x.record_stream(st)
+                rows.append(self.evaluate(y, x))
+        for st in streams:
+            main.wait_stream(st)
+        return torch.cat(rows) if rows else torch.zeros((0, 3), dtype=torch.float64, device=dev)
+
+    @torch.no_grad()
     def encode_latents(self, prob, latent_q, centres):
         """compress.py:131-136 for a batch: conditional PMF of every latent symbol given the decoded centres, 16-bit CDFs,
         arithmetic coding -- one .p.bin byte stream per cloud.  Returns (bytes uint8 [B, cap], nbytes int32 [B])."""

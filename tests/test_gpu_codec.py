@@ -293,3 +293,21 @@ def test_graphed_sweep_guards(setup):
     torch.cuda.synchronize()
     assert codec._sweep_graphs["graphs"] is not graphs_before
     assert all(all(torch.equal(a, b) for a, b in zip(got[s], e)) for s, e in enumerate(eager(start2)))
+
+
+def test_evaluate_sweep_equals_chunk_by_chunk_evaluate(setup):
+    """PatchCodec.evaluate_sweep (chunks alternating over two streams, inputs produced on the caller's stream) returns the rows of
+    evaluate() chunk by chunk, bit for bit -- ragged last chunk, and an empty sweep."""
+    _, codec, _ = setup
+    x = torch.from_numpy(synth.modelnet_like(7, 8192, seed=31)).cuda()
+    y = torch.from_numpy(synth.decompressed_like(x.cpu().numpy(), seed=32)).cuda()
+
+    def chunks():
+        for i in range(0, 7, 3):
+            yield y[i:i + 3] * 1.5, x[i:i + 3] * 1.5
+
+    got = codec.evaluate_sweep(chunks())
+    want = torch.cat([codec.evaluate(a, b) for a, b in chunks()])
+    assert got.shape == (7, 3) and torch.equal(got, want)
+    assert codec.evaluate_sweep(iter(())).shape == (0, 3)
+

@@ -99,13 +99,14 @@ def cfg4(clock, codec, dev, rank, world, total=10000, chunk=256):
     b, e = pdist.shard_range(total, rank, world)
     table = {}
 
-    def sweep():
-        rows = []
+    def chunks():
         for i in range(b, e, chunk):
             n = min(chunk, e - i)
             s = 1.0 - 1e-6 * (i // chunk)               # a different cloud set per chunk (uniform scaling keeps the structure)
-            rows.append(codec.evaluate(noisy[:n] * s, base[:n] * s))
-        local = torch.cat(rows) if rows else torch.zeros((0, 3), dtype=torch.float64, device=dev)
+            yield noisy[:n] * s, base[:n] * s
+
+    def sweep():
+        local = codec.evaluate_sweep(chunks())          # chunks alternate over two streams (build of one beside the search of the other)
         table["m"] = pdist.gather_rows(local, total)    # the sweep's only collective
 
     ms = clock.ms(sweep, 3, 1)
