@@ -20,10 +20,11 @@
 // exchange -- so the co-resident kernel runs the head of the sampling (head_iterations()) and hands over its running
 // distances; this kernel continues from the centre that kernel picked last.
 // Measured and not kept: the cloud's maximum by one shared-memory atomicMax per warp instead of phase D's reduction (a 64-bit
-// shared atomicMax is a compare-and-swap loop, ATOMS.CAST.SPIN: 16.6 ms against 15.6); a second level inside phase B (eight 32-point sub-buckets per bucket with their own boxes and records
-// in L2, only the reachable ones loaded: half the bytes) -- 31.5 ms against 18.9 ms: phase B is one L2 round trip deep and the
-// iteration waits for its slowest warp, so the extra dependent trip for the sub-records and the per-sub-bucket arg-max cost
-// more than the bytes they save.
+// shared atomicMax is a compare-and-swap loop, ATOMS.CAST.SPIN: 16.6 ms against 15.6); a second level inside phase B (eight
+// 32-point sub-buckets per bucket with their own boxes and records in L2, only the reachable ones loaded: half the bytes) --
+// 31.5 ms against 18.9 ms: phase B is one L2 round trip deep and the iteration waits for its slowest warp, so the extra
+// dependent trip for the sub-records and the per-sub-bucket arg-max cost more than the bytes they save.
+// clock64 ticks per iteration at 1M points (make ticks; 12.6 bucket visits on average): A 0.5 k, B 2.2 k, C + D 1.2 k clocks.
 //
 // Exactness of the skip.  For every point p of a bucket with box [lo, hi] and the exact gap vector g(c) to the box,
 // |p - c|^2 >= |g|^2.  dist2_rn is 5 roundings deep, so dist2_rn(p, c) >= |p - c|^2 (1 - 5u), u = 2^-24; the box distance
